@@ -1,0 +1,719 @@
+// sm_100a kernels for the Curvine sequential block-read path + their extern "C" launchers
+// (declared in include/curvine_b200_kernels.h, which cites the reference code each one replaces).
+//
+// This is a byte-stream / integer path: no tensor cores.  Design:
+//   * CRC is linear over GF(2).  Each warp owns a contiguous *segment* and walks it in 512-byte rows
+//     (one coalesced 16-byte vector per lane).  Every lane keeps 4 independent 32-bit Horner chains
+//     (one per word of its vector): a <- a * x^4096 (+) w.  The multiply by the row constant x^4096 is
+//     4 shared-memory lookups; the tables are replicated per lane ([table][byte][lane]) so bank == lane and
+//     the data-dependent lookups are bank-conflict free.
+//   * A segment ends with one fold per lane (weights x^(128*e)) and a warp-shuffle XOR reduction.
+//   * Segment partials are folded per block (Horner with x^(8*SEG)) by a tiny second kernel, which also
+//     applies init/xorout, so results are bit-identical to crc32fast / zlib (or CRC-32C).
+//   * The same row walker optionally stores the (re-aligned) vectors to a destination, which gives the
+//     fused frame-unpack+gather+CRC (K2), frame-pack+CRC (K4) and page scatter/gather (K3) kernels.
+// Persistent launch: one 1024-thread CTA per SM (148 on B200), contiguous unit ranges per CTA.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/curvine_b200_kernels.h"
+#include "crc_gf.h"
+
+namespace cv {
+
+struct Piece {
+    const uint8_t* src;
+    uint8_t* dst;  // nullptr when there is nothing to store
+    uint64_t len;
+};
+
+struct Geom {
+    uint32_t head;   // bytes before the first 16-byte aligned anchor address
+    uint32_t tail;   // bytes after the last whole 16-byte vector
+    uint64_t body;   // multiple of 16
+    uint32_t nseg;   // ceil(body / SEG)
+    uint32_t units;  // max(1, nseg) if len > 0 else 0
+};
+
+template <bool DST>
+__device__ __forceinline__ Geom piece_geom(const Piece& p, uint32_t seg_shift) {
+    Geom g;
+    const uintptr_t anchor = DST ? reinterpret_cast<uintptr_t>(p.dst) : reinterpret_cast<uintptr_t>(p.src);
+    uint32_t head = (16u - static_cast<uint32_t>(anchor & 15u)) & 15u;
+    if (head > p.len) head = static_cast<uint32_t>(p.len);
+    const uint64_t rest = p.len - head;
+    g.head = head;
+    g.body = rest & ~15ull;
+    g.tail = static_cast<uint32_t>(rest - g.body);
+    g.nseg = static_cast<uint32_t>((g.body + ((1ull << seg_shift) - 1)) >> seg_shift);
+    g.units = p.len ? (g.nseg ? g.nseg : 1u) : 0u;
+    return g;
+}
+
+// ------------------------------------------------------------------ piece preparation kernels
+
+__global__ void prep_blocks_kernel(const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t n,
+                                   uint32_t seg_shift, Piece* pieces, uint32_t* counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Piece p{base + off[i], nullptr, len[i]};
+    pieces[i] = p;
+    counts[i] = piece_geom<false>(p, seg_shift).units;
+}
+
+__device__ __forceinline__ uint32_t be32(const uint8_t* p) {
+    return (uint32_t(__ldg(p)) << 24) | (uint32_t(__ldg(p + 1)) << 16) | (uint32_t(__ldg(p + 2)) << 8) |
+           uint32_t(__ldg(p + 3));
+}
+
+// K2 front end: RpcMessage::decode_protocol + RawClient::check_response for every frame in parallel.
+__global__ void prep_unpack_kernel(const uint8_t* wire, const CvFrameDesc* desc, uint32_t n, uint8_t* dst,
+                                   uint32_t seg_shift, Piece* pieces, uint32_t* counts, uint32_t* err_flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CvFrameDesc d = desc[i];
+    const uint8_t* f = wire + d.wire_off;
+    const int32_t total_len = static_cast<int32_t>(be32(f));
+    const int32_t header_len = static_cast<int32_t>(be32(f + 4));
+    const uint8_t code = __ldg(f + 8), status = __ldg(f + 9);
+    const int64_t req_id = static_cast<int64_t>((uint64_t(be32(f + 10)) << 32) | be32(f + 14));
+    const int32_t seq_id = static_cast<int32_t>(be32(f + 18));
+    const int64_t data_len = int64_t(total_len) - header_len - CV_HEAD_SIZE;
+    uint32_t e = 0;
+    if (data_len < 0 || data_len > CV_MAX_DATA_SIZE) e |= CV_FERR_DATA_RANGE;
+    if (int64_t(total_len) != int64_t(CV_HEAD_SIZE) + d.header_len + d.data_len) e |= CV_FERR_TOTAL_LEN;
+    if (header_len != static_cast<int32_t>(d.header_len)) e |= CV_FERR_HEADER_LEN;
+    if (code != d.code) e |= CV_FERR_CODE;
+    if (status != d.status) e |= CV_FERR_STATUS;
+    if (req_id != d.req_id) e |= CV_FERR_REQ_ID;
+    if (seq_id != d.seq_id) e |= CV_FERR_SEQ_ID;
+    if (err_flags) err_flags[i] = e;
+    Piece p{f + CV_PROTOCOL_SIZE + d.header_len, dst + d.dst_off, d.data_len};
+    pieces[i] = p;
+    counts[i] = piece_geom<true>(p, seg_shift).units;
+}
+
+// K4 front end: RpcMessage::encode_protocol for every frame in parallel (big-endian prefix, no header).
+__global__ void prep_pack_kernel(const uint8_t* src, const CvFrameDesc* desc, uint32_t n, uint8_t* wire,
+                                 uint32_t seg_shift, Piece* pieces, uint32_t* counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CvFrameDesc d = desc[i];
+    uint8_t* f = wire + d.wire_off;
+    const uint32_t total_len = CV_HEAD_SIZE + d.data_len;
+    const uint64_t rid = static_cast<uint64_t>(d.req_id);
+    const uint32_t sid = static_cast<uint32_t>(d.seq_id);
+    f[0] = total_len >> 24, f[1] = total_len >> 16, f[2] = total_len >> 8, f[3] = total_len;
+    f[4] = f[5] = f[6] = f[7] = 0;
+    f[8] = d.code, f[9] = d.status;
+#pragma unroll
+    for (int k = 0; k < 8; k++) f[10 + k] = static_cast<uint8_t>(rid >> (56 - 8 * k));
+    f[18] = sid >> 24, f[19] = sid >> 16, f[20] = sid >> 8, f[21] = sid;
+    Piece p{src + d.dst_off, f + CV_PROTOCOL_SIZE, d.data_len};
+    pieces[i] = p;
+    counts[i] = piece_geom<true>(p, seg_shift).units;
+}
+
+__global__ void prep_segs_kernel(const uint8_t* src, const CvSeg* segs, uint32_t n, uint8_t* dst, uint32_t seg_shift,
+                                 Piece* pieces, uint32_t* counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CvSeg s = segs[i];
+    Piece p{src + s.src_off, dst + s.dst_off, s.len};
+    pieces[i] = p;
+    counts[i] = piece_geom<true>(p, seg_shift).units;
+}
+
+__global__ void prep_deinterleave_kernel(const uint8_t* gathered, uint64_t shard_stride, uint32_t world,
+                                         uint64_t block_size, uint64_t n_blocks, uint64_t file_len, uint8_t* dst,
+                                         uint32_t seg_shift, Piece* pieces, uint32_t* counts) {
+    const uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint64_t start = b * block_size;
+    const uint64_t len = start >= file_len ? 0 : (file_len - start < block_size ? file_len - start : block_size);
+    Piece p{gathered + (b % world) * shard_stride + (b / world) * block_size, dst + start, len};
+    pieces[b] = p;
+    counts[b] = piece_geom<true>(p, seg_shift).units;
+}
+
+__global__ void expand_streams_kernel(const CvStreamDesc* streams, uint32_t n_streams, CvFrameDesc* out,
+                                      uint32_t n_frames) {
+    // one warp per stream, lanes stride over its frames
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (s >= n_streams) return;
+    const CvStreamDesc d = streams[s];
+    const uint64_t nf = d.block_len ? (d.block_len + d.chunk_size - 1) / d.chunk_size : 0;
+    for (uint64_t f = lane; f < nf; f += 32) {
+        const uint64_t idx = uint64_t(d.first_frame) + f;
+        if (idx >= n_frames) break;
+        CvFrameDesc o;
+        o.wire_off = d.wire_off + f * (uint64_t(CV_PROTOCOL_SIZE) + d.chunk_size);
+        o.dst_off = d.dst_off + f * d.chunk_size;
+        const uint64_t rem = d.block_len - f * d.chunk_size;
+        o.data_len = static_cast<uint32_t>(rem < d.chunk_size ? rem : d.chunk_size);
+        o.header_len = 0;
+        o.req_id = d.req_id;
+        o.seq_id = d.first_seq_id + static_cast<int32_t>(f);
+        o.block = d.block;
+        o.code = d.code;
+        o.status = d.status;
+#pragma unroll
+        for (int k = 0; k < 6; k++) o.pad_[k] = 0;
+        out[idx] = o;
+    }
+}
+
+// first[b] / last[b]: frame range of block b (frames of a block are contiguous); zero-initialised by the caller
+__global__ void mark_block_ranges_kernel(const CvFrameDesc* desc, uint32_t n, uint32_t n_blocks, uint32_t* first,
+                                         uint32_t* last) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = desc[i].block;
+    if (b >= n_blocks) return;
+    if (i == 0 || desc[i - 1].block != b) first[b] = i;
+    if (i == n - 1 || desc[i + 1].block != b) last[b] = i + 1;
+}
+
+// exclusive prefix sum of counts[0..n) into prefix[0..n]; single CTA (n is a frame/block count, not bytes)
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* counts, uint32_t n, uint32_t* prefix) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        warp_sums[lane] = wi - w;  // exclusive
+        if (lane == 31) carry = wi;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[warp] + incl - sum;
+    for (uint32_t i = lo; i < hi; i++) {
+        prefix[i] = run;
+        run += counts[i];
+    }
+    if (tid == 0) prefix[n] = carry;
+}
+
+// ------------------------------------------------------------------ the row walker
+
+constexpr uint32_t kTmWords = 4 * 256 * 32;  // replicated x^4096 tables: [table][byte][lane]
+constexpr uint32_t kSmemWords = kTmWords + 256 + 64 + 16;
+constexpr uint32_t kSmemBytes = kSmemWords * 4;
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// a * x^4096 mod P: four conflict-free shared-memory lookups.  tb = shared byte address of the lane's
+// column (tables + lane*4); entry (table t, byte v) lives at tb + t*32768 + v*128.  Byte extraction is a PRMT
+// (ALU pipe) and the scale-and-add an IMAD (FMA pipe) so the two integer pipes share the address math.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t mul_row(uint32_t a, uint32_t tb) {
+    const uint32_t i0 = __byte_perm(a, 0, 0x4440) * 128u + tb;
+    const uint32_t i1 = __byte_perm(a, 0, 0x4441) * 128u + tb;
+    const uint32_t i2 = __byte_perm(a, 0, 0x4442) * 128u + tb;
+    const uint32_t i3 = __byte_perm(a, 0, 0x4443) * 128u + tb;
+    return lds_u32(i0) ^ lds_u32(i1 + 32768u) ^ lds_u32(i2 + 65536u) ^ lds_u32(i3 + 98304u);
+}
+
+// y * x^32 mod P via the byte table
+__device__ __forceinline__ uint32_t mul_word(uint32_t y, const uint32_t* t0) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) y = t0[y & 0xffu] ^ (y >> 8);
+    return y;
+}
+
+// raw CRC (init 0, no xorout) of one 16-byte vector
+__device__ __forceinline__ uint32_t raw_vec(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, const uint32_t* t0) {
+    uint32_t r = mul_word(w0, t0);
+    r = mul_word(r ^ w1, t0);
+    r = mul_word(r ^ w2, t0);
+    return mul_word(r ^ w3, t0);
+}
+
+// 16 source bytes starting at the (possibly unaligned) address s; sh = s & 15 is warp-uniform.
+__device__ __forceinline__ uint4 load_shifted(const uint8_t* s, uint32_t sh) {
+    const uint4* p = reinterpret_cast<const uint4*>(s - sh);
+    const uint4 A = __ldg(p);
+    if (sh == 0) return A;
+    const uint4 B = __ldg(p + 1);
+    const uint32_t r8 = (sh & 3u) * 8u;
+    uint4 o;
+    switch (sh >> 2) {
+        case 0:
+            o.x = __funnelshift_r(A.x, A.y, r8), o.y = __funnelshift_r(A.y, A.z, r8);
+            o.z = __funnelshift_r(A.z, A.w, r8), o.w = __funnelshift_r(A.w, B.x, r8);
+            break;
+        case 1:
+            o.x = __funnelshift_r(A.y, A.z, r8), o.y = __funnelshift_r(A.z, A.w, r8);
+            o.z = __funnelshift_r(A.w, B.x, r8), o.w = __funnelshift_r(B.x, B.y, r8);
+            break;
+        case 2:
+            o.x = __funnelshift_r(A.z, A.w, r8), o.y = __funnelshift_r(A.w, B.x, r8);
+            o.z = __funnelshift_r(B.x, B.y, r8), o.w = __funnelshift_r(B.y, B.z, r8);
+            break;
+        default:
+            o.x = __funnelshift_r(A.w, B.x, r8), o.y = __funnelshift_r(B.x, B.y, r8);
+            o.z = __funnelshift_r(B.y, B.z, r8), o.w = __funnelshift_r(B.z, B.w, r8);
+            break;
+    }
+    return o;
+}
+
+#define CV_STEP(v)                       \
+    do {                                 \
+        a0 = mul_row(a0, tl) ^ (v).x;    \
+        a1 = mul_row(a1, tl) ^ (v).y;    \
+        a2 = mul_row(a2, tl) ^ (v).z;    \
+        a3 = mul_row(a3, tl) ^ (v).w;    \
+    } while (0)
+
+// One warp walks L bytes (multiple of 16) starting at src (dst is 16-byte aligned when DST; src is 16-byte
+// aligned when !DST).  Returns the segment's raw CRC in every lane (0 when !CRC).
+template <bool CRC, bool DST>
+__device__ __forceinline__ uint32_t walk_segment(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane,
+                                                 const uint32_t* smem, uint32_t poly) {
+    const uint32_t tl = static_cast<uint32_t>(__cvta_generic_to_shared(smem)) + lane * 4u;
+    const uint32_t* t0 = smem + kTmWords;
+    const uint32_t* xp128 = t0 + 256;
+    const uint32_t R = L >> 9;
+    const uint32_t nv = (L & 511u) >> 4;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    uint4 vr = make_uint4(0, 0, 0, 0);
+
+    if (!DST) {
+        const uint4* sp = reinterpret_cast<const uint4*>(src) + lane;
+        uint32_t j = 0;
+        for (; j + 4 <= R; j += 4) {
+            const uint4 v0 = ld_stream(sp + (j + 0) * 32);
+            const uint4 v1 = ld_stream(sp + (j + 1) * 32);
+            const uint4 v2 = ld_stream(sp + (j + 2) * 32);
+            const uint4 v3 = ld_stream(sp + (j + 3) * 32);
+            CV_STEP(v0);
+            CV_STEP(v1);
+            CV_STEP(v2);
+            CV_STEP(v3);
+        }
+        for (; j < R; j++) {
+            const uint4 v = ld_stream(sp + j * 32);
+            CV_STEP(v);
+        }
+        if (lane < nv) vr = ld_stream(sp + R * 32);
+    } else {
+        const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint8_t* s = src + lane * 16u;
+        uint4* dp = reinterpret_cast<uint4*>(dst) + lane;
+        uint32_t j = 0;
+        for (; j + 2 <= R; j += 2) {
+            const uint4 v0 = load_shifted(s + (j + 0) * 512u, sh);
+            const uint4 v1 = load_shifted(s + (j + 1) * 512u, sh);
+            dp[(j + 0) * 32] = v0;
+            dp[(j + 1) * 32] = v1;
+            if (CRC) {
+                CV_STEP(v0);
+                CV_STEP(v1);
+            }
+        }
+        for (; j < R; j++) {
+            const uint4 v = load_shifted(s + j * 512u, sh);
+            dp[j * 32] = v;
+            if (CRC) CV_STEP(v);
+        }
+        if (lane < nv) {
+            vr = load_shifted(s + R * 512u, sh);
+            dp[R * 32] = vr;
+        }
+    }
+    if (!CRC) return 0;
+    // lane fold: rows weigh x^(128*(31-lane+nv)), the partial row x^(128*(nv-1-lane))
+    uint32_t t = gf_mul(raw_vec(a0, a1, a2, a3, t0), xp128[31u - lane + nv], poly);
+    if (lane < nv) t ^= gf_mul(raw_vec(vr.x, vr.y, vr.z, vr.w, t0), xp128[nv - 1u - lane], poly);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t ^= __shfl_xor_sync(0xffffffffu, t, d);
+    return t;
+}
+
+// bytewise raw CRC (+ optional copy) of a short run; single lane
+template <bool CRC, bool DST>
+__device__ __forceinline__ uint32_t walk_bytes(const uint8_t* src, uint8_t* dst, uint32_t n, const uint32_t* t0) {
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint8_t b = __ldg(src + i);
+        if (DST) dst[i] = b;
+        if (CRC) r = t0[(r ^ b) & 0xffu] ^ (r >> 8);
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t find_piece(const uint32_t* prefix, uint32_t n, uint32_t u) {
+    uint32_t lo = 0, hi = n;  // largest p in [0,n) with prefix[p] <= u
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= u)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t advance_piece(const uint32_t* prefix, uint32_t n, uint32_t p, uint32_t u,
+                                                  uint32_t lane) {
+    for (;;) {
+        const uint32_t idx = p + 1 + lane;
+        const uint32_t v = (idx <= n) ? __ldg(prefix + idx) : 0xffffffffu;
+        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, u >= v));
+        p += cnt;
+        if (cnt < 32) return p;
+    }
+}
+
+template <bool CRC, bool DST>
+__global__ void __launch_bounds__(1024, 1)
+    walk_kernel(const Piece* __restrict__ pieces, uint32_t n_pieces, const uint32_t* __restrict__ prefix,
+                uint32_t seg_shift, const CrcConsts* __restrict__ cc, uint32_t* __restrict__ partial,
+                uint32_t partial_cap, uint32_t* __restrict__ headraw, uint32_t* __restrict__ tailraw) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t total = min(__ldg(prefix + n_pieces), partial_cap);
+    const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
+    const uint32_t u0 = min(total, blockIdx.x * per), u1 = min(total, u0 + per);
+    if (u0 >= u1) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t poly = 0;
+    if (CRC) {
+        const uint32_t* m = &cc->m[0][0];
+        for (uint32_t i = tid; i < kTmWords; i += 1024) smem[i] = __ldg(m + (i >> 5));
+        if (tid < 256) smem[kTmWords + tid] = cc->t0[tid];
+        if (tid < 64) smem[kTmWords + 256 + tid] = cc->xp128[tid];
+        if (tid < 16) smem[kTmWords + 256 + 64 + tid] = cc->pw8[tid];
+        poly = cc->poly;
+        __syncthreads();
+    }
+    const uint32_t* t0 = smem + kTmWords;
+    if (u0 + warp >= u1) return;
+    uint32_t p = find_piece(prefix, n_pieces, u0 + warp);
+    for (uint32_t u = u0 + warp; u < u1; u += 32) {
+        p = advance_piece(prefix, n_pieces, p, u, lane);
+        const Piece pc = pieces[p];
+        const Geom g = piece_geom<DST>(pc, seg_shift);
+        const uint32_t s = u - __ldg(prefix + p);
+        const uint64_t seg_off = uint64_t(s) << seg_shift;
+        uint32_t L = 0;
+        if (s < g.nseg) {
+            const uint64_t rem = g.body - seg_off;
+            L = rem < (1ull << seg_shift) ? static_cast<uint32_t>(rem) : (1u << seg_shift);
+        }
+        const uint32_t raw =
+            walk_segment<CRC, DST>(pc.src + g.head + seg_off, DST ? pc.dst + g.head + seg_off : nullptr, L, lane, smem, poly);
+        if (CRC && lane == 0) partial[u] = raw;
+        if (s == 0 && g.head && lane == 1) {
+            const uint32_t r = walk_bytes<CRC, DST>(pc.src, pc.dst, g.head, t0);
+            if (CRC) headraw[p] = r;
+        }
+        if (s + 1 == g.units && g.tail && lane == 2) {
+            const uint64_t o = g.head + g.body;
+            const uint32_t r = walk_bytes<CRC, DST>(pc.src + o, DST ? pc.dst + o : nullptr, g.tail, t0);
+            if (CRC) tailraw[p] = r;
+        }
+    }
+}
+
+// Fold unit partials into one CRC per block: acc = 0xFFFFFFFF; acc = acc * x^(8*len_u) (+) raw_u; out = ~acc.
+// One thread per block.  first/last == nullptr: block b is piece b.
+template <bool DST>
+__global__ void fold_blocks_kernel(const Piece* __restrict__ pieces, const uint32_t* __restrict__ prefix,
+                                   const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
+                                   uint32_t n_blocks, uint32_t seg_shift, uint32_t xp_seg,
+                                   const CrcConsts* __restrict__ cc, const uint32_t* __restrict__ partial,
+                                   const uint32_t* __restrict__ headraw, const uint32_t* __restrict__ tailraw,
+                                   uint32_t* __restrict__ out) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint32_t poly = cc->poly;
+    const uint32_t p0 = first ? first[b] : b, p1 = first ? last[b] : b + 1;
+    uint32_t acc = 0xffffffffu;
+    for (uint32_t p = p0; p < p1; p++) {
+        const Piece pc = pieces[p];
+        const Geom g = piece_geom<DST>(pc, seg_shift);
+        if (g.head) acc = gf_mul(acc, cc->pw8[g.head], poly) ^ headraw[p];
+        const uint32_t ubase = prefix[p];
+        for (uint32_t s = 0; s < g.nseg; s++) {
+            const uint64_t rem = g.body - (uint64_t(s) << seg_shift);
+            const uint32_t mult = rem >= (1ull << seg_shift) ? xp_seg : gf_xpow(8 * rem, poly);
+            acc = gf_mul(acc, mult, poly) ^ partial[ubase + s];
+        }
+        if (g.tail) acc = gf_mul(acc, cc->pw8[g.tail], poly) ^ tailraw[p];
+    }
+    out[b] = ~acc;
+}
+
+__global__ void verify_crcs_kernel(const uint32_t* crc, const uint32_t* expect, uint32_t n, uint32_t* n_bad,
+                                   uint8_t* bad_mask) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && crc[i] != expect[i];
+    if (i < n && bad_mask) bad_mask[i] = bad;
+    const uint32_t m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_bad, __popc(m));
+}
+
+// ------------------------------------------------------------------ host side
+
+static std::atomic<uint64_t> g_launches{0};
+static std::mutex g_mu;
+constexpr int kMaxDev = 16;
+static CrcConsts* g_consts[kMaxDev][2];
+static int g_sm_count[kMaxDev];
+static bool g_ready[kMaxDev];
+
+#define CV_TRY(x)                             \
+    do {                                      \
+        cudaError_t e_ = (x);                 \
+        if (e_ != cudaSuccess) return int(e_); \
+    } while (0)
+
+static int ensure_device(int* dev_out) {
+    int dev = 0;
+    CV_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) return int(cudaErrorInvalidDevice);
+    *dev_out = dev;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ready[dev]) return 0;
+    for (int pid = 0; pid < 2; pid++) {
+        CrcConsts* h = new CrcConsts;
+        build_consts(poly_of(pid), h);
+        CrcConsts* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, sizeof(CrcConsts));
+        if (e == cudaSuccess) e = cudaMemcpy(d, h, sizeof(CrcConsts), cudaMemcpyHostToDevice);
+        delete h;
+        if (e != cudaSuccess) return int(e);
+        g_consts[dev][pid] = d;
+    }
+    CV_TRY(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    g_ready[dev] = true;
+    return 0;
+}
+
+static uint32_t pick_seg_shift(uint64_t total_bytes, int sm_count) {
+    // ~16 units per warp keeps the contiguous per-CTA ranges balanced; 4 KiB..1 MiB segments
+    const uint64_t target = total_bytes / (uint64_t(sm_count) * 32 * 16 + 1);
+    uint32_t s = 12;
+    while (s < 20 && (1ull << s) < target) s++;
+    return s;
+}
+
+struct Workspace {
+    Piece* pieces;
+    uint32_t *counts, *prefix, *headraw, *tailraw, *partial, *first, *last;
+    uint32_t partial_cap;
+    void* base;
+};
+
+static int ws_alloc(Workspace* w, uint32_t n_pieces, uint32_t n_blocks, uint64_t total_bytes, uint32_t seg_shift,
+                    cudaStream_t st) {
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const uint64_t cap64 = uint64_t(n_pieces) + (total_bytes >> seg_shift) + 1;
+    w->partial_cap = cap64 > 0xfffffff0ull ? 0xfffffff0u : uint32_t(cap64);
+    const size_t s_pieces = up(sizeof(Piece) * size_t(n_pieces));
+    const size_t s_n = up(4 * (size_t(n_pieces) + 1));
+    const size_t s_part = up(4 * size_t(w->partial_cap));
+    const size_t s_blk = up(4 * (size_t(n_blocks) + 1));
+    const size_t total = s_pieces + 4 * s_n + s_part + 2 * s_blk;
+    CV_TRY(cudaMallocAsync(&w->base, total, st));
+    uint8_t* p = static_cast<uint8_t*>(w->base);
+    w->pieces = reinterpret_cast<Piece*>(p), p += s_pieces;
+    w->counts = reinterpret_cast<uint32_t*>(p), p += s_n;
+    w->prefix = reinterpret_cast<uint32_t*>(p), p += s_n;
+    w->headraw = reinterpret_cast<uint32_t*>(p), p += s_n;
+    w->tailraw = reinterpret_cast<uint32_t*>(p), p += s_n;
+    w->partial = reinterpret_cast<uint32_t*>(p), p += s_part;
+    w->first = reinterpret_cast<uint32_t*>(p), p += s_blk;
+    w->last = reinterpret_cast<uint32_t*>(p);
+    CV_TRY(cudaMemsetAsync(w->first, 0, 2 * s_blk, st));
+    return 0;
+}
+
+static inline uint32_t cdiv(uint64_t a, uint32_t b) { return uint32_t((a + b - 1) / b); }
+static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace cv
+
+using namespace cv;
+
+extern "C" {
+
+int cvk_init(int device) {
+    int cur = 0;
+    CV_TRY(cudaGetDevice(&cur));
+    if (device != cur) CV_TRY(cudaSetDevice(device));
+    int dev;
+    const int rc = ensure_device(&dev);
+    if (device != cur) cudaSetDevice(cur);
+    return rc;
+}
+
+uint64_t cvk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t* d_len, uint32_t n, int poly,
+                   uint64_t total_bytes, uint32_t* d_crc_out, cv_stream_t stream) {
+    if (n == 0) return 0;
+    if (poly != 0 && poly != 1) return int(cudaErrorInvalidValue);
+    int dev;
+    if (int rc = ensure_device(&dev)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t seg_shift = pick_seg_shift(total_bytes, g_sm_count[dev]);
+    Workspace w;
+    if (int rc = ws_alloc(&w, n, n, total_bytes, seg_shift, st)) return rc;
+    const CrcConsts* cc = g_consts[dev][poly];
+    prep_blocks_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_base, d_off, d_len, n, seg_shift, w.pieces, w.counts);
+    scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
+    walk_kernel<true, false><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.pieces, n, w.prefix, seg_shift, cc,
+                                                                        w.partial, w.partial_cap, w.headraw, w.tailraw);
+    fold_blocks_kernel<false><<<cdiv(n, 128), 128, 0, st>>>(w.pieces, w.prefix, nullptr, nullptr, n, seg_shift,
+                                                            gf_xpow(8ull << seg_shift, poly_of(poly)), cc, w.partial,
+                                                            w.headraw, w.tailraw, d_crc_out);
+    count_launch(4);
+    CV_TRY(cudaGetLastError());
+    CV_TRY(cudaFreeAsync(w.base, st));
+    return 0;
+}
+
+int cvk_verify_crcs(const uint32_t* d_crc, const uint32_t* d_expect, uint32_t n, uint32_t* d_n_bad,
+                    uint8_t* d_bad_mask, cv_stream_t stream) {
+    if (n == 0) return 0;
+    verify_crcs_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_crc, d_expect, n, d_n_bad,
+                                                                                   d_bad_mask);
+    count_launch();
+    return int(cudaGetLastError());
+}
+
+int cvk_expand_streams(const CvStreamDesc* d_streams, uint32_t n_streams, CvFrameDesc* d_desc_out, uint32_t n_frames,
+                       cv_stream_t stream) {
+    if (n_streams == 0) return 0;
+    expand_streams_kernel<<<cdiv(uint64_t(n_streams) * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_streams, n_streams, d_desc_out, n_frames);
+    count_launch();
+    return int(cudaGetLastError());
+}
+
+static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_desc, uint32_t n_frames,
+                         uint32_t n_blocks, uint8_t* d_out, int poly, uint64_t total_bytes, uint32_t* d_block_crc,
+                         uint32_t* d_err_flags, cv_stream_t stream) {
+    if (n_frames == 0) return 0;
+    if (poly != 0 && poly != 1) return int(cudaErrorInvalidValue);
+    int dev;
+    if (int rc = ensure_device(&dev)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t seg_shift = pick_seg_shift(total_bytes, g_sm_count[dev]);
+    Workspace w;
+    if (int rc = ws_alloc(&w, n_frames, n_blocks, total_bytes, seg_shift, st)) return rc;
+    const CrcConsts* cc = g_consts[dev][poly];
+    if (pack)
+        prep_pack_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_in, d_desc, n_frames, d_out, seg_shift, w.pieces,
+                                                              w.counts);
+    else
+        prep_unpack_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_in, d_desc, n_frames, d_out, seg_shift, w.pieces,
+                                                                w.counts, d_err_flags);
+    scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n_frames, w.prefix);
+    count_launch(2);
+    if (d_block_crc) {
+        walk_kernel<true, true><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(
+            w.pieces, n_frames, w.prefix, seg_shift, cc, w.partial, w.partial_cap, w.headraw, w.tailraw);
+        mark_block_ranges_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_desc, n_frames, n_blocks, w.first, w.last);
+        fold_blocks_kernel<true><<<cdiv(n_blocks, 128), 128, 0, st>>>(
+            w.pieces, w.prefix, w.first, w.last, n_blocks, seg_shift, gf_xpow(8ull << seg_shift, poly_of(poly)), cc,
+            w.partial, w.headraw, w.tailraw, d_block_crc);
+        count_launch(3);
+    } else {
+        walk_kernel<false, true><<<g_sm_count[dev] * 2, 1024, 0, st>>>(w.pieces, n_frames, w.prefix, seg_shift, cc,
+                                                                       w.partial, w.partial_cap, w.headraw, w.tailraw);
+        count_launch();
+    }
+    CV_TRY(cudaGetLastError());
+    CV_TRY(cudaFreeAsync(w.base, st));
+    return 0;
+}
+
+int cvk_unpack_frames(const uint8_t* d_wire, const CvFrameDesc* d_desc, uint32_t n_frames, uint32_t n_blocks,
+                      uint8_t* d_dst, int poly, uint64_t total_bytes, uint32_t* d_block_crc, uint32_t* d_err_flags,
+                      cv_stream_t stream) {
+    return frames_common(false, d_wire, d_desc, n_frames, n_blocks, d_dst, poly, total_bytes, d_block_crc,
+                         d_err_flags, stream);
+}
+
+int cvk_pack_frames(const uint8_t* d_src, const CvFrameDesc* d_desc, uint32_t n_frames, uint32_t n_blocks,
+                    uint8_t* d_wire, int poly, uint64_t total_bytes, uint32_t* d_block_crc, cv_stream_t stream) {
+    return frames_common(true, d_src, d_desc, n_frames, n_blocks, d_wire, poly, total_bytes, d_block_crc, nullptr,
+                         stream);
+}
+
+static int copy_pieces(Workspace& w, uint32_t n, uint32_t seg_shift, int dev, cudaStream_t st) {
+    scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
+    walk_kernel<false, true><<<g_sm_count[dev] * 2, 1024, 0, st>>>(w.pieces, n, w.prefix, seg_shift, nullptr,
+                                                                   w.partial, w.partial_cap, w.headraw, w.tailraw);
+    count_launch(2);
+    CV_TRY(cudaGetLastError());
+    CV_TRY(cudaFreeAsync(w.base, st));
+    return 0;
+}
+
+int cvk_gather_pages(const uint8_t* d_src, const CvSeg* d_segs, uint32_t n, uint64_t total_bytes, uint8_t* d_dst,
+                     cv_stream_t stream) {
+    if (n == 0) return 0;
+    int dev;
+    if (int rc = ensure_device(&dev)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t seg_shift = pick_seg_shift(total_bytes, g_sm_count[dev]);
+    Workspace w;
+    if (int rc = ws_alloc(&w, n, 0, total_bytes, seg_shift, st)) return rc;
+    prep_segs_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_src, d_segs, n, d_dst, seg_shift, w.pieces, w.counts);
+    count_launch();
+    return copy_pieces(w, n, seg_shift, dev, st);
+}
+
+int cvk_deinterleave_blocks(const uint8_t* d_gathered, uint64_t shard_stride, uint32_t world, uint64_t block_size,
+                            uint64_t n_blocks, uint64_t file_len, uint8_t* d_dst, cv_stream_t stream) {
+    if (n_blocks == 0) return 0;
+    if (world == 0 || block_size == 0 || n_blocks > 0x7fffffffull) return int(cudaErrorInvalidValue);
+    int dev;
+    if (int rc = ensure_device(&dev)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t seg_shift = pick_seg_shift(file_len, g_sm_count[dev]);
+    Workspace w;
+    const uint32_t n = uint32_t(n_blocks);
+    if (int rc = ws_alloc(&w, n, 0, file_len, seg_shift, st)) return rc;
+    prep_deinterleave_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_gathered, shard_stride, world, block_size, n_blocks,
+                                                           file_len, d_dst, seg_shift, w.pieces, w.counts);
+    count_launch();
+    return copy_pieces(w, n, seg_shift, dev, st);
+}
+
+}  // extern "C"

@@ -55,11 +55,57 @@ def _declare(L):
     L.cvk_pack_frames.argtypes, L.cvk_pack_frames.restype = [u8p, vp, u32, u32, u8p, i, u64, vp, vp], i
     L.cvk_deinterleave_blocks.argtypes = [u8p, u64, u32, u64, u64, u64, u8p, vp]
     L.cvk_deinterleave_blocks.restype = i
-    for name, fn in list(_LATE.items()):
-        fn(L)
+    # ---- upper boundary (include/curvine_b200.h)
+    c, i64, i32, cp = ctypes.c_char_p, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER
+    L.cv_last_error.argtypes, L.cv_last_error.restype = [], c
+    L.cv_free.argtypes, L.cv_free.restype = [vp], None
+    L.cv_fs_new.argtypes, L.cv_fs_new.restype = [c, cp(vp)], i64
+    L.cv_fs_new_from_string.argtypes, L.cv_fs_new_from_string.restype = [c, cp(vp)], i64
+    L.cv_fs_load_namespace.argtypes, L.cv_fs_load_namespace.restype = [vp, c], i64
+    L.cv_fs_load_namespace_string.argtypes, L.cv_fs_load_namespace_string.restype = [vp, c], i64
+    L.cv_fs_close.argtypes, L.cv_fs_close.restype = [vp], i64
+    L.cv_fs_metrics.argtypes, L.cv_fs_metrics.restype = [vp, cp(i64)], i64
+    L.cv_open.argtypes, L.cv_open.restype = [vp, c, cp(vp), cp(i64)], i64
+    L.cv_read.argtypes, L.cv_read.restype = [vp, cp(vp), cp(i64)], i64
+    L.cv_read_buf.argtypes, L.cv_read_buf.restype = [vp, vp, i64, cp(i64)], i64
+    L.cv_read_full.argtypes, L.cv_read_full.restype = [vp, vp, i64, cp(i64)], i64
+    L.cv_fuse_read.argtypes = [vp, i64, i64, vp, cp(i64), cp(i64), i32, cp(i32)]
+    L.cv_fuse_read.restype = i64
+    L.cv_seek.argtypes, L.cv_seek.restype = [vp, i64], i64
+    L.cv_pos.argtypes, L.cv_pos.restype = [vp], i64
+    L.cv_len.argtypes, L.cv_len.restype = [vp], i64
+    L.cv_chunk_size.argtypes, L.cv_chunk_size.restype = [vp], i64
+    L.cv_close_reader.argtypes, L.cv_close_reader.restype = [vp], i64
+    L.cv_read_device.argtypes, L.cv_read_device.restype = [vp, vp, i64, vp, cp(i64)], i64
+    L.cv_read_device_sharded.argtypes = [vp, i32, i32, vp, i64, vp, cp(i64)]
+    L.cv_read_device_sharded.restype = i64
+    L.cv_fuse_read_device.argtypes = [vp, i64, i64, vp, vp, vp, i32, i64, vp, cp(i64)]
+    L.cv_fuse_read_device.restype = i64
+    L.cv_verify.argtypes, L.cv_verify.restype = [vp, cp(u64), cp(u32), cp(u64)], i64
+    L.cv_device_stats.argtypes, L.cv_device_stats.restype = [vp, cp(CvReadStats)], i64
+    L.cv_worker_start.argtypes, L.cv_worker_start.restype = [c, cp(vp), cp(i32)], i64
+    L.cv_worker_stop.argtypes, L.cv_worker_stop.restype = [vp], i64
+    L.cv_worker_metrics.argtypes, L.cv_worker_metrics.restype = [vp, cp(i64)], i64
+    L.cv_synth_create_file.argtypes = [vp, c, i64, i64, i64, i32, i32, i32, i32, c, cp(vp)]
+    L.cv_synth_create_file.restype = i64
+    L.cv_synth_block.argtypes, L.cv_synth_block.restype = [u64, u64, vp, ctypes.c_size_t], None
+    L.cv_host_crc.argtypes, L.cv_host_crc.restype = [i, vp, ctypes.c_size_t], u32
 
 
-_LATE = {}
+class CvReadStats(ctypes.Structure):
+    _fields_ = [("bytes", ctypes.c_uint64), ("blocks", ctypes.c_uint64), ("verified", ctypes.c_uint64),
+                ("h2d_bytes", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("fetch_sec", ctypes.c_double),
+                ("wall_sec", ctypes.c_double)]
+
+
+# every symbol include/*.h declares (tests check the .so exports all of them)
+EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_unpack_frames", "cvk_expand_streams", "cvk_gather_pages",
+           "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_launch_count", "cv_last_error", "cv_free", "cv_fs_new",
+           "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_metrics",
+           "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
+           "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_fuse_read_device",
+           "cv_verify", "cv_device_stats", "cv_worker_start", "cv_worker_stop", "cv_worker_metrics",
+           "cv_synth_create_file", "cv_synth_block", "cv_host_crc"]
 
 
 class CudaError(RuntimeError):

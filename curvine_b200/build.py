@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libcurvine_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-Wall,-pthread", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-O3,-Wall,-pthread,-msse4.2", "-cudart", "static"]
 
 
 def _nvcc():

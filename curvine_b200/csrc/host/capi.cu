@@ -1,0 +1,442 @@
+// extern "C" surface declared in include/curvine_b200.h (upper boundary).  Never throws, never aborts:
+// every failure becomes -(ErrorKind) plus a thread-local message (cv_last_error).
+#include <cuda_runtime.h>
+#include <nmmintrin.h>
+#include <stdlib.h>
+
+#include <thread>
+
+#include "../../../include/curvine_b200.h"
+#include "../crc_gf.h"
+#include "client.h"
+#include "gpu_reader.h"
+#include "worker.h"
+
+using namespace cv;
+
+static thread_local std::string g_last_error;
+
+static int64_t fail(const Err& e) {
+    g_last_error = e.msg;
+    return e.libc_kind();
+}
+static int64_t ok() { return 0; }
+
+#define API_TRY(expr)             \
+    do {                          \
+        Err e__ = (expr);         \
+        if (e__) return fail(e__); \
+    } while (0)
+#define API_GUARD_BEGIN try {
+#define API_GUARD_END                                                     \
+    }                                                                     \
+    catch (const std::exception& ex) {                                    \
+        return fail(Err::common(std::string("internal: ") + ex.what())); \
+    }                                                                     \
+    catch (...) {                                                         \
+        return fail(Err::common("internal: unknown exception"));         \
+    }
+
+struct cv_fs {
+    std::unique_ptr<FsContext> ctx;
+};
+
+struct cv_reader {
+    cv_fs* fs = nullptr;
+    std::string path;
+    std::unique_ptr<FsReader> host;
+    std::unique_ptr<GpuFsReader> dev;
+    std::vector<int64_t> fuse_segs;
+};
+
+struct cv_worker {
+    Worker w;
+    std::string hostname;
+};
+
+extern "C" {
+
+const char* cv_last_error(void) { return g_last_error.c_str(); }
+void cv_free(void* p) { free(p); }
+
+int64_t cv_fs_new_from_string(const char* conf_toml, cv_fs** out) {
+    API_GUARD_BEGIN
+    ClusterConf c;
+    API_TRY(ClusterConf::from_string(conf_toml ? conf_toml : "", &c));
+    std::unique_ptr<cv_fs> fs(new cv_fs());
+    fs->ctx.reset(new FsContext(c));
+    if (!c.namespace_manifest.empty()) API_TRY(fs->ctx->ns.load(c.namespace_manifest));
+    *out = fs.release();
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_fs_new(const char* conf_path, cv_fs** out) {
+    API_GUARD_BEGIN
+    ClusterConf c;
+    API_TRY(ClusterConf::from_file(conf_path ? conf_path : "", &c));
+    std::unique_ptr<cv_fs> fs(new cv_fs());
+    fs->ctx.reset(new FsContext(c));
+    if (!c.namespace_manifest.empty()) API_TRY(fs->ctx->ns.load(c.namespace_manifest));
+    *out = fs.release();
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_fs_load_namespace(cv_fs* fs, const char* manifest_path) {
+    API_GUARD_BEGIN
+    API_TRY(fs->ctx->ns.load(manifest_path));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_fs_load_namespace_string(cv_fs* fs, const char* text) {
+    API_GUARD_BEGIN
+    API_TRY(fs->ctx->ns.load_string(text));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_fs_close(cv_fs* fs) {
+    API_GUARD_BEGIN
+    if (!fs) return ok();
+    gpu_ingest_release(fs->ctx.get());
+    delete fs;
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]) {
+    out[0] = fs->ctx->read_bytes.load(), out[1] = fs->ctx->read_time_us.load();
+    return ok();
+}
+
+int64_t cv_open(cv_fs* fs, const char* path, cv_reader** out, int64_t* len) {
+    API_GUARD_BEGIN
+    std::unique_ptr<cv_reader> r(new cv_reader());
+    r->fs = fs, r->path = path;
+    API_TRY(FsReader::open(fs->ctx.get(), path, &r->host));
+    if (len) *len = r->host->len();
+    *out = r.release();
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_read(cv_reader* r, const uint8_t** ptr, int64_t* len) {
+    API_GUARD_BEGIN
+    API_TRY(r->host->read_chunk(ptr, len, -1));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_read_buf(cv_reader* r, uint8_t* buf, int64_t cap, int64_t* n) {
+    API_GUARD_BEGIN
+    API_TRY(r->host->read(buf, cap, n));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_read_full(cv_reader* r, uint8_t* buf, int64_t cap, int64_t* n) {
+    API_GUARD_BEGIN
+    API_TRY(r->host->read_full(buf, cap, n));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_fuse_read(cv_reader* r, int64_t pos, int64_t len, uint8_t* buf, int64_t* n, int64_t* seg_lens, int32_t max_segs,
+                     int32_t* n_segs) {
+    API_GUARD_BEGIN
+    API_TRY(r->host->seek(pos));
+    int64_t remaining = len, off = 0;
+    int32_t segs = 0;
+    while (remaining > 0) {
+        const uint8_t* p;
+        int64_t got;
+        API_TRY(r->host->read_chunk(&p, &got, remaining));
+        if (got == 0) break;
+        memcpy(buf + off, p, static_cast<size_t>(got));
+        if (seg_lens && segs < max_segs) seg_lens[segs] = got;
+        segs++, off += got, remaining -= got;
+    }
+    if (n) *n = off;
+    if (n_segs) *n_segs = segs;
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_seek(cv_reader* r, int64_t pos) {
+    API_GUARD_BEGIN
+    API_TRY(r->host->seek(pos));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_pos(cv_reader* r) { return r->host->pos(); }
+int64_t cv_len(cv_reader* r) { return r->host->len(); }
+int64_t cv_chunk_size(cv_reader* r) { return r->host->chunk_size(); }
+
+int64_t cv_close_reader(cv_reader* r) {
+    API_GUARD_BEGIN
+    if (!r) return ok();
+    Err e = r->host ? r->host->complete() : Err::ok();
+    if (r->dev) {
+        Err e2 = r->dev->complete();
+        if (!e && e2) e = e2;
+    }
+    delete r;
+    if (e) return fail(e);
+    return ok();
+    API_GUARD_END
+}
+
+static Err ensure_dev(cv_reader* r) {
+    if (r->dev) return Err::ok();
+    return GpuFsReader::open(r->fs->ctx.get(), r->path, &r->dev);
+}
+
+int64_t cv_read_device(cv_reader* r, void* d_dst, int64_t cap, cv_stream_t stream, int64_t* nbytes) {
+    API_GUARD_BEGIN
+    API_TRY(ensure_dev(r));
+    API_TRY(r->dev->seek(r->host->pos()));
+    int64_t n = 0;
+    API_TRY(r->dev->read_device(d_dst, cap, stream, &n));
+    API_TRY(r->host->seek(r->dev->pos()));
+    if (nbytes) *nbytes = n;
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_read_device_sharded(cv_reader* r, int32_t rank, int32_t world, void* d_dst, int64_t cap, cv_stream_t stream,
+                               int64_t* nbytes) {
+    API_GUARD_BEGIN
+    API_TRY(ensure_dev(r));
+    int64_t n = 0;
+    API_TRY(r->dev->read_device_sharded(rank, world, d_dst, cap, stream, &n));
+    if (nbytes) *nbytes = n;
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_fuse_read_device(cv_reader* r, int64_t pos, int64_t len, void* d_scratch, void* d_page_base, const uint64_t* page_offsets,
+                            int32_t n_pages, int64_t page_size, cv_stream_t stream, int64_t* nbytes) {
+    API_GUARD_BEGIN
+    API_TRY(ensure_dev(r));
+    API_TRY(r->host->seek(pos));
+    API_TRY(r->dev->seek(pos));
+    int64_t n = 0;
+    API_TRY(r->dev->read_device(d_scratch, len, stream, &n));
+    API_TRY(r->host->seek(r->dev->pos()));
+    // ResponseData::as_iovec analogue on the device: chunk bytes -> the reply's page buffers
+    const int64_t need_pages = (n + page_size - 1) / page_size;
+    if (need_pages > n_pages) return fail(Err::common("not enough page buffers for the reply"));
+    if (need_pages > 0) {
+        std::vector<CvSeg> segs(static_cast<size_t>(need_pages));
+        for (int64_t i = 0; i < need_pages; i++) {
+            segs[static_cast<size_t>(i)].src_off = static_cast<uint64_t>(i * page_size);
+            segs[static_cast<size_t>(i)].dst_off = page_offsets[i];
+            segs[static_cast<size_t>(i)].len = static_cast<uint64_t>(std::min(page_size, n - i * page_size));
+        }
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        CvSeg* d_segs = nullptr;
+        cudaError_t ce = cudaMallocAsync(&d_segs, sizeof(CvSeg) * segs.size(), st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_segs, segs.data(), sizeof(CvSeg) * segs.size(), cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // segs is a stack-lifetime pageable buffer
+        int rc = ce != cudaSuccess ? int(ce)
+                                   : cvk_gather_pages(static_cast<const uint8_t*>(d_scratch), d_segs, static_cast<uint32_t>(need_pages),
+                                                      static_cast<uint64_t>(n), static_cast<uint8_t*>(d_page_base), stream);
+        if (d_segs) cudaFreeAsync(d_segs, st);
+        if (rc) return fail(Err::io(str_printf("cvk_gather_pages: %s", cudaGetErrorString(cudaError_t(rc)))));
+    }
+    if (nbytes) *nbytes = n;
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_verify(cv_reader* r, uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified) {
+    API_GUARD_BEGIN
+    uint64_t s = 0, v = 0;
+    uint32_t b = 0;
+    if (r->dev) API_TRY(r->dev->verify(&s, &b, &v));
+    if (sum_crc) *sum_crc = s;
+    if (n_bad) *n_bad = b;
+    if (n_verified) *n_verified = v;
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_device_stats(cv_reader* r, CvReadStats* out) {
+    memset(out, 0, sizeof(*out));
+    if (!r->dev) return ok();
+    const GpuReadStats& s = r->dev->stats();
+    out->bytes = s.bytes, out->blocks = s.blocks, out->verified = s.verified, out->h2d_bytes = s.h2d_bytes;
+    out->kernel_launches = s.kernel_launches, out->fetch_sec = s.fetch_sec, out->wall_sec = s.wall_sec;
+    return ok();
+}
+
+// ------------------------------------------------------------------ fixture: worker + synthetic files
+
+int64_t cv_worker_start(const char* conf_toml, cv_worker** out, int32_t* port) {
+    API_GUARD_BEGIN
+    ClusterConf c;
+    API_TRY(ClusterConf::from_string(conf_toml ? conf_toml : "", &c));
+    std::unique_ptr<cv_worker> w(new cv_worker());
+    w->hostname = c.worker_hostname;
+    API_TRY(w->w.start(c.worker_dirs, c.cluster_id, "", c.worker_port, c.worker_enable_send_file));
+    if (port) *port = w->w.port();
+    *out = w.release();
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_worker_stop(cv_worker* w) {
+    API_GUARD_BEGIN
+    if (!w) return ok();
+    w->w.stop();
+    delete w;
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_worker_metrics(cv_worker* w, int64_t out[6]) {
+    WorkerMetrics& m = w->w.metrics();
+    out[0] = m.read_bytes, out[1] = m.read_time_us, out[2] = m.read_count, out[3] = m.read_blocks_local, out[4] = m.read_blocks_remote;
+    out[5] = static_cast<int64_t>(w->w.store().num_blocks());
+    return ok();
+}
+
+static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+void cv_synth_block(uint64_t file_id, uint64_t block_index, uint8_t* out, size_t len) {
+    uint64_t x = 0xC0FFEEB200ull ^ (file_id << 32) ^ block_index, s[4];
+    for (int i = 0; i < 4; i++) {
+        x += 0x9E3779B97F4A7C15ull;
+        uint64_t z = x;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        s[i] = z ^ (z >> 31);
+    }
+    size_t pos = 0;
+    while (pos < len) {
+        const uint64_t r = rotl64(s[1] * 5, 7) * 9, t = s[1] << 17;
+        s[2] ^= s[0], s[3] ^= s[1], s[1] ^= s[2], s[0] ^= s[3], s[2] ^= t, s[3] = rotl64(s[3], 45);
+        const size_t n = len - pos < 8 ? len - pos : 8;
+        memcpy(out + pos, &r, n);
+        pos += n;
+    }
+}
+
+uint32_t cv_host_crc(int poly, const uint8_t* buf, size_t len) {
+    if (poly == 1) {  // CRC-32C: SSE4.2 crc32 instruction
+        uint64_t r = 0xffffffffu;
+        while (len && (reinterpret_cast<uintptr_t>(buf) & 7)) r = _mm_crc32_u8(static_cast<uint32_t>(r), *buf++), len--;
+        while (len >= 8) {
+            uint64_t w;
+            memcpy(&w, buf, 8);
+            r = _mm_crc32_u64(r, w);
+            buf += 8, len -= 8;
+        }
+        while (len--) r = _mm_crc32_u8(static_cast<uint32_t>(r), *buf++);
+        return ~static_cast<uint32_t>(r);
+    }
+    static uint32_t T[8][256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t r = i;
+            for (int k = 0; k < 8; k++) r = gf_mulx(r, kPolyIeee);
+            T[0][i] = r;
+        }
+        for (uint32_t i = 0; i < 256; i++)
+            for (int s = 1; s < 8; s++) T[s][i] = (T[s - 1][i] >> 8) ^ T[0][T[s - 1][i] & 0xff];
+    });
+    uint32_t r = 0xffffffffu;
+    while (len >= 8) {
+        uint64_t w;
+        memcpy(&w, buf, 8);
+        const uint32_t lo = static_cast<uint32_t>(w) ^ r, hi = static_cast<uint32_t>(w >> 32);
+        r = T[7][lo & 0xff] ^ T[6][(lo >> 8) & 0xff] ^ T[5][(lo >> 16) & 0xff] ^ T[4][lo >> 24] ^ T[3][hi & 0xff] ^ T[2][(hi >> 8) & 0xff] ^
+            T[1][(hi >> 16) & 0xff] ^ T[0][hi >> 24];
+        buf += 8, len -= 8;
+    }
+    while (len--) r = T[0][(r ^ *buf++) & 0xff] ^ (r >> 8);
+    return ~r;
+}
+
+int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, int64_t len, int64_t block_size, int32_t storage_type,
+                             int32_t mode, int32_t hole_every, int32_t threads, const char* worker_hostname, char** manifest_out) {
+    API_GUARD_BEGIN
+    if (block_size <= 0 || len < 0) return fail(Err(kInvalidFileSize, "bad file or block size"));
+    const int64_t nb = (len + block_size - 1) / block_size;
+    FileBlocks fb;
+    fb.status.id = inode_id, fb.status.path = path, fb.status.len = len, fb.status.block_size = block_size, fb.status.mtime = 0;
+    fb.block_locs.resize(static_cast<size_t>(nb));
+    WorkerAddress addr;
+    addr.worker_id = 1, addr.hostname = worker_hostname && *worker_hostname ? worker_hostname : w->hostname, addr.ip_addr = "127.0.0.1";
+    addr.rpc_port = static_cast<uint32_t>(w->w.port());
+    std::string az;
+    if (mode == 1) {  // curvine-bench style content: one a-z buffer repeated (bench_action.rs:100-102)
+        az.resize(static_cast<size_t>(std::min<int64_t>(block_size, 128 * 1024)));
+        uint64_t x = 42;
+        for (auto& c : az) {
+            x += 0x9E3779B97F4A7C15ull;
+            uint64_t z = x;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull, z = (z ^ (z >> 27)) * 0x94D049BB133111EBull, z ^= z >> 31;
+            c = static_cast<char>('a' + z % 26);
+        }
+    }
+    std::atomic<int64_t> next{0};
+    std::mutex emu;
+    Err first;
+    const int T = std::max(1, std::min<int>(threads, static_cast<int>(std::max<int64_t>(nb, 1))));
+    auto work = [&] {
+        std::vector<uint8_t> buf(static_cast<size_t>(std::min(block_size, std::max<int64_t>(len, 1))));
+        for (;;) {
+            const int64_t b = next.fetch_add(1);
+            if (b >= nb) break;
+            const int64_t blen = std::min(block_size, len - b * block_size);
+            LocatedBlock& lb = fb.block_locs[static_cast<size_t>(b)];
+            int64_t id = 0;
+            Err e = create_block_id(inode_id, b, &id);
+            lb.block.id = id, lb.block.len = blen, lb.block.storage_type = storage_type;
+            if (!e && mode == 2 && hole_every > 0 && b % hole_every == hole_every - 1) {
+                lb.block.has_alloc_opts = true;  // allocated, never written, no location: BlockReaderHole
+                continue;
+            }
+            if (!e) {
+                if (mode == 1)
+                    for (int64_t o = 0; o < blen; o += static_cast<int64_t>(az.size()))
+                        memcpy(&buf[static_cast<size_t>(o)], az.data(), static_cast<size_t>(std::min<int64_t>(static_cast<int64_t>(az.size()), blen - o)));
+                else
+                    cv_synth_block(static_cast<uint64_t>(inode_id), static_cast<uint64_t>(b), buf.data(), static_cast<size_t>(blen));
+                lb.crc32 = cv_host_crc(0, buf.data(), static_cast<size_t>(blen));
+                lb.crc32c = cv_host_crc(1, buf.data(), static_cast<size_t>(blen));
+                lb.has_crc = true;
+                std::string p;
+                e = w->w.store().put_block(id, buf.data(), blen, storage_type, &p);
+                BlockMeta m;
+                if (!e && !w->w.store().get_block(id, &m)) lb.block.storage_type = m.storage_type;
+                lb.locs.push_back(addr);
+            }
+            if (e) {
+                std::lock_guard<std::mutex> lk(emu);
+                if (!first) first = e;
+                break;
+            }
+        }
+    };
+    std::vector<std::thread> ts;
+    for (int t = 0; t < T; t++) ts.emplace_back(work);
+    for (auto& t : ts) t.join();
+    if (first) return fail(first);
+    Namespace ns;
+    ns.put(fb);
+    const std::string text = ns.dump();
+    if (manifest_out) {
+        *manifest_out = static_cast<char*>(malloc(text.size() + 1));
+        memcpy(*manifest_out, text.c_str(), text.size() + 1);
+    }
+    return ok();
+    API_GUARD_END
+}
+
+}  // extern "C"

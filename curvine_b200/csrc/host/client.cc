@@ -1,0 +1,715 @@
+#include "client.h"
+
+#include <errno.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <fstream>
+#include <random>
+#include <sstream>
+
+#include "net.h"
+
+namespace cv {
+
+// ------------------------------------------------------------------ FileBlocks / Namespace
+
+void FileBlocks::build_index() {
+    starts.clear();
+    int64_t off = 0;
+    for (const auto& b : block_locs) {
+        starts.push_back(off);
+        off += b.block.len;
+    }
+}
+
+Err FileBlocks::get_read_block(int64_t pos, int64_t* block_off, size_t* index) const {
+    // partition_point(|x| x.end <= pos)
+    size_t lo = 0, hi = block_locs.size();
+    while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        if (starts[mid] + block_locs[mid].block.len <= pos) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo >= block_locs.size()) return Err::common(str_printf("Not found block for pos %lld", (long long)pos));
+    *block_off = pos - starts[lo];
+    *index = lo;
+    return Err::ok();
+}
+
+Err Namespace::load(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) return Err(kFileNotFound, "namespace manifest not found: " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return load_string(ss.str());
+}
+
+// manifest lines:
+//   file  <path> <inode_id> <len> <block_size> <mtime>
+//   block <block_id> <len> <storage_type> <crc32 hex|-> <crc32c hex|-> <h|-> <host:port:worker_id,...|->
+Err Namespace::load_string(const std::string& text) {
+    std::istringstream in(text);
+    std::string line;
+    FileBlocks cur;
+    bool have = false;
+    auto flush = [&] {
+        if (have) {
+            cur.build_index();
+            put(cur);
+        }
+        have = false;
+    };
+    while (std::getline(in, line)) {
+        if (line.empty() || line[0] == '#') continue;
+        std::istringstream ls(line);
+        std::string kind;
+        ls >> kind;
+        if (kind == "file") {
+            flush();
+            cur = FileBlocks();
+            ls >> cur.status.path >> cur.status.id >> cur.status.len >> cur.status.block_size >> cur.status.mtime;
+            if (ls.fail()) return Err::common("bad manifest line: " + line);
+            have = true;
+        } else if (kind == "block") {
+            if (!have) return Err::common("manifest: block before file");
+            LocatedBlock lb;
+            std::string c32, c32c, flags, locs;
+            ls >> lb.block.id >> lb.block.len >> lb.block.storage_type >> c32 >> c32c >> flags >> locs;
+            if (ls.fail()) return Err::common("bad manifest line: " + line);
+            if (c32 != "-" && c32c != "-") {
+                lb.crc32 = static_cast<uint32_t>(strtoul(c32.c_str(), nullptr, 16));
+                lb.crc32c = static_cast<uint32_t>(strtoul(c32c.c_str(), nullptr, 16));
+                lb.has_crc = true;
+            }
+            lb.block.has_alloc_opts = flags.find('h') != std::string::npos;
+            if (locs != "-") {
+                std::istringstream lss(locs);
+                std::string one;
+                while (std::getline(lss, one, ',')) {
+                    WorkerAddress a;
+                    const size_t c1 = one.find(':'), c2 = one.find(':', c1 + 1);
+                    if (c1 == std::string::npos) return Err::common("bad worker address: " + one);
+                    a.hostname = a.ip_addr = one.substr(0, c1);
+                    a.rpc_port = static_cast<uint32_t>(atoi(one.substr(c1 + 1, c2 == std::string::npos ? std::string::npos : c2 - c1 - 1).c_str()));
+                    if (c2 != std::string::npos) a.worker_id = static_cast<uint32_t>(atoi(one.substr(c2 + 1).c_str()));
+                    lb.locs.push_back(a);
+                }
+            }
+            cur.block_locs.push_back(lb);
+        } else {
+            return Err::common("bad manifest line: " + line);
+        }
+    }
+    flush();
+    return Err::ok();
+}
+
+std::string Namespace::dump() const {
+    std::lock_guard<std::mutex> lk(mu_);
+    std::string out = "# curvine-b200 namespace manifest v1\n";
+    for (const auto& kv : files_) {
+        const FileBlocks& f = kv.second;
+        out += str_printf("file %s %lld %lld %lld %lld\n", f.status.path.c_str(), (long long)f.status.id, (long long)f.status.len,
+                          (long long)f.status.block_size, (long long)f.status.mtime);
+        for (const auto& b : f.block_locs) {
+            std::string locs;
+            for (const auto& a : b.locs) locs += (locs.empty() ? "" : ",") + a.hostname + ":" + std::to_string(a.rpc_port) + ":" + std::to_string(a.worker_id);
+            if (locs.empty()) locs = "-";
+            const std::string c1 = b.has_crc ? str_printf("%08x", b.crc32) : "-", c2 = b.has_crc ? str_printf("%08x", b.crc32c) : "-";
+            out += str_printf("block %lld %lld %d %s %s %s %s\n", (long long)b.block.id, (long long)b.block.len, b.block.storage_type, c1.c_str(),
+                              c2.c_str(), b.block.has_alloc_opts ? "h" : "-", locs.c_str());
+        }
+    }
+    return out;
+}
+
+void Namespace::put(const FileBlocks& fb) {
+    std::lock_guard<std::mutex> lk(mu_);
+    FileBlocks c = fb;
+    c.build_index();
+    files_[fb.status.path] = std::move(c);
+}
+
+Err Namespace::get_block_locations(const std::string& path, FileBlocks* out) const {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = files_.find(path);
+    if (it == files_.end()) return Err(kFileNotFound, "File " + path + " not exists");
+    *out = it->second;
+    return Err::ok();
+}
+
+// ------------------------------------------------------------------ BlockClient
+
+BlockClient::~BlockClient() { close_fd(fd_); }
+
+Err BlockClient::send_request(const Protocol& req, const std::string& header) {
+    Protocol p = req;
+    p.header_len = static_cast<int32_t>(header.size());
+    p.data_len = 0;
+    std::string out(kProtocolSize, '\0');
+    encode_protocol(p, reinterpret_cast<uint8_t*>(&out[0]));
+    out += header;
+    Err e = send_all(fd_, out.data(), out.size());
+    if (e) broken = true;
+    return e;
+}
+
+Err BlockClient::recv_response_head(Protocol* resp, std::string* resp_header) {
+    uint8_t prefix[kProtocolSize];
+    for (;;) {
+        Err e = recv_exact(fd_, prefix, kProtocolSize);
+        if (!e) e = decode_protocol(prefix, resp);
+        if (!e && resp->header_len < 0) e = Err::common(str_printf("Invalid length %d", resp->header_len));
+        if (e) {
+            broken = true;
+            return e;
+        }
+        resp_header->resize(static_cast<size_t>(resp->header_len));
+        if (resp->header_len && (e = recv_exact(fd_, &(*resp_header)[0], resp_header->size()))) {
+            broken = true;
+            return e;
+        }
+        if (!resp->is_heartbeat()) return Err::ok();
+        std::string skip(static_cast<size_t>(resp->data_len), '\0');  // rpc_frame.rs:255-259
+        if (resp->data_len && (e = recv_exact(fd_, &skip[0], skip.size()))) {
+            broken = true;
+            return e;
+        }
+    }
+}
+
+static Err check_echo(const Protocol& req, const Protocol& resp) {  // raw_client.rs:100-116
+    if (req.req_id != resp.req_id || req.seq_id != resp.seq_id)
+        return Err::common(str_printf("response mismatch: request (req_id %lld, seq_id %d), response (req_id %lld, seq_id %d)", (long long)req.req_id,
+                                      req.seq_id, (long long)resp.req_id, resp.seq_id));
+    return Err::ok();
+}
+
+Err BlockClient::rpc(const Protocol& req, const std::string& header, Protocol* resp, std::string* resp_header, std::string* resp_data) {
+    CV_RETURN_IF_ERR(send_request(req, header));
+    CV_RETURN_IF_ERR(recv_response_head(resp, resp_header));
+    resp_data->resize(static_cast<size_t>(resp->data_len));
+    if (resp->data_len) {
+        Err e = recv_exact(fd_, &(*resp_data)[0], resp_data->size());
+        if (e) {
+            broken = true;
+            return e;
+        }
+    }
+    if (Err e = check_echo(req, *resp)) {
+        broken = true;
+        return e;
+    }
+    if (!resp->is_success()) return decode_error_body(reinterpret_cast<const uint8_t*>(resp_data->data()), resp_data->size());
+    return Err::ok();
+}
+
+Err BlockClient::rpc_into(const Protocol& req, const std::string& header, uint8_t* dst, size_t cap, size_t* n) {
+    CV_RETURN_IF_ERR(send_request(req, header));
+    Protocol resp;
+    std::string rh;
+    CV_RETURN_IF_ERR(recv_response_head(&resp, &rh));
+    if (!resp.is_success() || static_cast<size_t>(resp.data_len) > cap) {
+        std::string body(static_cast<size_t>(resp.data_len), '\0');
+        if (resp.data_len && recv_exact(fd_, &body[0], body.size())) {
+            broken = true;
+            return Err::io("connection closed");
+        }
+        if (!resp.is_success()) return decode_error_body(reinterpret_cast<const uint8_t*>(body.data()), body.size());
+        broken = true;
+        return Err::common("response payload larger than the receive buffer");
+    }
+    if (resp.data_len) {
+        Err e = recv_exact(fd_, dst, static_cast<size_t>(resp.data_len));
+        if (e) {
+            broken = true;
+            return e;
+        }
+    }
+    if (Err e = check_echo(req, resp)) {
+        broken = true;
+        return e;
+    }
+    *n = static_cast<size_t>(resp.data_len);
+    return Err::ok();
+}
+
+static Protocol request_proto(int8_t status, int64_t req_id, int32_t seq_id) {
+    Protocol p;
+    p.code = kCodeReadBlock, p.req_status = status, p.resp_status = kRespUndefined, p.req_id = req_id, p.seq_id = seq_id;
+    return p;
+}
+
+Err BlockClient::open_block(const ClientConf& conf, const ExtendedBlock& b, int64_t off, int64_t len, int64_t req_id, int32_t seq_id,
+                            bool short_circuit, int64_t chunk_size, BlockReadResponse* out) {
+    BlockReadRequest r;
+    r.id = b.id, r.off = off, r.len = len, r.chunk_size = static_cast<int32_t>(chunk_size), r.short_circuit = short_circuit;
+    r.enable_read_ahead = conf.enable_read_ahead, r.read_ahead_len = conf.read_ahead_len, r.drop_cache_len = conf.drop_cache_len;
+    Protocol resp;
+    std::string rh, rd;
+    CV_RETURN_IF_ERR(rpc(request_proto(kReqOpen, req_id, seq_id), r.encode(), &resp, &rh, &rd));
+    return BlockReadResponse::decode(reinterpret_cast<const uint8_t*>(rh.data()), rh.size(), out);
+}
+
+Err BlockClient::read_commit(const ExtendedBlock& b, int64_t req_id, int32_t seq_id) {
+    BlockReadRequest r;  // ..Default::default(): proto defaults for everything but id (block_client.rs:263-266)
+    r.id = b.id;
+    Protocol resp;
+    std::string rh, rd;
+    return rpc(request_proto(kReqComplete, req_id, seq_id), r.encode(), &resp, &rh, &rd);
+}
+
+// ------------------------------------------------------------------ FsContext (connection pool)
+
+FsContext::~FsContext() = default;
+
+Err FsContext::acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClient>* out) {
+    if (conf.client.enable_block_conn_pool) {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto& v = idle_[addr.str()];
+        if (!v.empty()) {
+            *out = std::move(v.back());  // LIFO
+            v.pop_back();
+            return Err::ok();
+        }
+    }
+    int fd = -1;
+    CV_RETURN_IF_ERR(tcp_connect(addr.ip_addr.empty() ? addr.hostname : addr.ip_addr, static_cast<int>(addr.rpc_port), &fd));
+    out->reset(new BlockClient(fd, addr));
+    return Err::ok();
+}
+
+void FsContext::release(std::unique_ptr<BlockClient> c) {
+    if (!c || c->broken || !conf.client.enable_block_conn_pool) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    auto& v = idle_[c->addr().str()];
+    if (static_cast<int64_t>(v.size()) < conf.client.block_conn_idle_size) v.push_back(std::move(c));
+}
+
+// ------------------------------------------------------------------ BlockReader
+
+BlockReader::~BlockReader() { drop_adapter(); }
+
+void BlockReader::drop_adapter() {
+    close_fd(fd_);
+    fd_ = -1;
+    if (client_) ctx_->release(std::move(client_));
+}
+
+Err BlockReader::create(FsContext* ctx, const LocatedBlock& lb, int64_t off, std::unique_ptr<BlockReader>* out) {
+    std::unique_ptr<BlockReader> r(new BlockReader());
+    r->ctx_ = ctx;
+    r->block_ = lb.block;
+    r->chunk_size_ = ctx->read_chunk_size();
+    r->locs_ = lb.locs;
+    // sort_locs (block_reader.rs:146-166): shuffle, then the local worker first when short-circuit is on
+    if (r->locs_.size() > 1) {
+        static thread_local std::mt19937 rng{std::random_device{}()};
+        std::shuffle(r->locs_.begin(), r->locs_.end(), rng);
+    }
+    if (ctx->conf.client.short_circuit)
+        for (size_t i = 0; i < r->locs_.size(); i++)
+            if (ctx->is_local_worker(r->locs_[i])) {
+                std::swap(r->locs_[0], r->locs_[i]);
+                break;
+            }
+    CV_RETURN_IF_ERR(r->open_adapter(off));
+    *out = std::move(r);
+    return Err::ok();
+}
+
+// BlockReader::get_reader (block_reader.rs:168-215).  As in the reference, the `?` on the adapter constructors
+// propagates the first candidate's open error out of the function: there is no open-time failover, only the
+// read-time failover in read().
+Err BlockReader::open_adapter(int64_t off) {
+    drop_adapter();
+    pos_ = off;
+    if (locs_.empty() && block_.has_alloc_opts) {
+        kind_ = kHole;
+        cur_addr_ = WorkerAddress();
+        return Err::ok();
+    }
+    if (locs_.empty()) return Err::common("There is no available worker, locs: [], failed workers: []");
+    const WorkerAddress& loc = locs_[0];
+    cur_addr_ = loc;
+    const bool sc = ctx_->conf.client.short_circuit && ctx_->is_local_worker(loc);
+    req_id_ = new_req_id();
+    seq_id_ = 0;
+    pending_seek_ = false;
+    CV_RETURN_IF_ERR(ctx_->acquire_read(loc, &client_));
+    BlockReadResponse resp;
+    Err e = client_->open_block(ctx_->conf.client, block_, off, block_.len, req_id_, seq_id_, sc, chunk_size_, &resp);
+    if (e) {
+        drop_adapter();
+        return e;
+    }
+    if (sc) {
+        if (!resp.has_path) {
+            drop_adapter();
+            return Err::common("read_context.path is none");
+        }
+        fd_ = ::open(resp.path.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd_ < 0) {
+            drop_adapter();
+            return Err::io(str_printf("open %s: %s", resp.path.c_str(), strerror(errno)));
+        }
+        ctx_->release(std::move(client_));  // BlockReaderLocal keeps no connection; complete() acquires a new one
+        kind_ = kLocal;
+    } else {
+        kind_ = kRemote;
+    }
+    return Err::ok();
+}
+
+Err BlockReader::seek(int64_t pos) {
+    pos_ = pos;
+    if (kind_ == kRemote) pending_seek_ = true;  // piggy-backed on the next Running request (block_reader_remote.rs:93-101)
+    return Err::ok();
+}
+
+Err BlockReader::read_once(std::string* buf) {
+    if (remaining() <= 0) return Err::common("No readable data");
+    const int64_t want = std::min<int64_t>(chunk_size_, remaining());
+    switch (kind_) {
+        case kHole:
+            buf->assign(static_cast<size_t>(want), '\0');
+            break;
+        case kLocal: {
+            buf->resize(static_cast<size_t>(want));
+            int64_t got = 0;
+            while (got < want) {
+                const ssize_t r = pread(fd_, &(*buf)[got], static_cast<size_t>(want - got), pos_ + got);
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) return Err::io(str_printf("read block file: %s", r == 0 ? "unexpected eof" : strerror(errno)));
+                got += r;
+            }
+            break;
+        }
+        case kRemote: {
+            std::string header;
+            if (pending_seek_) {
+                DataHeaderProto h;
+                h.offset = pos_;
+                header = h.encode();
+                pending_seek_ = false;
+            }
+            Protocol resp;
+            std::string rh;
+            CV_RETURN_IF_ERR(client_->rpc(request_proto(kReqRunning, req_id_, ++seq_id_), header, &resp, &rh, buf));
+            break;
+        }
+    }
+    pos_ += static_cast<int64_t>(buf->size());
+    return Err::ok();
+}
+
+Err BlockReader::read(std::string* buf) {
+    buf->clear();
+    if (!has_remaining()) return Err::ok();  // end of block file
+    for (;;) {
+        Err e = read_once(buf);
+        if (!e) return e;
+        if (kind_ == kHole || locs_.empty()) return e.ctx("failed to read block on " + cur_addr_.str());
+        // drop this worker, reopen at pos on the next replica (block_reader.rs:223-252)
+        locs_.erase(std::remove(locs_.begin(), locs_.end(), cur_addr_), locs_.end());
+        if (client_) client_->broken = true;
+        CV_RETURN_IF_ERR(open_adapter(pos_));
+    }
+}
+
+Err BlockReader::complete() {
+    Err e;
+    if (kind_ == kRemote && client_) {
+        e = client_->read_commit(block_, req_id_, ++seq_id_);
+    } else if (kind_ == kLocal) {
+        std::unique_ptr<BlockClient> c;
+        e = ctx_->acquire_read(cur_addr_, &c);
+        if (!e) e = c->read_commit(block_, req_id_, ++seq_id_);
+        if (c) ctx_->release(std::move(c));
+    }
+    drop_adapter();
+    kind_ = kHole;
+    locs_.clear();
+    return e;
+}
+
+// ------------------------------------------------------------------ split / detector
+
+std::vector<std::vector<std::pair<int64_t, int64_t>>> split_slices(int64_t total, int64_t slice_size, int64_t read_parallel) {
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> out;
+    if (total <= 0) return out;
+    if (read_parallel == 1) {
+        out.push_back({{0, total}});
+        return out;
+    }
+    const int64_t num = (total + slice_size - 1) / slice_size;
+    out.resize(static_cast<size_t>(read_parallel));
+    for (int64_t sid = 0; sid < num; sid++) {
+        const int64_t start = sid * slice_size, end = sid == num - 1 ? total : start + slice_size;
+        out[static_cast<size_t>(sid % read_parallel)].push_back({start, end});
+    }
+    return out;
+}
+
+ReadDetector::ReadDetector(const ClientConf& conf, int64_t file_size) {
+    read_parallel = conf.read_parallel;
+    if (conf.enable_smart_prefetch && file_size >= conf.large_file_size) {
+        const int64_t calc = (file_size + conf.large_file_size - 1) / conf.large_file_size;
+        read_parallel = std::min<int64_t>(conf.max_read_parallel, std::max<int64_t>(1, calc));
+    }
+    enabled = conf.enable_smart_prefetch;
+    threshold_ = static_cast<uint64_t>(conf.sequential_read_threshold);
+}
+
+void ReadDetector::record_seek() {
+    if (!enabled) return;
+    seq_count_ = 0;
+    last_read_pos_ = -1;
+    random_ = true;
+}
+
+bool ReadDetector::record_read(int64_t start, int64_t end) {
+    if (!enabled) return false;
+    if (last_read_pos_ == -1 || start == last_read_pos_) seq_count_++;
+    else seq_count_ = 0;
+    last_read_pos_ = end;
+    const bool now_random = seq_count_ >= threshold_ ? false : random_;
+    if (now_random != random_) {
+        random_ = now_random;
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ FsReaderBase / FsReaderParallel
+
+FsReaderBase::FsReaderBase(FsContext* ctx, const FileBlocks* fb, bool cache_handles)
+    : ctx_(ctx), fb_(fb), len_(fb->status.len), cache_limit_(cache_handles ? static_cast<size_t>(ctx->conf.client.max_cache_block_handles) : 0) {}
+
+FsReaderBase::~FsReaderBase() = default;
+
+Err FsReaderBase::update_reader(std::unique_ptr<BlockReader> cur, bool cache) {
+    std::unique_ptr<BlockReader> old = std::move(cur_);
+    cur_ = std::move(cur);
+    if (!old) return Err::ok();
+    if (cache && cache_limit_ > 0) {
+        if (cache_.size() >= cache_limit_) {
+            std::unique_ptr<BlockReader> removed = std::move(cache_.front());
+            cache_.pop_front();
+            CV_RETURN_IF_ERR(removed->complete());
+        }
+        cache_.push_back(std::move(old));
+        return Err::ok();
+    }
+    return old->complete();
+}
+
+Err FsReaderBase::get_reader() {
+    if (cur_ && cur_->has_remaining()) return Err::ok();
+    int64_t boff;
+    size_t idx;
+    CV_RETURN_IF_ERR(fb_->get_read_block(pos_, &boff, &idx));
+    const LocatedBlock& lb = fb_->block_locs[idx];
+    std::unique_ptr<BlockReader> nr;
+    for (auto it = cache_.begin(); it != cache_.end(); ++it)
+        if ((*it)->block_id() == lb.block.id) {
+            nr = std::move(*it);
+            cache_.erase(it);
+            CV_RETURN_IF_ERR(nr->seek(boff));
+            break;
+        }
+    if (!nr) CV_RETURN_IF_ERR(BlockReader::create(ctx_, lb, boff, &nr));
+    return update_reader(std::move(nr), false);
+}
+
+Err FsReaderBase::read(std::string* buf) {
+    buf->clear();
+    if (pos_ >= len_) return Err::ok();
+    CV_RETURN_IF_ERR(get_reader());
+    CV_RETURN_IF_ERR(cur_->read(buf));
+    pos_ += static_cast<int64_t>(buf->size());
+    return Err::ok();
+}
+
+Err FsReaderBase::seek(int64_t pos) {
+    if (pos == pos_) return Err::ok();
+    if (pos == len_) {
+        pos_ = pos;
+        return update_reader(nullptr, false);
+    }
+    if (pos > len_) return Err::common(str_printf("seek position %lld can not exceed file len %lld", (long long)pos, (long long)len_));
+    int64_t boff;
+    size_t idx;
+    CV_RETURN_IF_ERR(fb_->get_read_block(pos, &boff, &idx));
+    if (cur_) {
+        if (cur_->block_id() == fb_->block_locs[idx].block.id) CV_RETURN_IF_ERR(cur_->seek(boff));
+        else CV_RETURN_IF_ERR(update_reader(nullptr, true));
+    }
+    pos_ = pos;
+    return Err::ok();
+}
+
+Err FsReaderBase::complete() {
+    Err first;
+    if (cur_) {
+        Err e = cur_->complete();
+        if (e && !first) first = e;
+        cur_.reset();
+    }
+    for (auto& r : cache_) {
+        Err e = r->complete();
+        if (e && !first) first = e;
+    }
+    cache_.clear();
+    return first;
+}
+
+Err FsReaderParallel::read(int64_t* off, std::string* buf) {
+    buf->clear();
+    *off = 0;
+    if (slices_.empty()) return Err::ok();
+    if (cur_ < 0) {
+        cur_ = 0;
+        CV_RETURN_IF_ERR(inner_.seek(slices_[0].first));
+    } else if (inner_.pos() >= slices_[static_cast<size_t>(cur_)].second) {
+        const int64_t next = cur_ + 1;
+        if (next >= static_cast<int64_t>(slices_.size())) return Err::ok();  // FileChunk::default()
+        cur_ = next;
+        CV_RETURN_IF_ERR(inner_.seek(slices_[static_cast<size_t>(next)].first));
+    }
+    *off = inner_.pos();
+    return inner_.read(buf);
+}
+
+Err FsReaderParallel::seek(int64_t pos) {
+    // first slice with end > pos
+    size_t idx = 0;
+    while (idx < slices_.size() && slices_[idx].second <= pos) idx++;
+    if (idx < slices_.size()) {
+        CV_RETURN_IF_ERR(inner_.seek(std::max(pos, slices_[idx].first)));
+        cur_ = static_cast<int64_t>(idx);
+    } else if (!slices_.empty()) {
+        CV_RETURN_IF_ERR(inner_.seek(slices_.back().second));
+        cur_ = static_cast<int64_t>(slices_.size()) - 1;
+    } else {
+        CV_RETURN_IF_ERR(inner_.seek(0));
+        cur_ = -1;
+    }
+    return Err::ok();
+}
+
+// ------------------------------------------------------------------ FsReader
+
+Err FsReader::open(FsContext* ctx, const std::string& path, std::unique_ptr<FsReader>* out) {
+    std::unique_ptr<FsReader> r(new FsReader());
+    r->ctx_ = ctx;
+    CV_RETURN_IF_ERR(ctx->ns.get_block_locations(path, &r->fb_));
+    r->fb_.build_index();
+    const ClientConf& c = ctx->conf.client;
+    r->len_ = r->fb_.status.len;
+    r->chunk_size_ = c.read_chunk_size;
+    r->slice_size_ = c.read_slice_size;
+    r->det_ = ReadDetector(c, r->len_);
+    // FsReaderParallel::create_all checks (fs_reader_parallel.rs:62-71)
+    if (c.read_chunk_size % 4096 != 0 || c.read_chunk_size < 4096) return Err::common("chunk_size must be an integer multiple of 4096");
+    if (r->slice_size_ % c.read_chunk_size != 0 || r->slice_size_ < c.read_chunk_size)
+        return Err::common("The slice size must be an integer multiple of the chunk size.");
+    for (auto& s : split_slices(r->len_, r->slice_size_, r->det_.read_parallel))
+        if (!s.empty()) r->readers_.emplace_back(new FsReaderParallel(ctx, &r->fb_, std::move(s), false));
+    r->readers_.emplace_back(new FsReaderParallel(ctx, &r->fb_, {{0, r->len_}}, true));  // the random-read base reader
+    *out = std::move(r);
+    return Err::ok();
+}
+
+Err FsReader::buffer_read() {
+    chunk_.clear();
+    chunk_off_ = 0;
+    if (bpos_ >= len_) return Err::ok();
+    const int64_t id = det_.is_random() ? det_.read_parallel : (bpos_ / slice_size_) % det_.read_parallel;
+    if (id < 0 || id >= static_cast<int64_t>(readers_.size())) return Err::common(str_printf("reader %lld is not initialized", (long long)id));
+    const double t0 = now_sec();
+    int64_t off = 0;
+    CV_RETURN_IF_ERR(readers_[static_cast<size_t>(id)]->read(&off, &chunk_));
+    const int64_t diff = bpos_ - off;
+    if (diff == 0) {
+    } else if (diff > 0 && diff <= static_cast<int64_t>(chunk_.size())) {
+        chunk_off_ = static_cast<size_t>(diff);  // misaligned first chunk: drop the excess prefix
+    } else {
+        return Err::common(str_printf("read data error: chunk offset %lld, pos %lld, diff %lld", (long long)off, (long long)bpos_, (long long)diff));
+    }
+    const int64_t n = static_cast<int64_t>(chunk_.size() - chunk_off_);
+    const int64_t start = bpos_;
+    bpos_ += n;
+    if (det_.record_read(start, bpos_) && det_.is_sequential())
+        for (auto& r : readers_) CV_RETURN_IF_ERR(r->seek(bpos_));
+    ctx_->read_bytes += n;
+    ctx_->read_time_us += static_cast<int64_t>((now_sec() - t0) * 1e6);
+    return Err::ok();
+}
+
+Err FsReader::buffer_seek(int64_t pos) {
+    if (pos == bpos_) return Err::ok();
+    det_.record_seek();
+    for (auto& r : readers_) CV_RETURN_IF_ERR(r->seek(pos));
+    bpos_ = pos;
+    return Err::ok();
+}
+
+Err FsReader::read_chunk(const uint8_t** ptr, int64_t* n, int64_t max_len) {
+    if (chunk_off_ >= chunk_.size()) CV_RETURN_IF_ERR(buffer_read());
+    int64_t avail = static_cast<int64_t>(chunk_.size() - chunk_off_);
+    if (max_len >= 0 && max_len < avail) avail = max_len;
+    *ptr = reinterpret_cast<const uint8_t*>(chunk_.data()) + chunk_off_;
+    *n = avail;
+    chunk_off_ += static_cast<size_t>(avail);
+    pos_ += avail;
+    return Err::ok();
+}
+
+Err FsReader::read(uint8_t* buf, int64_t cap, int64_t* n) {
+    const uint8_t* p;
+    CV_RETURN_IF_ERR(read_chunk(&p, n, cap));
+    if (*n > 0) memcpy(buf, p, static_cast<size_t>(*n));
+    return Err::ok();
+}
+
+Err FsReader::read_full(uint8_t* buf, int64_t cap, int64_t* n) {
+    int64_t off = 0;
+    while (off < cap) {
+        int64_t got = 0;
+        CV_RETURN_IF_ERR(read(buf + off, cap - off, &got));
+        if (got == 0) break;
+        off += got;
+    }
+    *n = off;
+    return Err::ok();
+}
+
+Err FsReader::seek(int64_t pos) {
+    if (pos < 0) return Err::common("Cannot seek to negative offset");
+    if (pos == pos_) return Err::ok();
+    const int64_t skip = pos - pos_;
+    const int64_t have = static_cast<int64_t>(chunk_.size() - chunk_off_);
+    if (skip >= 0 && skip <= have) {
+        chunk_off_ += static_cast<size_t>(skip);
+    } else {
+        chunk_.clear();
+        chunk_off_ = 0;
+        CV_RETURN_IF_ERR(buffer_seek(pos));
+    }
+    pos_ = pos;
+    return Err::ok();
+}
+
+Err FsReader::complete() {
+    Err first;
+    for (auto& r : readers_) {
+        Err e = r->complete();
+        if (e && !first) first = e;
+    }
+    return first;
+}
+
+}  // namespace cv

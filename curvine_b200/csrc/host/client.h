@@ -1,0 +1,256 @@
+// Client reader stack (host side): namespace lookup, block RPC client + pool, block readers with replica
+// failover, and the file-level reader that implements the reference `Reader` trait semantics.
+//
+// Mirrors (reference, relative to /root/reference):
+//   curvine-common/src/state/block_info.rs:66-72,127-131,156-217   ExtendedBlock / LocatedBlock / FileBlocks / search
+//   curvine-client/src/block/block_client.rs:222-300               open_block / read_data / read_commit
+//   orpc/src/client/raw_client.rs:100-116                          req_id/seq_id echo check
+//   curvine-client/src/block/block_client_pool.rs:90-168           LIFO idle pool per worker
+//   curvine-client/src/block/block_reader.rs:116-254               replica choice + failover
+//   curvine-client/src/block/block_reader_{remote,local,hole}.rs   the three adapters
+//   curvine-client/src/file/fs_reader_base.rs:101-204              block cursor + parked-reader cache
+//   curvine-client/src/file/fs_reader_parallel.rs:94-187           slice striping
+//   curvine-client/src/file/fs_reader_buffer.rs:248-323            sub-reader choice, misaligned trim
+//   curvine-client/src/file/read_detector.rs:130-218               sequential/random detector
+//   curvine-client/src/file/fs_reader.rs:103-126                   seek fast path
+//   curvine-common/src/fs/reader.rs:50-141                         read_chunk / read / read_full / fuse_read
+// Prefetch tasks + mpsc channels of the reference are replaced by lazy sub-readers here: the delivered
+// byte/chunk sequence is identical, the overlap comes from the GPU ingest pipeline instead (gpu_reader.*).
+#pragma once
+#include <atomic>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "conf.h"
+#include "wire.h"
+
+namespace cv {
+
+struct WorkerAddress {
+    uint32_t worker_id = 0;
+    std::string hostname, ip_addr;
+    uint32_t rpc_port = 0, web_port = 0;
+    bool operator==(const WorkerAddress& o) const { return hostname == o.hostname && rpc_port == o.rpc_port && worker_id == o.worker_id; }
+    std::string str() const { return hostname + ":" + std::to_string(rpc_port); }
+};
+
+struct ExtendedBlock {
+    int64_t id = 0, len = 0;
+    int32_t storage_type = kStorageDisk;
+    bool has_alloc_opts = false;  // block allocated but never written -> hole when it has no locations
+};
+
+struct LocatedBlock {
+    ExtendedBlock block;
+    std::vector<WorkerAddress> locs;
+    uint32_t crc32 = 0, crc32c = 0;  // manifest: expected per-block CRCs (SURVEY.md §0 "what verify compares against")
+    bool has_crc = false;
+};
+
+struct FileStatus {
+    int64_t id = 0;
+    std::string path;
+    int64_t len = 0;
+    int64_t block_size = 0;
+    int64_t mtime = 0;
+};
+
+struct FileBlocks {
+    FileStatus status;
+    std::vector<LocatedBlock> block_locs;
+    std::vector<int64_t> starts;  // prefix offsets (SearchFileBlocks::search_off)
+    void build_index();
+    // (block_off, index); partition_point(|x| x.end <= pos); error past the end
+    Err get_read_block(int64_t pos, int64_t* block_off, size_t* index) const;
+};
+
+// file -> blocks table.  Stands in for master GetBlockLocations (master_handler.rs:409-418), which is out of scope.
+class Namespace {
+   public:
+    Err load(const std::string& manifest_path);
+    Err load_string(const std::string& text);
+    Err get_block_locations(const std::string& path, FileBlocks* out) const;
+    void put(const FileBlocks& fb);
+    std::string dump() const;
+
+   private:
+    mutable std::mutex mu_;
+    std::map<std::string, FileBlocks> files_;
+};
+
+// ------------------------------------------------------------------ block RPC client
+
+class BlockClient {
+   public:
+    BlockClient(int fd, WorkerAddress addr) : fd_(fd), addr_(std::move(addr)) {}
+    ~BlockClient();
+    int fd() const { return fd_; }
+    const WorkerAddress& addr() const { return addr_; }
+    // send one request frame, receive one response frame (heartbeats skipped), check echoes, map error responses
+    Err rpc(const Protocol& req, const std::string& header, Protocol* resp, std::string* resp_header, std::string* resp_data);
+    // like rpc but the payload is received straight into `dst` (cap bytes); *n = payload length
+    Err rpc_into(const Protocol& req, const std::string& header, uint8_t* dst, size_t cap, size_t* n);
+    Err open_block(const ClientConf& conf, const ExtendedBlock& b, int64_t off, int64_t len, int64_t req_id, int32_t seq_id, bool short_circuit,
+                   int64_t chunk_size, BlockReadResponse* out);
+    Err read_commit(const ExtendedBlock& b, int64_t req_id, int32_t seq_id);
+    Err send_request(const Protocol& req, const std::string& header);
+    Err recv_response_head(Protocol* resp, std::string* resp_header);  // prefix + header; payload left on the socket
+    bool broken = false;
+
+   private:
+    int fd_;
+    WorkerAddress addr_;
+};
+
+class FsContext {
+   public:
+    explicit FsContext(const ClusterConf& conf) : conf(conf) {}
+    ~FsContext();
+    ClusterConf conf;
+    Namespace ns;
+    // block_client_pool.rs: LIFO idle connections per worker, at most block_conn_idle_size
+    Err acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClient>* out);
+    void release(std::unique_ptr<BlockClient> c);
+    bool is_local_worker(const WorkerAddress& addr) const { return addr.hostname == conf.client.hostname; }
+    int64_t read_chunk_size() const { return conf.client.read_chunk_size; }
+    // client metrics (client_metrics.rs:24-35)
+    std::atomic<int64_t> read_bytes{0}, read_time_us{0};
+
+   private:
+    std::mutex mu_;
+    std::unordered_map<std::string, std::vector<std::unique_ptr<BlockClient>>> idle_;
+};
+
+// ------------------------------------------------------------------ block readers
+
+class BlockReader {
+   public:
+    // BlockReader::new: sort replicas (local first when short_circuit), open the first that works
+    static Err create(FsContext* ctx, const LocatedBlock& lb, int64_t off, std::unique_ptr<BlockReader>* out);
+    ~BlockReader();
+    // next chunk: min(chunk_size, len - pos) bytes into *buf (resized); empty at end of block
+    Err read(std::string* buf);
+    Err seek(int64_t pos);
+    Err complete();
+    int64_t pos() const { return pos_; }
+    int64_t len() const { return block_.len; }
+    int64_t remaining() const { return block_.len - pos_; }
+    bool has_remaining() const { return remaining() > 0; }
+    int64_t block_id() const { return block_.id; }
+    enum Kind { kLocal, kRemote, kHole };
+    Kind kind() const { return kind_; }
+
+   private:
+    BlockReader() = default;
+    Err open_adapter(int64_t off);
+    Err read_once(std::string* buf);
+    void drop_adapter();
+    FsContext* ctx_ = nullptr;
+    ExtendedBlock block_;
+    std::vector<WorkerAddress> locs_;
+    WorkerAddress cur_addr_;
+    Kind kind_ = kHole;
+    int64_t pos_ = 0;
+    int64_t chunk_size_ = 0;
+    // remote
+    std::unique_ptr<BlockClient> client_;
+    int64_t req_id_ = 0;
+    int32_t seq_id_ = 0;
+    bool pending_seek_ = false;
+    // local
+    int fd_ = -1;
+};
+
+// ------------------------------------------------------------------ file-level reader
+
+std::vector<std::vector<std::pair<int64_t, int64_t>>> split_slices(int64_t total, int64_t slice_size, int64_t read_parallel);
+
+class ReadDetector {
+   public:
+    ReadDetector() = default;
+    ReadDetector(const ClientConf& conf, int64_t file_size);
+    bool enabled = true;
+    int64_t read_parallel = 1;
+    bool is_random() const { return random_; }
+    bool is_sequential() const { return !random_; }
+    uint64_t seq_count() const { return seq_count_; }
+    void record_seek();
+    bool record_read(int64_t start, int64_t end);
+    void set_last_read_pos(int64_t p) { last_read_pos_ = p; }
+
+   private:
+    int64_t last_read_pos_ = -1;
+    uint64_t seq_count_ = 0, threshold_ = 7;
+    bool random_ = false;
+};
+
+class FsReaderBase {
+   public:
+    FsReaderBase(FsContext* ctx, const FileBlocks* fb, bool cache_handles);
+    ~FsReaderBase();
+    Err read(std::string* buf);  // empty at EOF
+    Err seek(int64_t pos);
+    Err complete();
+    int64_t pos() const { return pos_; }
+
+   private:
+    Err update_reader(std::unique_ptr<BlockReader> cur, bool cache);
+    Err get_reader();
+    FsContext* ctx_;
+    const FileBlocks* fb_;
+    int64_t pos_ = 0, len_ = 0;
+    std::unique_ptr<BlockReader> cur_;
+    size_t cache_limit_;
+    std::list<std::unique_ptr<BlockReader>> cache_;  // FIFO of parked (still open) readers
+};
+
+class FsReaderParallel {
+   public:
+    FsReaderParallel(FsContext* ctx, const FileBlocks* fb, std::vector<std::pair<int64_t, int64_t>> slices, bool cache_handles)
+        : inner_(ctx, fb, cache_handles), slices_(std::move(slices)) {}
+    Err read(int64_t* off, std::string* buf);
+    Err seek(int64_t pos);
+    Err complete() { return inner_.complete(); }
+
+   private:
+    FsReaderBase inner_;
+    std::vector<std::pair<int64_t, int64_t>> slices_;
+    int64_t cur_ = -1;
+};
+
+// FsReader + FsReaderBuffer + the provided methods of `trait Reader`
+class FsReader {
+   public:
+    static Err open(FsContext* ctx, const std::string& path, std::unique_ptr<FsReader>* out);
+    int64_t len() const { return len_; }
+    int64_t pos() const { return pos_; }
+    int64_t chunk_size() const { return chunk_size_; }
+    const FileBlocks& file_blocks() const { return fb_; }
+    FsContext* ctx() const { return ctx_; }
+    // Reader::read_chunk(None) + pos advance == blocking_read: borrowed pointer valid until the next call
+    Err read_chunk(const uint8_t** ptr, int64_t* n, int64_t max_len = -1);
+    Err read(uint8_t* buf, int64_t cap, int64_t* n);       // Reader::read
+    Err read_full(uint8_t* buf, int64_t cap, int64_t* n);  // Reader::read_full
+    Err seek(int64_t pos);
+    Err complete();
+    const ReadDetector& detector() const { return det_; }
+
+   private:
+    FsReader() = default;
+    Err buffer_read();
+    Err buffer_seek(int64_t pos);
+    FsContext* ctx_ = nullptr;
+    FileBlocks fb_;
+    int64_t len_ = 0, pos_ = 0, bpos_ = 0, chunk_size_ = 0, slice_size_ = 0;
+    ReadDetector det_;
+    std::vector<std::unique_ptr<FsReaderParallel>> readers_;
+    std::string chunk_;     // current chunk storage
+    size_t chunk_off_ = 0;  // consumed prefix
+    std::string tmp_;
+};
+
+}  // namespace cv

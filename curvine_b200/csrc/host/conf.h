@@ -1,0 +1,65 @@
+// Client/worker configuration: the reference's read knobs with the reference's defaults, plus the
+// [b200] section this implementation adds.
+//
+// Mirrors curvine-common/src/conf/client_conf.rs:228-281,315-420 (defaults + init()),
+// orpc/src/common/byte_unit.rs:29-34 (binary size strings: KB = 2^10 ...),
+// curvine-common/src/conf/worker_conf.rs:59-95,176-207 (data_dir tags "[MEM:10MB]/path", enable_send_file).
+#pragma once
+#include <map>
+#include <vector>
+
+#include "common.h"
+
+namespace cv {
+
+struct ClientConf {
+    int64_t block_size = 128ll << 20;
+    int64_t read_chunk_size = 128 << 10;
+    int64_t read_chunk_num = 8;
+    int64_t read_parallel = 1;
+    int64_t read_slice_size = 0;  // 0 -> chunk_num * chunk_size
+    bool short_circuit = true;
+    bool enable_read_ahead = true;
+    int64_t read_ahead_len = 0;  // 0 -> chunk_num * chunk_size
+    int64_t drop_cache_len = 1 << 20;
+    int64_t max_cache_block_handles = 10;
+    bool enable_smart_prefetch = true;
+    int64_t large_file_size = 10ll << 30;
+    int64_t max_read_parallel = 8;
+    int64_t sequential_read_threshold = 7;
+    bool enable_block_conn_pool = true;
+    int64_t block_conn_idle_size = 128;
+    std::string hostname;  // CURVINE_CLIENT_HOSTNAME override; default gethostname()
+    Err init();            // client_conf.rs:228-281
+};
+
+// [b200] section: the GPU ingest pipeline (no reference counterpart)
+struct B200Conf {
+    int device = 0;
+    int fetch_threads = 8;        // host threads pulling blocks into pinned slots
+    int pinned_slots = 32;        // ring depth (slots of max block bytes + frame overhead)
+    int verify_poly = 1;          // 0 = CRC-32 (reference tools), 1 = CRC-32C (north_star)
+    bool verify = true;           // compare per-block CRC with the manifest on the GPU
+    int verify_batch = 16;        // blocks per CRC launch
+    int64_t gpu_chunk_size = 4 << 20;  // Running-request chunk for the framed GPU path (<= 16 MiB frame cap)
+    int numa_node = -1;           // bind fetch threads to this node's CPUs (-1: the GPU's node if discoverable)
+};
+
+struct ClusterConf {
+    ClientConf client;
+    B200Conf b200;
+    std::string cluster_id = "curvine";
+    std::string namespace_manifest;        // file -> blocks table (stands in for master GetBlockLocations)
+    std::vector<std::string> worker_dirs;  // worker.data_dir entries, e.g. "[MEM]/dev/shm/cv"
+    std::string worker_hostname = "localhost";
+    int worker_port = 0;
+    bool worker_enable_send_file = true;
+
+    static Err from_file(const std::string& path, ClusterConf* out);
+    static Err from_string(const std::string& toml, ClusterConf* out);
+};
+
+// "128KB" -> 131072; plain integers pass through
+Err parse_byte_size(const std::string& s, int64_t* out);
+
+}  // namespace cv

@@ -1,0 +1,586 @@
+#include "gpu_reader.h"
+
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <unistd.h>
+
+#include <fstream>
+
+#include "../../../include/curvine_b200_kernels.h"
+#include "net.h"
+
+namespace cv {
+
+#define CU_TRY(x)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (x);                                                                       \
+        if (e_ != cudaSuccess) return Err::io(str_printf("%s: %s", #x, cudaGetErrorString(e_)));    \
+    } while (0)
+#define CVK_TRY(x)                                                                                  \
+    do {                                                                                            \
+        int e_ = (x);                                                                               \
+        if (e_ != 0) return Err::io(str_printf("%s: %s", #x, cudaGetErrorString(cudaError_t(e_)))); \
+    } while (0)
+
+// ------------------------------------------------------------------ GpuIngest: ring + streams
+
+class GpuIngest {
+   public:
+    int device = 0;
+    int nslots = 0;
+    size_t slot_bytes = 0;
+    uint8_t* pinned = nullptr;
+    uint8_t* d_stage = nullptr;  // framed mode only
+    size_t d_stage_bytes = 0;
+    std::vector<cudaEvent_t> copy_ev, free_ev;
+    std::vector<cudaStream_t> copy_streams;
+    cudaStream_t vstream = nullptr;
+    cudaEvent_t done_ev = nullptr;
+    std::vector<int> cpus;
+    std::mutex mu;  // one read_device at a time per context
+
+    Err init(const B200Conf& c) {
+        device = c.device;
+        CU_TRY(cudaSetDevice(device));
+        CVK_TRY(cvk_init(device));
+        nslots = std::max(c.pinned_slots, 2 * c.verify_batch + c.fetch_threads);
+        copy_ev.resize(nslots), free_ev.resize(nslots);
+        for (int i = 0; i < nslots; i++) {
+            CU_TRY(cudaEventCreateWithFlags(&copy_ev[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming));
+        }
+        copy_streams.resize(std::max(1, c.fetch_threads));
+        for (auto& s : copy_streams) CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&vstream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
+        // CPUs of the GPU's NUMA node: pinned pages and fetch threads stay next to the PCIe root
+        int node = c.numa_node;
+        if (node < 0) {
+            char bus[64] = {0};
+            if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) == cudaSuccess) {
+                for (char* p = bus; *p; p++) *p = static_cast<char>(tolower(*p));
+                std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+                if (f) f >> node;
+            }
+        }
+        if (node >= 0) {
+            std::ifstream f("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+            std::string s;
+            if (f && std::getline(f, s)) {
+                size_t p = 0;
+                while (p < s.size()) {
+                    const size_t c2 = s.find(',', p);
+                    const std::string r = s.substr(p, c2 == std::string::npos ? std::string::npos : c2 - p);
+                    const size_t d = r.find('-');
+                    const int a = atoi(r.c_str()), b = d == std::string::npos ? a : atoi(r.c_str() + d + 1);
+                    for (int x = a; x <= b; x++) cpus.push_back(x);
+                    if (c2 == std::string::npos) break;
+                    p = c2 + 1;
+                }
+            }
+        }
+        return Err::ok();
+    }
+
+    void bind_thread() const {
+        if (cpus.empty()) return;
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        for (int c : cpus) CPU_SET(c, &set);
+        sched_setaffinity(0, sizeof(set), &set);
+    }
+
+    Err ensure(size_t need_slot_bytes, bool framed) {
+        need_slot_bytes = (need_slot_bytes + 4095) & ~size_t(4095);
+        if (need_slot_bytes > slot_bytes) {
+            CU_TRY(cudaDeviceSynchronize());
+            if (pinned) cudaFreeHost(pinned);
+            if (d_stage) cudaFree(d_stage);
+            pinned = nullptr, d_stage = nullptr, d_stage_bytes = 0;
+            slot_bytes = need_slot_bytes;
+            // allocate (and first-touch) the ring from a thread bound to the GPU's node
+            Err err;
+            std::thread t([&] {
+                bind_thread();
+                cudaSetDevice(device);
+                cudaError_t e = cudaHostAlloc(&pinned, slot_bytes * nslots, cudaHostAllocDefault);
+                if (e != cudaSuccess) err = Err::io(str_printf("cudaHostAlloc(%zu): %s", slot_bytes * nslots, cudaGetErrorString(e)));
+                else memset(pinned, 0, slot_bytes * nslots);
+            });
+            t.join();
+            if (err) return err;
+        }
+        if (framed && d_stage_bytes < slot_bytes * nslots) {
+            if (d_stage) cudaFree(d_stage);
+            d_stage_bytes = slot_bytes * nslots;
+            CU_TRY(cudaMalloc(&d_stage, d_stage_bytes));
+        }
+        return Err::ok();
+    }
+
+    ~GpuIngest() {
+        cudaSetDevice(device);
+        cudaDeviceSynchronize();
+        if (pinned) cudaFreeHost(pinned);
+        if (d_stage) cudaFree(d_stage);
+        for (auto e : copy_ev) cudaEventDestroy(e);
+        for (auto e : free_ev) cudaEventDestroy(e);
+        for (auto s : copy_streams) cudaStreamDestroy(s);
+        if (vstream) cudaStreamDestroy(vstream);
+        if (done_ev) cudaEventDestroy(done_ev);
+    }
+};
+
+static std::mutex g_ing_mu;
+static std::map<FsContext*, GpuIngest*> g_ingests;
+
+GpuIngest* gpu_ingest_get(FsContext* ctx, Err* err) {
+    std::lock_guard<std::mutex> lk(g_ing_mu);
+    auto it = g_ingests.find(ctx);
+    if (it != g_ingests.end()) return it->second;
+    GpuIngest* g = new GpuIngest();
+    *err = g->init(ctx->conf.b200);
+    if (*err) {
+        delete g;
+        return nullptr;
+    }
+    g_ingests[ctx] = g;
+    return g;
+}
+
+void gpu_ingest_release(FsContext* ctx) {
+    std::lock_guard<std::mutex> lk(g_ing_mu);
+    auto it = g_ingests.find(ctx);
+    if (it == g_ingests.end()) return;
+    delete it->second;
+    g_ingests.erase(it);
+}
+
+// ------------------------------------------------------------------ GpuFsReader
+
+Err GpuFsReader::open(FsContext* ctx, const std::string& path, std::unique_ptr<GpuFsReader>* out) {
+    std::unique_ptr<GpuFsReader> r(new GpuFsReader());
+    r->ctx_ = ctx;
+    CV_RETURN_IF_ERR(ctx->ns.get_block_locations(path, &r->fb_));
+    r->fb_.build_index();
+    Err e;
+    r->ing_ = gpu_ingest_get(ctx, &e);
+    if (e) return e;
+    *out = std::move(r);
+    return Err::ok();
+}
+
+GpuFsReader::~GpuFsReader() {
+    if (d_tables_) {
+        cudaSetDevice(ing_->device);
+        cudaStreamSynchronize(ing_->vstream);
+        cudaFree(d_tables_);
+    }
+}
+
+Err GpuFsReader::seek(int64_t pos) {
+    if (pos < 0) return Err::common("Cannot seek to negative offset");
+    if (pos > len()) return Err::common(str_printf("seek position %lld can not exceed file len %lld", (long long)pos, (long long)len()));
+    pos_ = pos;
+    return Err::ok();
+}
+
+Err GpuFsReader::complete() {
+    uint64_t s, v;
+    uint32_t b;
+    return verify(&s, &b, &v);
+}
+
+Err GpuFsReader::read_device(void* d_dst, int64_t cap, void* stream, int64_t* n) {
+    *n = 0;
+    const int64_t end = std::min(len(), pos_ + std::max<int64_t>(cap, 0));
+    if (end <= pos_) return Err::ok();
+    std::vector<Job> jobs;
+    int64_t p = pos_;
+    while (p < end) {
+        int64_t boff;
+        size_t idx;
+        CV_RETURN_IF_ERR(fb_.get_read_block(p, &boff, &idx));
+        const int64_t blen = fb_.block_locs[idx].block.len;
+        const int64_t take = std::min(end - p, blen - boff);
+        jobs.push_back(Job{idx, boff, take, p - pos_, boff == 0 && take == blen});
+        p += take;
+    }
+    CV_RETURN_IF_ERR(run_jobs(jobs, static_cast<uint8_t*>(d_dst), stream));
+    *n = end - pos_;
+    pos_ = end;
+    return Err::ok();
+}
+
+Err GpuFsReader::read_device_sharded(int rank, int world, void* d_dst, int64_t cap, void* stream, int64_t* n) {
+    *n = 0;
+    if (world <= 0 || rank < 0 || rank >= world) return Err::common("bad shard spec");
+    const int64_t bs = fb_.status.block_size;
+    std::vector<Job> jobs;
+    int64_t total = 0;
+    for (size_t b = static_cast<size_t>(rank), j = 0; b < fb_.block_locs.size(); b += static_cast<size_t>(world), j++) {
+        const int64_t blen = fb_.block_locs[b].block.len;
+        if (static_cast<int64_t>(j) * bs + blen > cap) return Err::common("destination too small for this shard");
+        jobs.push_back(Job{b, 0, blen, static_cast<int64_t>(j) * bs, true});
+        total += blen;
+    }
+    CV_RETURN_IF_ERR(run_jobs(jobs, static_cast<uint8_t*>(d_dst), stream));
+    *n = total;
+    return Err::ok();
+}
+
+namespace {
+
+struct CallState {
+    std::atomic<size_t> next_job{0};
+    std::atomic<bool> abort{false};
+    std::mutex err_mu;
+    Err err;
+    std::vector<std::atomic<int>> copied;
+    std::vector<std::atomic<int64_t>> released;  // per slot: last job whose release event has been recorded
+    explicit CallState(size_t jobs, size_t slots) : copied(jobs), released(slots) {
+        for (auto& c : copied) c.store(0);
+        for (auto& r : released) r.store(-1);
+    }
+    void fail(const Err& e) {
+        std::lock_guard<std::mutex> lk(err_mu);
+        if (!err) err = e;
+        abort.store(true);
+    }
+};
+
+static Protocol read_req(int8_t status, int64_t req_id, int32_t seq_id) {
+    Protocol p;
+    p.code = kCodeReadBlock, p.req_status = status, p.resp_status = kRespUndefined, p.req_id = req_id, p.seq_id = seq_id;
+    return p;
+}
+
+}  // namespace
+
+// Fetch one job's bytes into `slot`.  short-circuit: payload only.  framed: verbatim wire image.
+static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, int64_t n, bool framed, int64_t chunk, uint8_t* slot,
+                     std::unique_ptr<BlockClient>* conn, int64_t* req_id_out, size_t* wire_bytes) {
+    Err last = Err::common("There is no available worker, locs: [], failed workers: []");
+    for (const WorkerAddress& loc : lb.locs) {
+        if (!*conn || !((*conn)->addr() == loc) || (*conn)->broken) {
+            if (*conn) ctx->release(std::move(*conn));
+            last = ctx->acquire_read(loc, conn);
+            if (last) continue;
+        }
+        BlockClient* c = conn->get();
+        const int64_t req_id = new_req_id();
+        *req_id_out = req_id;
+        BlockReadResponse resp;
+        last = c->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, req_id, 0, !framed, framed ? chunk : ctx->read_chunk_size(), &resp);
+        if (last) continue;
+        int32_t seq = 0;
+        if (!framed) {
+            if (!resp.has_path) {
+                last = Err::common("read_context.path is none");
+                continue;
+            }
+            const int fd = ::open(resp.path.c_str(), O_RDONLY | O_CLOEXEC);
+            if (fd < 0) {
+                last = Err::io(str_printf("open %s: %s", resp.path.c_str(), strerror(errno)));
+                continue;
+            }
+            int64_t got = 0;
+            while (got < n) {
+                const ssize_t r = pread(fd, slot + got, static_cast<size_t>(n - got), block_off + got);
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) {
+                    last = Err::io(str_printf("read block file: %s", r == 0 ? "unexpected eof" : strerror(errno)));
+                    break;
+                }
+                got += r;
+            }
+            ::close(fd);
+            if (got < n) continue;
+            *wire_bytes = static_cast<size_t>(n);
+        } else {
+            // all Running requests in one write (the worker serves them in order, read_handler.rs:143-183)
+            const int64_t nfr = (n + chunk - 1) / chunk;
+            std::string reqs(static_cast<size_t>(nfr) * kProtocolSize, '\0');
+            for (int64_t f = 0; f < nfr; f++) encode_protocol(read_req(kReqRunning, req_id, static_cast<int32_t>(f + 1)), reinterpret_cast<uint8_t*>(&reqs[f * kProtocolSize]));
+            last = send_all(c->fd(), reqs.data(), reqs.size());
+            uint8_t* w = slot;
+            int64_t left = n;
+            for (int64_t f = 0; f < nfr && !last; f++) {
+                last = recv_exact(c->fd(), w, kProtocolSize);
+                Protocol p;
+                if (!last) last = decode_protocol(w, &p);
+                if (last) break;
+                const int64_t want = std::min(chunk, left);
+                if (!p.is_success() || p.header_len != 0 || p.data_len != want) {
+                    // error response (or a short chunk): drain this frame and the rest of the pipeline, then report it
+                    std::string body(static_cast<size_t>(p.header_len + p.data_len), '\0');
+                    if (!body.empty() && recv_exact(c->fd(), &body[0], body.size())) c->broken = true;
+                    last = p.is_success() ? Err::common(str_printf("unexpected chunk length %d, expected %lld", p.data_len, (long long)want))
+                                          : decode_error_body(reinterpret_cast<const uint8_t*>(body.data()) + p.header_len, static_cast<size_t>(p.data_len));
+                    c->broken = true;  // responses of the remaining pipelined requests are still in flight
+                    break;
+                }
+                last = recv_exact(c->fd(), w + kProtocolSize, static_cast<size_t>(want));
+                w += kProtocolSize + want, left -= want;
+            }
+            if (last) {
+                c->broken = true;
+                continue;
+            }
+            seq = static_cast<int32_t>(nfr);
+            *wire_bytes = static_cast<size_t>(w - slot);
+        }
+        last = c->read_commit(lb.block, req_id, seq + 1);
+        if (last) continue;
+        return Err::ok();
+    }
+    return last;
+}
+
+// Pull the last call's per-block CRCs / mismatch count / frame flags (already copied to h_result_ on vstream).
+Err GpuFsReader::harvest() {
+    if (!pending_.active) return Err::ok();
+    cudaSetDevice(ing_->device);
+    CU_TRY(cudaStreamSynchronize(ing_->vstream));
+    const uint32_t* crc = reinterpret_cast<const uint32_t*>(h_result_);
+    const size_t J = pending_.jobs;
+    for (size_t j = pending_.f0; j < pending_.f1; j++) sum_crc_ += crc[j];
+    n_verified_ += pending_.n_compared;
+    n_bad_ += crc[J];  // mismatch counter written by cvk_verify_crcs
+    const uint32_t* ferr = crc + J + 4;
+    for (size_t f = 0; f < pending_.frames; f++)
+        if (ferr[f]) {
+            n_bad_frames_++;
+            if (!first_frame_err_) first_frame_err_ = ferr[f];
+        }
+    pending_.active = false;
+    if (n_bad_frames_) return Err(kAbnormalData, str_printf("%llu frame prefixes failed validation (first flags 0x%x)", (unsigned long long)n_bad_frames_, first_frame_err_));
+    return Err::ok();
+}
+
+Err GpuFsReader::verify(uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified) {
+    Err e = harvest();
+    *sum_crc = sum_crc_, *n_bad = n_bad_, *n_verified = n_verified_;
+    return e;
+}
+
+Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* user_stream) {
+    const size_t J = jobs.size();
+    if (J == 0) return Err::ok();
+    const double t_start = now_sec();
+    GpuIngest& G = *ing_;
+    std::lock_guard<std::mutex> call_lock(G.mu);
+    CU_TRY(cudaSetDevice(G.device));
+    CV_RETURN_IF_ERR(harvest());
+    const B200Conf& bc = ctx_->conf.b200;
+    const ClientConf& cc = ctx_->conf.client;
+    const int poly = bc.verify_poly ? 1 : 0;
+    const int64_t chunk = std::min<int64_t>(std::max<int64_t>(bc.gpu_chunk_size, 4096), kMaxDataSize);
+
+    // short-circuit (the reference default for a same-host worker, client_conf.rs:339) only when every block of
+    // this call has a local replica; otherwise the whole call runs framed (any worker serves framed reads)
+    std::vector<uint8_t> framed(J, 0), hole(J, 0);
+    bool any_framed = false;
+    for (size_t j = 0; j < J; j++) {
+        const LocatedBlock& lb = fb_.block_locs[jobs[j].block];
+        if (lb.locs.empty()) {
+            if (!lb.block.has_alloc_opts) return Err::common("There is no available worker, locs: [], failed workers: []");
+            hole[j] = 1;
+            continue;
+        }
+        bool local = false;
+        for (const auto& a : lb.locs) local |= ctx_->is_local_worker(a);
+        if (!(cc.short_circuit && local)) any_framed = true;
+    }
+    size_t need_slot = 0, F = 0;
+    std::vector<uint32_t> first_frame(J + 1, 0);
+    for (size_t j = 0; j < J; j++) {
+        framed[j] = any_framed && !hole[j];
+        first_frame[j] = static_cast<uint32_t>(F);
+        size_t bytes = static_cast<size_t>(jobs[j].n);
+        if (framed[j]) {
+            const size_t nfr = static_cast<size_t>((jobs[j].n + chunk - 1) / chunk);
+            bytes += nfr * kProtocolSize;
+            F += nfr;
+        }
+        need_slot = std::max(need_slot, bytes);
+    }
+    first_frame[J] = static_cast<uint32_t>(F);
+    CV_RETURN_IF_ERR(G.ensure(need_slot, any_framed));
+    const int B = std::max(1, bc.verify_batch);
+    const size_t S = static_cast<size_t>(G.nslots);
+
+    // ---- device tables: off[J] len[J] | expect[J] crc[J] nbad[4] ferr[F] | streams[J] fdesc[F]
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_off = 0, o_len = up(o_off + 8 * J), o_exp = up(o_len + 8 * J), o_crc = up(o_exp + 4 * J);
+    const size_t res_words = J + 4 + F;
+    const size_t o_streams = up(o_crc + 4 * res_words), o_fdesc = up(o_streams + sizeof(CvStreamDesc) * J);
+    const size_t tables_bytes = up(o_fdesc + sizeof(CvFrameDesc) * F);
+    if (tables_bytes > d_tables_cap_) {
+        if (d_tables_) cudaFree(d_tables_);
+        d_tables_cap_ = tables_bytes * 2;
+        CU_TRY(cudaMalloc(&d_tables_, d_tables_cap_));
+    }
+    if (4 * res_words > h_result_cap_) {
+        if (h_result_) cudaFreeHost(h_result_);
+        h_result_cap_ = 8 * res_words;
+        CU_TRY(cudaHostAlloc(&h_result_, h_result_cap_, cudaHostAllocDefault));
+    }
+    uint8_t* T = static_cast<uint8_t*>(d_tables_);
+    std::vector<uint8_t> h(o_crc);  // host image of off/len/expect
+    uint64_t* h_off = reinterpret_cast<uint64_t*>(&h[o_off]);
+    uint64_t* h_len = reinterpret_cast<uint64_t*>(&h[o_len]);
+    uint32_t* h_exp = reinterpret_cast<uint32_t*>(&h[o_exp]);
+    size_t f0 = J, f1 = 0, n_compared = 0;
+    for (size_t j = 0; j < J; j++) {
+        const LocatedBlock& lb = fb_.block_locs[jobs[j].block];
+        h_off[j] = static_cast<uint64_t>(jobs[j].dst_off);
+        h_len[j] = static_cast<uint64_t>(jobs[j].n);
+        h_exp[j] = poly ? lb.crc32c : lb.crc32;
+        if (jobs[j].full && lb.has_crc && !hole[j]) {
+            f0 = std::min(f0, j), f1 = std::max(f1, j + 1);
+            n_compared++;
+        }
+    }
+    if (f0 >= f1) f0 = f1 = 0;
+    // blocks inside [f0,f1) without a manifest CRC (or partial) must not count as mismatches: jobs are in file
+    // order so only the two ends can be partial; a missing manifest entry disables comparison for the call
+    const bool compare = bc.verify && n_compared == f1 - f0 && n_compared > 0;
+    CU_TRY(cudaMemcpyAsync(T, h.data(), o_crc, cudaMemcpyHostToDevice, G.vstream));
+    CU_TRY(cudaMemsetAsync(T + o_crc, 0, 4 * res_words, G.vstream));
+    std::vector<CvStreamDesc> sd;
+    if (any_framed) {
+        sd.resize(J);
+        for (size_t j = 0; j < J; j++) {
+            CvStreamDesc& d = sd[j];
+            memset(&d, 0, sizeof(d));
+            d.wire_off = (j % S) * G.slot_bytes, d.dst_off = h_off[j], d.block_len = framed[j] ? h_len[j] : 0;
+            d.chunk_size = static_cast<uint32_t>(chunk), d.first_seq_id = 1, d.block = static_cast<uint32_t>(j % B);
+            d.first_frame = first_frame[j], d.code = kCodeReadBlock, d.status = 0x03;
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(G.vstream));  // `h` goes out of scope semantics: pageable copies are staged, be explicit
+
+    // ---- fetch threads
+    CallState st(J, S);
+    std::vector<int64_t> req_ids(J, 0);
+    const int T_threads = static_cast<int>(std::min<size_t>(static_cast<size_t>(std::max(1, bc.fetch_threads)), J));
+    std::vector<double> fetch_sec(static_cast<size_t>(T_threads), 0.0);
+    std::vector<uint64_t> h2d(static_cast<size_t>(T_threads), 0);
+    auto worker = [&](int t) {
+        G.bind_thread();
+        cudaSetDevice(G.device);
+        cudaStream_t cs = G.copy_streams[static_cast<size_t>(t) % G.copy_streams.size()];
+        std::unique_ptr<BlockClient> conn;
+        for (;;) {
+            const size_t j = st.next_job.fetch_add(1);
+            if (j >= J || st.abort.load()) break;
+            const size_t slot = j % S;
+            if (j >= S) {  // wait until the slot's previous tenant (job j-S) has been released, then for its event
+                const int64_t want = static_cast<int64_t>(j - S);
+                while (st.released[slot].load(std::memory_order_acquire) < want) {
+                    if (st.abort.load()) break;
+                    std::this_thread::yield();
+                }
+                if (st.abort.load()) break;
+                cudaEventSynchronize(framed[j - S] ? G.free_ev[slot] : G.copy_ev[slot]);
+            }
+            uint8_t* hs = G.pinned + slot * G.slot_bytes;
+            const Job& job = jobs[j];
+            size_t wire = 0;
+            cudaError_t ce = cudaSuccess;
+            if (hole[j]) {
+                ce = cudaMemsetAsync(d_dst + job.dst_off, 0, static_cast<size_t>(job.n), cs);  // block_reader_hole.rs:69-79
+            } else {
+                const double t0 = now_sec();
+                Err e = fetch_job(ctx_, fb_.block_locs[job.block], job.block_off, job.n, framed[j], chunk, hs, &conn, &req_ids[j], &wire);
+                fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
+                if (e) {
+                    st.fail(e.ctx(str_printf("block %lld", (long long)fb_.block_locs[job.block].block.id)));
+                    break;
+                }
+                uint8_t* dst = framed[j] ? G.d_stage + slot * G.slot_bytes : d_dst + job.dst_off;
+                ce = cudaMemcpyAsync(dst, hs, wire, cudaMemcpyHostToDevice, cs);
+                h2d[static_cast<size_t>(t)] += wire;
+            }
+            if (ce == cudaSuccess) ce = cudaEventRecord(G.copy_ev[slot], cs);
+            if (ce != cudaSuccess) {
+                st.fail(Err::io(str_printf("H2D enqueue: %s", cudaGetErrorString(ce))));
+                break;
+            }
+            if (!framed[j]) st.released[slot].store(static_cast<int64_t>(j), std::memory_order_release);
+            st.copied[j].store(1, std::memory_order_release);
+        }
+        if (conn) ctx_->release(std::move(conn));
+    };
+    std::vector<std::thread> threads;
+    for (int t = 0; t < T_threads; t++) threads.emplace_back(worker, t);
+
+    // ---- verifier: this thread walks the jobs in order, B at a time
+    Err verr;
+    uint64_t launches0 = cvk_launch_count();
+    const uint64_t* d_off = reinterpret_cast<const uint64_t*>(T + o_off);
+    const uint64_t* d_len = reinterpret_cast<const uint64_t*>(T + o_len);
+    uint32_t* d_crc = reinterpret_cast<uint32_t*>(T + o_crc);
+    uint32_t* d_ferr = d_crc + J + 4;
+    CvStreamDesc* d_streams = reinterpret_cast<CvStreamDesc*>(T + o_streams);
+    CvFrameDesc* d_fdesc = reinterpret_cast<CvFrameDesc*>(T + o_fdesc);
+    for (size_t g0 = 0; g0 < J && !verr; g0 += static_cast<size_t>(B)) {
+        const size_t g1 = std::min(J, g0 + static_cast<size_t>(B));
+        for (size_t j = g0; j < g1; j++)
+            while (!st.copied[j].load(std::memory_order_acquire) && !st.abort.load()) std::this_thread::yield();
+        if (st.abort.load()) break;
+        uint64_t gbytes = 0;
+        bool gframed = false, gplain = false;
+        for (size_t j = g0; j < g1; j++) {
+            cudaStreamWaitEvent(G.vstream, G.copy_ev[j % S], 0);
+            gbytes += h_len[j];
+            (framed[j] ? gframed : gplain) = true;
+        }
+        if (gplain && !gframed && bc.verify) {  // short-circuit jobs: K1 over the landed bytes
+            int rc = cvk_crc_blocks(d_dst, d_off + g0, d_len + g0, static_cast<uint32_t>(g1 - g0), poly, gbytes, d_crc + g0, G.vstream);
+            if (rc) verr = Err::io(str_printf("cvk_crc_blocks: %s", cudaGetErrorString(cudaError_t(rc))));
+        }
+        if (gframed && !verr) {
+            // patch the request ids (known only after the fetch) and expand this group's stream descriptors
+            for (size_t j = g0; j < g1; j++) sd[j].req_id = req_ids[j];
+            cudaError_t ce = cudaMemcpyAsync(d_streams + g0, &sd[g0], sizeof(CvStreamDesc) * (g1 - g0), cudaMemcpyHostToDevice, G.vstream);
+            const uint32_t fr0 = first_frame[g0], nfr = first_frame[g1] - fr0;
+            int rc = ce != cudaSuccess ? int(ce) : 0;
+            // first_frame inside the descriptors is absolute; expand into the absolute table
+            if (!rc) rc = cvk_expand_streams(d_streams + g0, static_cast<uint32_t>(g1 - g0), d_fdesc, first_frame[J], G.vstream);
+            if (!rc && nfr)
+                rc = cvk_unpack_frames(G.d_stage, d_fdesc + fr0, nfr, static_cast<uint32_t>(g1 - g0), d_dst, poly, gbytes,
+                                       bc.verify ? d_crc + g0 : nullptr, d_ferr + fr0, G.vstream);
+            if (rc) verr = Err::io(str_printf("cvk_unpack_frames: %s", cudaGetErrorString(cudaError_t(rc))));
+            for (size_t j = g0; j < g1; j++)
+                if (framed[j]) {
+                    cudaEventRecord(G.free_ev[j % S], G.vstream);
+                    st.released[j % S].store(static_cast<int64_t>(j), std::memory_order_release);
+                }
+        }
+    }
+    if (verr) st.fail(verr);
+    for (auto& th : threads) th.join();
+    if (st.err) {
+        cudaStreamSynchronize(G.vstream);
+        for (auto s : G.copy_streams) cudaStreamSynchronize(s);
+        return st.err;
+    }
+    if (compare) CVK_TRY(cvk_verify_crcs(d_crc + f0, reinterpret_cast<const uint32_t*>(T + o_exp) + f0, static_cast<uint32_t>(f1 - f0), d_crc + J, nullptr, G.vstream));
+    CU_TRY(cudaMemcpyAsync(h_result_, d_crc, 4 * res_words, cudaMemcpyDeviceToHost, G.vstream));
+    CU_TRY(cudaEventRecord(G.done_ev, G.vstream));
+    CU_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(user_stream), G.done_ev, 0));
+    pending_.active = true, pending_.jobs = J, pending_.frames = F;
+    pending_.f0 = bc.verify ? f0 : 0, pending_.f1 = bc.verify ? f1 : 0, pending_.n_compared = compare ? n_compared : 0;
+    for (size_t j = 0; j < J; j++) stats_.bytes += h_len[j];
+    stats_.blocks += J;
+    stats_.kernel_launches += cvk_launch_count() - launches0;
+    for (int t = 0; t < T_threads; t++) stats_.fetch_sec += fetch_sec[static_cast<size_t>(t)], stats_.h2d_bytes += h2d[static_cast<size_t>(t)];
+    stats_.wall_sec += now_sec() - t_start;
+    return Err::ok();
+}
+
+}  // namespace cv

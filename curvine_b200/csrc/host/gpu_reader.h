@@ -1,0 +1,87 @@
+// GPU ingest pipeline: blocks of a file -> pinned host ring -> HBM on side streams -> on-GPU CRC verify.
+//
+// No reference counterpart (the reference has no GPU code); it replaces, for HBM destinations, the role of
+// FsReaderBuffer's prefetch tasks (curvine-client/src/file/fs_reader_buffer.rs:332-406) and the caller's
+// read_full + crc32 loop (curvine-tests/src/curvine_bench.rs:222-231), speaking the same worker protocol as
+// BlockReaderLocal / BlockReaderRemote (block_reader_local.rs:43-143, block_reader_remote.rs:36-122):
+//   short-circuit  Open(short_circuit=true) -> pread the block file straight into a pinned slot -> H2D to its
+//                  final place -> K1 CRC on the landed bytes -> Complete
+//   framed         Open -> all Running requests pipelined in one write -> the response stream (22-byte prefixes
+//                  + payloads) received verbatim into a pinned slot -> H2D wire image -> K2 validates the prefixes,
+//                  gathers payloads to their file offsets and CRCs them in the same pass -> Complete
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <thread>
+
+#include "client.h"
+
+namespace cv {
+
+struct GpuReadStats {
+    uint64_t bytes = 0;         // payload bytes landed in HBM
+    uint64_t blocks = 0;        // block jobs
+    uint64_t verified = 0;      // blocks whose CRC was compared with the manifest
+    uint64_t h2d_bytes = 0;     // bytes moved by cudaMemcpyAsync (payload, + prefixes when framed)
+    uint64_t kernel_launches = 0;
+    double fetch_sec = 0;       // summed over fetch threads: time inside pread/recv
+    double wall_sec = 0;
+};
+
+class GpuIngest;  // per-FsContext pinned ring + streams
+
+class GpuFsReader {
+   public:
+    static Err open(FsContext* ctx, const std::string& path, std::unique_ptr<GpuFsReader>* out);
+    ~GpuFsReader();
+    int64_t len() const { return fb_.status.len; }
+    int64_t pos() const { return pos_; }
+    Err seek(int64_t pos);
+    const FileBlocks& file_blocks() const { return fb_; }
+    // Next min(cap, remaining) bytes -> d_dst, ordered on `stream` when the call returns.  *n = bytes.
+    Err read_device(void* d_dst, int64_t cap, void* stream, int64_t* n);
+    // Round-robin shard of the whole file: blocks b with b % world == rank land back to back in slots of
+    // block_size bytes (slot j = block j*world + rank).  *n = bytes landed (sum of those block lengths).
+    Err read_device_sharded(int rank, int world, void* d_dst, int64_t cap, void* stream, int64_t* n);
+    // Waits for outstanding work; sum_crc = u64 sum of the per-block CRCs computed so far (verify_poly),
+    // n_bad = blocks whose CRC differed from the manifest.
+    Err verify(uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified);
+    const GpuReadStats& stats() const { return stats_; }
+    Err complete();
+
+   private:
+    struct Job {
+        size_t block;        // index into fb_.block_locs
+        int64_t block_off;   // first byte of the block this job needs
+        int64_t n;           // bytes
+        int64_t dst_off;     // where they go in d_dst
+        bool full;           // whole block -> CRC comparable with the manifest
+    };
+    GpuFsReader() = default;
+    Err run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* stream);
+    FsContext* ctx_ = nullptr;
+    FileBlocks fb_;
+    int64_t pos_ = 0;
+    GpuReadStats stats_;
+    GpuIngest* ing_ = nullptr;
+    uint64_t sum_crc_ = 0, n_verified_ = 0;
+    uint32_t n_bad_ = 0;
+    uint64_t n_bad_frames_ = 0;
+    uint32_t first_frame_err_ = 0;
+    // device-side per-call tables + pinned result mirror
+    void* d_tables_ = nullptr;
+    size_t d_tables_cap_ = 0;
+    void* h_result_ = nullptr;
+    size_t h_result_cap_ = 0;
+    struct Pending {
+        bool active = false;
+        size_t jobs = 0, frames = 0, f0 = 0, f1 = 0, n_compared = 0;
+    } pending_;
+    Err harvest();
+};
+
+// one per (process, device): pinned ring, device staging ring, streams, events
+GpuIngest* gpu_ingest_get(FsContext* ctx, Err* err);
+void gpu_ingest_release(FsContext* ctx);
+
+}  // namespace cv

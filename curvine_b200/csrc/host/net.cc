@@ -1,0 +1,122 @@
+#include "net.h"
+
+#include <arpa/inet.h>
+#include <errno.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/sendfile.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+namespace cv {
+
+void set_sock_opts(int fd) {
+    int one = 1;
+    setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+    setsockopt(fd, SOL_SOCKET, SO_KEEPALIVE, &one, sizeof(one));
+    int buf = 8 << 20;  // loopback throughput: large socket buffers
+    setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &buf, sizeof(buf));
+    setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &buf, sizeof(buf));
+}
+
+void close_fd(int fd) {
+    if (fd >= 0) ::close(fd);
+}
+
+static Err resolve(const std::string& host, int port, sockaddr_in* sa) {
+    memset(sa, 0, sizeof(*sa));
+    sa->sin_family = AF_INET;
+    sa->sin_port = htons(static_cast<uint16_t>(port));
+    const std::string h = (host.empty() || host == "localhost") ? "127.0.0.1" : host;
+    if (inet_pton(AF_INET, h.c_str(), &sa->sin_addr) == 1) return Err::ok();
+    addrinfo hints{}, *res = nullptr;
+    hints.ai_family = AF_INET;
+    hints.ai_socktype = SOCK_STREAM;
+    if (getaddrinfo(h.c_str(), nullptr, &hints, &res) != 0 || !res) {
+        // a same-host worker whose hostname does not resolve (containers): fall back to loopback
+        inet_pton(AF_INET, "127.0.0.1", &sa->sin_addr);
+        return Err::ok();
+    }
+    sa->sin_addr = reinterpret_cast<sockaddr_in*>(res->ai_addr)->sin_addr;
+    freeaddrinfo(res);
+    return Err::ok();
+}
+
+Err tcp_connect(const std::string& host, int port, int* fd_out) {
+    sockaddr_in sa;
+    CV_RETURN_IF_ERR(resolve(host, port, &sa));
+    const int fd = socket(AF_INET, SOCK_STREAM, 0);
+    if (fd < 0) return Err::io(str_printf("socket: %s", strerror(errno)));
+    set_sock_opts(fd);
+    if (connect(fd, reinterpret_cast<sockaddr*>(&sa), sizeof(sa)) != 0) {
+        const int e = errno;
+        ::close(fd);
+        return Err::io(str_printf("connect %s:%d: %s", host.c_str(), port, strerror(e)));
+    }
+    *fd_out = fd;
+    return Err::ok();
+}
+
+Err tcp_listen(const std::string& host, int port, int* fd_out, int* bound_port) {
+    sockaddr_in sa;
+    CV_RETURN_IF_ERR(resolve(host.empty() ? "0.0.0.0" : host, port, &sa));
+    if (host.empty()) sa.sin_addr.s_addr = htonl(INADDR_ANY);
+    const int fd = socket(AF_INET, SOCK_STREAM, 0);
+    if (fd < 0) return Err::io(str_printf("socket: %s", strerror(errno)));
+    int one = 1;
+    setsockopt(fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+    if (bind(fd, reinterpret_cast<sockaddr*>(&sa), sizeof(sa)) != 0 || listen(fd, 1024) != 0) {
+        const int e = errno;
+        ::close(fd);
+        return Err::io(str_printf("bind/listen :%d: %s", port, strerror(e)));
+    }
+    socklen_t sl = sizeof(sa);
+    getsockname(fd, reinterpret_cast<sockaddr*>(&sa), &sl);
+    *bound_port = ntohs(sa.sin_port);
+    *fd_out = fd;
+    return Err::ok();
+}
+
+Err send_all(int fd, const void* buf, size_t n) {
+    const uint8_t* p = static_cast<const uint8_t*>(buf);
+    while (n) {
+        const ssize_t w = ::send(fd, p, n, MSG_NOSIGNAL);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return Err::io(str_printf("send: %s", strerror(errno)));
+        }
+        p += w, n -= static_cast<size_t>(w);
+    }
+    return Err::ok();
+}
+
+Err recv_exact(int fd, void* buf, size_t n) {
+    uint8_t* p = static_cast<uint8_t*>(buf);
+    while (n) {
+        const ssize_t r = ::recv(fd, p, n, 0);
+        if (r == 0) return Err::io("connection closed");
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            return Err::io(str_printf("recv: %s", strerror(errno)));
+        }
+        p += r, n -= static_cast<size_t>(r);
+    }
+    return Err::ok();
+}
+
+Err send_file_full(int sock, int file_fd, int64_t off, size_t n) {
+    off_t o = off;
+    while (n) {
+        const ssize_t w = ::sendfile(sock, file_fd, &o, n);
+        if (w < 0) {
+            if (errno == EINTR || errno == EAGAIN) continue;
+            return Err::io(str_printf("sendfile: %s", strerror(errno)));
+        }
+        if (w == 0) return Err::io("sendfile: unexpected end of file");
+        n -= static_cast<size_t>(w);
+    }
+    return Err::ok();
+}
+
+}  // namespace cv

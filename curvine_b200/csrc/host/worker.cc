@@ -1,0 +1,221 @@
+#include "worker.h"
+
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <sys/vfs.h>
+#include <unistd.h>
+
+#include "net.h"
+
+namespace cv {
+
+static Protocol response_proto(const Protocol& req, int8_t resp_status) {
+    Protocol p = req;
+    p.resp_status = resp_status;
+    p.header_len = p.data_len = 0;
+    return p;
+}
+
+ReadHandler::~ReadHandler() { close_fd(fd_); }
+
+Err ReadHandler::handle(const RpcRequest& req, RpcResponse* resp) {
+    switch (req.proto.req_status) {
+        case kReqOpen: return open(req, resp);
+        case kReqRunning: return read(req, resp);
+        case kReqComplete: return complete(req, resp);
+        default: return Err::common("Unsupported request type");
+    }
+}
+
+Err ReadHandler::open(const RpcRequest& req, RpcResponse* resp) {
+    BlockReadRequest c;
+    CV_RETURN_IF_ERR(BlockReadRequest::decode(reinterpret_cast<const uint8_t*>(req.header.data()), req.header.size(), &c));
+    BlockMeta meta;
+    CV_RETURN_IF_ERR(store_->get_block(c.id, &meta));
+    if (c.off > meta.len)
+        return Err::common(str_printf("The length of the requested data exceeds the maximum length of the block file, request off %lld, file len %lld",
+                                      (long long)c.off, (long long)meta.len));
+    if (c.chunk_size <= 0) return Err::common("chunk_size must be greater than 0");
+    if (c.enable_read_ahead && c.read_ahead_len > 16 * 1024 * 1024)
+        return Err::common(str_printf("The pre-read size exceeds the maximum value allowed by the system.The current value is %lld. The maximum allowed value is: %d",
+                                      (long long)c.read_ahead_len, 16 * 1024 * 1024));
+    const bool short_circuit = c.short_circuit && meta.storage_type != kStorageSpdkDisk;
+    close_fd(fd_);
+    fd_ = -1;
+    if (!short_circuit) {
+        fd_ = ::open(meta.path.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd_ < 0) return Err::io(str_printf("open %s: %s", meta.path.c_str(), strerror(errno)));
+        struct stat st;
+        fstat(fd_, &st);
+        len_ = st.st_size;
+        pos_ = c.off;
+        struct statfs sfs;
+        is_tmpfs_ = fstatfs(fd_, &sfs) == 0 && sfs.f_type == 0x01021994;  // TMPFS_MAGIC (sys_libc.rs:320-339)
+        last_ahead_ = -1;
+    }
+    path_ = meta.path;
+    ctx_ = c;
+    ctx_req_id_ = req.proto.req_id;
+    has_ctx_ = true;
+    (short_circuit ? metrics_->read_blocks_local : metrics_->read_blocks_remote)++;
+    BlockReadResponse r;
+    r.id = c.id, r.len = meta.len, r.has_path = short_circuit, r.path = meta.path, r.storage_type = meta.storage_type;
+    resp->proto = response_proto(req.proto, kRespSuccess);
+    resp->header = r.encode();
+    return Err::ok();
+}
+
+// cache_manager.rs:99-147 / local_file.rs:202-213: fadvise(WILLNEED) ahead of a sequential cursor; never on tmpfs
+void ReadHandler::read_ahead() {
+    if (!ctx_.enable_read_ahead || is_tmpfs_ || len_ < 256 * 1024 || ctx_.read_ahead_len <= 0) return;
+    if (last_ahead_ < 0 || pos_ >= last_ahead_ + ctx_.read_ahead_len / 2) {
+        posix_fadvise(fd_, pos_, ctx_.read_ahead_len, POSIX_FADV_WILLNEED);
+        last_ahead_ = pos_;
+    }
+}
+
+Err ReadHandler::read(const RpcRequest& req, RpcResponse* resp) {
+    if (fd_ < 0) return Err::common("self.file is none");
+    if (!has_ctx_) return Err::common("self.context is none");
+    if (!req.header.empty()) {
+        DataHeaderProto h;
+        CV_RETURN_IF_ERR(DataHeaderProto::decode(reinterpret_cast<const uint8_t*>(req.header.data()), req.header.size(), &h));
+        if (h.offset != pos_) {  // local files: the header offset is absolute inside the block file
+            if (h.offset < 0) return Err::io("seek to negative offset");
+            pos_ = h.offset;
+        }
+    }
+    const double t0 = now_sec();
+    read_ahead();
+    const int64_t chunk = std::min<int64_t>(ctx_.chunk_size, len_ - pos_);
+    if (chunk <= 0) return Err::common(str_printf("offset exceeds file length, length=%lld, offset=%lld", (long long)len_, (long long)pos_));
+    resp->proto = response_proto(req.proto, kRespSuccess);
+    if (enable_send_file_) {
+        resp->file_fd = fd_, resp->file_off = pos_, resp->file_len = static_cast<int32_t>(chunk);
+    } else {
+        resp->data.resize(static_cast<size_t>(chunk));
+        int64_t got = 0;
+        while (got < chunk) {
+            const ssize_t r = pread(fd_, &resp->data[got], static_cast<size_t>(chunk - got), pos_ + got);
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) return Err::io(str_printf("pread %s: %s", path_.c_str(), r == 0 ? "unexpected eof" : strerror(errno)));
+            got += r;
+        }
+    }
+    pos_ += chunk;
+    metrics_->read_bytes += chunk;
+    metrics_->read_time_us += static_cast<int64_t>((now_sec() - t0) * 1e6);
+    metrics_->read_count++;
+    return Err::ok();
+}
+
+Err ReadHandler::complete(const RpcRequest& req, RpcResponse* resp) {
+    if (has_ctx_ && ctx_req_id_ != req.proto.req_id)
+        return Err::common(str_printf("Request id mismatch, expected %lld, actual %lld", (long long)ctx_req_id_, (long long)req.proto.req_id));
+    close_fd(fd_);
+    fd_ = -1;
+    resp->proto = response_proto(req.proto, kRespSuccess);
+    return Err::ok();
+}
+
+Worker::~Worker() { stop(); }
+
+Err Worker::start(const std::vector<std::string>& data_dirs, const std::string& cluster_id, const std::string& host, int port, bool enable_send_file) {
+    CV_RETURN_IF_ERR(store_.init(data_dirs, cluster_id));
+    enable_send_file_ = enable_send_file;
+    CV_RETURN_IF_ERR(tcp_listen(host, port, &listen_fd_, &port_));
+    stopping_ = false;
+    accept_thread_ = std::thread([this] { accept_loop(); });
+    return Err::ok();
+}
+
+void Worker::stop() {
+    if (listen_fd_ < 0) return;
+    stopping_ = true;
+    ::shutdown(listen_fd_, SHUT_RDWR);
+    close_fd(listen_fd_);
+    listen_fd_ = -1;
+    if (accept_thread_.joinable()) accept_thread_.join();
+    {
+        std::lock_guard<std::mutex> lk(conn_mu_);
+        for (int fd : conn_fds_) ::shutdown(fd, SHUT_RDWR);
+    }
+    while (live_conns_.load() > 0) usleep(1000);
+}
+
+void Worker::accept_loop() {
+    while (!stopping_) {
+        const int fd = ::accept(listen_fd_, nullptr, nullptr);
+        if (fd < 0) {
+            if (errno == EINTR) continue;
+            break;
+        }
+        set_sock_opts(fd);
+        {
+            std::lock_guard<std::mutex> lk(conn_mu_);
+            conn_fds_.push_back(fd);
+        }
+        live_conns_++;
+        std::thread([this, fd] {
+            serve(fd);
+            {
+                std::lock_guard<std::mutex> lk(conn_mu_);
+                for (auto& f : conn_fds_)
+                    if (f == fd) {
+                        f = conn_fds_.back();
+                        conn_fds_.pop_back();
+                        break;
+                    }
+            }
+            close_fd(fd);
+            live_conns_--;
+        }).detach();
+    }
+}
+
+// StreamHandler::run + WorkerHandler::handle for one connection
+void Worker::serve(int fd) {
+    std::unique_ptr<ReadHandler> handler;
+    uint8_t prefix[kProtocolSize];
+    RpcRequest req;
+    for (;;) {
+        if (recv_exact(fd, prefix, kProtocolSize)) return;  // peer closed
+        if (decode_protocol(prefix, &req.proto)) return;    // malformed frame ends the connection
+        if (req.proto.header_len < 0) return;
+        req.header.resize(static_cast<size_t>(req.proto.header_len));
+        if (req.proto.header_len && recv_exact(fd, &req.header[0], req.header.size())) return;
+        req.data.resize(static_cast<size_t>(req.proto.data_len));
+        if (req.proto.data_len && recv_exact(fd, &req.data[0], req.data.size())) return;
+        if (req.proto.is_heartbeat()) continue;
+
+        RpcResponse resp;
+        Err e;
+        if (req.proto.code != kCodeReadBlock) {
+            e = Err::common(str_printf("Unsupported request type: %d", int(req.proto.code)));
+        } else {
+            // worker_handler.rs:71-88: a fresh handler unless this is a Running message for the live one
+            if (!handler || req.proto.req_status != kReqRunning) handler.reset(new ReadHandler(&store_, &metrics_, enable_send_file_));
+            e = handler->handle(req, &resp);
+        }
+        if (e) {  // block_handler.rs:57-60 -> msg.error_ext(&e)
+            resp = RpcResponse();
+            resp.proto = response_proto(req.proto, kRespError);
+            resp.data = encode_error_body(e.kind, e.msg);
+        }
+        resp.proto.header_len = static_cast<int32_t>(resp.header.size());
+        resp.proto.data_len = resp.file_fd >= 0 ? resp.file_len : static_cast<int32_t>(resp.data.size());
+        uint8_t out[kProtocolSize];
+        encode_protocol(resp.proto, out);
+        // prefix + header in one write, then the payload region (rpc_frame.rs:205-220)
+        std::string head(reinterpret_cast<char*>(out), kProtocolSize);
+        head += resp.header;
+        if (resp.file_fd < 0) head += resp.data;
+        if (send_all(fd, head.data(), head.size())) return;
+        if (resp.file_fd >= 0 && send_file_full(fd, resp.file_fd, resp.file_off, static_cast<size_t>(resp.file_len))) return;
+        if (req.proto.req_status == kReqCancel || req.proto.req_status == kReqComplete) handler.reset();
+    }
+}
+
+}  // namespace cv

@@ -1,0 +1,92 @@
+// Worker-side read path: the per-connection ReadBlock handler over a BlockStore, served on TCP.
+//
+// Mirrors (reference):
+//   orpc/src/server/rpc_server.rs:163-193, orpc/src/handler/stream_handler.rs:47-100   accept loop, per-connection
+//        receive -> handle -> send; handler errors become error *responses* (block_handler.rs:57-60)
+//   curvine-server/src/worker/handler/worker_handler.rs:42-98    one stateful BlockHandler per connection,
+//        replaced on every non-Running message, dropped after Cancel/Complete
+//   curvine-server/src/worker/handler/read_handler.rs:60-207     open / read / complete
+//   curvine-server/src/worker/handler/context.rs:61-78           ReadContext::from_req
+//   orpc/src/io/local_file.rs:103-117                            read_region: chunk = min(chunk_size, len - pos)
+//   orpc/src/handler/rpc_frame.rs:97-121, orpc/src/sys/sys_libc.rs:76-122  payload by sendfile(2)
+#pragma once
+#include <atomic>
+#include <memory>
+#include <thread>
+
+#include "block_store.h"
+#include "wire.h"
+
+namespace cv {
+
+struct WorkerMetrics {  // worker_metrics.rs:25-44
+    std::atomic<int64_t> read_bytes{0}, read_time_us{0}, read_count{0}, read_blocks_local{0}, read_blocks_remote{0};
+};
+
+// One request message as received from the socket.
+struct RpcRequest {
+    Protocol proto;
+    std::string header;
+    std::string data;
+};
+
+// What to send back: prefix(+header) and either inline data or a file region.
+struct RpcResponse {
+    Protocol proto;
+    std::string header;
+    std::string data;   // inline payload (errors, pread mode)
+    int file_fd = -1;   // sendfile region when >= 0
+    int64_t file_off = 0;
+    int32_t file_len = 0;
+    bool empty = false;
+};
+
+class ReadHandler {
+   public:
+    ReadHandler(BlockStore* store, WorkerMetrics* m, bool enable_send_file) : store_(store), metrics_(m), enable_send_file_(enable_send_file) {}
+    ~ReadHandler();
+    Err handle(const RpcRequest& req, RpcResponse* resp);
+
+   private:
+    Err open(const RpcRequest& req, RpcResponse* resp);
+    Err read(const RpcRequest& req, RpcResponse* resp);
+    Err complete(const RpcRequest& req, RpcResponse* resp);
+    void read_ahead();
+    BlockStore* store_;
+    WorkerMetrics* metrics_;
+    bool enable_send_file_;
+    bool has_ctx_ = false;
+    BlockReadRequest ctx_;
+    int64_t ctx_req_id_ = 0;
+    int fd_ = -1;
+    int64_t pos_ = 0, len_ = 0, last_ahead_ = -1;
+    bool is_tmpfs_ = false;
+    std::string path_;
+};
+
+class Worker {
+   public:
+    Worker() = default;
+    ~Worker();
+    Err start(const std::vector<std::string>& data_dirs, const std::string& cluster_id, const std::string& host, int port, bool enable_send_file);
+    void stop();
+    int port() const { return port_; }
+    BlockStore& store() { return store_; }
+    WorkerMetrics& metrics() { return metrics_; }
+
+   private:
+    void accept_loop();
+    void serve(int fd);
+    BlockStore store_;
+    WorkerMetrics metrics_;
+    int listen_fd_ = -1;
+    int port_ = 0;
+    bool enable_send_file_ = true;
+    std::atomic<bool> stopping_{false};
+    std::thread accept_thread_;
+    std::mutex conn_mu_;
+    std::vector<int> conn_fds_;
+    std::atomic<int> live_conns_{0};
+};
+
+}  // namespace cv

@@ -1,0 +1,204 @@
+"""Python mirror of the reference reader surface over the C ABI (include/curvine_b200.h).
+
+Names and behaviour follow the reference traits so tests read like the reference's own:
+  CurvineFileSystem.open(path) -> Reader          curvine-common/src/fs/filesystem.rs:35
+  Reader.{read_chunk, read, read_full, fuse_read, seek, pos, len, complete}
+                                                   curvine-common/src/fs/reader.rs:23-156
+plus the CUDA counterpart (read_device / read_device_sharded / verify) on the same handle.
+Errors raise FsError carrying the reference's ErrorKind (fs_error.rs:35-66).
+"""
+import ctypes
+from typing import List, Optional
+
+from . import _lib
+
+
+class FsError(Exception):
+    def __init__(self, kind: int, msg: str):
+        super().__init__("[kind %d] %s" % (kind, msg))
+        self.kind = kind
+        self.msg = msg
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise FsError(-rc, _lib.lib().cv_last_error().decode(errors="replace"))
+
+
+class MiniWorker:
+    """In-process worker over a BlockStore directory tree (fixture; worker_test.rs:35-48 analogue)."""
+
+    def __init__(self, data_dirs: List[str], cluster_id: str = "curvine", hostname: str = "localhost",
+                 enable_send_file: bool = True, port: int = 0):
+        conf = 'cluster_id = "%s"\n[worker]\ndata_dir = [%s]\nhostname = "%s"\nrpc_port = %d\nenable_send_file = %s\n' % (
+            cluster_id, ", ".join('"%s"' % d for d in data_dirs), hostname, port, "true" if enable_send_file else "false")
+        self.hostname = hostname
+        self._h = ctypes.c_void_p()
+        p = ctypes.c_int32()
+        _check(_lib.lib().cv_worker_start(conf.encode(), ctypes.byref(self._h), ctypes.byref(p)))
+        self.port = p.value
+
+    def create_file(self, path: str, inode_id: int, length: int, block_size: int, storage_type: int = 0, mode: int = 0,
+                    hole_every: int = 0, threads: int = 8, worker_hostname: Optional[str] = None) -> str:
+        """Writes synthetic blocks in the reference layout; returns the namespace manifest text."""
+        out = ctypes.c_void_p()
+        _check(_lib.lib().cv_synth_create_file(self._h, path.encode(), inode_id, length, block_size, storage_type, mode,
+                                               hole_every, threads, (worker_hostname or self.hostname).encode(),
+                                               ctypes.byref(out)))
+        text = ctypes.string_at(out).decode()
+        _lib.lib().cv_free(out)
+        return text
+
+    def metrics(self) -> dict:
+        a = (ctypes.c_int64 * 6)()
+        _check(_lib.lib().cv_worker_metrics(self._h, a))
+        return dict(zip(["read_bytes", "read_time_us", "read_count", "read_blocks_local", "read_blocks_remote", "num_blocks"], a))
+
+    def stop(self):
+        if self._h:
+            _check(_lib.lib().cv_worker_stop(self._h))
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.stop()
+
+
+class Reader:
+    def __init__(self, h):
+        self._h = h
+
+    def len(self) -> int:
+        return _lib.lib().cv_len(self._h)
+
+    def pos(self) -> int:
+        return _lib.lib().cv_pos(self._h)
+
+    def chunk_size(self) -> int:
+        return _lib.lib().cv_chunk_size(self._h)
+
+    def remaining(self) -> int:
+        return self.len() - self.pos()
+
+    def read_chunk(self) -> bytes:
+        """blocking_read: the whole current chunk (copied out of the reader-owned buffer)."""
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        _check(_lib.lib().cv_read(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p, n.value) if n.value else b""
+
+    def read(self, size: int) -> bytes:
+        buf = ctypes.create_string_buffer(max(size, 1))
+        n = ctypes.c_int64()
+        _check(_lib.lib().cv_read_buf(self._h, buf, size, ctypes.byref(n)))
+        return buf.raw[:n.value]
+
+    def read_full(self, size: int) -> bytes:
+        buf = ctypes.create_string_buffer(max(size, 1))
+        n = ctypes.c_int64()
+        _check(_lib.lib().cv_read_full(self._h, buf, size, ctypes.byref(n)))
+        return buf.raw[:n.value]
+
+    def read_full_into(self, ptr: int, size: int) -> int:
+        n = ctypes.c_int64()
+        _check(_lib.lib().cv_read_full(self._h, ctypes.c_void_p(ptr), size, ctypes.byref(n)))
+        return n.value
+
+    def fuse_read(self, pos: int, size: int) -> List[bytes]:
+        buf = ctypes.create_string_buffer(max(size, 1))
+        n, ns = ctypes.c_int64(), ctypes.c_int32()
+        segs = (ctypes.c_int64 * 4096)()
+        _check(_lib.lib().cv_fuse_read(self._h, pos, size, buf, ctypes.byref(n), segs, 4096, ctypes.byref(ns)))
+        out, off = [], 0
+        for i in range(ns.value):
+            out.append(buf.raw[off:off + segs[i]])
+            off += segs[i]
+        return out
+
+    def seek(self, pos: int):
+        _check(_lib.lib().cv_seek(self._h, pos))
+
+    # ---- CUDA counterpart
+    def read_device(self, d_ptr: int, cap: int, stream: int = 0) -> int:
+        n = ctypes.c_int64()
+        _check(_lib.lib().cv_read_device(self._h, ctypes.c_void_p(d_ptr), cap, ctypes.c_void_p(stream), ctypes.byref(n)))
+        return n.value
+
+    def read_device_sharded(self, rank: int, world: int, d_ptr: int, cap: int, stream: int = 0) -> int:
+        n = ctypes.c_int64()
+        _check(_lib.lib().cv_read_device_sharded(self._h, rank, world, ctypes.c_void_p(d_ptr), cap, ctypes.c_void_p(stream),
+                                                 ctypes.byref(n)))
+        return n.value
+
+    def fuse_read_device(self, pos: int, size: int, d_scratch: int, d_page_base: int, page_offsets, page_size: int,
+                         stream: int = 0) -> int:
+        arr = (ctypes.c_uint64 * len(page_offsets))(*page_offsets)
+        n = ctypes.c_int64()
+        _check(_lib.lib().cv_fuse_read_device(self._h, pos, size, ctypes.c_void_p(d_scratch), ctypes.c_void_p(d_page_base), arr,
+                                              len(page_offsets), page_size, ctypes.c_void_p(stream), ctypes.byref(n)))
+        return n.value
+
+    def verify(self):
+        """-> (sum_crc, n_bad, n_verified); blocks until outstanding device reads finished."""
+        s, b, v = ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_uint64()
+        _check(_lib.lib().cv_verify(self._h, ctypes.byref(s), ctypes.byref(b), ctypes.byref(v)))
+        return s.value, b.value, v.value
+
+    def device_stats(self) -> dict:
+        st = _lib.CvReadStats()
+        _check(_lib.lib().cv_device_stats(self._h, ctypes.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def complete(self):
+        if self._h:
+            h, self._h = self._h, None
+            _check(_lib.lib().cv_close_reader(h))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.complete()
+
+
+class CurvineFileSystem:
+    def __init__(self, conf_toml: str = "", conf_path: Optional[str] = None):
+        self._h = ctypes.c_void_p()
+        if conf_path:
+            _check(_lib.lib().cv_fs_new(conf_path.encode(), ctypes.byref(self._h)))
+        else:
+            _check(_lib.lib().cv_fs_new_from_string(conf_toml.encode(), ctypes.byref(self._h)))
+
+    def load_namespace(self, text: Optional[str] = None, path: Optional[str] = None):
+        if text is not None:
+            _check(_lib.lib().cv_fs_load_namespace_string(self._h, text.encode()))
+        if path is not None:
+            _check(_lib.lib().cv_fs_load_namespace(self._h, path.encode()))
+
+    def open(self, path: str) -> Reader:
+        h, n = ctypes.c_void_p(), ctypes.c_int64()
+        _check(_lib.lib().cv_open(self._h, path.encode(), ctypes.byref(h), ctypes.byref(n)))
+        return Reader(h)
+
+    def metrics(self) -> dict:
+        a = (ctypes.c_int64 * 2)()
+        _check(_lib.lib().cv_fs_metrics(self._h, a))
+        return {"read_bytes": a[0], "read_time_us": a[1]}
+
+    def close(self):
+        if self._h:
+            h, self._h = self._h, None
+            _check(_lib.lib().cv_fs_close(h))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def client_conf(hostname: str = "localhost", short_circuit: bool = True, read_chunk_size: str = "128KB", read_chunk_num: int = 8,
+                read_parallel: int = 1, extra_client: str = "", b200: str = "") -> str:
+    return ('[client]\nhostname = "%s"\nshort_circuit = %s\nread_chunk_size = "%s"\nread_chunk_num = %d\nread_parallel = %d\n%s\n[b200]\n%s\n'
+            % (hostname, "true" if short_circuit else "false", read_chunk_size, read_chunk_num, read_parallel, extra_client, b200))

@@ -1,0 +1,123 @@
+/*
+ * curvine_b200.h -- upper boundary: the reader surface a Curvine client binds to (C ABI).
+ *
+ * Drop-in for the reference's reader path only.  Semantics, ownership, error and threading conventions are
+ * the reference's own FFI conventions (curvine-libsdk, paths relative to /root/reference):
+ *   handles      opaque pointers (Box::into_raw as i64: orpc/src/sys/ffi_utils.rs:47-49,64-66)
+ *   errors       0 == SUCCESS (curvine-libsdk/src/java/mod.rs:23); failure returns -(ErrorKind)
+ *                (curvine-common/src/error/fs_error.rs:35-66,324-326); EOF is not an error (length 0)
+ *   cv_read      (address,length) of a buffer OWNED BY THE READER, valid until the next read/seek/close on
+ *                that handle (curvine-libsdk/src/java/java_abi.rs:128-142, lib_fs_reader.rs:49-53)
+ *   threading    a filesystem handle is shareable; a reader handle is single-threaded, no internal locking
+ *                (lib_filesystem.rs:25-40); every call blocks
+ * Entry point <- reference interface it replaces:
+ *   cv_fs_new / cv_fs_close      LibFilesystem::new / closeFilesystem      curvine-libsdk/src/lib_filesystem.rs:25-40
+ *   cv_open                      FileSystem::open -> Reader                curvine-common/src/fs/filesystem.rs:35,
+ *                                                                          java_abi.rs:110-125
+ *   cv_read                      Reader::blocking_read (read_chunk(None))  curvine-common/src/fs/reader.rs:84-88
+ *   cv_read_buf / cv_read_full   Reader::read / Reader::read_full          reader.rs:71-81,126-141
+ *   cv_fuse_read                 Reader::fuse_read                         reader.rs:101-124
+ *   cv_seek / cv_pos / cv_len    Reader::seek / pos / len                  reader.rs:23-48, fs_reader.rs:109-126
+ *   cv_close_reader              Reader::complete + drop                   java_abi.rs:157-166
+ *   cv_read_device, cv_read_device_sharded, cv_verify, cv_fuse_read_device
+ *                                the CUDA counterpart the north_star adds behind the same reader handle
+ *                                (no reference counterpart: the reference has no GPU code)
+ * The cv_worker_* and cv_synth_* entry points are the test/bench fixture (the analogue of the reference's
+ * in-process MiniCluster + Worker::start_standalone, curvine-server/tests/worker_test.rs:35-48); they are not
+ * part of the drop-in surface.
+ */
+#ifndef CURVINE_B200_H
+#define CURVINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "curvine_b200_kernels.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cv_fs cv_fs;
+typedef struct cv_reader cv_reader;
+typedef struct cv_worker cv_worker;
+
+/* -(ErrorKind) values a caller is likely to test for (fs_error.rs:35-66) */
+#define CV_OK 0
+#define CV_ERR_IO (-1)
+#define CV_ERR_TIMEOUT (-4)
+#define CV_ERR_PB_DECODE (-5)
+#define CV_ERR_FILE_NOT_FOUND (-8)
+#define CV_ERR_ABNORMAL_DATA (-12)
+#define CV_ERR_UNSUPPORTED (-19)
+#define CV_ERR_COMMON (-10000)
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char* cv_last_error(void);
+void cv_free(void* p);
+
+/* ---- filesystem handle: conf (TOML subset: [client] read knobs with the reference's names and defaults,
+ *      [worker], [b200]) + the file->blocks namespace (stand-in for master GetBlockLocations) */
+int64_t cv_fs_new(const char* conf_path, cv_fs** out);
+int64_t cv_fs_new_from_string(const char* conf_toml, cv_fs** out);
+int64_t cv_fs_load_namespace(cv_fs* fs, const char* manifest_path);
+int64_t cv_fs_load_namespace_string(cv_fs* fs, const char* manifest_text);
+int64_t cv_fs_close(cv_fs* fs);
+/* client metrics (client_metrics.rs:24-35): out[0]=read_bytes out[1]=read_time_us */
+int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]);
+
+/* ---- reader */
+int64_t cv_open(cv_fs* fs, const char* path, cv_reader** out, int64_t* len);
+int64_t cv_read(cv_reader* r, const uint8_t** ptr, int64_t* len);
+int64_t cv_read_buf(cv_reader* r, uint8_t* buf, int64_t cap, int64_t* n);
+int64_t cv_read_full(cv_reader* r, uint8_t* buf, int64_t cap, int64_t* n);
+/* seek(pos) then whole chunks until len bytes: payload copied to buf, chunk boundaries to seg_lens[0..*n_segs) */
+int64_t cv_fuse_read(cv_reader* r, int64_t pos, int64_t len, uint8_t* buf, int64_t* n, int64_t* seg_lens,
+                     int32_t max_segs, int32_t* n_segs);
+int64_t cv_seek(cv_reader* r, int64_t pos);
+int64_t cv_pos(cv_reader* r);
+int64_t cv_len(cv_reader* r);
+int64_t cv_chunk_size(cv_reader* r);
+int64_t cv_close_reader(cv_reader* r);
+
+/* ---- CUDA counterpart (same handle, same pos).  d_dst is device memory; work is ordered on `stream`. */
+int64_t cv_read_device(cv_reader* r, void* d_dst, int64_t cap, cv_stream_t stream, int64_t* nbytes);
+/* blocks b with b % world == rank, back to back in block_size slots (slot j = block j*world+rank) */
+int64_t cv_read_device_sharded(cv_reader* r, int32_t rank, int32_t world, void* d_dst, int64_t cap,
+                               cv_stream_t stream, int64_t* nbytes);
+/* FUSE-shaped device read: seek(pos), read len bytes into HBM scratch, then scatter them into n_pages page
+ * buffers (d_page_base + page_offsets[i], page_size each; last one partial) with the K3 gather kernel. */
+int64_t cv_fuse_read_device(cv_reader* r, int64_t pos, int64_t len, void* d_scratch, void* d_page_base,
+                            const uint64_t* page_offsets, int32_t n_pages, int64_t page_size, cv_stream_t stream,
+                            int64_t* nbytes);
+/* Blocks until outstanding device reads of this handle finished.  sum_crc = u64 sum of per-block CRCs of every
+ * whole block read so far; n_bad = blocks whose CRC differs from the manifest; n_verified = blocks compared. */
+int64_t cv_verify(cv_reader* r, uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified);
+
+typedef struct CvReadStats {
+    uint64_t bytes, blocks, verified, h2d_bytes, kernel_launches;
+    double fetch_sec, wall_sec;
+} CvReadStats;
+int64_t cv_device_stats(cv_reader* r, CvReadStats* out);
+
+/* ---- fixture: in-process worker over a BlockStore directory tree + synthetic files */
+int64_t cv_worker_start(const char* conf_toml, cv_worker** out, int32_t* port);
+int64_t cv_worker_stop(cv_worker* w);
+/* out[0]=read_bytes [1]=read_time_us [2]=read_count [3]=read_blocks{local} [4]=read_blocks{remote} [5]=num_blocks */
+int64_t cv_worker_metrics(cv_worker* w, int64_t out[6]);
+/* Write `len` bytes of synthetic content as blocks of `block_size` into the worker's BlockStore (reference
+ * layout) and return the manifest text (malloc'd, cv_free) with per-block CRC-32 / CRC-32C.
+ * mode 0: xoshiro256** per block; mode 1: "az" repeated lowercase buffer; mode 2: every
+ * hole_every-th block is a hole (no file, no location). */
+int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, int64_t len, int64_t block_size,
+                             int32_t storage_type, int32_t mode, int32_t hole_every, int32_t threads,
+                             const char* worker_hostname, char** manifest_out);
+/* fill buf with block `block_index` of file `file_id` (mode 0 generator) */
+void cv_synth_block(uint64_t file_id, uint64_t block_index, uint8_t* buf, size_t len);
+/* host CRC used for manifests (slicing / SSE4.2) */
+uint32_t cv_host_crc(int poly, const uint8_t* buf, size_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -47,6 +47,8 @@ def _declare(L):
     vp, u8p, u32, u64, i = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
     L.cvk_init.argtypes, L.cvk_init.restype = [i], i
     L.cvk_launch_count.argtypes, L.cvk_launch_count.restype = [], u64
+    L.cvk_profile_enable.argtypes, L.cvk_profile_enable.restype = [i], i
+    L.cvk_profile_collect.argtypes, L.cvk_profile_collect.restype = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u32)], i
     L.cvk_crc_blocks.argtypes, L.cvk_crc_blocks.restype = [u8p, vp, vp, u32, i, u64, vp, vp], i
     L.cvk_verify_crcs.argtypes, L.cvk_verify_crcs.restype = [vp, vp, u32, vp, vp, vp], i
     L.cvk_unpack_frames.argtypes, L.cvk_unpack_frames.restype = [u8p, vp, u32, u32, u8p, i, u64, vp, vp, vp], i
@@ -100,7 +102,7 @@ class CvReadStats(ctypes.Structure):
 
 # every symbol include/*.h declares (tests check the .so exports all of them)
 EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_unpack_frames", "cvk_expand_streams", "cvk_gather_pages",
-           "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_launch_count", "cv_last_error", "cv_free", "cv_fs_new",
+           "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_launch_count", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
            "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_metrics",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_fuse_read_device",

@@ -17,6 +17,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/curvine_b200_kernels.h"
 #include "crc_gf.h"
@@ -562,6 +563,29 @@ static int ws_alloc(Workspace* w, uint32_t n_pieces, uint32_t n_blocks, uint64_t
 }
 
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return uint32_t((a + b - 1) / b); }
+
+// optional timing of the dominant (walk) kernel: events on the launching stream, summed by cvk_profile_collect
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+struct WalkTimer {
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit WalkTimer(cudaStream_t s) : st(s) {
+        if (!g_prof_on.load(std::memory_order_relaxed)) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+            a = b = nullptr;
+            return;
+        }
+        cudaEventRecord(a, st);
+    }
+    ~WalkTimer() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_events.emplace_back(a, b);
+    }
+};
 static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace cv
@@ -582,6 +606,32 @@ int cvk_init(int device) {
 
 uint64_t cvk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int cvk_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& p : g_prof_events) cudaEventDestroy(p.first), cudaEventDestroy(p.second);
+    g_prof_events.clear();
+    g_prof_on.store(on != 0);
+    return 0;
+}
+
+int cvk_profile_collect(double* walk_ms_total, uint32_t* walk_launches) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double total = 0;
+    uint32_t n = 0;
+    for (auto& p : g_prof_events) {
+        float ms = 0;
+        cudaError_t e = cudaEventSynchronize(p.second);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, p.first, p.second);
+        cudaEventDestroy(p.first), cudaEventDestroy(p.second);
+        if (e != cudaSuccess) return int(e);
+        total += ms, n++;
+    }
+    g_prof_events.clear();
+    if (walk_ms_total) *walk_ms_total = total;
+    if (walk_launches) *walk_launches = n;
+    return 0;
+}
+
 int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t* d_len, uint32_t n, int poly,
                    uint64_t total_bytes, uint32_t* d_crc_out, cv_stream_t stream) {
     if (n == 0) return 0;
@@ -595,8 +645,11 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
     const CrcConsts* cc = g_consts[dev][poly];
     prep_blocks_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_base, d_off, d_len, n, seg_shift, w.pieces, w.counts);
     scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
-    walk_kernel<true, false><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.pieces, n, w.prefix, seg_shift, cc,
-                                                                        w.partial, w.partial_cap, w.headraw, w.tailraw);
+    {
+        WalkTimer wt(st);
+        walk_kernel<true, false><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.pieces, n, w.prefix, seg_shift, cc,
+                                                                            w.partial, w.partial_cap, w.headraw, w.tailraw);
+    }
     fold_blocks_kernel<false><<<cdiv(n, 128), 128, 0, st>>>(w.pieces, w.prefix, nullptr, nullptr, n, seg_shift,
                                                             gf_xpow(8ull << seg_shift, poly_of(poly)), cc, w.partial,
                                                             w.headraw, w.tailraw, d_crc_out);
@@ -645,8 +698,11 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
     scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n_frames, w.prefix);
     count_launch(2);
     if (d_block_crc) {
-        walk_kernel<true, true><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(
-            w.pieces, n_frames, w.prefix, seg_shift, cc, w.partial, w.partial_cap, w.headraw, w.tailraw);
+        {
+            WalkTimer wt(st);
+            walk_kernel<true, true><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(
+                w.pieces, n_frames, w.prefix, seg_shift, cc, w.partial, w.partial_cap, w.headraw, w.tailraw);
+        }
         mark_block_ranges_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_desc, n_frames, n_blocks, w.first, w.last);
         fold_blocks_kernel<true><<<cdiv(n_blocks, 128), 128, 0, st>>>(
             w.pieces, w.prefix, w.first, w.last, n_blocks, seg_shift, gf_xpow(8ull << seg_shift, poly_of(poly)), cc,

@@ -130,6 +130,12 @@ int cvk_pack_frames(const uint8_t* d_src, const CvFrameDesc* d_desc, uint32_t n_
 int cvk_deinterleave_blocks(const uint8_t* d_gathered, uint64_t shard_stride, uint32_t world, uint64_t block_size,
                             uint64_t n_blocks, uint64_t file_len, uint8_t* d_dst, cv_stream_t stream);
 
+/* Time the dominant row-walker kernel (K1/K2/K4 bodies) with CUDA events on the launching stream.
+ * enable(1) starts collecting (and clears), collect() synchronises the recorded events and returns the summed
+ * duration in ms and the number of walker launches; enable(0) stops. */
+int cvk_profile_enable(int on);
+int cvk_profile_collect(double* walk_ms_total, uint32_t* walk_launches);
+
 /* Number of kernel launches issued by this library in this process (bench.py's gpu_launches claim). */
 uint64_t cvk_launch_count(void);
 

@@ -1,0 +1,192 @@
+"""End-to-end GPU reader through the C ABI vs the oracle: bytes in HBM bit-exact, on-GPU CRC verify, sharding."""
+import os
+
+import numpy as np
+import pytest
+
+from curvine_b200 import fs as F
+from oracle import clib, layout, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cluster(tmp_path_factory):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tmp_path_factory.mktemp("gw") if base is None else __import__("pathlib").Path(__import__("tempfile").mkdtemp(prefix="cvgpu", dir=base))
+    w = F.MiniWorker(["[MEM]" + str(d / "mem")])
+    yield w, d
+    w.stop()
+    __import__("shutil").rmtree(str(d), ignore_errors=True)
+
+
+def _dev_buf(n, cuda):
+    import torch
+    return torch.full((n,), 0xA5, dtype=torch.uint8, device=cuda)
+
+
+def _conf(sc, poly=1, chunk="4MB", threads=4, batch=4):
+    return F.client_conf(short_circuit=sc, b200='verify_poly = %d\ngpu_chunk_size = "%s"\nfetch_threads = %d\nverify_batch = %d\npinned_slots = 12\n'
+                         % (poly, chunk, threads, batch))
+
+
+@pytest.mark.parametrize("sc,chunk", [(True, "4MB"), (False, "128KB"), (False, "1MB"), (False, "4MB")])
+@pytest.mark.parametrize("poly", [0, 1])
+def test_c1_file_lands_bit_exact_and_verifies(cuda, cluster, sc, chunk, poly):
+    """C1 shape: 64 MiB, 1 MiB blocks.  Bytes == oracle generator; per-block CRC == manifest == oracle."""
+    import torch
+    w, _ = cluster
+    n, bs, ino = (64 << 20) - 4321, 1 << 20, 7001
+    man = w.create_file("/c1", ino, n, bs)
+    want = synth.file_bytes(ino, n, bs)
+    with F.CurvineFileSystem(_conf(sc, poly, chunk)) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/c1")
+        dst = _dev_buf(n + 64, cuda)
+        got = r.read_device(dst.data_ptr(), n + 64, torch.cuda.current_stream().cuda_stream)
+        assert got == n and r.pos() == n
+        torch.cuda.synchronize()
+        assert dst[:n].cpu().numpy().tobytes() == want
+        assert (dst[n:] == 0xA5).all()
+        s, bad, ver = r.verify()
+        nb = (n + bs - 1) // bs
+        assert bad == 0 and ver == nb
+        assert s == int(clib.crc_blocks(poly, np.frombuffer(want, dtype=np.uint8), bs).astype(np.uint64).sum())
+        st = r.device_stats()
+        assert st["bytes"] == n and st["blocks"] == nb and st["kernel_launches"] > 0
+        assert st["h2d_bytes"] >= n
+        assert r.read_device(dst.data_ptr(), 10) == 0  # EOF is not an error
+        r.complete()
+    m = w.metrics()
+    assert (m["read_blocks_local"] if sc else m["read_blocks_remote"]) >= nb
+
+
+@pytest.mark.parametrize("sc", [True, False])
+def test_partial_ranges_and_seeks(cuda, cluster, sc):
+    import torch
+    w, _ = cluster
+    n, bs, ino = (9 << 20) + 777, 1 << 20, 7002
+    man = w.create_file("/p1", ino, n, bs)
+    want = synth.file_bytes(ino, n, bs)
+    with F.CurvineFileSystem(_conf(sc, 0, "128KB")) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/p1")
+        for pos, cap in [(0, 100), (bs - 1, 2), (bs + 12345, 3 * bs + 17), (n - 5, 100), (3, 5 * bs)]:
+            r.seek(pos)
+            dst = _dev_buf(cap + 8, cuda)
+            got = r.read_device(dst.data_ptr(), cap, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            exp = want[pos:pos + cap]
+            assert got == len(exp) and r.pos() == pos + got
+            assert dst[:got].cpu().numpy().tobytes() == exp and (dst[got:] == 0xA5).all()
+        # host and device reads share one position
+        r.seek(2 * bs + 5)
+        assert r.read(10) == want[2 * bs + 5:2 * bs + 15]
+        dst = _dev_buf(64, cuda)
+        assert r.read_device(dst.data_ptr(), 64, 0) == 64
+        torch.cuda.synchronize()
+        assert dst.cpu().numpy().tobytes() == want[2 * bs + 15:2 * bs + 79]
+        assert r.read(5) == want[2 * bs + 79:2 * bs + 84]
+        assert r.verify()[1] == 0
+        r.complete()
+
+
+@pytest.mark.parametrize("sc", [True, False])
+def test_corruption_is_caught_on_the_gpu(cuda, cluster, sc):
+    """A flipped byte in one block file after the manifest was written -> exactly one bad block."""
+    import torch
+    w, d = cluster
+    n, bs, ino = 8 << 20, 1 << 20, 7003 + int(sc)
+    man = w.create_file("/bad%d" % sc, ino, n, bs)
+    path = layout.block_path(str(d / "mem" / "curvine"), layout.create_block_id(ino, 5))
+    with open(path, "r+b") as f:
+        f.seek(123456)
+        b = f.read(1)
+        f.seek(123456)
+        f.write(bytes([b[0] ^ 0x10]))
+    with F.CurvineFileSystem(_conf(sc)) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/bad%d" % sc)
+        dst = _dev_buf(n, cuda)
+        assert r.read_device(dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
+        s, bad, ver = r.verify()
+        assert bad == 1 and ver == 8
+        r.complete()
+
+
+def test_holes_on_device(cuda, cluster):
+    import torch
+    w, _ = cluster
+    n, bs, ino = (6 << 20) + 9, 1 << 20, 7010
+    man = w.create_file("/dh", ino, n, bs, mode=2, hole_every=3)
+    want = bytearray(synth.file_bytes(ino, n, bs))
+    for i in (2, 5):
+        want[i * bs:(i + 1) * bs] = bytes(min(bs, n - i * bs))
+    with F.CurvineFileSystem(_conf(True)) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/dh")
+        dst = _dev_buf(n, cuda)
+        assert r.read_device(dst.data_ptr(), n, 0) == n
+        torch.cuda.synchronize()
+        assert dst.cpu().numpy().tobytes() == bytes(want)
+        assert r.verify()[1] == 0
+        r.complete()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("sc", [True, False])
+def test_sharded_read_plus_deinterleave_restores_file_order(cuda, cluster, world, sc):
+    """Block b -> rank b % world (fs_reader_parallel.rs:112-122 analogue); gather + K-deinterleave == file."""
+    import torch
+    from curvine_b200 import kernels as K
+    w, _ = cluster
+    bs, nb, ino = 1 << 20, 19, 7020
+    n = bs * nb - 1000
+    man = w.create_file("/sh", ino, n, bs)
+    want = synth.file_bytes(ino, n, bs)
+    per = (nb + world - 1) // world
+    gathered = torch.zeros(world * per * bs, dtype=torch.uint8, device=cuda)
+    total_sum, total_ver = 0, 0
+    with F.CurvineFileSystem(_conf(sc, 1, "1MB")) as fs:
+        fs.load_namespace(man)
+        for rank in range(world):
+            r = fs.open("/sh")
+            shard = gathered[rank * per * bs:(rank + 1) * per * bs]
+            got = r.read_device_sharded(rank, world, shard.data_ptr(), per * bs, 0)
+            assert got == sum(min(bs, n - b * bs) for b in range(rank, nb, world))
+            s, bad, ver = r.verify()
+            assert bad == 0 and ver == len(range(rank, nb, world))
+            total_sum += s
+            total_ver += ver
+            r.complete()
+    assert total_ver == nb
+    assert total_sum == int(clib.crc_blocks(1, np.frombuffer(want, dtype=np.uint8), bs).astype(np.uint64).sum())
+    out = torch.zeros(n, dtype=torch.uint8, device=cuda)
+    K.deinterleave_blocks(gathered, per * bs, world, bs, nb, n, out)
+    torch.cuda.synchronize()
+    assert out.cpu().numpy().tobytes() == want
+
+
+def test_fuse_shaped_device_read_scatters_into_pages(cuda, cluster):
+    """C5 shape: 256 KiB single-block files; reply scattered into 4 KiB page buffers (fuse_response.rs:49-60 analogue)."""
+    import torch
+    w, _ = cluster
+    n, ino = 256 * 1024, 7030
+    man = w.create_file("/small", ino, n, n)
+    want = synth.file_bytes(ino, n, n)
+    with F.CurvineFileSystem(_conf(True)) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/small")
+        scratch = _dev_buf(n, cuda)
+        pages = torch.zeros(128 * 4096 + 64, dtype=torch.uint8, device=cuda)
+        rng = np.random.default_rng(1)
+        order = rng.permutation(128)[:64]  # 64 pages, scattered, not in order
+        offs = [int(p) * 4096 + 7 for p in order]  # deliberately unaligned page buffers
+        got = r.fuse_read_device(4096, 64 * 4096 - 100, scratch.data_ptr(), pages.data_ptr(), offs, 4096, 0)
+        torch.cuda.synchronize()
+        assert got == 64 * 4096 - 100 and r.pos() == 4096 + got
+        host = pages.cpu().numpy()
+        for i, o in enumerate(offs):
+            seg = want[4096 + i * 4096:4096 + min((i + 1) * 4096, got)]
+            assert host[o:o + len(seg)].tobytes() == seg
+        r.complete()

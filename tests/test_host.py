@@ -1,0 +1,284 @@
+"""Host side of the product through the C ABI vs the oracle: worker protocol, reader stack, layout, errors.
+
+CPU only (no kernels are launched).  Scenarios follow the reference's own tests:
+  curvine-server/tests/worker_test.rs:49-176   hand-built Open -> Running x N -> Complete, sum-crc both sides
+  orpc/tests/file_test.rs:44-134               100 x 64 KiB frames
+  curvine-tests/tests/block_test.rs:33-103,209-302   full stack, {short-circuit, remote} x {parallel 1, 4} x chunk sizes
+"""
+import ctypes
+import os
+import socket
+import zlib
+
+import numpy as np
+import pytest
+
+from curvine_b200 import _lib, fs as F
+from oracle import clib, layout, synth
+from oracle import reader_model as RM
+from oracle import wire as W
+
+
+@pytest.fixture(scope="module")
+def cluster(tmp_path_factory):
+    d = tmp_path_factory.mktemp("worker")
+    w = F.MiniWorker(["[MEM:10MB]" + str(d / "mem"), "[SSD]" + str(d / "ssd")], cluster_id="curvine")
+    yield w, d
+    w.stop()
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    for name in _lib.EXPORTS:
+        assert hasattr(L, name), name
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set()
+    for h in ("curvine_b200.h", "curvine_b200_kernels.h"):
+        declared |= set(re.findall(r"\b(cvk?_[a-z0-9_]+)\s*\(", open(os.path.join(root, "include", h)).read()))
+    declared -= {"cv_stream_t"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+
+
+def test_host_crc_and_generator_match_oracle():
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 4095, 4096, 1 << 20):
+        d = rng.bytes(n)
+        for p in (0, 1):
+            assert L.cv_host_crc(p, d, n) == clib.crc(p, d)
+    buf = ctypes.create_string_buffer(100003)
+    L.cv_synth_block(1001, 7, buf, 100003)
+    assert buf.raw == synth.block_bytes(1001, 7, 100003)
+
+
+def _recv(sock, n):
+    out = bytearray()
+    while len(out) < n:
+        c = sock.recv(n - len(out))
+        assert c, "connection closed"
+        out += c
+    return bytes(out)
+
+
+def _rpc(sock, msg):
+    sock.sendall(W.encode(msg))
+    code, rq, rs, req_id, seq_id, hsz, dsz = W.decode_protocol(_recv(sock, 22))
+    return W.Message(code, rq, rs, req_id, seq_id, _recv(sock, hsz), _recv(sock, dsz))
+
+
+@pytest.mark.parametrize("chunk,count", [(1024, 100), (65536, 100)])
+def test_worker_protocol_hand_built_messages(cluster, chunk, count):
+    """worker_test.rs:49-176 / file_test.rs:44-134: the oracle codec drives the product worker over TCP."""
+    w, d = cluster
+    n = chunk * count + 37
+    ino = 2000 + chunk
+    man = w.create_file("/wt/%d" % chunk, ino, n, 1 << 30, storage_type=0)
+    want = synth.block_bytes(ino, 0, n)
+    bid = layout.create_block_id(ino, 0)
+    # on-disk layout is the reference's (block_meta.rs:199-237); [MEM:10MB] dir chosen for storage_type Mem
+    path = layout.block_path(str(d / "mem" / "curvine"), bid)
+    assert os.path.getsize(path) == n and open(path, "rb").read() == want
+    assert (" %d " % 0) in man.splitlines()[2]
+    s = socket.create_connection(("127.0.0.1", w.port))
+    rid = 0x1122334455667788
+    o = _rpc(s, W.request(81, W.REQ_OPEN, rid, 0, W.BlockReadRequest(bid, 0, n, chunk, False, True, 1 << 20, 1 << 20).encode()))
+    assert (o.code, o.req_status, o.resp_status, o.req_id, o.seq_id) == (81, W.REQ_OPEN, W.RESP_SUCCESS, rid, 0)
+    r = W.BlockReadResponse.decode(o.header)
+    assert (r.id, r.len, r.path, r.storage_type) == (bid, n, None, W.STORAGE_MEM)
+    got, seq, rsum = bytearray(), 0, 0
+    while len(got) < n:
+        seq += 1
+        m = _rpc(s, W.request(81, W.REQ_RUNNING, rid, seq))
+        assert m.is_success() and m.seq_id == seq and m.req_id == rid and m.header == b""
+        assert len(m.data) == min(chunk, n - len(got))  # local_file.rs:103-117
+        rsum += zlib.crc32(m.data)
+        got += m.data
+    assert bytes(got) == want
+    assert rsum == sum(zlib.crc32(want[i:i + chunk]) for i in range(0, n, chunk))  # write-side sum == read-side sum
+    # reading past the end is an error *response* (0x13), not a dropped connection (block_handler.rs:57-60)
+    e = _rpc(s, W.request(81, W.REQ_RUNNING, rid, seq + 1))
+    assert e.resp_status == W.RESP_ERROR and e.status_byte() == 19 and "offset exceeds file length" in W.decode_error(e.data)[1]
+    # seek piggy-backed on a Running request (DataHeaderProto.offset is absolute in the block file)
+    m = _rpc(s, W.request(81, W.REQ_RUNNING, rid, seq + 2, W.DataHeaderProto(12345).encode()))
+    assert m.data == want[12345:12345 + chunk]
+    c = _rpc(s, W.request(81, W.REQ_COMPLETE, rid, seq + 3, W.BlockReadRequest(id=bid).encode()))
+    assert c.is_success() and c.req_status == W.REQ_COMPLETE and c.data == b"" and c.header == b""
+    # short-circuit open returns the block file path and no data is served (read_handler.rs:87-95,115-120)
+    o = _rpc(s, W.request(81, W.REQ_OPEN, rid + 1, 0, W.BlockReadRequest(bid, 0, n, chunk, True).encode()))
+    assert W.BlockReadResponse.decode(o.header).path == path
+    e = _rpc(s, W.request(81, W.REQ_RUNNING, rid + 1, 1))
+    assert e.resp_status == W.RESP_ERROR
+    # errors: unknown block, bad chunk size, oversized read-ahead, unsupported code
+    e = _rpc(s, W.request(81, W.REQ_OPEN, 5, 0, W.BlockReadRequest(424242, 0, 1, chunk).encode()))
+    assert e.resp_status == W.RESP_ERROR and W.decode_error(e.data)[0] == 10000
+    e = _rpc(s, W.request(81, W.REQ_OPEN, 5, 0, W.BlockReadRequest(bid, 0, n, 0).encode()))
+    assert "chunk_size must be greater than 0" in W.decode_error(e.data)[1]
+    e = _rpc(s, W.request(81, W.REQ_OPEN, 5, 0, W.BlockReadRequest(bid, 0, n, chunk, False, True, (16 << 20) + 1).encode()))
+    assert e.resp_status == W.RESP_ERROR
+    e = _rpc(s, W.request(81, W.REQ_OPEN, 5, 0, W.BlockReadRequest(bid, n + 1, n, chunk).encode()))
+    assert "exceeds the maximum length" in W.decode_error(e.data)[1]
+    e = _rpc(s, W.request(99, W.REQ_OPEN, 5, 0))
+    assert e.resp_status == W.RESP_ERROR
+    # heartbeats are skipped (rpc_frame.rs:255-259)
+    s.sendall(W.encode(W.Message(0, W.REQ_HEARTBEAT, W.RESP_UNDEFINED, -1, -1)))
+    assert _rpc(s, W.request(81, W.REQ_COMPLETE, 9, 9)).is_success()
+    s.close()
+    assert w.metrics()["read_count"] >= count
+
+
+def _model_for(ino, n, bs, conf, hole_every=0):
+    data = bytearray(synth.file_bytes(ino, n, bs))
+    blocks = []
+    for i in range((n + bs - 1) // bs):
+        blen = min(bs, n - i * bs)
+        hole = hole_every > 0 and i % hole_every == hole_every - 1
+        if hole:
+            data[i * bs:i * bs + blen] = bytes(blen)
+        blocks.append(RM.BlockSpec(layout.create_block_id(ino, i), blen, hole))
+    return RM.ReaderModel(RM.FileModel(blocks, bytes(data)), conf), bytes(data)
+
+
+@pytest.mark.parametrize("short_circuit", [True, False])
+@pytest.mark.parametrize("chunk_kb,chunk_num,parallel", [(128, 8, 1), (64, 1, 1), (64, 4, 4)])
+def test_block_test_scenario_matrix(cluster, short_circuit, chunk_kb, chunk_num, parallel):
+    """block_test.rs:33-103,209-302: 1 MiB blocks, 1 KiB reads, sum-crc + length, then seeks across block/chunk edges."""
+    w, _ = cluster
+    bs, n = 1 << 20, 10240 * 1024 + 13
+    ino = 3000 + chunk_kb + parallel + (500 if short_circuit else 0)
+    man = w.create_file("/bt/%d" % ino, ino, n, bs)
+    conf = F.client_conf(short_circuit=short_circuit, read_chunk_size="%dKB" % chunk_kb, read_chunk_num=chunk_num, read_parallel=parallel)
+    mconf = RM.ClientConf(read_chunk_size=chunk_kb * 1024, read_chunk_num=chunk_num, read_parallel=parallel, short_circuit=short_circuit)
+    model, data = _model_for(ino, n, bs, mconf)
+    with F.CurvineFileSystem(conf) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/bt/%d" % ino)
+        assert r.len() == n and r.chunk_size() == chunk_kb * 1024
+        total, cks = 0, 0
+        while True:
+            b = r.read(1024)
+            assert b == model.read(1024)  # same bytes AND the same short reads at chunk boundaries
+            if not b:
+                break
+            total += len(b)
+            cks += zlib.crc32(b)
+        assert total == n and r.pos() == n == model.pos
+        assert cks & (2 ** 64 - 1) == sum(zlib.crc32(data[i:i + 1024]) for i in range(0, n, 1024))
+        for pos in (bs, bs, bs - 1, bs + 64 * 1024 - 1024, bs + 64 * 1024, 0, n - 5, n):
+            r.seek(pos)
+            model.seek(pos)
+            got = r.read_full(1024)
+            assert got == data[pos:pos + 1024] == model.read_full(1024)
+            assert r.pos() == min(n, pos + 1024) == model.pos
+        # fuse-shaped read: whole chunks after a seek (reader.rs:101-124)
+        segs = r.fuse_read(3 * bs + 4096, 300000)
+        assert segs == model.fuse_read(3 * bs + 4096, 300000) and b"".join(segs) == data[3 * bs + 4096:3 * bs + 4096 + 300000]
+        # blocking_read hands out the whole current chunk
+        r.seek(5 * bs - 100)
+        model.seek(5 * bs - 100)
+        assert r.read_chunk() == model.blocking_read() == data[5 * bs - 100:5 * bs]
+        r.seek(n + 1)  # clamped by FsReaderParallel::seek in the reference: no error, reads return nothing
+        assert r.read(10) == b"" and r.pos() == n + 1
+        with pytest.raises(F.FsError):
+            r.seek(-1)
+        r.complete()
+        assert fs.metrics()["read_bytes"] >= n
+
+
+def test_hole_blocks_read_as_zeros(cluster):
+    """block_reader_hole.rs:69-79."""
+    w, _ = cluster
+    bs, n, ino = 1 << 20, (5 << 20) + 100, 4100
+    man = w.create_file("/holes", ino, n, bs, mode=2, hole_every=2)
+    model, data = _model_for(ino, n, bs, RM.ClientConf(), hole_every=2)
+    assert data[bs:2 * bs] == bytes(bs)
+    with F.CurvineFileSystem(F.client_conf()) as fs:
+        fs.load_namespace(man)
+        with fs.open("/holes") as r:
+            assert r.read_full(n) == data
+
+
+def test_az_mode_and_bench_checksum(cluster):
+    """curvine-bench shape: repeated a-z buffer, 128 KiB read_full loop, sum of crc32 (curvine_bench.rs:212-236)."""
+    w, _ = cluster
+    n = 3 * (1 << 20) + 128 * 1024
+    man = w.create_file("/az", 4200, n, 1 << 20, mode=1)
+    with F.CurvineFileSystem(F.client_conf(short_circuit=False)) as fs:
+        fs.load_namespace(man)
+        with fs.open("/az") as r:
+            cks, total, whole = 0, 0, bytearray()
+            while True:
+                b = r.read_full(128 * 1024)
+                if not b:
+                    break
+                cks += zlib.crc32(b)
+                total += len(b)
+                whole += b
+    assert total == n and set(whole) <= set(range(ord("a"), ord("z") + 1))
+    assert whole[:131072] == whole[131072:262144]
+    assert cks == clib.bench_checksum(bytes(whole), 128 * 1024)
+
+
+def test_errors_map_to_reference_error_kinds(cluster):
+    w, d = cluster
+    with F.CurvineFileSystem(F.client_conf()) as fs:
+        with pytest.raises(F.FsError) as ei:
+            fs.open("/nope")
+        assert ei.value.kind == 8  # FileNotFound
+        # chunk_size must be a multiple of 4 KiB; slice a multiple of chunk (fs_reader_parallel.rs:62-71)
+    man = w.create_file("/e1", 4300, 1 << 20, 1 << 20)
+    with F.CurvineFileSystem(F.client_conf(read_chunk_size="5000")) as fs:
+        fs.load_namespace(man)
+        with pytest.raises(F.FsError) as ei:
+            fs.open("/e1")
+        assert "integer multiple" in ei.value.msg
+    # a block file that vanished: short-circuit open fails on the client, remote gets an error response; kind Common / IO
+    bid = layout.create_block_id(4300, 0)
+    os.remove(layout.block_path(str(d / "mem" / "curvine"), bid))
+    for sc in (True, False):
+        with F.CurvineFileSystem(F.client_conf(short_circuit=sc)) as fs:
+            fs.load_namespace(man)
+            r = fs.open("/e1")
+            with pytest.raises(F.FsError) as ei:
+                r.read(10)
+            assert ei.value.kind in (1, 10000)
+    # a worker that is not there
+    man2 = man.replace(":%d:" % w.port, ":1:")
+    with F.CurvineFileSystem(F.client_conf()) as fs:
+        fs.load_namespace(man2)
+        r = fs.open("/e1")
+        with pytest.raises(F.FsError) as ei:
+            r.read(10)
+        assert ei.value.kind == 1  # IO
+
+
+def test_conf_parsing_matches_reference_rules():
+    """ByteUnit binary sizes (byte_unit.rs:29-34,76-125); read_slice/read_ahead defaults (client_conf.rs:228-281)."""
+    with F.CurvineFileSystem('[client]\nread_chunk_size = "64kb"\nread_chunk_num = 4\n') as fs:
+        pass
+    with pytest.raises(F.FsError):
+        F.CurvineFileSystem('[client]\nread_chunk_size = "64XB"\n')
+
+
+def test_storage_tier_selection(cluster):
+    """storage policy: blocks go to a dir of the file's storage type, falling back to Disk dirs (policy.rs:56-105)."""
+    w, d = cluster
+    w.create_file("/ssd1", 4400, 1 << 20, 1 << 20, storage_type=1)
+    assert os.path.exists(layout.block_path(str(d / "ssd" / "curvine"), layout.create_block_id(4400, 0)))
+
+
+@pytest.mark.parametrize("sc", [True, False])
+@pytest.mark.parametrize("parallel", [1, 3])
+def test_oracle_cpu_reader_against_product_worker(cluster, sc, parallel):
+    """The C restatement of the reference client (oracle/cpu_reader.c) reads the product worker's blocks and
+    reproduces the curvine-bench checksum (sum of crc32 over 128 KiB buffers) of the oracle generator's bytes."""
+    w, _ = cluster
+    bs, n, ino = 1 << 20, (7 << 20) + 4096 * 3, 4500 + parallel
+    w.create_file("/cpu%d" % ino, ino, n, bs)
+    ids = [layout.create_block_id(ino, i) for i in range((n + bs - 1) // bs)]
+    data = synth.file_bytes(ino, n, bs)
+    got, cks, threads = clib.cpu_read_file(w.port, sc, n, bs, ids, 131072, 8, parallel, 131072)
+    assert got == n and threads == parallel + 1 and cks == clib.bench_checksum(data, 131072)
+    got, cks, _ = clib.cpu_read_file(w.port, sc, n, bs, ids, 65536, 4, parallel, 131072, limit=3 << 20, checksum=0)
+    assert got == 3 << 20 and cks == clib.bench_checksum(data[:3 << 20], 131072)
+    assert clib.crc32_pclmul(data) == zlib.crc32(data)

@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--fetch-threads", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--verify-batch", type=int, default=16)
+    ap.add_argument("--copy-group", type=int, default=4)
     ap.add_argument("--gpu-chunk", default="4MB")
     ap.add_argument("--poly", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -154,8 +155,8 @@ def teardown(state):
 
 def client_conf(args, sc, device, threads, slots):
     from curvine_b200 import fs as F
-    b200 = ('device = %d\nfetch_threads = %d\npinned_slots = %d\nverify_poly = %d\nverify = true\nverify_batch = %d\ngpu_chunk_size = "%s"\n'
-            % (device, threads, slots, args.poly, args.verify_batch, args.gpu_chunk))
+    b200 = ('device = %d\nfetch_threads = %d\npinned_slots = %d\nverify_poly = %d\nverify = true\nverify_batch = %d\ncopy_group = %d\ngpu_chunk_size = "%s"\n'
+            % (device, threads, slots, args.poly, args.verify_batch, args.copy_group, args.gpu_chunk))
     return F.client_conf(hostname="localhost", short_circuit=sc, b200=b200)
 
 
@@ -306,12 +307,13 @@ def main():
                 "config": {"workload": "C2: 16 GiB synthetic file per GPU, 4 MiB blocks, mem-tier (tmpfs) BlockStore, "
                                        "blocks round-robin across GPUs (C3 shape at N=8), on-GPU CRC-%s verify" % ("32C" if args.poly else "32"),
                            "file_bytes": total_bytes, "block_bytes": BLOCK, "blocks_per_gpu": my_blocks, "read_path": args.mode,
-                           "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch,
+                           "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch, "copy_group": args.copy_group,
                            "l2": "inputs (16 GiB per GPU) are larger than L2; no flush needed", "host_cpus": ncpu},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) if world == 1 else shard_bytes * world,
                         "d2h_bytes_per_step": 4 * (my_blocks + 4) * world, "ms_per_step": e2e_step_ms, "best_ms": e2e_best_ms,
                         "per_gpu_GBps": e2e_val / world, "frac_of_pcie_gen5_x16_raw_63GBps": e2e_val / world / pcie_raw,
-                        "frac_of_measured_h2d_55.6GBps": e2e_val / world / 55.6},
+                        "frac_of_measured_h2d_55.6GBps": e2e_val / world / 55.6,
+                        "last_step_fetch_thread_sec": stats["fetch_sec"], "last_step_wall_sec": stats["wall_sec"]},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "walk_kernel<CRC,!DST> (K1 CRC verify)",
                              "achieved": shard_bytes / walk_avg_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",

@@ -40,12 +40,34 @@ class GpuIngest {
     cudaEvent_t done_ev = nullptr;
     std::vector<int> cpus;
     std::mutex mu;  // one read_device at a time per context
+    // per-call device tables + pinned result mirror, shared by every reader of the context
+    uint8_t* d_tables = nullptr;
+    size_t d_tables_cap = 0;
+    uint8_t* h_result = nullptr;
+    size_t h_result_cap = 0;
+    GpuFsReader* pending_owner = nullptr;  // reader whose results still sit in h_result
+
+    Err ensure_tables(size_t tables_bytes, size_t result_bytes) {
+        if (tables_bytes > d_tables_cap) {
+            if (d_tables) cudaFree(d_tables);
+            d_tables_cap = tables_bytes * 2;
+            CU_TRY(cudaMalloc(&d_tables, d_tables_cap));
+        }
+        if (result_bytes > h_result_cap) {
+            if (h_result) cudaFreeHost(h_result);
+            h_result_cap = result_bytes * 2;
+            CU_TRY(cudaHostAlloc(&h_result, h_result_cap, cudaHostAllocDefault));
+        }
+        return Err::ok();
+    }
 
     Err init(const B200Conf& c) {
         device = c.device;
         CU_TRY(cudaSetDevice(device));
         CVK_TRY(cvk_init(device));
-        nslots = std::max(c.pinned_slots, 2 * c.verify_batch + c.fetch_threads);
+        const int kk = std::max(1, c.copy_group);
+        nslots = std::max(c.pinned_slots, (2 * ((c.verify_batch + kk - 1) / kk) + c.fetch_threads + 2) * kk);
+        nslots = (nslots + kk - 1) / kk * kk;
         copy_ev.resize(nslots), free_ev.resize(nslots);
         for (int i = 0; i < nslots; i++) {
             CU_TRY(cudaEventCreateWithFlags(&copy_ev[i], cudaEventDisableTiming));
@@ -125,6 +147,8 @@ class GpuIngest {
         cudaDeviceSynchronize();
         if (pinned) cudaFreeHost(pinned);
         if (d_stage) cudaFree(d_stage);
+        if (d_tables) cudaFree(d_tables);
+        if (h_result) cudaFreeHost(h_result);
         for (auto e : copy_ev) cudaEventDestroy(e);
         for (auto e : free_ev) cudaEventDestroy(e);
         for (auto s : copy_streams) cudaStreamDestroy(s);
@@ -173,10 +197,10 @@ Err GpuFsReader::open(FsContext* ctx, const std::string& path, std::unique_ptr<G
 }
 
 GpuFsReader::~GpuFsReader() {
-    if (d_tables_) {
-        cudaSetDevice(ing_->device);
-        cudaStreamSynchronize(ing_->vstream);
-        cudaFree(d_tables_);
+    if (ing_) {
+        std::lock_guard<std::mutex> lk(ing_->mu);
+        harvest();
+        if (ing_->pending_owner == this) ing_->pending_owner = nullptr;
     }
 }
 
@@ -233,24 +257,6 @@ Err GpuFsReader::read_device_sharded(int rank, int world, void* d_dst, int64_t c
 
 namespace {
 
-struct CallState {
-    std::atomic<size_t> next_job{0};
-    std::atomic<bool> abort{false};
-    std::mutex err_mu;
-    Err err;
-    std::vector<std::atomic<int>> copied;
-    std::vector<std::atomic<int64_t>> released;  // per slot: last job whose release event has been recorded
-    explicit CallState(size_t jobs, size_t slots) : copied(jobs), released(slots) {
-        for (auto& c : copied) c.store(0);
-        for (auto& r : released) r.store(-1);
-    }
-    void fail(const Err& e) {
-        std::lock_guard<std::mutex> lk(err_mu);
-        if (!err) err = e;
-        abort.store(true);
-    }
-};
-
 static Protocol read_req(int8_t status, int64_t req_id, int32_t seq_id) {
     Protocol p;
     p.code = kCodeReadBlock, p.req_status = status, p.resp_status = kRespUndefined, p.req_id = req_id, p.seq_id = seq_id;
@@ -259,8 +265,14 @@ static Protocol read_req(int8_t status, int64_t req_id, int32_t seq_id) {
 
 }  // namespace
 
-// Fetch one job's bytes into `slot`.  short-circuit: payload only.  framed: verbatim wire image.
-static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, int64_t n, bool framed, int64_t chunk, uint8_t* slot,
+enum FetchMode { kFetchShortCircuit = 0, kFetchFramedVerbatim = 1, kFetchFramedUnpacked = 2 };
+
+// Fetch one job's bytes into `slot`.
+//   short-circuit    payload only (pread of the block file the worker named)
+//   framed verbatim  the response stream exactly as received: 22-byte prefixes + payloads (unpacked on the GPU by K2)
+//   framed unpacked  per-chunk request/response like BlockReaderRemote, payload only; used for ranges that do not
+//                    end at a block end, where the worker's last chunk overshoots the wanted range
+static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, int64_t n, FetchMode mode, int64_t chunk, uint8_t* slot,
                      std::unique_ptr<BlockClient>* conn, int64_t* req_id_out, size_t* wire_bytes) {
     Err last = Err::common("There is no available worker, locs: [], failed workers: []");
     for (const WorkerAddress& loc : lb.locs) {
@@ -273,10 +285,11 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
         const int64_t req_id = new_req_id();
         *req_id_out = req_id;
         BlockReadResponse resp;
-        last = c->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, req_id, 0, !framed, framed ? chunk : ctx->read_chunk_size(), &resp);
+        const int64_t open_chunk = mode == kFetchFramedVerbatim ? chunk : ctx->read_chunk_size();
+        last = c->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, req_id, 0, mode == kFetchShortCircuit, open_chunk, &resp);
         if (last) continue;
         int32_t seq = 0;
-        if (!framed) {
+        if (mode == kFetchShortCircuit) {
             if (!resp.has_path) {
                 last = Err::common("read_context.path is none");
                 continue;
@@ -299,7 +312,7 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
             ::close(fd);
             if (got < n) continue;
             *wire_bytes = static_cast<size_t>(n);
-        } else {
+        } else if (mode == kFetchFramedVerbatim) {
             // all Running requests in one write (the worker serves them in order, read_handler.rs:143-183)
             const int64_t nfr = (n + chunk - 1) / chunk;
             std::string reqs(static_cast<size_t>(nfr) * kProtocolSize, '\0');
@@ -314,23 +327,50 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
                 if (last) break;
                 const int64_t want = std::min(chunk, left);
                 if (!p.is_success() || p.header_len != 0 || p.data_len != want) {
-                    // error response (or a short chunk): drain this frame and the rest of the pipeline, then report it
+                    // error response (or an unexpected chunk): drain this frame, report it, drop the connection
                     std::string body(static_cast<size_t>(p.header_len + p.data_len), '\0');
                     if (!body.empty() && recv_exact(c->fd(), &body[0], body.size())) c->broken = true;
                     last = p.is_success() ? Err::common(str_printf("unexpected chunk length %d, expected %lld", p.data_len, (long long)want))
                                           : decode_error_body(reinterpret_cast<const uint8_t*>(body.data()) + p.header_len, static_cast<size_t>(p.data_len));
-                    c->broken = true;  // responses of the remaining pipelined requests are still in flight
                     break;
                 }
                 last = recv_exact(c->fd(), w + kProtocolSize, static_cast<size_t>(want));
                 w += kProtocolSize + want, left -= want;
             }
             if (last) {
-                c->broken = true;
+                c->broken = true;  // responses of the remaining pipelined requests may still be in flight
                 continue;
             }
             seq = static_cast<int32_t>(nfr);
             *wire_bytes = static_cast<size_t>(w - slot);
+        } else {
+            std::string spill;
+            int64_t got = 0;
+            while (got < n && !last) {
+                last = c->send_request(read_req(kReqRunning, req_id, ++seq), std::string());
+                Protocol p;
+                std::string rh;
+                if (!last) last = c->recv_response_head(&p, &rh);
+                if (last) break;
+                if (!p.is_success() || p.seq_id != seq || p.req_id != req_id || p.data_len <= 0) {
+                    std::string body(static_cast<size_t>(p.data_len), '\0');
+                    if (!body.empty() && recv_exact(c->fd(), &body[0], body.size())) c->broken = true;
+                    last = p.is_success() ? Err::common("response mismatch") : decode_error_body(reinterpret_cast<const uint8_t*>(body.data()), body.size());
+                    break;
+                }
+                const int64_t take = std::min<int64_t>(p.data_len, n - got);
+                last = recv_exact(c->fd(), slot + got, static_cast<size_t>(take));
+                if (!last && p.data_len > take) {  // the worker's chunk runs past the wanted range: discard the rest
+                    spill.resize(static_cast<size_t>(p.data_len - take));
+                    last = recv_exact(c->fd(), &spill[0], spill.size());
+                }
+                got += take;
+            }
+            if (last) {
+                c->broken = true;
+                continue;
+            }
+            *wire_bytes = static_cast<size_t>(n);
         }
         last = c->read_commit(lb.block, req_id, seq + 1);
         if (last) continue;
@@ -339,15 +379,17 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
     return last;
 }
 
-// Pull the last call's per-block CRCs / mismatch count / frame flags (already copied to h_result_ on vstream).
+// Pull the last call's per-block CRCs / mismatch count / frame flags (already copied to the pinned mirror on vstream).
 Err GpuFsReader::harvest() {
     if (!pending_.active) return Err::ok();
-    cudaSetDevice(ing_->device);
-    CU_TRY(cudaStreamSynchronize(ing_->vstream));
-    const uint32_t* crc = reinterpret_cast<const uint32_t*>(h_result_);
+    GpuIngest& G = *ing_;
+    cudaSetDevice(G.device);
+    CU_TRY(cudaStreamSynchronize(G.vstream));
+    const uint32_t* crc = reinterpret_cast<const uint32_t*>(G.h_result);
     const size_t J = pending_.jobs;
     for (size_t j = pending_.f0; j < pending_.f1; j++) sum_crc_ += crc[j];
     n_verified_ += pending_.n_compared;
+    stats_.verified += pending_.n_compared;
     n_bad_ += crc[J];  // mismatch counter written by cvk_verify_crcs
     const uint32_t* ferr = crc + J + 4;
     for (size_t f = 0; f < pending_.frames; f++)
@@ -356,12 +398,17 @@ Err GpuFsReader::harvest() {
             if (!first_frame_err_) first_frame_err_ = ferr[f];
         }
     pending_.active = false;
+    if (G.pending_owner == this) G.pending_owner = nullptr;
     if (n_bad_frames_) return Err(kAbnormalData, str_printf("%llu frame prefixes failed validation (first flags 0x%x)", (unsigned long long)n_bad_frames_, first_frame_err_));
     return Err::ok();
 }
 
 Err GpuFsReader::verify(uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified) {
-    Err e = harvest();
+    Err e;
+    if (ing_) {
+        std::lock_guard<std::mutex> lk(ing_->mu);
+        e = harvest();
+    }
     *sum_crc = sum_crc_, *n_bad = n_bad_, *n_verified = n_verified_;
     return e;
 }
@@ -373,62 +420,65 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     GpuIngest& G = *ing_;
     std::lock_guard<std::mutex> call_lock(G.mu);
     CU_TRY(cudaSetDevice(G.device));
+    if (G.pending_owner && G.pending_owner != this) CV_RETURN_IF_ERR(G.pending_owner->harvest());  // shared tables
     CV_RETURN_IF_ERR(harvest());
     const B200Conf& bc = ctx_->conf.b200;
     const ClientConf& cc = ctx_->conf.client;
     const int poly = bc.verify_poly ? 1 : 0;
     const int64_t chunk = std::min<int64_t>(std::max<int64_t>(bc.gpu_chunk_size, 4096), kMaxDataSize);
 
-    // short-circuit (the reference default for a same-host worker, client_conf.rs:339) only when every block of
-    // this call has a local replica; otherwise the whole call runs framed (any worker serves framed reads)
-    std::vector<uint8_t> framed(J, 0), hole(J, 0);
-    bool any_framed = false;
+    // ---- per-job mode.  Short-circuit (the reference default for a same-host worker, client_conf.rs:339) only when
+    // every block of this call has a local replica; otherwise the whole call runs framed (any worker serves those).
+    enum : uint8_t { kPlain = 0, kFramed = 1, kUnpacked = 2, kHole = 3 };
+    std::vector<uint8_t> mode(J, kPlain);
+    bool call_framed = false;
     for (size_t j = 0; j < J; j++) {
         const LocatedBlock& lb = fb_.block_locs[jobs[j].block];
         if (lb.locs.empty()) {
             if (!lb.block.has_alloc_opts) return Err::common("There is no available worker, locs: [], failed workers: []");
-            hole[j] = 1;
+            mode[j] = kHole;
             continue;
         }
         bool local = false;
         for (const auto& a : lb.locs) local |= ctx_->is_local_worker(a);
-        if (!(cc.short_circuit && local)) any_framed = true;
+        if (!(cc.short_circuit && local)) call_framed = true;
     }
     size_t need_slot = 0, F = 0;
     std::vector<uint32_t> first_frame(J + 1, 0);
+    bool any_verbatim = false;
     for (size_t j = 0; j < J; j++) {
-        framed[j] = any_framed && !hole[j];
         first_frame[j] = static_cast<uint32_t>(F);
         size_t bytes = static_cast<size_t>(jobs[j].n);
-        if (framed[j]) {
-            const size_t nfr = static_cast<size_t>((jobs[j].n + chunk - 1) / chunk);
-            bytes += nfr * kProtocolSize;
-            F += nfr;
+        if (mode[j] != kHole && call_framed) {
+            const bool to_block_end = jobs[j].block_off + jobs[j].n == fb_.block_locs[jobs[j].block].block.len;
+            mode[j] = to_block_end ? kFramed : kUnpacked;
+            if (mode[j] == kFramed) {
+                const size_t nfr = static_cast<size_t>((jobs[j].n + chunk - 1) / chunk);
+                bytes += nfr * kProtocolSize;
+                F += nfr;
+                any_verbatim = true;
+            }
         }
         need_slot = std::max(need_slot, bytes);
     }
     first_frame[J] = static_cast<uint32_t>(F);
-    CV_RETURN_IF_ERR(G.ensure(need_slot, any_framed));
-    const int B = std::max(1, bc.verify_batch);
-    const size_t S = static_cast<size_t>(G.nslots);
+    CV_RETURN_IF_ERR(G.ensure(need_slot, any_verbatim));
 
-    // ---- device tables: off[J] len[J] | expect[J] crc[J] nbad[4] ferr[F] | streams[J] fdesc[F]
+    // ---- copy groups: k consecutive jobs share one super-slot and, when they are contiguous, one cudaMemcpyAsync
+    const size_t k = static_cast<size_t>(std::max(1, std::min(bc.copy_group, G.nslots / 4)));
+    const size_t NG = (J + k - 1) / k;                    // copy groups in this call
+    const size_t NS = static_cast<size_t>(G.nslots) / k;  // super-slots in the ring
+    const size_t vgroups = std::max<size_t>(1, (static_cast<size_t>(std::max(1, bc.verify_batch)) + k - 1) / k);  // copy groups per verify launch
+    const size_t B = vgroups * k;
+
+    // ---- device tables (shared by all readers of this context): off[J] len[J] | expect[J] crc[J] nbad[4] ferr[F] | streams[J] fdesc[F]
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_off = 0, o_len = up(o_off + 8 * J), o_exp = up(o_len + 8 * J), o_crc = up(o_exp + 4 * J);
     const size_t res_words = J + 4 + F;
     const size_t o_streams = up(o_crc + 4 * res_words), o_fdesc = up(o_streams + sizeof(CvStreamDesc) * J);
     const size_t tables_bytes = up(o_fdesc + sizeof(CvFrameDesc) * F);
-    if (tables_bytes > d_tables_cap_) {
-        if (d_tables_) cudaFree(d_tables_);
-        d_tables_cap_ = tables_bytes * 2;
-        CU_TRY(cudaMalloc(&d_tables_, d_tables_cap_));
-    }
-    if (4 * res_words > h_result_cap_) {
-        if (h_result_) cudaFreeHost(h_result_);
-        h_result_cap_ = 8 * res_words;
-        CU_TRY(cudaHostAlloc(&h_result_, h_result_cap_, cudaHostAllocDefault));
-    }
-    uint8_t* T = static_cast<uint8_t*>(d_tables_);
+    CV_RETURN_IF_ERR(G.ensure_tables(tables_bytes, 4 * res_words));
+    uint8_t* T = G.d_tables;
     std::vector<uint8_t> h(o_crc);  // host image of off/len/expect
     uint64_t* h_off = reinterpret_cast<uint64_t*>(&h[o_off]);
     uint64_t* h_len = reinterpret_cast<uint64_t*>(&h[o_len]);
@@ -439,34 +489,52 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         h_off[j] = static_cast<uint64_t>(jobs[j].dst_off);
         h_len[j] = static_cast<uint64_t>(jobs[j].n);
         h_exp[j] = poly ? lb.crc32c : lb.crc32;
-        if (jobs[j].full && lb.has_crc && !hole[j]) {
+        if (jobs[j].full && lb.has_crc && mode[j] != kHole) {
             f0 = std::min(f0, j), f1 = std::max(f1, j + 1);
             n_compared++;
         }
     }
     if (f0 >= f1) f0 = f1 = 0;
-    // blocks inside [f0,f1) without a manifest CRC (or partial) must not count as mismatches: jobs are in file
-    // order so only the two ends can be partial; a missing manifest entry disables comparison for the call
+    // jobs are in file order, so only the two ends can be partial; a hole or a block without a manifest CRC inside
+    // [f0,f1) disables the comparison for this call (the CRCs are still computed and summed)
     const bool compare = bc.verify && n_compared == f1 - f0 && n_compared > 0;
     CU_TRY(cudaMemcpyAsync(T, h.data(), o_crc, cudaMemcpyHostToDevice, G.vstream));
     CU_TRY(cudaMemsetAsync(T + o_crc, 0, 4 * res_words, G.vstream));
     std::vector<CvStreamDesc> sd;
-    if (any_framed) {
+    if (any_verbatim) {
         sd.resize(J);
         for (size_t j = 0; j < J; j++) {
             CvStreamDesc& d = sd[j];
             memset(&d, 0, sizeof(d));
-            d.wire_off = (j % S) * G.slot_bytes, d.dst_off = h_off[j], d.block_len = framed[j] ? h_len[j] : 0;
+            const size_t ss = (j / k) % NS;
+            d.wire_off = (ss * k + j % k) * G.slot_bytes, d.dst_off = h_off[j], d.block_len = mode[j] == kFramed ? h_len[j] : 0;
             d.chunk_size = static_cast<uint32_t>(chunk), d.first_seq_id = 1, d.block = static_cast<uint32_t>(j % B);
             d.first_frame = first_frame[j], d.code = kCodeReadBlock, d.status = 0x03;
         }
     }
-    CU_TRY(cudaStreamSynchronize(G.vstream));  // `h` goes out of scope semantics: pageable copies are staged, be explicit
+    CU_TRY(cudaStreamSynchronize(G.vstream));  // tables are in place (and `h` was pageable) before any kernel uses them
 
     // ---- fetch threads
-    CallState st(J, S);
+    struct Shared {
+        std::atomic<size_t> next_group{0};
+        std::atomic<bool> abort{false};
+        std::mutex err_mu;
+        Err err;
+        void fail(const Err& e) {
+            std::lock_guard<std::mutex> lk(err_mu);
+            if (!err) err = e;
+            abort.store(true);
+        }
+    } st;
+    std::vector<std::atomic<int>> copied(NG);
+    std::vector<std::atomic<int64_t>> released(NS);  // per super-slot: last copy group whose release event is recorded
+    for (auto& c : copied) c.store(0);
+    for (auto& r : released) r.store(-1);
+    std::vector<uint8_t> group_verbatim(NG, 0);
+    for (size_t g = 0; g < NG; g++)
+        for (size_t j = g * k; j < std::min(J, g * k + k); j++) group_verbatim[g] |= mode[j] == kFramed;
     std::vector<int64_t> req_ids(J, 0);
-    const int T_threads = static_cast<int>(std::min<size_t>(static_cast<size_t>(std::max(1, bc.fetch_threads)), J));
+    const int T_threads = static_cast<int>(std::min<size_t>(static_cast<size_t>(std::max(1, bc.fetch_threads)), NG));
     std::vector<double> fetch_sec(static_cast<size_t>(T_threads), 0.0);
     std::vector<uint64_t> h2d(static_cast<size_t>(T_threads), 0);
     auto worker = [&](int t) {
@@ -475,90 +543,120 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         cudaStream_t cs = G.copy_streams[static_cast<size_t>(t) % G.copy_streams.size()];
         std::unique_ptr<BlockClient> conn;
         for (;;) {
-            const size_t j = st.next_job.fetch_add(1);
-            if (j >= J || st.abort.load()) break;
-            const size_t slot = j % S;
-            if (j >= S) {  // wait until the slot's previous tenant (job j-S) has been released, then for its event
-                const int64_t want = static_cast<int64_t>(j - S);
-                while (st.released[slot].load(std::memory_order_acquire) < want) {
+            const size_t g = st.next_group.fetch_add(1);
+            if (g >= NG || st.abort.load()) break;
+            const size_t ss = g % NS, j0 = g * k, j1 = std::min(J, j0 + k);
+            if (g >= NS) {  // wait until the super-slot's previous tenant has been released, then for its event
+                const int64_t want = static_cast<int64_t>(g - NS);
+                while (released[ss].load(std::memory_order_acquire) < want) {
                     if (st.abort.load()) break;
                     std::this_thread::yield();
                 }
                 if (st.abort.load()) break;
-                cudaEventSynchronize(framed[j - S] ? G.free_ev[slot] : G.copy_ev[slot]);
+                cudaEventSynchronize(group_verbatim[g - NS] ? G.free_ev[ss] : G.copy_ev[ss]);
             }
-            uint8_t* hs = G.pinned + slot * G.slot_bytes;
-            const Job& job = jobs[j];
-            size_t wire = 0;
+            uint8_t* hs = G.pinned + ss * k * G.slot_bytes;
+            uint8_t* ds = G.d_stage ? G.d_stage + ss * k * G.slot_bytes : nullptr;
+            // plain jobs mirror the destination layout inside the super-slot so that one copy moves the whole group
+            bool one_copy = !group_verbatim[g];
+            for (size_t j = j0; j < j1 && one_copy; j++) {
+                one_copy = mode[j] == kPlain || mode[j] == kUnpacked;
+                if (j > j0) one_copy = one_copy && jobs[j].dst_off == jobs[j - 1].dst_off + jobs[j - 1].n;
+            }
+            if (one_copy && static_cast<size_t>(jobs[j1 - 1].dst_off + jobs[j1 - 1].n - jobs[j0].dst_off) > k * G.slot_bytes) one_copy = false;
             cudaError_t ce = cudaSuccess;
-            if (hole[j]) {
-                ce = cudaMemsetAsync(d_dst + job.dst_off, 0, static_cast<size_t>(job.n), cs);  // block_reader_hole.rs:69-79
-            } else {
+            size_t wire_extent = 0;
+            bool failed = false;
+            for (size_t j = j0; j < j1 && !failed; j++) {
+                const Job& job = jobs[j];
+                if (mode[j] == kHole) {
+                    ce = cudaMemsetAsync(d_dst + job.dst_off, 0, static_cast<size_t>(job.n), cs);  // block_reader_hole.rs:69-79
+                    failed = ce != cudaSuccess;
+                    continue;
+                }
+                const size_t in_slot = one_copy ? static_cast<size_t>(job.dst_off - jobs[j0].dst_off) : (j - j0) * G.slot_bytes;
+                size_t wire = 0;
                 const double t0 = now_sec();
-                Err e = fetch_job(ctx_, fb_.block_locs[job.block], job.block_off, job.n, framed[j], chunk, hs, &conn, &req_ids[j], &wire);
+                const FetchMode fm = mode[j] == kPlain ? kFetchShortCircuit : mode[j] == kFramed ? kFetchFramedVerbatim : kFetchFramedUnpacked;
+                Err e = fetch_job(ctx_, fb_.block_locs[job.block], job.block_off, job.n, fm, chunk, hs + in_slot, &conn, &req_ids[j], &wire);
                 fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
                 if (e) {
                     st.fail(e.ctx(str_printf("block %lld", (long long)fb_.block_locs[job.block].block.id)));
+                    failed = true;
                     break;
                 }
-                uint8_t* dst = framed[j] ? G.d_stage + slot * G.slot_bytes : d_dst + job.dst_off;
-                ce = cudaMemcpyAsync(dst, hs, wire, cudaMemcpyHostToDevice, cs);
-                h2d[static_cast<size_t>(t)] += wire;
+                if (group_verbatim[g]) {
+                    if (mode[j] == kFramed) wire_extent = in_slot + wire;  // copied below in one piece
+                    else ce = cudaMemcpyAsync(d_dst + job.dst_off, hs + in_slot, wire, cudaMemcpyHostToDevice, cs), h2d[static_cast<size_t>(t)] += wire;
+                } else if (!one_copy) {
+                    ce = cudaMemcpyAsync(d_dst + job.dst_off, hs + in_slot, wire, cudaMemcpyHostToDevice, cs), h2d[static_cast<size_t>(t)] += wire;
+                }
+                failed = ce != cudaSuccess;
             }
-            if (ce == cudaSuccess) ce = cudaEventRecord(G.copy_ev[slot], cs);
+            if (st.abort.load() && failed && ce == cudaSuccess) break;
+            if (!failed && group_verbatim[g] && wire_extent) {
+                ce = cudaMemcpyAsync(ds, hs, wire_extent, cudaMemcpyHostToDevice, cs);
+                h2d[static_cast<size_t>(t)] += wire_extent;
+            } else if (!failed && one_copy) {
+                const size_t extent = static_cast<size_t>(jobs[j1 - 1].dst_off + jobs[j1 - 1].n - jobs[j0].dst_off);
+                ce = cudaMemcpyAsync(d_dst + jobs[j0].dst_off, hs, extent, cudaMemcpyHostToDevice, cs);
+                h2d[static_cast<size_t>(t)] += extent;
+            }
+            if (ce == cudaSuccess && !failed) ce = cudaEventRecord(G.copy_ev[ss], cs);
             if (ce != cudaSuccess) {
                 st.fail(Err::io(str_printf("H2D enqueue: %s", cudaGetErrorString(ce))));
                 break;
             }
-            if (!framed[j]) st.released[slot].store(static_cast<int64_t>(j), std::memory_order_release);
-            st.copied[j].store(1, std::memory_order_release);
+            if (failed) break;
+            if (!group_verbatim[g]) released[ss].store(static_cast<int64_t>(g), std::memory_order_release);
+            copied[g].store(1, std::memory_order_release);
         }
         if (conn) ctx_->release(std::move(conn));
     };
     std::vector<std::thread> threads;
     for (int t = 0; t < T_threads; t++) threads.emplace_back(worker, t);
 
-    // ---- verifier: this thread walks the jobs in order, B at a time
+    // ---- verifier: this thread walks the copy groups in order, `vgroups` at a time
     Err verr;
-    uint64_t launches0 = cvk_launch_count();
+    const uint64_t launches0 = cvk_launch_count();
     const uint64_t* d_off = reinterpret_cast<const uint64_t*>(T + o_off);
     const uint64_t* d_len = reinterpret_cast<const uint64_t*>(T + o_len);
     uint32_t* d_crc = reinterpret_cast<uint32_t*>(T + o_crc);
     uint32_t* d_ferr = d_crc + J + 4;
     CvStreamDesc* d_streams = reinterpret_cast<CvStreamDesc*>(T + o_streams);
     CvFrameDesc* d_fdesc = reinterpret_cast<CvFrameDesc*>(T + o_fdesc);
-    for (size_t g0 = 0; g0 < J && !verr; g0 += static_cast<size_t>(B)) {
-        const size_t g1 = std::min(J, g0 + static_cast<size_t>(B));
-        for (size_t j = g0; j < g1; j++)
-            while (!st.copied[j].load(std::memory_order_acquire) && !st.abort.load()) std::this_thread::yield();
+    for (size_t v0 = 0; v0 < NG && !verr; v0 += vgroups) {
+        const size_t v1 = std::min(NG, v0 + vgroups);
+        for (size_t g = v0; g < v1; g++)
+            while (!copied[g].load(std::memory_order_acquire) && !st.abort.load()) std::this_thread::yield();
         if (st.abort.load()) break;
+        const size_t g0 = v0 * k, g1 = std::min(J, v1 * k);
         uint64_t gbytes = 0;
-        bool gframed = false, gplain = false;
-        for (size_t j = g0; j < g1; j++) {
-            cudaStreamWaitEvent(G.vstream, G.copy_ev[j % S], 0);
-            gbytes += h_len[j];
-            (framed[j] ? gframed : gplain) = true;
+        bool gframed = false;
+        for (size_t g = v0; g < v1; g++) {
+            cudaStreamWaitEvent(G.vstream, G.copy_ev[g % NS], 0);
+            gframed |= group_verbatim[g] != 0;
         }
-        if (gplain && !gframed && bc.verify) {  // short-circuit jobs: K1 over the landed bytes
+        for (size_t j = g0; j < g1; j++) gbytes += h_len[j];
+        if (!gframed && bc.verify) {  // K1 over the landed bytes
             int rc = cvk_crc_blocks(d_dst, d_off + g0, d_len + g0, static_cast<uint32_t>(g1 - g0), poly, gbytes, d_crc + g0, G.vstream);
             if (rc) verr = Err::io(str_printf("cvk_crc_blocks: %s", cudaGetErrorString(cudaError_t(rc))));
         }
-        if (gframed && !verr) {
-            // patch the request ids (known only after the fetch) and expand this group's stream descriptors
+        if (gframed) {
+            // patch the request ids (known only after the fetch), expand this batch's stream descriptors, run K2
             for (size_t j = g0; j < g1; j++) sd[j].req_id = req_ids[j];
             cudaError_t ce = cudaMemcpyAsync(d_streams + g0, &sd[g0], sizeof(CvStreamDesc) * (g1 - g0), cudaMemcpyHostToDevice, G.vstream);
             const uint32_t fr0 = first_frame[g0], nfr = first_frame[g1] - fr0;
             int rc = ce != cudaSuccess ? int(ce) : 0;
-            // first_frame inside the descriptors is absolute; expand into the absolute table
             if (!rc) rc = cvk_expand_streams(d_streams + g0, static_cast<uint32_t>(g1 - g0), d_fdesc, first_frame[J], G.vstream);
             if (!rc && nfr)
                 rc = cvk_unpack_frames(G.d_stage, d_fdesc + fr0, nfr, static_cast<uint32_t>(g1 - g0), d_dst, poly, gbytes,
                                        bc.verify ? d_crc + g0 : nullptr, d_ferr + fr0, G.vstream);
             if (rc) verr = Err::io(str_printf("cvk_unpack_frames: %s", cudaGetErrorString(cudaError_t(rc))));
-            for (size_t j = g0; j < g1; j++)
-                if (framed[j]) {
-                    cudaEventRecord(G.free_ev[j % S], G.vstream);
-                    st.released[j % S].store(static_cast<int64_t>(j), std::memory_order_release);
+            for (size_t g = v0; g < v1; g++)
+                if (group_verbatim[g]) {
+                    cudaEventRecord(G.free_ev[g % NS], G.vstream);
+                    released[g % NS].store(static_cast<int64_t>(g), std::memory_order_release);
                 }
         }
     }
@@ -570,11 +668,12 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         return st.err;
     }
     if (compare) CVK_TRY(cvk_verify_crcs(d_crc + f0, reinterpret_cast<const uint32_t*>(T + o_exp) + f0, static_cast<uint32_t>(f1 - f0), d_crc + J, nullptr, G.vstream));
-    CU_TRY(cudaMemcpyAsync(h_result_, d_crc, 4 * res_words, cudaMemcpyDeviceToHost, G.vstream));
+    CU_TRY(cudaMemcpyAsync(G.h_result, d_crc, 4 * res_words, cudaMemcpyDeviceToHost, G.vstream));
     CU_TRY(cudaEventRecord(G.done_ev, G.vstream));
     CU_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(user_stream), G.done_ev, 0));
     pending_.active = true, pending_.jobs = J, pending_.frames = F;
     pending_.f0 = bc.verify ? f0 : 0, pending_.f1 = bc.verify ? f1 : 0, pending_.n_compared = compare ? n_compared : 0;
+    G.pending_owner = this;
     for (size_t j = 0; j < J; j++) stats_.bytes += h_len[j];
     stats_.blocks += J;
     stats_.kernel_launches += cvk_launch_count() - launches0;

@@ -68,16 +68,12 @@ class GpuFsReader {
     uint32_t n_bad_ = 0;
     uint64_t n_bad_frames_ = 0;
     uint32_t first_frame_err_ = 0;
-    // device-side per-call tables + pinned result mirror
-    void* d_tables_ = nullptr;
-    size_t d_tables_cap_ = 0;
-    void* h_result_ = nullptr;
-    size_t h_result_cap_ = 0;
     struct Pending {
         bool active = false;
         size_t jobs = 0, frames = 0, f0 = 0, f1 = 0, n_compared = 0;
     } pending_;
     Err harvest();
+    friend class GpuIngest;
 };
 
 // one per (process, device): pinned ring, device staging ring, streams, events

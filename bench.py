@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--verify-batch", type=int, default=16)
     ap.add_argument("--copy-group", type=int, default=4)
+    ap.add_argument("--zero-copy", type=int, default=1, help="short-circuit: DMA from registered mmaps of the mem-tier block files")
+    ap.add_argument("--also-pread", action="store_true", help="additionally report e2e over the pinned-ring (pread) path")
     ap.add_argument("--gpu-chunk", default="4MB")
     ap.add_argument("--poly", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -153,10 +155,13 @@ def teardown(state):
         shutil.rmtree(state["dir"], ignore_errors=True)
 
 
-def client_conf(args, sc, device, threads, slots):
+def client_conf(args, sc, device, threads, slots, zero_copy=None, copy_group=None):
     from curvine_b200 import fs as F
+    zc = args.zero_copy if zero_copy is None else zero_copy
     b200 = ('device = %d\nfetch_threads = %d\npinned_slots = %d\nverify_poly = %d\nverify = true\nverify_batch = %d\ncopy_group = %d\ngpu_chunk_size = "%s"\n'
-            % (device, threads, slots, args.poly, args.verify_batch, args.copy_group, args.gpu_chunk))
+            'zero_copy = %s\nregister_cache = "%dGB"\n'
+            % (device, threads, slots, args.poly, args.verify_batch, args.copy_group if copy_group is None else copy_group, args.gpu_chunk,
+               "true" if zc else "false", int(args.gib_per_gpu * 1.5) + 1))
     return F.client_conf(hostname="localhost", short_circuit=sc, b200=b200)
 
 
@@ -261,7 +266,14 @@ def main():
         assert int(d_bad.item()) == 0, "resident verify found mismatches"
         assert int(d_crc.cpu().numpy().view(np.uint32).astype(np.uint64).sum()) == sum_crc
 
-        # ---- optional: e2e over the framed path
+        # ---- optional: e2e over the pinned-ring (pread) path and over the framed path
+        pread = None
+        if args.also_pread:
+            fs3 = F.CurvineFileSystem(client_conf(args, True, local, max(threads, 32 // world), slots, zero_copy=0, copy_group=1))
+            fs3.load_namespace(state["manifest"])
+            p_ms, p_stats, _ = run_e2e(fs3, "/bench/file", rank, world, dst, shard_bytes, max(2, args.steps // 2), 2, dist)
+            pread = (p_ms, p_stats)
+            fs3.close()
         framed = None
         if args.also_framed:
             fs2 = F.CurvineFileSystem(client_conf(args, False, local, threads, slots))
@@ -284,6 +296,7 @@ def main():
         val_ms = maxr(val_ms)
         walk_avg_ms = maxr(walk_ms.value / max(1, walk_n.value))
         framed_ms = maxr(sum(framed[0]) / len(framed[0])) if framed else None
+        pread_ms = maxr(sum(pread[0]) / len(pread[0])) if pread else None
 
         if rank == 0:
             peaks = {}
@@ -306,11 +319,11 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": "C2: 16 GiB synthetic file per GPU, 4 MiB blocks, mem-tier (tmpfs) BlockStore, "
                                        "blocks round-robin across GPUs (C3 shape at N=8), on-GPU CRC-%s verify" % ("32C" if args.poly else "32"),
-                           "file_bytes": total_bytes, "block_bytes": BLOCK, "blocks_per_gpu": my_blocks, "read_path": args.mode,
+                           "file_bytes": total_bytes, "block_bytes": BLOCK, "blocks_per_gpu": my_blocks, "read_path": args.mode, "zero_copy": bool(args.zero_copy and args.mode == "short_circuit"),
                            "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch, "copy_group": args.copy_group,
                            "l2": "inputs (16 GiB per GPU) are larger than L2; no flush needed", "host_cpus": ncpu},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) if world == 1 else shard_bytes * world,
-                        "d2h_bytes_per_step": 4 * (my_blocks + 4) * world, "ms_per_step": e2e_step_ms, "best_ms": e2e_best_ms,
+                        "d2h_bytes_per_step": 4 * (my_blocks + 4) * world, "ms_per_step": e2e_step_ms, "best_ms": e2e_best_ms, "timed_steps_ms": e2e_ms,
                         "per_gpu_GBps": e2e_val / world, "frac_of_pcie_gen5_x16_raw_63GBps": e2e_val / world / pcie_raw,
                         "frac_of_measured_h2d_55.6GBps": e2e_val / world / 55.6,
                         "last_step_fetch_thread_sec": stats["fetch_sec"], "last_step_wall_sec": stats["wall_sec"]},
@@ -323,6 +336,10 @@ def main():
                 "clocks_e2e": sampler.summary(t_a, t_b),
                 "setup": {"file_gen_sec": state.get("gen_sec"), "sum_crc": sum_crc},
             }
+            if pread_ms:
+                out["e2e_pread"] = {"value": total_bytes / pread_ms / 1e6, "unit": UNIT, "ms_per_step": pread_ms,
+                                    "note": "short-circuit via pread into the pinned ring (no registered mappings), copy_group=1",
+                                    "fetch_thread_sec": pread[1]["fetch_sec"]}
             if framed_ms:
                 out["e2e_framed"] = {"value": total_bytes / framed_ms / 1e6, "unit": UNIT, "ms_per_step": framed_ms,
                                      "h2d_bytes_per_step": int(framed[1]["h2d_bytes"]), "gpu_chunk": args.gpu_chunk}

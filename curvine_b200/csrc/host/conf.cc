@@ -148,6 +148,8 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "copy_group") b.copy_group = static_cast<int>(as_int(v));
             else if (k == "gpu_chunk_size") e = as_size(v, &b.gpu_chunk_size);
             else if (k == "numa_node") b.numa_node = static_cast<int>(as_int(v));
+            else if (k == "zero_copy") b.zero_copy = as_bool(v);
+            else if (k == "register_cache") e = as_size(v, &b.register_cache);
         }
         if (e) return e.ctx("conf key " + k);
     }

@@ -43,6 +43,8 @@ struct B200Conf {
     int verify_batch = 16;        // blocks per CRC launch
     int copy_group = 4;           // consecutive blocks moved by one cudaMemcpyAsync (bigger copies: closer to PCIe peak)
     int64_t gpu_chunk_size = 4 << 20;  // Running-request chunk for the framed GPU path (<= 16 MiB frame cap)
+    bool zero_copy = false;       // short-circuit reads: DMA straight from cudaHostRegister'ed mmaps of the block files
+    int64_t register_cache = 64ll << 30;  // bytes of registered mappings kept across calls (LRU)
     int numa_node = -1;           // bind fetch threads to this node's CPUs (-1: the GPU's node if discoverable)
 };
 

@@ -4,7 +4,11 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
+
+#include <list>
 
 #include <fstream>
 
@@ -23,6 +27,132 @@ namespace cv {
         int e_ = (x);                                                                               \
         if (e_ != 0) return Err::io(str_printf("%s: %s", #x, cudaGetErrorString(cudaError_t(e_)))); \
     } while (0)
+
+// ------------------------------------------------------------------ registered mem-tier mappings (zero-copy ingest)
+//
+// A mem-tier block file lives in tmpfs page-cache pages.  Instead of pread()ing it into a pinned slot (one CPU copy
+// per byte), map the block files of one copy group back to back into a reserved VA range, cudaHostRegister the range
+// once, and let the copy engine DMA straight out of the page cache.  Mappings are cached (LRU by bytes) and
+// revalidated by (inode, size, mtime) on every use; block files are write-once in Curvine.
+struct RegMapping {
+    std::string key;
+    uint8_t* base = nullptr;
+    size_t bytes = 0;     // registered extent (page-rounded)
+    std::vector<uint64_t> stamps;  // inode, size, mtime_ns per member file
+    bool registered = false;
+    ~RegMapping() {
+        if (registered) cudaHostUnregister(base);
+        if (base) munmap(base, bytes);
+    }
+};
+
+class RegCache {
+   public:
+    size_t capacity = 0;  // bytes; 0 disables caching (mappings live for one call)
+    std::shared_ptr<RegMapping> find(const std::string& key, const std::vector<uint64_t>& stamps) {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = map_.find(key);
+        if (it == map_.end()) return nullptr;
+        if (it->second->second->stamps != stamps) {  // file replaced: drop the stale mapping
+            bytes_ -= it->second->second->bytes;
+            lru_.erase(it->second);
+            map_.erase(it);
+            return nullptr;
+        }
+        lru_.splice(lru_.begin(), lru_, it->second);
+        hits++;
+        return it->second->second;
+    }
+    void insert(const std::shared_ptr<RegMapping>& m) {
+        std::vector<std::shared_ptr<RegMapping>> evicted;  // destroyed outside the lock
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            misses++;
+            if (capacity == 0) return;
+            lru_.emplace_front(m->key, m);
+            map_[m->key] = lru_.begin();
+            bytes_ += m->bytes;
+            while (bytes_ > capacity && lru_.size() > 1) {
+                auto& back = lru_.back();
+                if (back.second.use_count() > 1) break;  // still referenced by a call in flight
+                bytes_ -= back.second->bytes;
+                evicted.push_back(back.second);
+                map_.erase(back.first);
+                lru_.pop_back();
+            }
+        }
+    }
+    void clear() {
+        std::lock_guard<std::mutex> lk(mu_);
+        map_.clear();
+        lru_.clear();
+        bytes_ = 0;
+    }
+    std::atomic<uint64_t> hits{0}, misses{0};
+
+   private:
+    std::mutex mu_;
+    std::list<std::pair<std::string, std::shared_ptr<RegMapping>>> lru_;
+    std::unordered_map<std::string, std::list<std::pair<std::string, std::shared_ptr<RegMapping>>>::iterator> map_;
+    size_t bytes_ = 0;
+};
+
+// Map `paths` (lens[i] bytes each; all but the last a multiple of the page size) contiguously and register the range.
+static Err map_and_register(const std::vector<std::string>& paths, const std::vector<int64_t>& lens, std::shared_ptr<RegMapping>* out,
+                            std::vector<uint64_t>* stamps_out) {
+    const size_t page = 4096;
+    size_t total = 0;
+    for (size_t i = 0; i < paths.size(); i++) {
+        if (i + 1 < paths.size() && lens[i] % static_cast<int64_t>(page)) return Err::common("block length is not page aligned");
+        total += (static_cast<size_t>(lens[i]) + page - 1) / page * page;
+    }
+    std::shared_ptr<RegMapping> m(new RegMapping());
+    void* base = mmap(nullptr, total, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (base == MAP_FAILED) return Err::io(str_printf("mmap reserve: %s", strerror(errno)));
+    m->base = static_cast<uint8_t*>(base), m->bytes = total;
+    size_t off = 0;
+    for (size_t i = 0; i < paths.size(); i++) {
+        const int fd = ::open(paths[i].c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd < 0) return Err::io(str_printf("open %s: %s", paths[i].c_str(), strerror(errno)));
+        struct stat st;
+        fstat(fd, &st);
+        if (st.st_size < lens[i]) {
+            ::close(fd);
+            return Err::io("block file shorter than the block length");
+        }
+        m->stamps.push_back(static_cast<uint64_t>(st.st_ino)), m->stamps.push_back(static_cast<uint64_t>(st.st_size));
+        m->stamps.push_back(static_cast<uint64_t>(st.st_mtim.tv_sec) * 1000000000ull + static_cast<uint64_t>(st.st_mtim.tv_nsec));
+        const size_t span = (static_cast<size_t>(lens[i]) + page - 1) / page * page;
+        void* p = mmap(m->base + off, span, PROT_READ, MAP_SHARED | MAP_FIXED | MAP_POPULATE, fd, 0);
+        ::close(fd);
+        if (p == MAP_FAILED) return Err::io(str_printf("mmap %s: %s", paths[i].c_str(), strerror(errno)));
+        off += span;
+    }
+    cudaError_t e = cudaHostRegister(m->base, total, cudaHostRegisterReadOnly);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaHostRegister(m->base, total, cudaHostRegisterDefault);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return Err(kUnsupported, str_printf("cudaHostRegister(%zu): %s", total, cudaGetErrorString(e)));
+    }
+    m->registered = true;
+    *stamps_out = m->stamps;
+    *out = std::move(m);
+    return Err::ok();
+}
+
+static bool stat_stamps(const std::vector<std::string>& paths, std::vector<uint64_t>* stamps) {
+    stamps->clear();
+    for (const auto& p : paths) {
+        struct stat st;
+        if (stat(p.c_str(), &st) != 0) return false;
+        stamps->push_back(static_cast<uint64_t>(st.st_ino)), stamps->push_back(static_cast<uint64_t>(st.st_size));
+        stamps->push_back(static_cast<uint64_t>(st.st_mtim.tv_sec) * 1000000000ull + static_cast<uint64_t>(st.st_mtim.tv_nsec));
+    }
+    return true;
+}
 
 // ------------------------------------------------------------------ GpuIngest: ring + streams
 
@@ -46,6 +176,7 @@ class GpuIngest {
     uint8_t* h_result = nullptr;
     size_t h_result_cap = 0;
     GpuFsReader* pending_owner = nullptr;  // reader whose results still sit in h_result
+    RegCache reg;
 
     Err ensure_tables(size_t tables_bytes, size_t result_bytes) {
         if (tables_bytes > d_tables_cap) {
@@ -77,6 +208,7 @@ class GpuIngest {
         for (auto& s : copy_streams) CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         CU_TRY(cudaStreamCreateWithFlags(&vstream, cudaStreamNonBlocking));
         CU_TRY(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
+        reg.capacity = c.zero_copy ? static_cast<size_t>(std::max<int64_t>(c.register_cache, 0)) : 0;
         // CPUs of the GPU's NUMA node: pinned pages and fetch threads stay next to the PCIe root
         int node = c.numa_node;
         if (node < 0) {
@@ -145,6 +277,7 @@ class GpuIngest {
     ~GpuIngest() {
         cudaSetDevice(device);
         cudaDeviceSynchronize();
+        reg.clear();
         if (pinned) cudaFreeHost(pinned);
         if (d_stage) cudaFree(d_stage);
         if (d_tables) cudaFree(d_tables);
@@ -256,6 +389,20 @@ Err GpuFsReader::read_device_sharded(int rank, int world, void* d_dst, int64_t c
 }
 
 namespace {
+
+// Wait for `cond()`: a short spin, then sleep in growing steps so waiting threads do not starve the worker threads.
+template <typename F>
+static inline void backoff_wait(F cond) {
+    for (int i = 0; i < 64; i++) {
+        if (cond()) return;
+        std::this_thread::yield();
+    }
+    unsigned us = 10;
+    while (!cond()) {
+        usleep(us);
+        if (us < 200) us *= 2;
+    }
+}
 
 static Protocol read_req(int8_t status, int64_t req_id, int32_t seq_id) {
     Protocol p;
@@ -379,6 +526,30 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
     return last;
 }
 
+// Open(short_circuit=true) on the first replica that answers; returns the block file path.
+static Err open_short_circuit(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, std::unique_ptr<BlockClient>* conn, int64_t* req_id,
+                              std::string* path) {
+    Err last = Err::common("There is no available worker, locs: [], failed workers: []");
+    for (const WorkerAddress& loc : lb.locs) {
+        if (!*conn || !((*conn)->addr() == loc) || (*conn)->broken) {
+            if (*conn) ctx->release(std::move(*conn));
+            last = ctx->acquire_read(loc, conn);
+            if (last) continue;
+        }
+        *req_id = new_req_id();
+        BlockReadResponse resp;
+        last = (*conn)->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, *req_id, 0, true, ctx->read_chunk_size(), &resp);
+        if (last) continue;
+        if (!resp.has_path) {
+            last = Err::common("read_context.path is none");
+            continue;
+        }
+        *path = resp.path;
+        return Err::ok();
+    }
+    return last;
+}
+
 // Pull the last call's per-block CRCs / mismatch count / frame flags (already copied to the pinned mirror on vstream).
 Err GpuFsReader::harvest() {
     if (!pending_.active) return Err::ok();
@@ -398,6 +569,7 @@ Err GpuFsReader::harvest() {
             if (!first_frame_err_) first_frame_err_ = ferr[f];
         }
     pending_.active = false;
+    held_maps_.clear();  // every copy that read from these mappings has completed (vstream waited on them)
     if (G.pending_owner == this) G.pending_owner = nullptr;
     if (n_bad_frames_) return Err(kAbnormalData, str_printf("%llu frame prefixes failed validation (first flags 0x%x)", (unsigned long long)n_bad_frames_, first_frame_err_));
     return Err::ok();
@@ -534,6 +706,8 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     for (size_t g = 0; g < NG; g++)
         for (size_t j = g * k; j < std::min(J, g * k + k); j++) group_verbatim[g] |= mode[j] == kFramed;
     std::vector<int64_t> req_ids(J, 0);
+    std::atomic<bool> use_mapped{bc.zero_copy};
+    std::mutex held_mu;
     const int T_threads = static_cast<int>(std::min<size_t>(static_cast<size_t>(std::max(1, bc.fetch_threads)), NG));
     std::vector<double> fetch_sec(static_cast<size_t>(T_threads), 0.0);
     std::vector<uint64_t> h2d(static_cast<size_t>(T_threads), 0);
@@ -548,12 +722,76 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
             const size_t ss = g % NS, j0 = g * k, j1 = std::min(J, j0 + k);
             if (g >= NS) {  // wait until the super-slot's previous tenant has been released, then for its event
                 const int64_t want = static_cast<int64_t>(g - NS);
-                while (released[ss].load(std::memory_order_acquire) < want) {
-                    if (st.abort.load()) break;
-                    std::this_thread::yield();
-                }
+                backoff_wait([&] { return released[ss].load(std::memory_order_acquire) >= want || st.abort.load(); });
                 if (st.abort.load()) break;
                 cudaEventSynchronize(group_verbatim[g - NS] ? G.free_ev[ss] : G.copy_ev[ss]);
+            }
+            // ---- zero-copy: DMA out of registered mmaps of the block files (mem tier), no pinned-slot copy
+            bool all_plain = true;
+            for (size_t j = j0; j < j1; j++) all_plain = all_plain && mode[j] == kPlain;
+            if (all_plain && use_mapped.load(std::memory_order_relaxed)) {
+                const double t0 = now_sec();
+                std::vector<std::string> paths(j1 - j0);
+                std::vector<int64_t> lens(j1 - j0), rids(j1 - j0);
+                Err e;
+                for (size_t j = j0; j < j1 && !e; j++) {
+                    const LocatedBlock& lb = fb_.block_locs[jobs[j].block];
+                    e = open_short_circuit(ctx_, lb, jobs[j].block_off, &conn, &rids[j - j0], &paths[j - j0]);
+                    lens[j - j0] = lb.block.len;
+                }
+                std::shared_ptr<RegMapping> m;
+                if (!e) {
+                    std::string key;
+                    for (const auto& p : paths) key += p, key += '|';
+                    std::vector<uint64_t> stamps;
+                    if (stat_stamps(paths, &stamps)) m = G.reg.find(key, stamps);
+                    if (!m) {
+                        e = map_and_register(paths, lens, &m, &stamps);
+                        if (!e) {
+                            m->key = key;
+                            G.reg.insert(m);
+                        }
+                    }
+                }
+                cudaError_t ce = cudaSuccess;
+                if (!e) {
+                    // one copy when the group is whole blocks landing back to back, else one per job
+                    bool whole = true;
+                    for (size_t j = j0; j < j1; j++) {
+                        whole = whole && jobs[j].block_off == 0 && (j + 1 == j1 || jobs[j].n == lens[j - j0]);
+                        if (j > j0) whole = whole && jobs[j].dst_off == jobs[j - 1].dst_off + jobs[j - 1].n;
+                    }
+                    if (whole) {
+                        const size_t extent = static_cast<size_t>(jobs[j1 - 1].dst_off + jobs[j1 - 1].n - jobs[j0].dst_off);
+                        ce = cudaMemcpyAsync(d_dst + jobs[j0].dst_off, m->base, extent, cudaMemcpyHostToDevice, cs);
+                        h2d[static_cast<size_t>(t)] += extent;
+                    } else {
+                        size_t moff = 0;
+                        for (size_t j = j0; j < j1 && ce == cudaSuccess; j++) {
+                            ce = cudaMemcpyAsync(d_dst + jobs[j].dst_off, m->base + moff + jobs[j].block_off, static_cast<size_t>(jobs[j].n), cudaMemcpyHostToDevice, cs);
+                            h2d[static_cast<size_t>(t)] += static_cast<size_t>(jobs[j].n);
+                            moff += (static_cast<size_t>(lens[j - j0]) + 4095) / 4096 * 4096;
+                        }
+                    }
+                    if (ce == cudaSuccess) ce = cudaEventRecord(G.copy_ev[ss], cs);
+                    {
+                        std::lock_guard<std::mutex> lk(held_mu);
+                        held_maps_.push_back(m);
+                    }
+                    for (size_t j = j0; j < j1 && !e; j++) e = conn->read_commit(fb_.block_locs[jobs[j].block].block, rids[j - j0], 1);
+                }
+                fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
+                if (e && e.kind == kUnsupported) {
+                    use_mapped.store(false);  // cannot register file mappings here: fall back to the pinned ring below
+                } else {
+                    if (e || ce != cudaSuccess) {
+                        st.fail(e ? e : Err::io(str_printf("H2D enqueue: %s", cudaGetErrorString(ce))));
+                        break;
+                    }
+                    released[ss].store(static_cast<int64_t>(g), std::memory_order_release);
+                    copied[g].store(1, std::memory_order_release);
+                    continue;
+                }
             }
             uint8_t* hs = G.pinned + ss * k * G.slot_bytes;
             uint8_t* ds = G.d_stage ? G.d_stage + ss * k * G.slot_bytes : nullptr;
@@ -628,7 +866,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     for (size_t v0 = 0; v0 < NG && !verr; v0 += vgroups) {
         const size_t v1 = std::min(NG, v0 + vgroups);
         for (size_t g = v0; g < v1; g++)
-            while (!copied[g].load(std::memory_order_acquire) && !st.abort.load()) std::this_thread::yield();
+            backoff_wait([&] { return copied[g].load(std::memory_order_acquire) != 0 || st.abort.load(); });
         if (st.abort.load()) break;
         const size_t g0 = v0 * k, g1 = std::min(J, v1 * k);
         uint64_t gbytes = 0;

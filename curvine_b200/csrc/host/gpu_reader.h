@@ -29,6 +29,7 @@ struct GpuReadStats {
 };
 
 class GpuIngest;  // per-FsContext pinned ring + streams
+struct RegMapping;
 
 class GpuFsReader {
    public:
@@ -68,6 +69,7 @@ class GpuFsReader {
     uint32_t n_bad_ = 0;
     uint64_t n_bad_frames_ = 0;
     uint32_t first_frame_err_ = 0;
+    std::vector<std::shared_ptr<struct RegMapping>> held_maps_;  // registered mappings with copies still in flight
     struct Pending {
         bool active = false;
         size_t jobs = 0, frames = 0, f0 = 0, f1 = 0, n_compared = 0;

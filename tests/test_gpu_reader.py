@@ -25,9 +25,10 @@ def _dev_buf(n, cuda):
     return torch.full((n,), 0xA5, dtype=torch.uint8, device=cuda)
 
 
-def _conf(sc, poly=1, chunk="4MB", threads=4, batch=4):
+def _conf(sc, poly=1, chunk="4MB", threads=4, batch=4, zero_copy=False, copy_group=2):
     return F.client_conf(short_circuit=sc, b200='verify_poly = %d\ngpu_chunk_size = "%s"\nfetch_threads = %d\nverify_batch = %d\npinned_slots = 12\n'
-                         % (poly, chunk, threads, batch))
+                         'zero_copy = %s\ncopy_group = %d\nregister_cache = "48MB"\n'
+                         % (poly, chunk, threads, batch, "true" if zero_copy else "false", copy_group))
 
 
 @pytest.mark.parametrize("sc,chunk", [(True, "4MB"), (False, "128KB"), (False, "1MB"), (False, "4MB")])
@@ -180,13 +181,64 @@ def test_fuse_shaped_device_read_scatters_into_pages(cuda, cluster):
         scratch = _dev_buf(n, cuda)
         pages = torch.zeros(128 * 4096 + 64, dtype=torch.uint8, device=cuda)
         rng = np.random.default_rng(1)
-        order = rng.permutation(128)[:64]  # 64 pages, scattered, not in order
+        order = rng.permutation(128)[:60]  # 60 pages, scattered, not in order
         offs = [int(p) * 4096 + 7 for p in order]  # deliberately unaligned page buffers
-        got = r.fuse_read_device(4096, 64 * 4096 - 100, scratch.data_ptr(), pages.data_ptr(), offs, 4096, 0)
+        got = r.fuse_read_device(4096, 60 * 4096 - 100, scratch.data_ptr(), pages.data_ptr(), offs, 4096, 0)
         torch.cuda.synchronize()
-        assert got == 64 * 4096 - 100 and r.pos() == 4096 + got
+        assert got == 60 * 4096 - 100 and r.pos() == 4096 + got
         host = pages.cpu().numpy()
         for i, o in enumerate(offs):
             seg = want[4096 + i * 4096:4096 + min((i + 1) * 4096, got)]
             assert host[o:o + len(seg)].tobytes() == seg
+        r.complete()
+
+
+@pytest.mark.parametrize("copy_group", [1, 4])
+def test_zero_copy_registered_mappings(cuda, cluster, copy_group):
+    """Mem-tier zero-copy: DMA straight from cudaHostRegister'ed mmaps of the block files.  Same bytes, same CRCs;
+    in-place corruption and file replacement are both seen (mappings revalidated by inode/size/mtime); the LRU
+    (48 MB here, file 64 MiB) evicts without breaking anything."""
+    import torch
+    w, d = cluster
+    n, bs, ino = (64 << 20) - 4096 * 3 - 5, 1 << 20, 7040 + copy_group
+    man = w.create_file("/zc%d" % copy_group, ino, n, bs)
+    want = bytearray(synth.file_bytes(ino, n, bs))
+    nb = (n + bs - 1) // bs
+    with F.CurvineFileSystem(_conf(True, 1, zero_copy=True, copy_group=copy_group)) as fs:
+        fs.load_namespace(man)
+        for rep in range(3):
+            r = fs.open("/zc%d" % copy_group)
+            dst = _dev_buf(n + 16, cuda)
+            assert r.read_device(dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
+            s, bad, ver = r.verify()
+            torch.cuda.synchronize()
+            assert bad == 0 and ver == nb
+            assert dst[:n].cpu().numpy().tobytes() == bytes(want) and (dst[n:] == 0xA5).all()
+            r.complete()
+        # partial range through the mapped path
+        r = fs.open("/zc%d" % copy_group)
+        r.seek(3 * bs + 17)
+        dst = _dev_buf(2 * bs + 100, cuda)
+        assert r.read_device(dst.data_ptr(), 2 * bs + 100, 0) == 2 * bs + 100
+        torch.cuda.synchronize()
+        assert dst.cpu().numpy().tobytes() == bytes(want[3 * bs + 17:5 * bs + 117])
+        r.complete()
+        # corrupt block 7 in place, replace block 9 by a new file with different content
+        p7 = layout.block_path(str(d / "mem" / "curvine"), layout.create_block_id(ino, 7))
+        with open(p7, "r+b") as f:
+            f.seek(4096)
+            f.write(b"\x00\x01\x02")
+        p9 = layout.block_path(str(d / "mem" / "curvine"), layout.create_block_id(ino, 9))
+        blk9 = bytes(bs)
+        os.remove(p9)
+        with open(p9, "wb") as f:
+            f.write(blk9)
+        want[7 * bs + 4096:7 * bs + 4099] = b"\x00\x01\x02"
+        want[9 * bs:10 * bs] = blk9
+        r = fs.open("/zc%d" % copy_group)
+        dst = _dev_buf(n, cuda)
+        assert r.read_device(dst.data_ptr(), n, 0) == n
+        s, bad, ver = r.verify()
+        torch.cuda.synchronize()
+        assert bad == 2 and dst.cpu().numpy().tobytes() == bytes(want)
         r.complete()

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--verify-batch", type=int, default=16)
     ap.add_argument("--copy-group", type=int, default=4)
+    ap.add_argument("--copy-streams", type=int, default=1)
     ap.add_argument("--zero-copy", type=int, default=1, help="short-circuit: DMA from registered mmaps of the mem-tier block files")
     ap.add_argument("--also-pread", action="store_true", help="additionally report e2e over the pinned-ring (pread) path")
     ap.add_argument("--gpu-chunk", default="4MB")
@@ -159,9 +160,9 @@ def client_conf(args, sc, device, threads, slots, zero_copy=None, copy_group=Non
     from curvine_b200 import fs as F
     zc = args.zero_copy if zero_copy is None else zero_copy
     b200 = ('device = %d\nfetch_threads = %d\npinned_slots = %d\nverify_poly = %d\nverify = true\nverify_batch = %d\ncopy_group = %d\ngpu_chunk_size = "%s"\n'
-            'zero_copy = %s\nregister_cache = "%dGB"\n'
+            'zero_copy = %s\nregister_cache = "%dGB"\ncopy_streams = %d\n'
             % (device, threads, slots, args.poly, args.verify_batch, args.copy_group if copy_group is None else copy_group, args.gpu_chunk,
-               "true" if zc else "false", int(args.gib_per_gpu * 1.5) + 1))
+               "true" if zc else "false", int(args.gib_per_gpu * 1.5) + 1, args.copy_streams))
     return F.client_conf(hostname="localhost", short_circuit=sc, b200=b200)
 
 
@@ -326,7 +327,8 @@ def main():
                         "d2h_bytes_per_step": 4 * (my_blocks + 4) * world, "ms_per_step": e2e_step_ms, "best_ms": e2e_best_ms, "timed_steps_ms": e2e_ms,
                         "per_gpu_GBps": e2e_val / world, "frac_of_pcie_gen5_x16_raw_63GBps": e2e_val / world / pcie_raw,
                         "frac_of_measured_h2d_55.6GBps": e2e_val / world / 55.6,
-                        "last_step_fetch_thread_sec": stats["fetch_sec"], "last_step_wall_sec": stats["wall_sec"]},
+                        "last_step_fetch_thread_sec": stats["fetch_sec"], "last_step_wall_sec": stats["wall_sec"],
+                        "registered_mapping_cache": {"hits": stats["reg_hits"], "misses": stats["reg_misses"]}},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "walk_kernel<CRC,!DST> (K1 CRC verify)",
                              "achieved": shard_bytes / walk_avg_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",

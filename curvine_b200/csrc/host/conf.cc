@@ -145,6 +145,7 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "verify_poly") b.verify_poly = static_cast<int>(as_int(v));
             else if (k == "verify") b.verify = as_bool(v);
             else if (k == "verify_batch") b.verify_batch = static_cast<int>(as_int(v));
+            else if (k == "copy_streams") b.copy_streams = static_cast<int>(as_int(v));
             else if (k == "copy_group") b.copy_group = static_cast<int>(as_int(v));
             else if (k == "gpu_chunk_size") e = as_size(v, &b.gpu_chunk_size);
             else if (k == "numa_node") b.numa_node = static_cast<int>(as_int(v));

@@ -41,6 +41,7 @@ struct B200Conf {
     int verify_poly = 1;          // 0 = CRC-32 (reference tools), 1 = CRC-32C (north_star)
     bool verify = true;           // compare per-block CRC with the manifest on the GPU
     int verify_batch = 16;        // blocks per CRC launch
+    int copy_streams = 1;         // H2D streams shared by the fetch threads (1 measured best on B200: no channel switching)
     int copy_group = 4;           // consecutive blocks moved by one cudaMemcpyAsync (bigger copies: closer to PCIe peak)
     int64_t gpu_chunk_size = 4 << 20;  // Running-request chunk for the framed GPU path (<= 16 MiB frame cap)
     bool zero_copy = false;       // short-circuit reads: DMA straight from cudaHostRegister'ed mmaps of the block files

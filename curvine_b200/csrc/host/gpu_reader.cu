@@ -112,8 +112,10 @@ static Err map_and_register(const std::vector<std::string>& paths, const std::ve
     m->base = static_cast<uint8_t*>(base), m->bytes = total;
     size_t off = 0;
     for (size_t i = 0; i < paths.size(); i++) {
-        const int fd = ::open(paths[i].c_str(), O_RDONLY | O_CLOEXEC);
-        if (fd < 0) return Err::io(str_printf("open %s: %s", paths[i].c_str(), strerror(errno)));
+        // cudaHostRegister needs a writable shared mapping here (cudaHostRegisterReadOnly is not supported on this
+        // platform); nothing ever writes through it.  Read-only block files fall back to the pinned ring.
+        const int fd = ::open(paths[i].c_str(), O_RDWR | O_CLOEXEC);
+        if (fd < 0) return Err(kUnsupported, str_printf("open %s read-write: %s", paths[i].c_str(), strerror(errno)));
         struct stat st;
         fstat(fd, &st);
         if (st.st_size < lens[i]) {
@@ -123,16 +125,12 @@ static Err map_and_register(const std::vector<std::string>& paths, const std::ve
         m->stamps.push_back(static_cast<uint64_t>(st.st_ino)), m->stamps.push_back(static_cast<uint64_t>(st.st_size));
         m->stamps.push_back(static_cast<uint64_t>(st.st_mtim.tv_sec) * 1000000000ull + static_cast<uint64_t>(st.st_mtim.tv_nsec));
         const size_t span = (static_cast<size_t>(lens[i]) + page - 1) / page * page;
-        void* p = mmap(m->base + off, span, PROT_READ, MAP_SHARED | MAP_FIXED | MAP_POPULATE, fd, 0);
+        void* p = mmap(m->base + off, span, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED | MAP_POPULATE, fd, 0);
         ::close(fd);
         if (p == MAP_FAILED) return Err::io(str_printf("mmap %s: %s", paths[i].c_str(), strerror(errno)));
         off += span;
     }
-    cudaError_t e = cudaHostRegister(m->base, total, cudaHostRegisterReadOnly);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        e = cudaHostRegister(m->base, total, cudaHostRegisterDefault);
-    }
+    cudaError_t e = cudaHostRegister(m->base, total, cudaHostRegisterDefault);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return Err(kUnsupported, str_printf("cudaHostRegister(%zu): %s", total, cudaGetErrorString(e)));
@@ -204,7 +202,7 @@ class GpuIngest {
             CU_TRY(cudaEventCreateWithFlags(&copy_ev[i], cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming));
         }
-        copy_streams.resize(std::max(1, c.fetch_threads));
+        copy_streams.resize(static_cast<size_t>(std::max(1, std::min(c.copy_streams, c.fetch_threads))));
         for (auto& s : copy_streams) CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         CU_TRY(cudaStreamCreateWithFlags(&vstream, cudaStreamNonBlocking));
         CU_TRY(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
@@ -917,6 +915,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     stats_.kernel_launches += cvk_launch_count() - launches0;
     for (int t = 0; t < T_threads; t++) stats_.fetch_sec += fetch_sec[static_cast<size_t>(t)], stats_.h2d_bytes += h2d[static_cast<size_t>(t)];
     stats_.wall_sec += now_sec() - t_start;
+    stats_.reg_hits = G.reg.hits.load(), stats_.reg_misses = G.reg.misses.load();
     return Err::ok();
 }
 

@@ -24,6 +24,7 @@ struct GpuReadStats {
     uint64_t verified = 0;      // blocks whose CRC was compared with the manifest
     uint64_t h2d_bytes = 0;     // bytes moved by cudaMemcpyAsync (payload, + prefixes when framed)
     uint64_t kernel_launches = 0;
+    uint64_t reg_hits = 0, reg_misses = 0;  // registered-mapping cache (zero-copy path), context-wide
     double fetch_sec = 0;       // summed over fetch threads: time inside pread/recv
     double wall_sec = 0;
 };

@@ -97,6 +97,7 @@ int64_t cv_verify(cv_reader* r, uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_
 typedef struct CvReadStats {
     uint64_t bytes, blocks, verified, h2d_bytes, kernel_launches;
     double fetch_sec, wall_sec;
+    uint64_t reg_hits, reg_misses; /* registered-mapping cache of the zero-copy path */
 } CvReadStats;
 int64_t cv_device_stats(cv_reader* r, CvReadStats* out);
 

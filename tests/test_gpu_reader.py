@@ -214,6 +214,8 @@ def test_zero_copy_registered_mappings(cuda, cluster, copy_group):
             torch.cuda.synchronize()
             assert bad == 0 and ver == nb
             assert dst[:n].cpu().numpy().tobytes() == bytes(want) and (dst[n:] == 0xA5).all()
+            st = r.device_stats()
+            assert st["reg_misses"] > 0, "the registered-mapping path did not run (silent fallback to the pinned ring)"
             r.complete()
         # partial range through the mapped path
         r = fs.open("/zc%d" % copy_group)

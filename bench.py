@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--fetch-threads", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--verify-batch", type=int, default=16)
-    ap.add_argument("--copy-group", type=int, default=4)
+    ap.add_argument("--copy-group", type=int, default=8)
     ap.add_argument("--copy-streams", type=int, default=1)
     ap.add_argument("--zero-copy", type=int, default=1, help="short-circuit: DMA from registered mmaps of the mem-tier block files")
     ap.add_argument("--also-pread", action="store_true", help="additionally report e2e over the pinned-ring (pread) path")
@@ -270,7 +270,7 @@ def main():
         # ---- optional: e2e over the pinned-ring (pread) path and over the framed path
         pread = None
         if args.also_pread:
-            fs3 = F.CurvineFileSystem(client_conf(args, True, local, max(threads, 32 // world), slots, zero_copy=0, copy_group=1))
+            fs3 = F.CurvineFileSystem(client_conf(args, True, local, threads, slots, zero_copy=0, copy_group=1))
             fs3.load_namespace(state["manifest"])
             p_ms, p_stats, _ = run_e2e(fs3, "/bench/file", rank, world, dst, shard_bytes, max(2, args.steps // 2), 2, dist)
             pread = (p_ms, p_stats)

@@ -36,13 +36,13 @@ struct ClientConf {
 // [b200] section: the GPU ingest pipeline (no reference counterpart)
 struct B200Conf {
     int device = 0;
-    int fetch_threads = 8;        // host threads pulling blocks into pinned slots
+    int fetch_threads = 16;       // host threads pulling blocks into pinned slots
     int pinned_slots = 32;        // ring depth (slots of max block bytes + frame overhead)
     int verify_poly = 1;          // 0 = CRC-32 (reference tools), 1 = CRC-32C (north_star)
     bool verify = true;           // compare per-block CRC with the manifest on the GPU
     int verify_batch = 16;        // blocks per CRC launch
     int copy_streams = 1;         // H2D streams shared by the fetch threads (1 measured best on B200: no channel switching)
-    int copy_group = 4;           // consecutive blocks moved by one cudaMemcpyAsync (bigger copies: closer to PCIe peak)
+    int copy_group = 8;           // consecutive blocks moved by one cudaMemcpyAsync (bigger copies: closer to PCIe peak)
     int64_t gpu_chunk_size = 4 << 20;  // Running-request chunk for the framed GPU path (<= 16 MiB frame cap)
     bool zero_copy = false;       // short-circuit reads: DMA straight from cudaHostRegister'ed mmaps of the block files
     int64_t register_cache = 64ll << 30;  // bytes of registered mappings kept across calls (LRU)

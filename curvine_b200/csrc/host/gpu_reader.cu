@@ -632,7 +632,15 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         need_slot = std::max(need_slot, bytes);
     }
     first_frame[J] = static_cast<uint32_t>(F);
-    CV_RETURN_IF_ERR(G.ensure(need_slot, any_verbatim));
+    // the pinned ring (and the device staging ring for verbatim frames) is only materialised when a group needs it:
+    // the zero-copy path never touches it
+    std::once_flag ring_once;
+    Err ring_err;
+    auto ensure_ring = [&]() -> Err {
+        std::call_once(ring_once, [&] { ring_err = G.ensure(need_slot, any_verbatim); });
+        return ring_err;
+    };
+    if (!(bc.zero_copy && !call_framed)) CV_RETURN_IF_ERR(ensure_ring());
 
     // ---- copy groups: k consecutive jobs share one super-slot and, when they are contiguous, one cudaMemcpyAsync
     const size_t k = static_cast<size_t>(std::max(1, std::min(bc.copy_group, G.nslots / 4)));
@@ -790,6 +798,10 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                     copied[g].store(1, std::memory_order_release);
                     continue;
                 }
+            }
+            if (Err re = ensure_ring()) {
+                st.fail(re);
+                break;
             }
             uint8_t* hs = G.pinned + ss * k * G.slot_bytes;
             uint8_t* ds = G.d_stage ? G.d_stage + ss * k * G.slot_bytes : nullptr;

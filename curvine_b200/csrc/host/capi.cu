@@ -217,6 +217,24 @@ int64_t cv_read_device_sharded(cv_reader* r, int32_t rank, int32_t world, void* 
     API_GUARD_END
 }
 
+int64_t cv_shard_plan(cv_reader* r, int32_t rank, int32_t world, int64_t* block_index, int64_t* file_off, int64_t* len, int64_t* dst_off,
+                      int32_t cap, int32_t* n, int64_t* total_bytes) {
+    API_GUARD_BEGIN
+    std::vector<ShardJob> plan;
+    int64_t total = 0;
+    API_TRY(plan_shard(r->host->file_blocks(), rank, world, -1, &plan, &total));
+    if (n) *n = static_cast<int32_t>(plan.size());
+    if (total_bytes) *total_bytes = total;
+    for (size_t i = 0; i < plan.size() && static_cast<int32_t>(i) < cap; i++) {
+        if (block_index) block_index[i] = static_cast<int64_t>(plan[i].block);
+        if (file_off) file_off[i] = plan[i].file_off;
+        if (len) len[i] = plan[i].len;
+        if (dst_off) dst_off[i] = plan[i].dst_off;
+    }
+    return ok();
+    API_GUARD_END
+}
+
 int64_t cv_fuse_read_device(cv_reader* r, int64_t pos, int64_t len, void* d_scratch, void* d_page_base, const uint64_t* page_offsets,
                             int32_t n_pages, int64_t page_size, cv_stream_t stream, int64_t* nbytes) {
     API_GUARD_BEGIN

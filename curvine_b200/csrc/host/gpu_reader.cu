@@ -369,18 +369,27 @@ Err GpuFsReader::read_device(void* d_dst, int64_t cap, void* stream, int64_t* n)
     return Err::ok();
 }
 
+Err plan_shard(const FileBlocks& fb, int rank, int world, int64_t cap, std::vector<ShardJob>* out, int64_t* total) {
+    out->clear();
+    *total = 0;
+    if (world <= 0 || rank < 0 || rank >= world) return Err::common("bad shard spec");
+    const int64_t bs = fb.status.block_size;
+    for (size_t b = static_cast<size_t>(rank), j = 0; b < fb.block_locs.size(); b += static_cast<size_t>(world), j++) {
+        const int64_t blen = fb.block_locs[b].block.len;
+        if (cap >= 0 && static_cast<int64_t>(j) * bs + blen > cap) return Err::common("destination too small for this shard");
+        out->push_back(ShardJob{b, fb.starts[b], blen, static_cast<int64_t>(j) * bs});
+        *total += blen;
+    }
+    return Err::ok();
+}
+
 Err GpuFsReader::read_device_sharded(int rank, int world, void* d_dst, int64_t cap, void* stream, int64_t* n) {
     *n = 0;
-    if (world <= 0 || rank < 0 || rank >= world) return Err::common("bad shard spec");
-    const int64_t bs = fb_.status.block_size;
-    std::vector<Job> jobs;
+    std::vector<ShardJob> plan;
     int64_t total = 0;
-    for (size_t b = static_cast<size_t>(rank), j = 0; b < fb_.block_locs.size(); b += static_cast<size_t>(world), j++) {
-        const int64_t blen = fb_.block_locs[b].block.len;
-        if (static_cast<int64_t>(j) * bs + blen > cap) return Err::common("destination too small for this shard");
-        jobs.push_back(Job{b, 0, blen, static_cast<int64_t>(j) * bs, true});
-        total += blen;
-    }
+    CV_RETURN_IF_ERR(plan_shard(fb_, rank, world, cap, &plan, &total));
+    std::vector<Job> jobs;
+    for (const auto& p : plan) jobs.push_back(Job{p.block, 0, p.len, p.dst_off, true});
     CV_RETURN_IF_ERR(run_jobs(jobs, static_cast<uint8_t*>(d_dst), stream));
     *n = total;
     return Err::ok();

@@ -29,6 +29,16 @@ struct GpuReadStats {
     double wall_sec = 0;
 };
 
+// Round-robin shard of a file: block b -> rank b % world (the analogue of slice_id % read_parallel,
+// fs_reader_parallel.rs:112-122).  Slot j of the rank's destination (block_size bytes each) holds block j*world+rank.
+struct ShardJob {
+    size_t block;      // index into FileBlocks::block_locs
+    int64_t file_off;  // where the block starts in the file
+    int64_t len;
+    int64_t dst_off;   // j * block_size
+};
+Err plan_shard(const FileBlocks& fb, int rank, int world, int64_t cap, std::vector<ShardJob>* out, int64_t* total);
+
 class GpuIngest;  // per-FsContext pinned ring + streams
 struct RegMapping;
 

@@ -131,6 +131,14 @@ class Reader:
                                                  ctypes.byref(n)))
         return n.value
 
+    def shard_plan(self, rank: int, world: int):
+        """-> list of (block_index, file_off, len, dst_off): what read_device_sharded(rank, world) executes."""
+        n, tot = ctypes.c_int32(), ctypes.c_int64()
+        _check(_lib.lib().cv_shard_plan(self._h, rank, world, None, None, None, None, 0, ctypes.byref(n), ctypes.byref(tot)))
+        arrs = [(ctypes.c_int64 * max(1, n.value))() for _ in range(4)]
+        _check(_lib.lib().cv_shard_plan(self._h, rank, world, arrs[0], arrs[1], arrs[2], arrs[3], n.value, ctypes.byref(n), ctypes.byref(tot)))
+        return [tuple(a[i] for a in arrs) for i in range(n.value)]
+
     def fuse_read_device(self, pos: int, size: int, d_scratch: int, d_page_base: int, page_offsets, page_size: int,
                          stream: int = 0) -> int:
         arr = (ctypes.c_uint64 * len(page_offsets))(*page_offsets)

@@ -85,6 +85,10 @@ int64_t cv_read_device(cv_reader* r, void* d_dst, int64_t cap, cv_stream_t strea
 /* blocks b with b % world == rank, back to back in block_size slots (slot j = block j*world+rank) */
 int64_t cv_read_device_sharded(cv_reader* r, int32_t rank, int32_t world, void* d_dst, int64_t cap,
                                cv_stream_t stream, int64_t* nbytes);
+/* The plan cv_read_device_sharded executes (host-only, no GPU needed): for i < *n, block_index[i] of the file starts
+ * at file_off[i], is len[i] bytes long and lands at dst_off[i] = i * block_size.  Arrays may be NULL; cap = their length. */
+int64_t cv_shard_plan(cv_reader* r, int32_t rank, int32_t world, int64_t* block_index, int64_t* file_off, int64_t* len,
+                      int64_t* dst_off, int32_t cap, int32_t* n, int64_t* total_bytes);
 /* FUSE-shaped device read: seek(pos), read len bytes into HBM scratch, then scatter them into n_pages page
  * buffers (d_page_base + page_offsets[i], page_size each; last one partial) with the K3 gather kernel. */
 int64_t cv_fuse_read_device(cv_reader* r, int64_t pos, int64_t len, void* d_scratch, void* d_page_base,

@@ -446,33 +446,58 @@ __global__ void __launch_bounds__(1024, 1)
     }
 }
 
-// Fold unit partials into one CRC per block: acc = 0xFFFFFFFF; acc = acc * x^(8*len_u) (+) raw_u; out = ~acc.
-// One thread per block.  first/last == nullptr: block b is piece b.
+// Fold unit partials into one CRC per block.  One WARP per block: the block's units [prefix[p0], prefix[p1]) are cut into
+// 32 contiguous lane ranges; every lane runs the Horner recurrence acc <- acc * x^(8*len_u) (+) raw_u over its range while
+// also accumulating the product of the multipliers, then (acc, mult) pairs are combined across lanes with a shuffle tree
+// ((a1,m1) o (a2,m2) = (a1*m2 + a2, m1*m2)).  Start value 0xFFFFFFFF and final complement make the result bit-identical
+// to crc32fast / zlib (or CRC-32C).  first/last == nullptr: block b is piece b.
 template <bool DST>
-__global__ void fold_blocks_kernel(const Piece* __restrict__ pieces, const uint32_t* __restrict__ prefix,
-                                   const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
-                                   uint32_t n_blocks, uint32_t seg_shift, uint32_t xp_seg,
-                                   const CrcConsts* __restrict__ cc, const uint32_t* __restrict__ partial,
-                                   const uint32_t* __restrict__ headraw, const uint32_t* __restrict__ tailraw,
-                                   uint32_t* __restrict__ out) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+    fold_blocks_kernel(const Piece* __restrict__ pieces, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ first,
+                       const uint32_t* __restrict__ last, uint32_t n_blocks, uint32_t n_pieces, uint32_t seg_shift, uint32_t xp_seg,
+                       const CrcConsts* __restrict__ cc, const uint32_t* __restrict__ partial, const uint32_t* __restrict__ headraw,
+                       const uint32_t* __restrict__ tailraw, uint32_t* __restrict__ out) {
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= n_blocks) return;
     const uint32_t poly = cc->poly;
     const uint32_t p0 = first ? first[b] : b, p1 = first ? last[b] : b + 1;
-    uint32_t acc = 0xffffffffu;
-    for (uint32_t p = p0; p < p1; p++) {
-        const Piece pc = pieces[p];
-        const Geom g = piece_geom<DST>(pc, seg_shift);
-        if (g.head) acc = gf_mul(acc, cc->pw8[g.head], poly) ^ headraw[p];
-        const uint32_t ubase = prefix[p];
-        for (uint32_t s = 0; s < g.nseg; s++) {
-            const uint64_t rem = g.body - (uint64_t(s) << seg_shift);
-            const uint32_t mult = rem >= (1ull << seg_shift) ? xp_seg : gf_xpow(8 * rem, poly);
-            acc = gf_mul(acc, mult, poly) ^ partial[ubase + s];
+    uint32_t acc = 0, mult = kOne;
+    if (p1 > p0) {
+        const uint32_t u0 = prefix[p0], u1 = prefix[p1];
+        const uint32_t per = (u1 - u0 + 31) / 32;
+        const uint32_t ua = min(u1, u0 + lane * per), ub = min(u1, ua + per);
+        if (ua < ub) {
+            uint32_t p = find_piece(prefix, n_pieces, ua);
+            for (uint32_t u = ua; u < ub; u++) {
+                while (u >= prefix[p + 1]) p++;
+                const Piece pc = pieces[p];
+                const Geom g = piece_geom<DST>(pc, seg_shift);
+                const uint32_t s = u - prefix[p];
+                if (s == 0 && g.head) {
+                    const uint32_t m = cc->pw8[g.head];
+                    acc = gf_mul(acc, m, poly) ^ headraw[p], mult = gf_mul(mult, m, poly);
+                }
+                if (s < g.nseg) {
+                    const uint64_t rem = g.body - (uint64_t(s) << seg_shift);
+                    const uint32_t m = rem >= (1ull << seg_shift) ? xp_seg : gf_xpow(8 * rem, poly);
+                    acc = gf_mul(acc, m, poly) ^ partial[u], mult = gf_mul(mult, m, poly);
+                }
+                if (s + 1 == g.units && g.tail) {
+                    const uint32_t m = cc->pw8[g.tail];
+                    acc = gf_mul(acc, m, poly) ^ tailraw[p], mult = gf_mul(mult, m, poly);
+                }
+            }
         }
-        if (g.tail) acc = gf_mul(acc, cc->pw8[g.tail], poly) ^ tailraw[p];
     }
-    out[b] = ~acc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a2 = __shfl_down_sync(0xffffffffu, acc, d), m2 = __shfl_down_sync(0xffffffffu, mult, d);
+        if ((lane & (2 * d - 1)) == 0) {
+            acc = gf_mul(acc, m2, poly) ^ a2;
+            mult = gf_mul(mult, m2, poly);
+        }
+    }
+    if (lane == 0) out[b] = ~(gf_mul(0xffffffffu, mult, poly) ^ acc);
 }
 
 __global__ void verify_crcs_kernel(const uint32_t* crc, const uint32_t* expect, uint32_t n, uint32_t* n_bad,
@@ -650,9 +675,9 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
         walk_kernel<true, false><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.pieces, n, w.prefix, seg_shift, cc,
                                                                             w.partial, w.partial_cap, w.headraw, w.tailraw);
     }
-    fold_blocks_kernel<false><<<cdiv(n, 128), 128, 0, st>>>(w.pieces, w.prefix, nullptr, nullptr, n, seg_shift,
-                                                            gf_xpow(8ull << seg_shift, poly_of(poly)), cc, w.partial,
-                                                            w.headraw, w.tailraw, d_crc_out);
+    fold_blocks_kernel<false><<<cdiv(uint64_t(n) * 32, 256), 256, 0, st>>>(w.pieces, w.prefix, nullptr, nullptr, n, n, seg_shift,
+                                                                           gf_xpow(8ull << seg_shift, poly_of(poly)), cc,
+                                                                           w.partial, w.headraw, w.tailraw, d_crc_out);
     count_launch(4);
     CV_TRY(cudaGetLastError());
     CV_TRY(cudaFreeAsync(w.base, st));
@@ -704,8 +729,8 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
                 w.pieces, n_frames, w.prefix, seg_shift, cc, w.partial, w.partial_cap, w.headraw, w.tailraw);
         }
         mark_block_ranges_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_desc, n_frames, n_blocks, w.first, w.last);
-        fold_blocks_kernel<true><<<cdiv(n_blocks, 128), 128, 0, st>>>(
-            w.pieces, w.prefix, w.first, w.last, n_blocks, seg_shift, gf_xpow(8ull << seg_shift, poly_of(poly)), cc,
+        fold_blocks_kernel<true><<<cdiv(uint64_t(n_blocks) * 32, 256), 256, 0, st>>>(
+            w.pieces, w.prefix, w.first, w.last, n_blocks, n_frames, seg_shift, gf_xpow(8ull << seg_shift, poly_of(poly)), cc,
             w.partial, w.headraw, w.tailraw, d_block_crc);
         count_launch(3);
     } else {

@@ -110,7 +110,7 @@ std::string Namespace::dump() const {
     std::lock_guard<std::mutex> lk(mu_);
     std::string out = "# curvine-b200 namespace manifest v1\n";
     for (const auto& kv : files_) {
-        const FileBlocks& f = kv.second;
+        const FileBlocks& f = *kv.second;
         out += str_printf("file %s %lld %lld %lld %lld\n", f.status.path.c_str(), (long long)f.status.id, (long long)f.status.len,
                           (long long)f.status.block_size, (long long)f.status.mtime);
         for (const auto& b : f.block_locs) {
@@ -126,13 +126,13 @@ std::string Namespace::dump() const {
 }
 
 void Namespace::put(const FileBlocks& fb) {
+    std::shared_ptr<FileBlocks> c(new FileBlocks(fb));
+    c->build_index();
     std::lock_guard<std::mutex> lk(mu_);
-    FileBlocks c = fb;
-    c.build_index();
     files_[fb.status.path] = std::move(c);
 }
 
-Err Namespace::get_block_locations(const std::string& path, FileBlocks* out) const {
+Err Namespace::get_block_locations(const std::string& path, std::shared_ptr<const FileBlocks>* out) const {
     std::lock_guard<std::mutex> lk(mu_);
     auto it = files_.find(path);
     if (it == files_.end()) return Err(kFileNotFound, "File " + path + " not exists");
@@ -606,9 +606,8 @@ Err FsReader::open(FsContext* ctx, const std::string& path, std::unique_ptr<FsRe
     std::unique_ptr<FsReader> r(new FsReader());
     r->ctx_ = ctx;
     CV_RETURN_IF_ERR(ctx->ns.get_block_locations(path, &r->fb_));
-    r->fb_.build_index();
     const ClientConf& c = ctx->conf.client;
-    r->len_ = r->fb_.status.len;
+    r->len_ = r->fb_->status.len;
     r->chunk_size_ = c.read_chunk_size;
     r->slice_size_ = c.read_slice_size;
     r->det_ = ReadDetector(c, r->len_);
@@ -617,8 +616,8 @@ Err FsReader::open(FsContext* ctx, const std::string& path, std::unique_ptr<FsRe
     if (r->slice_size_ % c.read_chunk_size != 0 || r->slice_size_ < c.read_chunk_size)
         return Err::common("The slice size must be an integer multiple of the chunk size.");
     for (auto& s : split_slices(r->len_, r->slice_size_, r->det_.read_parallel))
-        if (!s.empty()) r->readers_.emplace_back(new FsReaderParallel(ctx, &r->fb_, std::move(s), false));
-    r->readers_.emplace_back(new FsReaderParallel(ctx, &r->fb_, {{0, r->len_}}, true));  // the random-read base reader
+        if (!s.empty()) r->readers_.emplace_back(new FsReaderParallel(ctx, r->fb_.get(), std::move(s), false));
+    r->readers_.emplace_back(new FsReaderParallel(ctx, r->fb_.get(), {{0, r->len_}}, true));  // the random-read base reader
     *out = std::move(r);
     return Err::ok();
 }

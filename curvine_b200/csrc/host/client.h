@@ -73,13 +73,13 @@ class Namespace {
    public:
     Err load(const std::string& manifest_path);
     Err load_string(const std::string& text);
-    Err get_block_locations(const std::string& path, FileBlocks* out) const;
+    Err get_block_locations(const std::string& path, std::shared_ptr<const FileBlocks>* out) const;  // shared, immutable
     void put(const FileBlocks& fb);
     std::string dump() const;
 
    private:
     mutable std::mutex mu_;
-    std::map<std::string, FileBlocks> files_;
+    std::map<std::string, std::shared_ptr<const FileBlocks>> files_;
 };
 
 // ------------------------------------------------------------------ block RPC client
@@ -229,7 +229,7 @@ class FsReader {
     int64_t len() const { return len_; }
     int64_t pos() const { return pos_; }
     int64_t chunk_size() const { return chunk_size_; }
-    const FileBlocks& file_blocks() const { return fb_; }
+    const FileBlocks& file_blocks() const { return *fb_; }
     FsContext* ctx() const { return ctx_; }
     // Reader::read_chunk(None) + pos advance == blocking_read: borrowed pointer valid until the next call
     Err read_chunk(const uint8_t** ptr, int64_t* n, int64_t max_len = -1);
@@ -244,7 +244,7 @@ class FsReader {
     Err buffer_read();
     Err buffer_seek(int64_t pos);
     FsContext* ctx_ = nullptr;
-    FileBlocks fb_;
+    std::shared_ptr<const FileBlocks> fb_;
     int64_t len_ = 0, pos_ = 0, bpos_ = 0, chunk_size_ = 0, slice_size_ = 0;
     ReadDetector det_;
     std::vector<std::unique_ptr<FsReaderParallel>> readers_;

@@ -318,8 +318,7 @@ void gpu_ingest_release(FsContext* ctx) {
 Err GpuFsReader::open(FsContext* ctx, const std::string& path, std::unique_ptr<GpuFsReader>* out) {
     std::unique_ptr<GpuFsReader> r(new GpuFsReader());
     r->ctx_ = ctx;
-    CV_RETURN_IF_ERR(ctx->ns.get_block_locations(path, &r->fb_));
-    r->fb_.build_index();
+    CV_RETURN_IF_ERR(ctx->ns.get_block_locations(path, &r->fbp_));
     Err e;
     r->ing_ = gpu_ingest_get(ctx, &e);
     if (e) return e;
@@ -357,8 +356,8 @@ Err GpuFsReader::read_device(void* d_dst, int64_t cap, void* stream, int64_t* n)
     while (p < end) {
         int64_t boff;
         size_t idx;
-        CV_RETURN_IF_ERR(fb_.get_read_block(p, &boff, &idx));
-        const int64_t blen = fb_.block_locs[idx].block.len;
+        CV_RETURN_IF_ERR((*fbp_).get_read_block(p, &boff, &idx));
+        const int64_t blen = (*fbp_).block_locs[idx].block.len;
         const int64_t take = std::min(end - p, blen - boff);
         jobs.push_back(Job{idx, boff, take, p - pos_, boff == 0 && take == blen});
         p += take;
@@ -387,7 +386,7 @@ Err GpuFsReader::read_device_sharded(int rank, int world, void* d_dst, int64_t c
     *n = 0;
     std::vector<ShardJob> plan;
     int64_t total = 0;
-    CV_RETURN_IF_ERR(plan_shard(fb_, rank, world, cap, &plan, &total));
+    CV_RETURN_IF_ERR(plan_shard(*fbp_, rank, world, cap, &plan, &total));
     std::vector<Job> jobs;
     for (const auto& p : plan) jobs.push_back(Job{p.block, 0, p.len, p.dst_off, true});
     CV_RETURN_IF_ERR(run_jobs(jobs, static_cast<uint8_t*>(d_dst), stream));
@@ -612,7 +611,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     std::vector<uint8_t> mode(J, kPlain);
     bool call_framed = false;
     for (size_t j = 0; j < J; j++) {
-        const LocatedBlock& lb = fb_.block_locs[jobs[j].block];
+        const LocatedBlock& lb = (*fbp_).block_locs[jobs[j].block];
         if (lb.locs.empty()) {
             if (!lb.block.has_alloc_opts) return Err::common("There is no available worker, locs: [], failed workers: []");
             mode[j] = kHole;
@@ -629,7 +628,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         first_frame[j] = static_cast<uint32_t>(F);
         size_t bytes = static_cast<size_t>(jobs[j].n);
         if (mode[j] != kHole && call_framed) {
-            const bool to_block_end = jobs[j].block_off + jobs[j].n == fb_.block_locs[jobs[j].block].block.len;
+            const bool to_block_end = jobs[j].block_off + jobs[j].n == (*fbp_).block_locs[jobs[j].block].block.len;
             mode[j] = to_block_end ? kFramed : kUnpacked;
             if (mode[j] == kFramed) {
                 const size_t nfr = static_cast<size_t>((jobs[j].n + chunk - 1) / chunk);
@@ -672,7 +671,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     uint32_t* h_exp = reinterpret_cast<uint32_t*>(&h[o_exp]);
     size_t f0 = J, f1 = 0, n_compared = 0;
     for (size_t j = 0; j < J; j++) {
-        const LocatedBlock& lb = fb_.block_locs[jobs[j].block];
+        const LocatedBlock& lb = (*fbp_).block_locs[jobs[j].block];
         h_off[j] = static_cast<uint64_t>(jobs[j].dst_off);
         h_len[j] = static_cast<uint64_t>(jobs[j].n);
         h_exp[j] = poly ? lb.crc32c : lb.crc32;
@@ -750,7 +749,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                 std::vector<int64_t> lens(j1 - j0), rids(j1 - j0);
                 Err e;
                 for (size_t j = j0; j < j1 && !e; j++) {
-                    const LocatedBlock& lb = fb_.block_locs[jobs[j].block];
+                    const LocatedBlock& lb = (*fbp_).block_locs[jobs[j].block];
                     e = open_short_circuit(ctx_, lb, jobs[j].block_off, &conn, &rids[j - j0], &paths[j - j0]);
                     lens[j - j0] = lb.block.len;
                 }
@@ -793,7 +792,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                         std::lock_guard<std::mutex> lk(held_mu);
                         held_maps_.push_back(m);
                     }
-                    for (size_t j = j0; j < j1 && !e; j++) e = conn->read_commit(fb_.block_locs[jobs[j].block].block, rids[j - j0], 1);
+                    for (size_t j = j0; j < j1 && !e; j++) e = conn->read_commit((*fbp_).block_locs[jobs[j].block].block, rids[j - j0], 1);
                 }
                 fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
                 if (e && e.kind == kUnsupported) {
@@ -835,10 +834,10 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                 size_t wire = 0;
                 const double t0 = now_sec();
                 const FetchMode fm = mode[j] == kPlain ? kFetchShortCircuit : mode[j] == kFramed ? kFetchFramedVerbatim : kFetchFramedUnpacked;
-                Err e = fetch_job(ctx_, fb_.block_locs[job.block], job.block_off, job.n, fm, chunk, hs + in_slot, &conn, &req_ids[j], &wire);
+                Err e = fetch_job(ctx_, (*fbp_).block_locs[job.block], job.block_off, job.n, fm, chunk, hs + in_slot, &conn, &req_ids[j], &wire);
                 fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
                 if (e) {
-                    st.fail(e.ctx(str_printf("block %lld", (long long)fb_.block_locs[job.block].block.id)));
+                    st.fail(e.ctx(str_printf("block %lld", (long long)(*fbp_).block_locs[job.block].block.id)));
                     failed = true;
                     break;
                 }

@@ -46,10 +46,10 @@ class GpuFsReader {
    public:
     static Err open(FsContext* ctx, const std::string& path, std::unique_ptr<GpuFsReader>* out);
     ~GpuFsReader();
-    int64_t len() const { return fb_.status.len; }
+    int64_t len() const { return fbp_->status.len; }
     int64_t pos() const { return pos_; }
     Err seek(int64_t pos);
-    const FileBlocks& file_blocks() const { return fb_; }
+    const FileBlocks& file_blocks() const { return *fbp_; }
     // Next min(cap, remaining) bytes -> d_dst, ordered on `stream` when the call returns.  *n = bytes.
     Err read_device(void* d_dst, int64_t cap, void* stream, int64_t* n);
     // Round-robin shard of the whole file: blocks b with b % world == rank land back to back in slots of
@@ -72,7 +72,7 @@ class GpuFsReader {
     GpuFsReader() = default;
     Err run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* stream);
     FsContext* ctx_ = nullptr;
-    FileBlocks fb_;
+    std::shared_ptr<const FileBlocks> fbp_;
     int64_t pos_ = 0;
     GpuReadStats stats_;
     GpuIngest* ing_ = nullptr;

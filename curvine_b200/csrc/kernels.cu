@@ -332,14 +332,20 @@ __device__ __forceinline__ uint32_t walk_segment(const uint8_t* src, uint8_t* ds
         const uint8_t* s = src + lane * 16u;
         uint4* dp = reinterpret_cast<uint4*>(dst) + lane;
         uint32_t j = 0;
-        for (; j + 2 <= R; j += 2) {
+        for (; j + 4 <= R; j += 4) {  // 4 rows (8 aligned loads when shifted) in flight per lane
             const uint4 v0 = load_shifted(s + (j + 0) * 512u, sh);
             const uint4 v1 = load_shifted(s + (j + 1) * 512u, sh);
+            const uint4 v2 = load_shifted(s + (j + 2) * 512u, sh);
+            const uint4 v3 = load_shifted(s + (j + 3) * 512u, sh);
             dp[(j + 0) * 32] = v0;
             dp[(j + 1) * 32] = v1;
+            dp[(j + 2) * 32] = v2;
+            dp[(j + 3) * 32] = v3;
             if (CRC) {
                 CV_STEP(v0);
                 CV_STEP(v1);
+                CV_STEP(v2);
+                CV_STEP(v3);
             }
         }
         for (; j < R; j++) {
@@ -549,9 +555,10 @@ static int ensure_device(int* dev_out) {
 }
 
 static uint32_t pick_seg_shift(uint64_t total_bytes, int sm_count) {
-    // ~16 units per warp keeps the contiguous per-CTA ranges balanced; 4 KiB..1 MiB segments
+    // ~16 units per warp keeps the contiguous per-CTA ranges balanced for big inputs; small inputs get 16 KiB segments
+    // (4 KiB below 4 MiB) so the per-block fold stays short.  4 KiB..1 MiB.
     const uint64_t target = total_bytes / (uint64_t(sm_count) * 32 * 16 + 1);
-    uint32_t s = 12;
+    uint32_t s = total_bytes >= (4u << 20) ? 14 : 12;
     while (s < 20 && (1ull << s) < target) s++;
     return s;
 }

@@ -260,6 +260,19 @@ def main():
         barrier(dist)
         t_d = sampler.mark()
         val_ms = a.elapsed_time(b) / args.steps
+        if os.environ.get("CVB_DEBUG"):
+            ev = []
+            for _ in range(3):
+                x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.time()
+                x.record()
+                resident_step()
+                y.record()
+                t1 = time.time()
+                y.synchronize()
+                ev.append((x.elapsed_time(y), (t1 - t0) * 1e3))
+            print("[debug rank %d] torch dev %d val_ms %.3f per-step (gpu_ms, host_enqueue_ms) %s" % (rank, torch.cuda.current_device(), val_ms, ev),
+                  file=sys.stderr, flush=True)
         walk_ms, walk_n = ctypes.c_double(), ctypes.c_uint32()
         _lib.check(L.cvk_profile_collect(ctypes.byref(walk_ms), ctypes.byref(walk_n)), "cvk_profile_collect")
         L.cvk_profile_enable(0)

@@ -598,6 +598,15 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     GpuIngest& G = *ing_;
     std::lock_guard<std::mutex> call_lock(G.mu);
     CU_TRY(cudaSetDevice(G.device));
+    {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, d_dst) != cudaSuccess || pa.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            return Err::common("cv_read_device: destination is not device memory");
+        }
+        if (pa.device != G.device)
+            return Err::common(str_printf("cv_read_device: destination lives on device %d but [b200] device = %d", pa.device, G.device));
+    }
     if (G.pending_owner && G.pending_owner != this) CV_RETURN_IF_ERR(G.pending_owner->harvest());  // shared tables
     CV_RETURN_IF_ERR(harvest());
     const B200Conf& bc = ctx_->conf.b200;

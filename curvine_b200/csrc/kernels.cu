@@ -530,6 +530,24 @@ static bool g_ready[kMaxDev];
         if (e_ != cudaSuccess) return int(e_); \
     } while (0)
 
+// Launch on the device that owns the data, whatever the calling thread's current device is (a host that links
+// its own CUDA runtime -- torch, a Rust crate -- may not share "current device" state with this library).
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const void* device_ptr) {
+        cudaGetDevice(&prev);
+        dev = prev;
+        cudaPointerAttributes a;
+        if (device_ptr && cudaPointerGetAttributes(&a, device_ptr) == cudaSuccess && a.type == cudaMemoryTypeDevice) dev = a.device;
+        else cudaGetLastError();
+        if (dev != prev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 static int ensure_device(int* dev_out) {
     int dev = 0;
     CV_TRY(cudaGetDevice(&dev));
@@ -668,6 +686,7 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
                    uint64_t total_bytes, uint32_t* d_crc_out, cv_stream_t stream) {
     if (n == 0) return 0;
     if (poly != 0 && poly != 1) return int(cudaErrorInvalidValue);
+    DeviceGuard guard(d_crc_out);
     int dev;
     if (int rc = ensure_device(&dev)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -694,6 +713,7 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
 int cvk_verify_crcs(const uint32_t* d_crc, const uint32_t* d_expect, uint32_t n, uint32_t* d_n_bad,
                     uint8_t* d_bad_mask, cv_stream_t stream) {
     if (n == 0) return 0;
+    DeviceGuard guard(d_crc);
     verify_crcs_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_crc, d_expect, n, d_n_bad,
                                                                                    d_bad_mask);
     count_launch();
@@ -703,6 +723,7 @@ int cvk_verify_crcs(const uint32_t* d_crc, const uint32_t* d_expect, uint32_t n,
 int cvk_expand_streams(const CvStreamDesc* d_streams, uint32_t n_streams, CvFrameDesc* d_desc_out, uint32_t n_frames,
                        cv_stream_t stream) {
     if (n_streams == 0) return 0;
+    DeviceGuard guard(d_desc_out);
     expand_streams_kernel<<<cdiv(uint64_t(n_streams) * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         d_streams, n_streams, d_desc_out, n_frames);
     count_launch();
@@ -714,6 +735,7 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
                          uint32_t* d_err_flags, cv_stream_t stream) {
     if (n_frames == 0) return 0;
     if (poly != 0 && poly != 1) return int(cudaErrorInvalidValue);
+    DeviceGuard guard(d_out);
     int dev;
     if (int rc = ensure_device(&dev)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -776,6 +798,7 @@ static int copy_pieces(Workspace& w, uint32_t n, uint32_t seg_shift, int dev, cu
 int cvk_gather_pages(const uint8_t* d_src, const CvSeg* d_segs, uint32_t n, uint64_t total_bytes, uint8_t* d_dst,
                      cv_stream_t stream) {
     if (n == 0) return 0;
+    DeviceGuard guard(d_dst);
     int dev;
     if (int rc = ensure_device(&dev)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -791,6 +814,7 @@ int cvk_deinterleave_blocks(const uint8_t* d_gathered, uint64_t shard_stride, ui
                             uint64_t n_blocks, uint64_t file_len, uint8_t* d_dst, cv_stream_t stream) {
     if (n_blocks == 0) return 0;
     if (world == 0 || block_size == 0 || n_blocks > 0x7fffffffull) return int(cudaErrorInvalidValue);
+    DeviceGuard guard(d_dst);
     int dev;
     if (int rc = ensure_device(&dev)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -193,8 +193,26 @@ def run_e2e(fs, path, rank, world, dst, shard_bytes, steps, warmup, dist):
     return times, stats, last
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything incidental (NCCL's version banner, library chatter) goes to stderr: stdout carries exactly one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         return main_reference(args)
     import numpy as np
@@ -367,7 +385,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
 
 
 def cpu_run(state, n_total, sc, parallel, limit, checksum=1):
@@ -437,7 +455,7 @@ def main_reference(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":

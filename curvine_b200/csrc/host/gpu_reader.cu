@@ -734,8 +734,8 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     const int T_threads = static_cast<int>(std::min<size_t>(static_cast<size_t>(std::max(1, bc.fetch_threads)), NG));
     std::vector<double> fetch_sec(static_cast<size_t>(T_threads), 0.0);
     std::vector<uint64_t> h2d(static_cast<size_t>(T_threads), 0);
-    auto worker = [&](int t) {
-        G.bind_thread();
+    auto worker = [&](int t, bool own_thread) {
+        if (own_thread) G.bind_thread();  // an inline call (single copy group: small reads) must not re-pin the caller
         cudaSetDevice(G.device);
         cudaStream_t cs = G.copy_streams[static_cast<size_t>(t) % G.copy_streams.size()];
         std::unique_ptr<BlockClient> conn;
@@ -879,7 +879,9 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         if (conn) ctx_->release(std::move(conn));
     };
     std::vector<std::thread> threads;
-    for (int t = 0; t < T_threads; t++) threads.emplace_back(worker, t);
+    if (T_threads == 1) worker(0, false);  // small read (FUSE-shaped, C5): no thread spawn on the latency path
+    else
+        for (int t = 0; t < T_threads; t++) threads.emplace_back(worker, t, true);
 
     // ---- verifier: this thread walks the copy groups in order, `vgroups` at a time
     Err verr;

@@ -282,3 +282,35 @@ def test_oracle_cpu_reader_against_product_worker(cluster, sc, parallel):
     got, cks, _ = clib.cpu_read_file(w.port, sc, n, bs, ids, 65536, 4, parallel, 131072, limit=3 << 20, checksum=0)
     assert got == 3 << 20 and cks == clib.bench_checksum(data[:3 << 20], 131072)
     assert clib.crc32_pclmul(data) == zlib.crc32(data)
+
+
+def test_replica_failover_on_read_error(tmp_path):
+    """block_reader.rs:217-254: a read error drops that worker and reopens at pos on the next replica.
+    (Open-time errors are NOT failed over in the reference -- the `?` inside get_reader's block propagates,
+    block_reader.rs:168-215 -- so the test kills the worker that serves the block being read, mid-block.)"""
+    import shutil
+    d1, d2 = tmp_path / "w1", tmp_path / "w2"
+    n, ino = (4 << 20) + 99, 4600
+    w1 = F.MiniWorker(["[MEM]" + str(d1)])
+    man = w1.create_file("/ha", ino, n, 8 << 20)  # one block
+    shutil.copytree(str(d1), str(d2))
+    w2 = F.MiniWorker(["[MEM]" + str(d2)])  # rescans active/ on start (vfs_dir.rs:339-362)
+    assert w2.metrics()["num_blocks"] == 1
+    want = synth.file_bytes(ino, n, 8 << 20)
+    man2 = "\n".join(l + ",localhost:%d:2" % w2.port if l.startswith("block ") else l for l in man.splitlines())
+    try:
+        with F.CurvineFileSystem(F.client_conf(short_circuit=False, read_chunk_size="64KB")) as fs:
+            fs.load_namespace(man2)
+            r = fs.open("/ha")
+            got = r.read_full((1 << 20) + 5000)
+            serving = w1 if w1.metrics()["read_blocks_remote"] else w2
+            assert (w1.metrics()["read_blocks_remote"] + w2.metrics()["read_blocks_remote"]) == 1
+            serving.stop()
+            got += r.read_full(n)
+            assert got == want and r.pos() == n
+            other = w2 if serving is w1 else w1
+            assert other.metrics()["read_blocks_remote"] == 1  # reopened at pos on the surviving replica
+            r.complete()
+    finally:
+        w1.stop()
+        w2.stop()

@@ -216,3 +216,25 @@ def test_deinterleave_blocks(cuda, world):
     dst = torch.zeros(file_len, dtype=torch.uint8, device=cuda)
     K.deinterleave_blocks(_to_dev(gathered, cuda), stride, world, bs, nb, file_len, dst)
     assert dst.cpu().numpy().tobytes() == data.tobytes()
+
+
+def test_crc_hypothesis_random_buffers(cuda):
+    """SURVEY §7 parity test 7: GPU == zlib.crc32 (== crc32fast) and == CRC-32C oracle on generated buffers,
+    lengths and base alignments drawn by hypothesis."""
+    from hypothesis import given, settings, strategies as st
+    from curvine_b200 import kernels as K
+    big = _rand(3 << 20, 77)
+    d_big = _to_dev(big, cuda)
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, (3 << 20) - 1), st.integers(0, 300000)), min_size=1, max_size=12), st.integers(0, 1))
+    def run(spans, poly):
+        offs = [o for o, _ in spans]
+        lens = [min(n, len(big) - o) for o, n in spans]
+        got = K.u32(K.crc_blocks(d_big, offs, lens, poly))
+        for g, o, n in zip(got, offs, lens):
+            assert int(g) == clib.crc(poly, big[o:o + n])
+            if poly == 0:
+                assert int(g) == zlib.crc32(big[o:o + n].tobytes())
+
+    run()

@@ -1,0 +1,75 @@
+"""Config C5: 4096 x 256 KiB single-block files, mem tier, random order, 1 GPU.  FUSE-shaped access per file:
+open -> fuse_read(0, 256 KiB) -> close.  Reports files/s, GB/s and p50/p99 per-file latency for
+  gpu   cv_open + cv_fuse_read_device (bytes into HBM scratch, scattered into 64 x 4 KiB page buffers by K3, CRC-verified) + close
+  cpu   the oracle's reference-shaped CPU reader (oracle/cpu_reader.c) reading each file into host memory with crc32."""
+import argparse
+import json
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--files", type=int, default=4096)
+    ap.add_argument("--size", type=int, default=256 * 1024)
+    ap.add_argument("--zero-copy", type=int, default=1)
+    a = ap.parse_args()
+    import torch
+    from curvine_b200 import fs as F
+    from oracle import clib, layout
+    torch.cuda.set_device(0)
+    d = tempfile.mkdtemp(prefix="cvc5_", dir="/dev/shm")
+    res = {}
+    try:
+        with F.MiniWorker(["[MEM]" + d], hostname="localhost") as w:
+            mans = [w.create_file("/small/f%d" % i, 100000 + i, a.size, a.size, threads=1) for i in range(a.files)]
+            order = np.random.default_rng(7).permutation(a.files)  # Fisher-Yates, seed 7
+            conf = F.client_conf(hostname="localhost", short_circuit=True,
+                                 b200='zero_copy = %s\nregister_cache = "4GB"\nfetch_threads = 4\nverify_batch = 4\ncopy_group = 1\n' % ("true" if a.zero_copy else "false"))
+            with F.CurvineFileSystem(conf) as fs:
+                fs.load_namespace("\n".join(mans))
+                scratch = torch.empty(a.size, dtype=torch.uint8, device="cuda")
+                npages = a.size // 4096
+                pages = torch.empty(npages * 4096, dtype=torch.uint8, device="cuda")
+                offs = [i * 4096 for i in range(npages)]
+                stream = torch.cuda.current_stream().cuda_stream
+                for rep in range(2):  # rep 0 warms (registers mappings); rep 1 is reported
+                    lat = []
+                    t0 = time.perf_counter()
+                    for i in order:
+                        t1 = time.perf_counter()
+                        r = fs.open("/small/f%d" % i)
+                        got = r.fuse_read_device(0, a.size, scratch.data_ptr(), pages.data_ptr(), offs, 4096, stream)
+                        s, bad, ver = r.verify()
+                        r.complete()
+                        torch.cuda.current_stream().synchronize()
+                        assert got == a.size and bad == 0 and ver == 1
+                        lat.append(time.perf_counter() - t1)
+                    dt = time.perf_counter() - t0
+                    lat = np.array(lat) * 1e6
+                    res["gpu_rep%d" % rep] = {"files_per_s": a.files / dt, "GBps": a.files * a.size / dt / 1e9, "p50_us": float(np.percentile(lat, 50)),
+                                              "p99_us": float(np.percentile(lat, 99))}
+            lat = []
+            t0 = time.perf_counter()
+            for i in order:
+                t1 = time.perf_counter()
+                clib.cpu_read_file(w.port, True, a.size, a.size, [layout.create_block_id(100000 + int(i), 0)], 131072, 8, 1, 131072, 0, 1)
+                lat.append(time.perf_counter() - t1)
+            dt = time.perf_counter() - t0
+            lat = np.array(lat) * 1e6
+            res["cpu_reference_port"] = {"files_per_s": a.files / dt, "GBps": a.files * a.size / dt / 1e9, "p50_us": float(np.percentile(lat, 50)),
+                                         "p99_us": float(np.percentile(lat, 99)), "note": "open+read+crc32 into host memory, 2 threads (1 sub-reader + caller)"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,8 @@ def _declare(L):
     L.cv_read_device.argtypes, L.cv_read_device.restype = [vp, vp, i64, vp, cp(i64)], i64
     L.cv_read_device_sharded.argtypes = [vp, i32, i32, vp, i64, vp, cp(i64)]
     L.cv_read_device_sharded.restype = i64
+    L.cv_read_many_device.argtypes = [vp, cp(c), i32, vp, vp, i64, vp, cp(u64), cp(u32), cp(u64), cp(i64)]
+    L.cv_read_many_device.restype = i64
     L.cv_shard_plan.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, cp(i32), cp(i64)]
     L.cv_shard_plan.restype = i64
     L.cv_fuse_read_device.argtypes = [vp, i64, i64, vp, vp, vp, i32, i64, vp, cp(i64)]
@@ -107,7 +109,7 @@ EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_unpack_frames",
            "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_launch_count", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
            "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_metrics",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
-           "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_shard_plan", "cv_fuse_read_device",
+           "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device",
            "cv_verify", "cv_device_stats", "cv_worker_start", "cv_worker_stop", "cv_worker_metrics",
            "cv_synth_create_file", "cv_synth_block", "cv_host_crc"]
 

@@ -217,6 +217,23 @@ int64_t cv_read_device_sharded(cv_reader* r, int32_t rank, int32_t world, void* 
     API_GUARD_END
 }
 
+int64_t cv_read_many_device(cv_fs* fs, const char* const* paths, int32_t n, void* d_dst, const int64_t* dst_offs, int64_t cap, cv_stream_t stream,
+                            uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified, int64_t* total_bytes) {
+    API_GUARD_BEGIN
+    std::vector<std::string> ps;
+    for (int32_t i = 0; i < n; i++) ps.emplace_back(paths[i]);
+    uint64_t s = 0, v = 0;
+    uint32_t b = 0;
+    int64_t t = 0;
+    API_TRY(GpuFsReader::read_many(fs->ctx.get(), ps, dst_offs, d_dst, cap, stream, &s, &b, &v, &t));
+    if (sum_crc) *sum_crc = s;
+    if (n_bad) *n_bad = b;
+    if (n_verified) *n_verified = v;
+    if (total_bytes) *total_bytes = t;
+    return ok();
+    API_GUARD_END
+}
+
 int64_t cv_shard_plan(cv_reader* r, int32_t rank, int32_t world, int64_t* block_index, int64_t* file_off, int64_t* len, int64_t* dst_off,
                       int32_t cap, int32_t* n, int64_t* total_bytes) {
     API_GUARD_BEGIN

@@ -359,7 +359,7 @@ Err GpuFsReader::read_device(void* d_dst, int64_t cap, void* stream, int64_t* n)
         CV_RETURN_IF_ERR((*fbp_).get_read_block(p, &boff, &idx));
         const int64_t blen = (*fbp_).block_locs[idx].block.len;
         const int64_t take = std::min(end - p, blen - boff);
-        jobs.push_back(Job{idx, boff, take, p - pos_, boff == 0 && take == blen});
+        jobs.push_back(Job{&(*fbp_).block_locs[idx], boff, take, p - pos_, boff == 0 && take == blen});
         p += take;
     }
     CV_RETURN_IF_ERR(run_jobs(jobs, static_cast<uint8_t*>(d_dst), stream));
@@ -388,7 +388,7 @@ Err GpuFsReader::read_device_sharded(int rank, int world, void* d_dst, int64_t c
     int64_t total = 0;
     CV_RETURN_IF_ERR(plan_shard(*fbp_, rank, world, cap, &plan, &total));
     std::vector<Job> jobs;
-    for (const auto& p : plan) jobs.push_back(Job{p.block, 0, p.len, p.dst_off, true});
+    for (const auto& p : plan) jobs.push_back(Job{&(*fbp_).block_locs[p.block], 0, p.len, p.dst_off, true});
     CV_RETURN_IF_ERR(run_jobs(jobs, static_cast<uint8_t*>(d_dst), stream));
     *n = total;
     return Err::ok();
@@ -620,7 +620,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     std::vector<uint8_t> mode(J, kPlain);
     bool call_framed = false;
     for (size_t j = 0; j < J; j++) {
-        const LocatedBlock& lb = (*fbp_).block_locs[jobs[j].block];
+        const LocatedBlock& lb = (*jobs[j].lb);
         if (lb.locs.empty()) {
             if (!lb.block.has_alloc_opts) return Err::common("There is no available worker, locs: [], failed workers: []");
             mode[j] = kHole;
@@ -637,7 +637,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         first_frame[j] = static_cast<uint32_t>(F);
         size_t bytes = static_cast<size_t>(jobs[j].n);
         if (mode[j] != kHole && call_framed) {
-            const bool to_block_end = jobs[j].block_off + jobs[j].n == (*fbp_).block_locs[jobs[j].block].block.len;
+            const bool to_block_end = jobs[j].block_off + jobs[j].n == (*jobs[j].lb).block.len;
             mode[j] = to_block_end ? kFramed : kUnpacked;
             if (mode[j] == kFramed) {
                 const size_t nfr = static_cast<size_t>((jobs[j].n + chunk - 1) / chunk);
@@ -680,7 +680,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     uint32_t* h_exp = reinterpret_cast<uint32_t*>(&h[o_exp]);
     size_t f0 = J, f1 = 0, n_compared = 0;
     for (size_t j = 0; j < J; j++) {
-        const LocatedBlock& lb = (*fbp_).block_locs[jobs[j].block];
+        const LocatedBlock& lb = (*jobs[j].lb);
         h_off[j] = static_cast<uint64_t>(jobs[j].dst_off);
         h_len[j] = static_cast<uint64_t>(jobs[j].n);
         h_exp[j] = poly ? lb.crc32c : lb.crc32;
@@ -758,7 +758,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                 std::vector<int64_t> lens(j1 - j0), rids(j1 - j0);
                 Err e;
                 for (size_t j = j0; j < j1 && !e; j++) {
-                    const LocatedBlock& lb = (*fbp_).block_locs[jobs[j].block];
+                    const LocatedBlock& lb = (*jobs[j].lb);
                     e = open_short_circuit(ctx_, lb, jobs[j].block_off, &conn, &rids[j - j0], &paths[j - j0]);
                     lens[j - j0] = lb.block.len;
                 }
@@ -801,7 +801,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                         std::lock_guard<std::mutex> lk(held_mu);
                         held_maps_.push_back(m);
                     }
-                    for (size_t j = j0; j < j1 && !e; j++) e = conn->read_commit((*fbp_).block_locs[jobs[j].block].block, rids[j - j0], 1);
+                    for (size_t j = j0; j < j1 && !e; j++) e = conn->read_commit((*jobs[j].lb).block, rids[j - j0], 1);
                 }
                 fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
                 if (e && e.kind == kUnsupported) {
@@ -843,10 +843,10 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                 size_t wire = 0;
                 const double t0 = now_sec();
                 const FetchMode fm = mode[j] == kPlain ? kFetchShortCircuit : mode[j] == kFramed ? kFetchFramedVerbatim : kFetchFramedUnpacked;
-                Err e = fetch_job(ctx_, (*fbp_).block_locs[job.block], job.block_off, job.n, fm, chunk, hs + in_slot, &conn, &req_ids[j], &wire);
+                Err e = fetch_job(ctx_, (*job.lb), job.block_off, job.n, fm, chunk, hs + in_slot, &conn, &req_ids[j], &wire);
                 fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
                 if (e) {
-                    st.fail(e.ctx(str_printf("block %lld", (long long)(*fbp_).block_locs[job.block].block.id)));
+                    st.fail(e.ctx(str_printf("block %lld", (long long)(*job.lb).block.id)));
                     failed = true;
                     break;
                 }
@@ -948,6 +948,32 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     stats_.wall_sec += now_sec() - t_start;
     stats_.reg_hits = G.reg.hits.load(), stats_.reg_misses = G.reg.misses.load();
     return Err::ok();
+}
+
+Err GpuFsReader::read_many(FsContext* ctx, const std::vector<std::string>& paths, const int64_t* dst_offs, void* d_dst, int64_t cap, void* stream,
+                            uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified, int64_t* total_bytes) {
+    std::unique_ptr<GpuFsReader> r(new GpuFsReader());
+    r->ctx_ = ctx;
+    Err e;
+    r->ing_ = gpu_ingest_get(ctx, &e);
+    if (e) return e;
+    std::vector<Job> jobs;
+    int64_t total = 0;
+    for (size_t i = 0; i < paths.size(); i++) {
+        std::shared_ptr<const FileBlocks> fb;
+        CV_RETURN_IF_ERR(ctx->ns.get_block_locations(paths[i], &fb));
+        r->held_files_.push_back(fb);
+        if (dst_offs[i] < 0 || dst_offs[i] + fb->status.len > cap) return Err::common("destination too small for " + paths[i]);
+        for (size_t b = 0; b < fb->block_locs.size(); b++) {
+            const int64_t blen = fb->block_locs[b].block.len;
+            if (blen > 0) jobs.push_back(Job{&fb->block_locs[b], 0, blen, dst_offs[i] + fb->starts[b], true});
+        }
+        total += fb->status.len;
+    }
+    if (!r->held_files_.empty()) r->fbp_ = r->held_files_[0];
+    CV_RETURN_IF_ERR(r->run_jobs(jobs, static_cast<uint8_t*>(d_dst), stream));
+    if (total_bytes) *total_bytes = total;
+    return r->verify(sum_crc, n_bad, n_verified);
 }
 
 }  // namespace cv

@@ -60,10 +60,14 @@ class GpuFsReader {
     Err verify(uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified);
     const GpuReadStats& stats() const { return stats_; }
     Err complete();
+    // Many whole files in one pipelined call (small-file batching, C5): file i lands at d_dst + dst_offs[i].
+    // Blocks until verified.  Static: uses a throw-away reader on the context's ingest.
+    static Err read_many(FsContext* ctx, const std::vector<std::string>& paths, const int64_t* dst_offs, void* d_dst, int64_t cap, void* stream,
+                         uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified, int64_t* total_bytes);
 
    private:
     struct Job {
-        size_t block;        // index into fb_.block_locs
+        const LocatedBlock* lb;  // the block (owned by a FileBlocks kept alive for the call)
         int64_t block_off;   // first byte of the block this job needs
         int64_t n;           // bytes
         int64_t dst_off;     // where they go in d_dst
@@ -80,7 +84,8 @@ class GpuFsReader {
     uint32_t n_bad_ = 0;
     uint64_t n_bad_frames_ = 0;
     uint32_t first_frame_err_ = 0;
-    std::vector<std::shared_ptr<struct RegMapping>> held_maps_;  // registered mappings with copies still in flight
+    std::vector<std::shared_ptr<struct RegMapping>> held_maps_;
+    std::vector<std::shared_ptr<const FileBlocks>> held_files_;  // read_many: keeps the LocatedBlocks alive  // registered mappings with copies still in flight
     struct Pending {
         bool active = false;
         size_t jobs = 0, frames = 0, f0 = 0, f1 = 0, n_compared = 0;

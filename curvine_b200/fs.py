@@ -189,6 +189,16 @@ class CurvineFileSystem:
         _check(_lib.lib().cv_open(self._h, path.encode(), ctypes.byref(h), ctypes.byref(n)))
         return Reader(h)
 
+    def read_many_device(self, paths, d_ptr: int, dst_offs, cap: int, stream: int = 0):
+        """Small-file batching: every file of ``paths`` lands at d_ptr + dst_offs[i] in one pipelined pass.
+        -> (total_bytes, sum_crc, n_bad, n_verified)."""
+        arr = (ctypes.c_char_p * len(paths))(*[p.encode() for p in paths])
+        offs = (ctypes.c_int64 * len(paths))(*dst_offs)
+        s, b, v, t = ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_uint64(), ctypes.c_int64()
+        _check(_lib.lib().cv_read_many_device(self._h, arr, len(paths), ctypes.c_void_p(d_ptr), offs, cap, ctypes.c_void_p(stream),
+                                              ctypes.byref(s), ctypes.byref(b), ctypes.byref(v), ctypes.byref(t)))
+        return t.value, s.value, b.value, v.value
+
     def metrics(self) -> dict:
         a = (ctypes.c_int64 * 2)()
         _check(_lib.lib().cv_fs_metrics(self._h, a))

@@ -19,7 +19,7 @@
  *   cv_fuse_read                 Reader::fuse_read                         reader.rs:101-124
  *   cv_seek / cv_pos / cv_len    Reader::seek / pos / len                  reader.rs:23-48, fs_reader.rs:109-126
  *   cv_close_reader              Reader::complete + drop                   java_abi.rs:157-166
- *   cv_read_device, cv_read_device_sharded, cv_verify, cv_fuse_read_device
+ *   cv_read_device, cv_read_device_sharded, cv_read_many_device, cv_verify, cv_fuse_read_device
  *                                the CUDA counterpart the north_star adds behind the same reader handle
  *                                (no reference counterpart: the reference has no GPU code)
  * The cv_worker_* and cv_synth_* entry points are the test/bench fixture (the analogue of the reference's
@@ -85,6 +85,11 @@ int64_t cv_read_device(cv_reader* r, void* d_dst, int64_t cap, cv_stream_t strea
 /* blocks b with b % world == rank, back to back in block_size slots (slot j = block j*world+rank) */
 int64_t cv_read_device_sharded(cv_reader* r, int32_t rank, int32_t world, void* d_dst, int64_t cap,
                                cv_stream_t stream, int64_t* nbytes);
+/* Small-file batching (config C5): n whole files in ONE pipelined pass; file i lands at d_dst + dst_offs[i].
+ * Open/Complete RPCs, H2D copies and CRC launches of all files overlap; returns after verification
+ * (sum_crc / n_bad / n_verified as in cv_verify).  Replaces n x (FileSystem::open + Reader::fuse_read + complete). */
+int64_t cv_read_many_device(cv_fs* fs, const char* const* paths, int32_t n, void* d_dst, const int64_t* dst_offs, int64_t cap,
+                            cv_stream_t stream, uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified, int64_t* total_bytes);
 /* The plan cv_read_device_sharded executes (host-only, no GPU needed): for i < *n, block_index[i] of the file starts
  * at file_off[i], is len[i] bytes long and lands at dst_off[i] = i * block_size.  Arrays may be NULL; cap = their length. */
 int64_t cv_shard_plan(cv_reader* r, int32_t rank, int32_t world, int64_t* block_index, int64_t* file_off, int64_t* len,

@@ -244,3 +244,31 @@ def test_zero_copy_registered_mappings(cuda, cluster, copy_group):
         torch.cuda.synchronize()
         assert bad == 2 and dst.cpu().numpy().tobytes() == bytes(want)
         r.complete()
+
+
+@pytest.mark.parametrize("zero_copy", [False, True])
+def test_read_many_small_files_in_one_pass(cuda, cluster, zero_copy):
+    """C5 batching: many single-block files in one pipelined call; bytes, CRC sum and verify count match the oracle."""
+    import torch
+    w, _ = cluster
+    size, nfiles = 256 * 1024, 48
+    mans = [w.create_file("/many/f%d" % i, 7100 + i, size - (i % 3) * 4096, size, threads=1) for i in range(nfiles)]
+    order = list(np.random.default_rng(7).permutation(nfiles))
+    with F.CurvineFileSystem(_conf(True, 1, zero_copy=zero_copy, copy_group=1)) as fs:
+        fs.load_namespace("\n".join(mans))
+        dst = _dev_buf(nfiles * size, cuda)
+        paths = ["/many/f%d" % i for i in order]
+        offs = [k * size for k in range(nfiles)]
+        total, s, bad, ver = fs.read_many_device(paths, dst.data_ptr(), offs, nfiles * size, 0)
+        torch.cuda.synchronize()
+        host = dst.cpu().numpy()
+        exp_sum = 0
+        for k, i in enumerate(order):
+            n = size - (i % 3) * 4096
+            want = synth.block_bytes(7100 + i, 0, n)
+            assert host[k * size:k * size + n].tobytes() == want
+            assert (host[k * size + n:(k + 1) * size] == 0xA5).all()
+            exp_sum += clib.crc(1, want)
+        assert bad == 0 and ver == nfiles and s == exp_sum and total == sum(size - (i % 3) * 4096 for i in range(nfiles))
+        with pytest.raises(F.FsError):
+            fs.read_many_device(["/many/nope"], dst.data_ptr(), [0], size, 0)

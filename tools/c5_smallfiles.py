@@ -56,6 +56,17 @@ def main():
                     lat = np.array(lat) * 1e6
                     res["gpu_rep%d" % rep] = {"files_per_s": a.files / dt, "GBps": a.files * a.size / dt / 1e9, "p50_us": float(np.percentile(lat, 50)),
                                               "p99_us": float(np.percentile(lat, 99))}
+                # batched: all files in ONE pipelined call (cv_read_many_device), files land back to back in HBM
+                big = torch.empty(a.files * a.size, dtype=torch.uint8, device="cuda")
+                paths = ["/small/f%d" % i for i in order]
+                doffs = [k * a.size for k in range(a.files)]
+                for rep in range(3):
+                    t0 = time.perf_counter()
+                    total, s, bad, ver = fs.read_many_device(paths, big.data_ptr(), doffs, a.files * a.size, stream)
+                    torch.cuda.current_stream().synchronize()
+                    dt = time.perf_counter() - t0
+                    assert bad == 0 and ver == a.files and total == a.files * a.size
+                    res["gpu_batched_rep%d" % rep] = {"files_per_s": a.files / dt, "GBps": total / dt / 1e9, "ms_total": dt * 1e3}
             lat = []
             t0 = time.perf_counter()
             for i in order:

@@ -253,7 +253,7 @@ def test_read_many_small_files_in_one_pass(cuda, cluster, zero_copy):
     w, _ = cluster
     size, nfiles = 256 * 1024, 48
     mans = [w.create_file("/many/f%d" % i, 7100 + i, size - (i % 3) * 4096, size, threads=1) for i in range(nfiles)]
-    order = list(np.random.default_rng(7).permutation(nfiles))
+    order = [int(x) for x in np.random.default_rng(7).permutation(nfiles)]
     with F.CurvineFileSystem(_conf(True, 1, zero_copy=zero_copy, copy_group=1)) as fs:
         fs.load_namespace("\n".join(mans))
         dst = _dev_buf(nfiles * size, cuda)

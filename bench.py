@@ -138,6 +138,9 @@ def make_cluster(args, rank, world, dist, gib_total):
         base = args.dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
         d = tempfile.mkdtemp(prefix="cvbench_", dir=base)
         w = F.MiniWorker(["[MEM]" + d], hostname="localhost")
+        if world > 1:  # mem tier placed NUMA-locally to the GPU that will ingest each block (b % world)
+            from curvine_b200 import _lib
+            _lib.lib().cv_synth_set_shard_world(world)
         t0 = time.time()
         man = w.create_file("/bench/file", 4242, n, BLOCK, storage_type=0, threads=min(64, os.cpu_count() or 8))
         state.update(dir=d, worker=w, gen_sec=time.time() - t0)

@@ -94,6 +94,7 @@ def _declare(L):
     L.cv_worker_metrics.argtypes, L.cv_worker_metrics.restype = [vp, cp(i64)], i64
     L.cv_synth_create_file.argtypes = [vp, c, i64, i64, i64, i32, i32, i32, i32, c, cp(vp)]
     L.cv_synth_create_file.restype = i64
+    L.cv_synth_set_shard_world.argtypes, L.cv_synth_set_shard_world.restype = [i32], i64
     L.cv_synth_block.argtypes, L.cv_synth_block.restype = [u64, u64, vp, ctypes.c_size_t], None
     L.cv_host_crc.argtypes, L.cv_host_crc.restype = [i, vp, ctypes.c_size_t], u32
 
@@ -111,7 +112,7 @@ EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_unpack_frames",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device",
            "cv_verify", "cv_device_stats", "cv_worker_start", "cv_worker_stop", "cv_worker_metrics",
-           "cv_synth_create_file", "cv_synth_block", "cv_host_crc"]
+           "cv_synth_create_file", "cv_synth_set_shard_world", "cv_synth_block", "cv_host_crc"]
 
 
 class CudaError(RuntimeError):

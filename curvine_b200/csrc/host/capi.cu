@@ -2,8 +2,10 @@
 // every failure becomes -(ErrorKind) plus a thread-local message (cv_last_error).
 #include <cuda_runtime.h>
 #include <nmmintrin.h>
+#include <sched.h>
 #include <stdlib.h>
 
+#include <fstream>
 #include <thread>
 
 #include "../../../include/curvine_b200.h"
@@ -398,9 +400,58 @@ uint32_t cv_host_crc(int poly, const uint8_t* buf, size_t len) {
     return ~r;
 }
 
+// CPUs of the NUMA node each CUDA device hangs off (empty when unknown)
+static std::vector<std::vector<int>> gpu_node_cpus() {
+    std::vector<std::vector<int>> out;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return out;
+    }
+    for (int d = 0; d < n; d++) {
+        std::vector<int> cpus;
+        char bus[64] = {0};
+        int node = -1;
+        if (cudaDeviceGetPCIBusId(bus, sizeof(bus), d) == cudaSuccess) {
+            for (char* p = bus; *p; p++) *p = static_cast<char>(tolower(*p));
+            std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+            if (f) f >> node;
+        }
+        if (node >= 0) {
+            std::ifstream f("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+            std::string line;
+            if (f && std::getline(f, line)) {
+                size_t p = 0;
+                while (p < line.size()) {
+                    const size_t c2 = line.find(',', p);
+                    const std::string r = line.substr(p, c2 == std::string::npos ? std::string::npos : c2 - p);
+                    const size_t dd = r.find('-');
+                    const int a = atoi(r.c_str()), b = dd == std::string::npos ? a : atoi(r.c_str() + dd + 1);
+                    for (int x = a; x <= b; x++) cpus.push_back(x);
+                    if (c2 == std::string::npos) break;
+                    p = c2 + 1;
+                }
+            }
+        }
+        out.push_back(cpus);
+    }
+    return out;
+}
+
+static int g_synth_shard_world = 0;
+
+// NUMA-aware mem-tier placement for round-robin shards: with shard_world = G, block b of files created afterwards is
+// first-touched (tmpfs pages allocated) on the NUMA node of GPU b % G, so every GPU later DMAs from local memory.
+int64_t cv_synth_set_shard_world(int32_t shard_world) {
+    g_synth_shard_world = shard_world;
+    return ok();
+}
+
 int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, int64_t len, int64_t block_size, int32_t storage_type,
                              int32_t mode, int32_t hole_every, int32_t threads, const char* worker_hostname, char** manifest_out) {
     API_GUARD_BEGIN
+    std::vector<std::vector<int>> node_cpus;
+    if (g_synth_shard_world > 1) node_cpus = gpu_node_cpus();
     if (block_size <= 0 || len < 0) return fail(Err(kInvalidFileSize, "bad file or block size"));
     const int64_t nb = (len + block_size - 1) / block_size;
     FileBlocks fb;
@@ -430,6 +481,15 @@ int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, i
             const int64_t b = next.fetch_add(1);
             if (b >= nb) break;
             const int64_t blen = std::min(block_size, len - b * block_size);
+            if (!node_cpus.empty()) {
+                const std::vector<int>& cpus = node_cpus[static_cast<size_t>(b % g_synth_shard_world) % node_cpus.size()];
+                if (!cpus.empty()) {
+                    cpu_set_t set;
+                    CPU_ZERO(&set);
+                    for (int c : cpus) CPU_SET(c, &set);
+                    sched_setaffinity(0, sizeof(set), &set);
+                }
+            }
             LocatedBlock& lb = fb.block_locs[static_cast<size_t>(b)];
             int64_t id = 0;
             Err e = create_block_id(inode_id, b, &id);

@@ -122,6 +122,9 @@ int64_t cv_worker_metrics(cv_worker* w, int64_t out[6]);
 int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, int64_t len, int64_t block_size,
                              int32_t storage_type, int32_t mode, int32_t hole_every, int32_t threads,
                              const char* worker_hostname, char** manifest_out);
+/* NUMA-aware mem-tier placement for round-robin shards: after cv_synth_set_shard_world(G), block b of newly created
+ * files is first-touched on the NUMA node of GPU b % G (0 or 1 turns it off). */
+int64_t cv_synth_set_shard_world(int32_t shard_world);
 /* fill buf with block `block_index` of file `file_id` (mode 0 generator) */
 void cv_synth_block(uint64_t file_id, uint64_t block_index, uint8_t* buf, size_t len);
 /* host CRC used for manifests (slicing / SSE4.2) */

@@ -57,6 +57,7 @@ def _declare(L):
     L.cvk_pack_frames.argtypes, L.cvk_pack_frames.restype = [u8p, vp, u32, u32, u8p, i, u64, vp, vp], i
     L.cvk_deinterleave_blocks.argtypes = [u8p, u64, u32, u64, u64, u64, u8p, vp]
     L.cvk_deinterleave_blocks.restype = i
+    L.cvk_gather_shards_p2p.argtypes, L.cvk_gather_shards_p2p.restype = [vp, u32, u64, u64, u64, u8p, vp], i
     # ---- upper boundary (include/curvine_b200.h)
     c, i64, i32, cp = ctypes.c_char_p, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER
     L.cv_last_error.argtypes, L.cv_last_error.restype = [], c
@@ -107,7 +108,7 @@ class CvReadStats(ctypes.Structure):
 
 # every symbol include/*.h declares (tests check the .so exports all of them)
 EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_unpack_frames", "cvk_expand_streams", "cvk_gather_pages",
-           "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_launch_count", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
+           "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_gather_shards_p2p", "cvk_launch_count", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
            "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_metrics",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device",

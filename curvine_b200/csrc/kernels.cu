@@ -139,6 +139,18 @@ __global__ void prep_deinterleave_kernel(const uint8_t* gathered, uint64_t shard
     counts[b] = piece_geom<true>(p, seg_shift).units;
 }
 
+// Like prep_deinterleave_kernel, but every rank's shard has its own base pointer (peer memory mapped over NVLink).
+__global__ void prep_gather_shards_kernel(const uint8_t* const* shard_ptrs, uint32_t world, uint64_t block_size, uint64_t n_blocks,
+                                          uint64_t file_len, uint8_t* dst, uint32_t seg_shift, Piece* pieces, uint32_t* counts) {
+    const uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint64_t start = b * block_size;
+    const uint64_t len = start >= file_len ? 0 : (file_len - start < block_size ? file_len - start : block_size);
+    Piece p{shard_ptrs[b % world] + (b / world) * block_size, dst + start, len};
+    pieces[b] = p;
+    counts[b] = piece_geom<true>(p, seg_shift).units;
+}
+
 __global__ void expand_streams_kernel(const CvStreamDesc* streams, uint32_t n_streams, CvFrameDesc* out,
                                       uint32_t n_frames) {
     // one warp per stream, lanes stride over its frames
@@ -818,6 +830,27 @@ int cvk_deinterleave_blocks(const uint8_t* d_gathered, uint64_t shard_stride, ui
     if (int rc = ws_alloc(&w, n, 0, file_len, seg_shift, st)) return rc;
     prep_deinterleave_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_gathered, shard_stride, world, block_size, n_blocks,
                                                            file_len, d_dst, seg_shift, w.pieces, w.counts);
+    count_launch();
+    return copy_pieces(w, n, seg_shift, dev, st);
+}
+
+int cvk_gather_shards_p2p(const uint8_t* const* shard_ptrs, uint32_t world, uint64_t block_size, uint64_t n_blocks, uint64_t file_len,
+                          uint8_t* d_dst, cv_stream_t stream) {
+    if (n_blocks == 0) return 0;
+    if (world == 0 || world > 64 || block_size == 0 || n_blocks > 0x7fffffffull) return int(cudaErrorInvalidValue);
+    DeviceGuard guard(d_dst);
+    int dev;
+    if (int rc = ensure_device(&dev)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t seg_shift = pick_seg_shift(file_len, g_sm_count[dev]);
+    Workspace w;
+    const uint32_t n = uint32_t(n_blocks);
+    if (int rc = ws_alloc(&w, n, 64, file_len, seg_shift, st)) return rc;  // w.first doubles as the pointer table (>= 64*8 bytes)
+    static_assert(sizeof(uint8_t*) == 8, "64-bit pointers");
+    const uint8_t** d_ptrs = reinterpret_cast<const uint8_t**>(w.first);
+    CV_TRY(cudaMemcpyAsync(d_ptrs, shard_ptrs, sizeof(uint8_t*) * world, cudaMemcpyHostToDevice, st));
+    CV_TRY(cudaStreamSynchronize(st));  // shard_ptrs is the caller's (pageable) array
+    prep_gather_shards_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_ptrs, world, block_size, n_blocks, file_len, d_dst, seg_shift, w.pieces, w.counts);
     count_launch();
     return copy_pieces(w, n, seg_shift, dev, st);
 }

@@ -103,6 +103,13 @@ def deinterleave_blocks(gathered, shard_stride, world, block_size, n_blocks, fil
                                              _ptr(dst), _stream_ptr(stream)), "cvk_deinterleave_blocks")
 
 
+def gather_shards_p2p(shard_ptrs, block_size, n_blocks, file_len, dst, stream=None):
+    """shard_ptrs: list of device pointers (ints), one per rank, local or peer-mapped."""
+    arr = (ctypes.c_uint64 * len(shard_ptrs))(*shard_ptrs)
+    check(_lib.lib().cvk_gather_shards_p2p(arr, len(shard_ptrs), block_size, n_blocks, file_len, _ptr(dst), _stream_ptr(stream)),
+          "cvk_gather_shards_p2p")
+
+
 def u32(t: torch.Tensor) -> np.ndarray:
     """int32 CUDA tensor -> uint32 numpy."""
     return t.cpu().numpy().view(np.uint32)

@@ -19,7 +19,7 @@
  *   cvk_pack_frames     RpcMessage::encode_protocol +       orpc/src/message/rpc_message.rs:301-311,
  *                       RpcFrame::send/write_region          orpc/src/handler/rpc_frame.rs:97-121,205-220
  *                       (worker ReadHandler::read response)  curvine-server/src/worker/handler/read_handler.rs:143-183
- *   cvk_deinterleave_blocks  (no reference counterpart: post-all-gather reorder, config C4)
+ *   cvk_deinterleave_blocks, cvk_gather_shards_p2p  (no reference counterpart: model-distribution exchange, config C4)
  */
 #ifndef CURVINE_B200_KERNELS_H
 #define CURVINE_B200_KERNELS_H
@@ -129,6 +129,14 @@ int cvk_pack_frames(const uint8_t* d_src, const CvFrameDesc* d_desc, uint32_t n_
  * (file_len).  Algorithmic bytes: reads N, writes N. */
 int cvk_deinterleave_blocks(const uint8_t* d_gathered, uint64_t shard_stride, uint32_t world, uint64_t block_size,
                             uint64_t n_blocks, uint64_t file_len, uint8_t* d_dst, cv_stream_t stream);
+
+/* Fused all-gather + de-interleave over peer memory (config C4, NVLink/NVSwitch): shard_ptrs[g] (HOST array of
+ * `world` device pointers, the local shard and the peers' shards mapped with CUDA IPC / peer access) is rank g's shard
+ * in the layout cv_read_device_sharded produces; every block is pulled straight from its owner's HBM into file order
+ * at d_dst -- no intermediate gathered buffer, no second pass.  Algorithmic bytes: reads N (N*(G-1)/G of it over
+ * NVLink), writes N. */
+int cvk_gather_shards_p2p(const uint8_t* const* shard_ptrs, uint32_t world, uint64_t block_size, uint64_t n_blocks,
+                          uint64_t file_len, uint8_t* d_dst, cv_stream_t stream);
 
 /* Time the dominant row-walker kernel (K1/K2/K4 bodies) with CUDA events on the launching stream.
  * enable(1) starts collecting (and clears), collect() synchronises the recorded events and returns the summed

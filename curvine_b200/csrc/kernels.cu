@@ -271,12 +271,20 @@ __device__ __forceinline__ uint32_t raw_vec(uint32_t w0, uint32_t w1, uint32_t w
     return mul_word(r ^ w3, t0);
 }
 
+// plain (coherent-path) 16-byte load: the source of a DST walk may be PEER memory mapped over NVLink
+// (cvk_gather_shards_p2p), where the non-coherent ld.global.nc path faults
+__device__ __forceinline__ uint4 ld_plain(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
 // 16 source bytes starting at the (possibly unaligned) address s; sh = s & 15 is warp-uniform.
 __device__ __forceinline__ uint4 load_shifted(const uint8_t* s, uint32_t sh) {
     const uint4* p = reinterpret_cast<const uint4*>(s - sh);
-    const uint4 A = __ldg(p);
+    const uint4 A = ld_plain(p);
     if (sh == 0) return A;
-    const uint4 B = __ldg(p + 1);
+    const uint4 B = ld_plain(p + 1);
     const uint32_t r8 = (sh & 3u) * 8u;
     uint4 o;
     switch (sh >> 2) {
@@ -378,7 +386,7 @@ template <bool CRC, bool DST>
 __device__ __forceinline__ uint32_t walk_bytes(const uint8_t* src, uint8_t* dst, uint32_t n, const uint32_t* t0) {
     uint32_t r = 0;
     for (uint32_t i = 0; i < n; i++) {
-        const uint8_t b = __ldg(src + i);
+        const uint8_t b = DST ? *reinterpret_cast<const volatile uint8_t*>(src + i) : __ldg(src + i);
         if (DST) dst[i] = b;
         if (CRC) r = t0[(r ^ b) & 0xffu] ^ (r >> 8);
     }
@@ -847,6 +855,19 @@ int cvk_gather_shards_p2p(const uint8_t* const* shard_ptrs, uint32_t world, uint
     const uint32_t n = uint32_t(n_blocks);
     if (int rc = ws_alloc(&w, n, 64, file_len, seg_shift, st)) return rc;  // w.first doubles as the pointer table (>= 64*8 bytes)
     static_assert(sizeof(uint8_t*) == 8, "64-bit pointers");
+    // kernels on this device read the peers' HBM directly: make sure peer access (this device -> owner) is enabled in the
+    // primary context (idempotent; another runtime instance in the process may or may not have done it already)
+    for (uint32_t g = 0; g < world; g++) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, shard_ptrs[g]) == cudaSuccess && a.type == cudaMemoryTypeDevice && a.device != dev) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                cudaFreeAsync(w.base, st);
+                return int(e);
+            }
+        }
+        cudaGetLastError();
+    }
     const uint8_t** d_ptrs = reinterpret_cast<const uint8_t**>(w.first);
     CV_TRY(cudaMemcpyAsync(d_ptrs, shard_ptrs, sizeof(uint8_t*) * world, cudaMemcpyHostToDevice, st));
     CV_TRY(cudaStreamSynchronize(st));  // shard_ptrs is the caller's (pageable) array

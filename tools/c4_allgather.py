@@ -4,8 +4,8 @@
 
 Each rank ingests its round-robin shard (cv_read_device_sharded, CRC-32C verified on the GPU), then the exchange runs two ways:
   A  NCCL all_gather_into_tensor (in place) + cvk_deinterleave_blocks            (collective, then a 2N HBM pass)
-  B  cvk_gather_shards_p2p: ONE kernel pulls every block straight from its owner's HBM over NVLink (CUDA IPC peer
-     pointers) into file order -- no gathered staging buffer, no second pass
+  B  cvk_gather_shards_p2p: ONE kernel pulls every block straight from its owner's HBM over NVLink (peer pointers from
+     torch symmetric memory) into file order -- no gathered staging buffer, no second pass
 and every GPU re-verifies the whole file with K1 against the manifest.  Times are CUDA events, max over ranks."""
 import argparse
 import ctypes
@@ -66,7 +66,11 @@ def main():
         fs = F.CurvineFileSystem(conf)
         fs.load_namespace(man)
         final = torch.empty(n, dtype=torch.uint8, device="cuda")
-        shard = torch.empty(per * BLOCK, dtype=torch.uint8, device="cuda")
+        # the shard lives in symmetric memory: every rank gets a directly loadable pointer to every peer's shard
+        import torch.distributed._symmetric_memory as symm_mem
+        shard = symm_mem.empty(per * BLOCK, dtype=torch.uint8, device="cuda")
+        hdl = symm_mem.rendezvous(shard, dist.group.WORLD.group_name)
+        peers = [int(p) for p in hdl.buffer_ptrs]
         stream = torch.cuda.current_stream().cuda_stream
         # ---- ingest (twice: the second pass has the mappings registered)
         for rep in range(2):
@@ -98,16 +102,6 @@ def main():
             res[tag + "_verify_ms"] = maxr(e0.elapsed_time(e1))
 
         # ---- B: fused peer gather over NVLink
-        handles = [None] * world
-        dist.all_gather_object(handles, shard.untyped_storage()._share_cuda_())
-        peers, keep = [], []
-        for g in range(world):
-            if g == rank:
-                peers.append(shard.data_ptr())
-            else:
-                st = torch.UntypedStorage._new_shared_cuda(*handles[g])
-                keep.append(st)
-                peers.append(st.data_ptr())
         for rep in range(3):
             final.zero_()
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -122,7 +116,6 @@ def main():
         res["p2p_nvlink_GBps_per_gpu"] = n * (world - 1) / world / res["p2p_gather_ms_rep2"] / 1e6
         # ---- A: NCCL all-gather + de-interleave
         if not a.skip_nccl:
-            del keep
             gathered = torch.empty(world * per * BLOCK, dtype=torch.uint8, device="cuda")
             mine = gathered[rank * per * BLOCK:(rank + 1) * per * BLOCK]
             mine.copy_(shard)

@@ -164,6 +164,29 @@ Err BlockStore::register_block(int64_t id, int64_t len, int32_t storage_type, co
     return Err::ok();
 }
 
+Err BlockStore::open_block_path(int64_t id, int32_t storage_type, std::string* path_out, int32_t* dir_storage_type) {
+    {
+        std::lock_guard<std::mutex> lk(mu_);  // re-opening an existing block writes to the same file
+        auto it = blocks_.find(id);
+        if (it != blocks_.end()) {
+            *path_out = it->second.path;
+            *dir_storage_type = it->second.storage_type;
+            return Err::ok();
+        }
+    }
+    const StorageDir* d = choose_dir(storage_type);
+    if (!d) return Err::common("no storage dir");
+    CV_RETURN_IF_ERR(mkdirs(block_dir(d->base_path, id)));
+    *path_out = block_path(d->base_path, id);
+    *dir_storage_type = d->storage_type;
+    return Err::ok();
+}
+
+void BlockStore::remove_block(int64_t id) {
+    std::lock_guard<std::mutex> lk(mu_);
+    blocks_.erase(id);
+}
+
 Err BlockStore::put_block(int64_t id, const void* data, int64_t len, int32_t storage_type, std::string* path_out) {
     const StorageDir* d = choose_dir(storage_type);
     if (!d) return Err::common("no storage dir");

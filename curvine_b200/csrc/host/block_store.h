@@ -48,6 +48,9 @@ class BlockStore {
     // create/overwrite a finalized block file in the next dir of `storage_type` (round robin, policy.rs:56-105)
     Err put_block(int64_t id, const void* data, int64_t len, int32_t storage_type, std::string* path_out);
     Err register_block(int64_t id, int64_t len, int32_t storage_type, const std::string& path);
+    // writer side: directory + path a new block of `storage_type` is written to (BlockStore::open_block)
+    Err open_block_path(int64_t id, int32_t storage_type, std::string* path_out, int32_t* dir_storage_type);
+    void remove_block(int64_t id);
     size_t num_blocks() const;
     const std::vector<StorageDir>& dirs() const { return dirs_; }
     // pick the directory a new block of `storage_type` goes to (falls back to Disk dirs, then any)

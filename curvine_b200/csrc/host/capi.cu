@@ -13,6 +13,7 @@
 #include "client.h"
 #include "gpu_reader.h"
 #include "worker.h"
+#include "writer.h"
 
 using namespace cv;
 
@@ -49,6 +50,10 @@ struct cv_reader {
     std::unique_ptr<FsReader> host;
     std::unique_ptr<GpuFsReader> dev;
     std::vector<int64_t> fuse_segs;
+};
+
+struct cv_writer {
+    std::unique_ptr<FsWriter> w;
 };
 
 struct cv_worker {
@@ -309,6 +314,50 @@ int64_t cv_device_stats(cv_reader* r, CvReadStats* out) {
     out->kernel_launches = s.kernel_launches, out->fetch_sec = s.fetch_sec, out->wall_sec = s.wall_sec;
     out->reg_hits = s.reg_hits, out->reg_misses = s.reg_misses;
     return ok();
+}
+
+// ------------------------------------------------------------------ write-side mirror
+
+int64_t cv_writer_open(cv_fs* fs, const char* path, int64_t inode_id, int64_t block_size, int32_t storage_type, const char* worker_host,
+                       int32_t worker_port, int64_t chunk_size, cv_writer** out) {
+    API_GUARD_BEGIN
+    WorkerAddress a;
+    a.worker_id = 1, a.hostname = worker_host, a.ip_addr = "127.0.0.1", a.rpc_port = static_cast<uint32_t>(worker_port);
+    if (a.hostname != "localhost") a.ip_addr = a.hostname;
+    std::unique_ptr<cv_writer> w(new cv_writer());
+    API_TRY(FsWriter::create(fs->ctx.get(), path, inode_id, block_size, storage_type, a, chunk_size > 0 ? chunk_size : 128 * 1024, &w->w));
+    *out = w.release();
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_write(cv_writer* w, const uint8_t* buf, int64_t n) {
+    API_GUARD_BEGIN
+    API_TRY(w->w->write(buf, n));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_write_device(cv_writer* w, const void* d_src, int64_t n, cv_stream_t stream) {
+    API_GUARD_BEGIN
+    API_TRY(w->w->write_device(d_src, n, stream));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_writer_close(cv_writer* w, int32_t cancel, char** manifest_out) {
+    API_GUARD_BEGIN
+    if (!w) return ok();
+    Err e = cancel ? w->w->cancel() : w->w->complete();
+    if (!e && manifest_out) {
+        const std::string text = w->w->manifest();
+        *manifest_out = static_cast<char*>(malloc(text.size() + 1));
+        memcpy(*manifest_out, text.c_str(), text.size() + 1);
+    }
+    delete w;
+    if (e) return fail(e);
+    return ok();
+    API_GUARD_END
 }
 
 // ------------------------------------------------------------------ fixture: worker + synthetic files

@@ -192,6 +192,79 @@ Err DataHeaderProto::decode(const uint8_t* p, size_t n, DataHeaderProto* o) {
     return Err::ok();
 }
 
+std::string BlockWriteRequest::encode() const {
+    std::string b;
+    put_field(&b, 1, block.id), put_field(&b, 2, block.block_size), put_field(&b, 3, block.storage_type), put_field(&b, 4, block.file_type);
+    std::string s;
+    put_bytes(&s, 1, b);
+    put_field(&s, 2, off), put_field(&s, 3, block_size), put_field(&s, 4, short_circuit);
+    put_bytes(&s, 5, client_name);
+    put_field(&s, 6, chunk_size);
+    return s;
+}
+
+Err BlockWriteRequest::decode(const uint8_t* p, size_t n, BlockWriteRequest* o) {
+    const uint8_t* end = p + n;
+    uint32_t seen = 0;
+    Field f;
+    while (p < end) {
+        if (!next_field(p, end, &f)) return Err(kPBDecode, "failed to decode BlockWriteRequest");
+        switch (f.no) {
+            case 1: {
+                const uint8_t* q = f.p;
+                const uint8_t* qe = f.p + f.n;
+                Field g;
+                uint32_t bs = 0;
+                while (q < qe) {
+                    if (!next_field(q, qe, &g)) return Err(kPBDecode, "failed to decode ExtendedBlockProto");
+                    if (g.no == 1) o->block.id = int64_t(g.v), bs |= 1;
+                    else if (g.no == 2) o->block.block_size = int64_t(g.v), bs |= 2;
+                    else if (g.no == 3) o->block.storage_type = int32_t(g.v), bs |= 4;
+                    else if (g.no == 4) o->block.file_type = int32_t(g.v), bs |= 8;
+                }
+                if (bs != 15) return Err(kPBDecode, "failed to decode ExtendedBlockProto: missing required field");
+                seen |= 1;
+                break;
+            }
+            case 2: o->off = int64_t(f.v), seen |= 2; break;
+            case 3: o->block_size = int64_t(f.v), seen |= 4; break;
+            case 4: o->short_circuit = f.v != 0, seen |= 8; break;
+            case 5: o->client_name.assign(reinterpret_cast<const char*>(f.p), f.n), seen |= 16; break;
+            case 6: o->chunk_size = int32_t(f.v), seen |= 32; break;
+            default: break;
+        }
+    }
+    if (seen != 63) return Err(kPBDecode, "failed to decode BlockWriteRequest: missing required field");
+    return Err::ok();
+}
+
+std::string BlockWriteResponse::encode() const {
+    std::string s;
+    put_field(&s, 1, id);
+    if (has_path) put_bytes(&s, 2, path);
+    put_field(&s, 3, off), put_field(&s, 4, block_size), put_field(&s, 5, storage_type);
+    return s;
+}
+
+Err BlockWriteResponse::decode(const uint8_t* p, size_t n, BlockWriteResponse* o) {
+    const uint8_t* end = p + n;
+    uint32_t seen = 0;
+    Field f;
+    while (p < end) {
+        if (!next_field(p, end, &f)) return Err(kPBDecode, "failed to decode BlockWriteResponse");
+        switch (f.no) {
+            case 1: o->id = int64_t(f.v), seen |= 1; break;
+            case 2: o->has_path = true, o->path.assign(reinterpret_cast<const char*>(f.p), f.n); break;
+            case 3: o->off = int64_t(f.v), seen |= 2; break;
+            case 4: o->block_size = int64_t(f.v), seen |= 4; break;
+            case 5: o->storage_type = int32_t(f.v), seen |= 8; break;
+            default: break;
+        }
+    }
+    if (seen != 15) return Err(kPBDecode, "failed to decode BlockWriteResponse: missing required field");
+    return Err::ok();
+}
+
 std::string encode_error_body(int32_t kind, const std::string& msg) {
     std::string s(8, '\0');
     put_be32(reinterpret_cast<uint8_t*>(&s[0]), static_cast<uint32_t>(kind));

@@ -77,6 +77,31 @@ struct DataHeaderProto {  // worker.proto:56-60
     static Err decode(const uint8_t* p, size_t n, DataHeaderProto* out);
 };
 
+struct ExtendedBlockWire {  // common.proto:98-104 (ExtendedBlockProto); block_size carries the block's current length
+    int64_t id = 0, block_size = 0;
+    int32_t storage_type = kStorageDisk, file_type = 1;  // FILE_TYPE_PROTO_FILE
+};
+
+struct BlockWriteRequest {  // worker.proto:10-18
+    ExtendedBlockWire block;
+    int64_t off = 0, block_size = 0;
+    bool short_circuit = false;
+    std::string client_name;
+    int32_t chunk_size = 0;
+    std::string encode() const;
+    static Err decode(const uint8_t* p, size_t n, BlockWriteRequest* out);
+};
+
+struct BlockWriteResponse {  // worker.proto:27-34
+    int64_t id = 0;
+    bool has_path = false;
+    std::string path;
+    int64_t off = 0, block_size = 0;
+    int32_t storage_type = kStorageDisk;
+    std::string encode() const;
+    static Err decode(const uint8_t* p, size_t n, BlockWriteResponse* out);
+};
+
 std::string encode_error_body(int32_t kind, const std::string& msg);
 Err decode_error_body(const uint8_t* p, size_t n);  // always returns a failure Err carrying kind + message
 

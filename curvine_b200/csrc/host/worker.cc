@@ -120,6 +120,108 @@ Err ReadHandler::complete(const RpcRequest& req, RpcResponse* resp) {
     return Err::ok();
 }
 
+// ------------------------------------------------------------------ WriteHandler
+
+WriteHandler::~WriteHandler() { close_fd(fd_); }
+
+Err WriteHandler::handle(const RpcRequest& req, RpcResponse* resp) {
+    switch (req.proto.req_status) {
+        case kReqOpen: return open(req, resp);
+        case kReqRunning: return write(req, resp);
+        case kReqComplete: return complete(req, resp, true);
+        case kReqCancel: return complete(req, resp, false);
+        default: return Err::common("Unsupported request type");
+    }
+}
+
+Err WriteHandler::open(const RpcRequest& req, RpcResponse* resp) {
+    BlockWriteRequest c;
+    CV_RETURN_IF_ERR(BlockWriteRequest::decode(reinterpret_cast<const uint8_t*>(req.header.data()), req.header.size(), &c));
+    if (c.off > c.block_size) return Err::common(str_printf("Invalid write offset: %lld, block size: %lld", (long long)c.off, (long long)c.block_size));
+    CV_RETURN_IF_ERR(store_->open_block_path(c.block.id, c.block.storage_type, &path_, &dir_storage_type_));
+    const bool short_circuit = c.short_circuit;
+    close_fd(fd_);
+    fd_ = -1;
+    if (!short_circuit) {
+        fd_ = ::open(path_.c_str(), O_WRONLY | O_CREAT | O_CLOEXEC, 0644);
+        if (fd_ < 0) return Err::io(str_printf("open %s: %s", path_.c_str(), strerror(errno)));
+        pos_ = c.off;
+    }
+    ctx_ = c, ctx_req_id_ = req.proto.req_id, has_ctx_ = true, is_commit_ = false;
+    metrics_->write_blocks++;
+    BlockWriteResponse r;
+    r.id = c.block.id, r.has_path = short_circuit, r.path = path_, r.off = c.off, r.block_size = c.block_size, r.storage_type = dir_storage_type_;
+    resp->proto = response_proto(req.proto, kRespSuccess);
+    resp->header = r.encode();
+    return Err::ok();
+}
+
+Err WriteHandler::write(const RpcRequest& req, RpcResponse* resp) {
+    if (fd_ < 0) return Err::common("self.file is none");
+    if (!has_ctx_) return Err::common("self.context is none");
+    if (ctx_req_id_ != req.proto.req_id)
+        return Err::common(str_printf("Request id mismatch, expected %lld, actual %lld", (long long)ctx_req_id_, (long long)req.proto.req_id));
+    if (!req.header.empty()) {
+        DataHeaderProto h;
+        CV_RETURN_IF_ERR(DataHeaderProto::decode(reinterpret_cast<const uint8_t*>(req.header.data()), req.header.size(), &h));
+        if (!h.flush) {  // a flush must not seek (write_handler.rs:168-186)
+            if (h.offset < 0 || h.offset >= ctx_.block_size)
+                return Err::common(str_printf("Invalid seek offset: %lld, block length: %lld", (long long)h.offset, (long long)ctx_.block_size));
+            pos_ = h.offset;
+        }
+    }
+    const int64_t n = static_cast<int64_t>(req.data.size());
+    if (n > 0) {
+        if (pos_ + n > ctx_.block_size)
+            return Err::common(str_printf("Write range [%lld, %lld) exceeds block size %lld", (long long)pos_, (long long)(pos_ + n), (long long)ctx_.block_size));
+        const double t0 = now_sec();
+        int64_t done = 0;
+        while (done < n) {
+            const ssize_t w = pwrite(fd_, req.data.data() + done, static_cast<size_t>(n - done), pos_ + done);
+            if (w < 0 && errno == EINTR) continue;
+            if (w <= 0) return Err::io(str_printf("write %s: %s", path_.c_str(), strerror(errno)));
+            done += w;
+        }
+        pos_ += n;
+        metrics_->write_bytes += n;
+        metrics_->write_time_us += static_cast<int64_t>((now_sec() - t0) * 1e6);
+        metrics_->write_count++;
+    }
+    resp->proto = response_proto(req.proto, kRespSuccess);
+    return Err::ok();
+}
+
+Err WriteHandler::complete(const RpcRequest& req, RpcResponse* resp, bool commit) {
+    resp->proto = response_proto(req.proto, kRespSuccess);
+    if (is_commit_) {
+        if (!req.data.empty()) return Err::common("The block has been committed and data cannot be written anymore.");
+        return Err::ok();
+    }
+    if (has_ctx_ && ctx_req_id_ != req.proto.req_id)
+        return Err::common(str_printf("Request id mismatch, expected %lld, actual %lld", (long long)ctx_req_id_, (long long)req.proto.req_id));
+    has_ctx_ = false;
+    BlockWriteRequest c;
+    CV_RETURN_IF_ERR(BlockWriteRequest::decode(reinterpret_cast<const uint8_t*>(req.header.data()), req.header.size(), &c));
+    close_fd(fd_);
+    fd_ = -1;
+    if (c.block.block_size > c.block_size)
+        return Err::common(str_printf("Invalid write offset: %lld, block size: %lld", (long long)c.block.block_size, (long long)c.block_size));
+    std::string path;
+    int32_t st_type = kStorageDisk;
+    CV_RETURN_IF_ERR(store_->open_block_path(c.block.id, c.block.storage_type, &path, &st_type));
+    if (commit) {  // finalize: the block's length is what the client committed
+        if (truncate(path.c_str(), c.block.block_size) != 0 && errno != ENOENT) return Err::io(str_printf("truncate %s: %s", path.c_str(), strerror(errno)));
+        struct stat st;
+        if (stat(path.c_str(), &st) != 0) return Err::io(str_printf("finalize %s: %s", path.c_str(), strerror(errno)));
+        CV_RETURN_IF_ERR(store_->register_block(c.block.id, st.st_size, st_type, path));
+    } else {  // abort
+        ::unlink(path.c_str());
+        store_->remove_block(c.block.id);
+    }
+    is_commit_ = true;
+    return Err::ok();
+}
+
 Worker::~Worker() { stop(); }
 
 Err Worker::start(const std::vector<std::string>& data_dirs, const std::string& cluster_id, const std::string& host, int port, bool enable_send_file) {
@@ -178,6 +280,7 @@ void Worker::accept_loop() {
 // StreamHandler::run + WorkerHandler::handle for one connection
 void Worker::serve(int fd) {
     std::unique_ptr<ReadHandler> handler;
+    std::unique_ptr<WriteHandler> whandler;
     uint8_t prefix[kProtocolSize];
     RpcRequest req;
     for (;;) {
@@ -192,9 +295,14 @@ void Worker::serve(int fd) {
 
         RpcResponse resp;
         Err e;
-        if (req.proto.code != kCodeReadBlock) {
+        if (req.proto.code == kCodeWriteBlock) {
+            handler.reset();  // handler_matches_code (worker_handler.rs:89-98): a different code replaces the live handler
+            if (!whandler || req.proto.req_status != kReqRunning) whandler.reset(new WriteHandler(&store_, &metrics_));
+            e = whandler->handle(req, &resp);
+        } else if (req.proto.code != kCodeReadBlock) {
             e = Err::common(str_printf("Unsupported request type: %d", int(req.proto.code)));
         } else {
+            whandler.reset();
             // worker_handler.rs:71-88: a fresh handler unless this is a Running message for the live one
             if (!handler || req.proto.req_status != kReqRunning) handler.reset(new ReadHandler(&store_, &metrics_, enable_send_file_));
             e = handler->handle(req, &resp);
@@ -214,7 +322,7 @@ void Worker::serve(int fd) {
         if (resp.file_fd < 0) head += resp.data;
         if (send_all(fd, head.data(), head.size())) return;
         if (resp.file_fd >= 0 && send_file_full(fd, resp.file_fd, resp.file_off, static_cast<size_t>(resp.file_len))) return;
-        if (req.proto.req_status == kReqCancel || req.proto.req_status == kReqComplete) handler.reset();
+        if (req.proto.req_status == kReqCancel || req.proto.req_status == kReqComplete) handler.reset(), whandler.reset();
     }
 }
 

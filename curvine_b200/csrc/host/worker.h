@@ -21,6 +21,7 @@ namespace cv {
 
 struct WorkerMetrics {  // worker_metrics.rs:25-44
     std::atomic<int64_t> read_bytes{0}, read_time_us{0}, read_count{0}, read_blocks_local{0}, read_blocks_remote{0};
+    std::atomic<int64_t> write_bytes{0}, write_time_us{0}, write_count{0}, write_blocks{0};
 };
 
 // One request message as received from the socket.
@@ -62,6 +63,30 @@ class ReadHandler {
     int64_t pos_ = 0, len_ = 0, last_ahead_ = -1;
     bool is_tmpfs_ = false;
     std::string path_;
+};
+
+// Write-side mirror: WriteBlock = 80, Open{BlockWriteRequest} -> Running{payload, optional
+// DataHeaderProto for seek/flush} x N -> Complete{BlockWriteRequest{block.len}} | Cancel
+// (curvine-server/src/worker/handler/write_handler.rs:90-300).
+class WriteHandler {
+   public:
+    WriteHandler(BlockStore* store, WorkerMetrics* m) : store_(store), metrics_(m) {}
+    ~WriteHandler();
+    Err handle(const RpcRequest& req, RpcResponse* resp);
+
+   private:
+    Err open(const RpcRequest& req, RpcResponse* resp);
+    Err write(const RpcRequest& req, RpcResponse* resp);
+    Err complete(const RpcRequest& req, RpcResponse* resp, bool commit);
+    BlockStore* store_;
+    WorkerMetrics* metrics_;
+    bool has_ctx_ = false, is_commit_ = false;
+    BlockWriteRequest ctx_;
+    int64_t ctx_req_id_ = 0;
+    int fd_ = -1;
+    int64_t pos_ = 0;
+    std::string path_;
+    int32_t dir_storage_type_ = kStorageDisk;
 };
 
 class Worker {

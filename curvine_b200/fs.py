@@ -170,6 +170,28 @@ class Reader:
         self.complete()
 
 
+class Writer:
+    """Write-side mirror: Writer::{write, complete, cancel} (curvine-common/src/fs/writer.rs) + write_device."""
+
+    def __init__(self, h):
+        self._h = h
+
+    def write(self, data: bytes):
+        _check(_lib.lib().cv_write(self._h, data, len(data)))
+
+    def write_device(self, d_ptr: int, n: int, stream: int = 0):
+        _check(_lib.lib().cv_write_device(self._h, ctypes.c_void_p(d_ptr), n, ctypes.c_void_p(stream)))
+
+    def complete(self, cancel: bool = False) -> str:
+        out = ctypes.c_void_p()
+        h, self._h = self._h, None
+        _check(_lib.lib().cv_writer_close(h, 1 if cancel else 0, ctypes.byref(out)))
+        text = ctypes.string_at(out).decode() if out else ""
+        if out:
+            _lib.lib().cv_free(out)
+        return text
+
+
 class CurvineFileSystem:
     def __init__(self, conf_toml: str = "", conf_path: Optional[str] = None):
         self._h = ctypes.c_void_p()
@@ -198,6 +220,13 @@ class CurvineFileSystem:
         _check(_lib.lib().cv_read_many_device(self._h, arr, len(paths), ctypes.c_void_p(d_ptr), offs, cap, ctypes.c_void_p(stream),
                                               ctypes.byref(s), ctypes.byref(b), ctypes.byref(v), ctypes.byref(t)))
         return t.value, s.value, b.value, v.value
+
+    def create(self, path: str, inode_id: int, block_size: int, worker_port: int, worker_host: str = "localhost", storage_type: int = 0,
+               chunk_size: int = 0) -> Writer:
+        h = ctypes.c_void_p()
+        _check(_lib.lib().cv_writer_open(self._h, path.encode(), inode_id, block_size, storage_type, worker_host.encode(), worker_port, chunk_size,
+                                         ctypes.byref(h)))
+        return Writer(h)
 
     def metrics(self) -> dict:
         a = (ctypes.c_int64 * 2)()

@@ -41,6 +41,7 @@ extern "C" {
 typedef struct cv_fs cv_fs;
 typedef struct cv_reader cv_reader;
 typedef struct cv_worker cv_worker;
+typedef struct cv_writer cv_writer;
 
 /* -(ErrorKind) values a caller is likely to test for (fs_error.rs:35-66) */
 #define CV_OK 0
@@ -109,6 +110,20 @@ typedef struct CvReadStats {
     uint64_t reg_hits, reg_misses; /* registered-mapping cache of the zero-copy path */
 } CvReadStats;
 int64_t cv_device_stats(cv_reader* r, CvReadStats* out);
+
+/* ---- write-side mirror ("next" row 8f-1): WriteBlock = 80, Open -> Running x N -> Complete per block
+ * (curvine-client/src/block/block_writer_remote.rs:36-140, block_client.rs:97-219; worker write_handler.rs:90-300).
+ * Blocks of block_size are allocated one after another (block_id = inode<<24 | seq); per-block CRC-32/CRC-32C are
+ * computed at write time and land in the manifest, so a later cv_verify compares read-side with write-side CRCs.
+ * cv_write takes host bytes; cv_write_device takes HBM bytes: K4 (cvk_pack_frames) writes the request prefixes, copies the
+ * payload behind them and CRCs the source in one pass, the wire image goes D2H once and onto the socket verbatim.
+ * cv_writer_close(cancel=0) commits and registers the file in the filesystem handle's namespace (manifest text returned,
+ * cv_free); cancel=1 aborts the open block. */
+int64_t cv_writer_open(cv_fs* fs, const char* path, int64_t inode_id, int64_t block_size, int32_t storage_type,
+                       const char* worker_host, int32_t worker_port, int64_t chunk_size, cv_writer** out);
+int64_t cv_write(cv_writer* w, const uint8_t* buf, int64_t n);
+int64_t cv_write_device(cv_writer* w, const void* d_src, int64_t n, cv_stream_t stream);
+int64_t cv_writer_close(cv_writer* w, int32_t cancel, char** manifest_out);
 
 /* ---- fixture: in-process worker over a BlockStore directory tree + synthetic files */
 int64_t cv_worker_start(const char* conf_toml, cv_worker** out, int32_t* port);

@@ -268,6 +268,54 @@ class DataHeaderProto:  # worker.proto:56-60
         return DataHeaderProto(_s64(f[1]), bool(f[2]), bool(f[3]))
 
 
+FILE_TYPE_FILE = 1
+
+
+@dataclass
+class BlockWriteRequest:  # worker.proto:10-18 (block = ExtendedBlockProto, common.proto:98-104)
+    block_id: int = 0
+    block_len: int = 0  # ExtendedBlockProto.block_size: the block's current length
+    storage_type: int = STORAGE_DISK
+    file_type: int = FILE_TYPE_FILE
+    off: int = 0
+    block_size: int = 0
+    short_circuit: bool = False
+    client_name: str = ""
+    chunk_size: int = 0
+
+    def encode(self) -> bytes:
+        blk = (_field_varint(1, self.block_id) + _field_varint(2, self.block_len) + _field_varint(3, self.storage_type)
+               + _field_varint(4, self.file_type))
+        return (_field_bytes(1, blk) + _field_varint(2, self.off) + _field_varint(3, self.block_size)
+                + _field_varint(4, self.short_circuit) + _field_bytes(5, self.client_name.encode()) + _field_varint(6, self.chunk_size))
+
+    @staticmethod
+    def decode(buf: bytes) -> "BlockWriteRequest":
+        f = _parse(buf)
+        b = _parse(f[1])
+        return BlockWriteRequest(_s64(b[1]), _s64(b[2]), int(b[3]), int(b[4]), _s64(f[2]), _s64(f[3]), bool(f[4]), f[5].decode(), _s64(f[6]))
+
+
+@dataclass
+class BlockWriteResponse:  # worker.proto:27-34
+    id: int = 0
+    path: Optional[str] = None
+    off: int = 0
+    block_size: int = 0
+    storage_type: int = STORAGE_DISK
+
+    def encode(self) -> bytes:
+        out = _field_varint(1, self.id)
+        if self.path is not None:
+            out += _field_bytes(2, self.path.encode())
+        return out + _field_varint(3, self.off) + _field_varint(4, self.block_size) + _field_varint(5, self.storage_type)
+
+    @staticmethod
+    def decode(buf: bytes) -> "BlockWriteResponse":
+        f = _parse(buf)
+        return BlockWriteResponse(_s64(f[1]), f[2].decode() if 2 in f else None, _s64(f[3]), _s64(f[4]), int(f[5]))
+
+
 # ----------------------- one remote block read, as bytes -----------------------
 
 def block_read_exchange(block_id: int, block: bytes, chunk_size: int, req_id: int, off: int = 0,

@@ -272,3 +272,59 @@ def test_read_many_small_files_in_one_pass(cuda, cluster, zero_copy):
         assert bad == 0 and ver == nfiles and s == exp_sum and total == sum(size - (i % 3) * 4096 for i in range(nfiles))
         with pytest.raises(F.FsError):
             fs.read_many_device(["/many/nope"], dst.data_ptr(), [0], size, 0)
+
+
+@pytest.mark.parametrize("sc", [True, False])
+def test_edge_shapes_on_device(cuda, cluster, sc):
+    """Empty file, 5-byte file, ragged last block; framed mode with the 16 MiB maximum frame (rpc_message.rs:41)."""
+    import torch
+    w, _ = cluster
+    bs = 20 << 20
+    n = bs + (16 << 20) + 3
+    man = w.create_file("/dedge/empty", 7200, 0, 1 << 20) + w.create_file("/dedge/tiny", 7201, 5, 1 << 20) + w.create_file("/dedge/big", 7202, n, bs)
+    with F.CurvineFileSystem(_conf(sc, 1, "16MB", threads=2, batch=2)) as fs:
+        fs.load_namespace(man)
+        dst = _dev_buf(n + 8, cuda)
+        with fs.open("/dedge/empty") as r:
+            assert r.read_device(dst.data_ptr(), 100, 0) == 0 and r.verify() == (0, 0, 0)
+        with fs.open("/dedge/tiny") as r:
+            assert r.read_device(dst.data_ptr(), 100, 0) == 5
+            s, bad, ver = r.verify()
+            torch.cuda.synchronize()
+            assert bad == 0 and ver == 1 and dst[:5].cpu().numpy().tobytes() == synth.block_bytes(7201, 0, 5) and s == clib.crc(1, synth.block_bytes(7201, 0, 5))
+        with fs.open("/dedge/big") as r:  # 20 MiB block = a 16 MiB frame + a 4 MiB frame when framed
+            assert r.read_device(dst.data_ptr(), n, 0) == n
+            s, bad, ver = r.verify()
+            torch.cuda.synchronize()
+            assert bad == 0 and ver == 2 and dst[:n].cpu().numpy().tobytes() == synth.file_bytes(7202, n, bs)
+
+
+def test_write_device_then_read_device_roundtrip(cuda, cluster):
+    """Write-side mirror on the GPU: HBM bytes -> K4 (prefix write + copy + CRC at source) -> wire image -> worker;
+    then read back into HBM through K2/K1.  Bytes identical, write-time CRCs in the manifest == read-time CRCs."""
+    import torch
+    w, d = cluster
+    bs, n, ino = 1 << 20, (5 << 20) + 12345, 7300
+    g = torch.Generator(device=cuda).manual_seed(11)
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device=cuda, generator=g)
+    host = src.cpu().numpy()
+    for sc in (True, False):
+        with F.CurvineFileSystem(_conf(sc, 1, "128KB")) as fs:
+            wr = fs.create("/wd/f%d" % sc, ino + int(sc), bs, w.port, chunk_size=131072)
+            wr.write_device(src.data_ptr(), 3 * bs + 100, torch.cuda.current_stream().cuda_stream)  # ends mid-block
+            wr.write_device(src.data_ptr() + 3 * bs + 100, n - 3 * bs - 100, torch.cuda.current_stream().cuda_stream)
+            man = wr.complete()
+            blocks = [l.split() for l in man.splitlines() if l.startswith("block ")]
+            assert [int(b[4], 16) for b in blocks] == clib.crc_blocks(0, host, bs).tolist()
+            assert [int(b[5], 16) for b in blocks] == clib.crc_blocks(1, host, bs).tolist()
+            for i in range(len(blocks)):  # the worker wrote the reference layout
+                p = layout.block_path(str(d / "mem" / "curvine"), layout.create_block_id(ino + int(sc), i))
+                assert open(p, "rb").read() == host[i * bs:(i + 1) * bs].tobytes()
+            r = fs.open("/wd/f%d" % sc)
+            dst = _dev_buf(n, cuda)
+            assert r.read_device(dst.data_ptr(), n, 0) == n
+            s, bad, ver = r.verify()
+            torch.cuda.synchronize()
+            assert bad == 0 and ver == len(blocks) and torch.equal(dst, src)
+            assert s == int(clib.crc_blocks(1, host, bs).astype(np.uint64).sum())
+            r.complete()

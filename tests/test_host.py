@@ -314,3 +314,126 @@ def test_replica_failover_on_read_error(tmp_path):
     finally:
         w1.stop()
         w2.stop()
+
+
+def test_empty_and_ragged_files(cluster):
+    """Edge shapes: empty file; file shorter than a chunk; block size that is not a multiple of the chunk size
+    (chunks restart at every block: local_file.rs:103-117, fs_reader_base.rs:181-204)."""
+    w, _ = cluster
+    man = w.create_file("/edge/empty", 4700, 0, 1 << 20) + w.create_file("/edge/tiny", 4701, 5, 1 << 20) \
+        + w.create_file("/edge/ragged", 4702, 3 * ((1 << 20) + 4096) + 777, (1 << 20) + 4096)
+    for sc in (True, False):
+        with F.CurvineFileSystem(F.client_conf(short_circuit=sc)) as fs:
+            fs.load_namespace(man)
+            with fs.open("/edge/empty") as r:
+                assert r.len() == 0 and r.read(10) == b"" and r.read_full(10) == b"" and r.read_chunk() == b"" and r.pos() == 0
+                r.seek(0)
+                assert r.fuse_read(0, 100) == []
+            with fs.open("/edge/tiny") as r:
+                assert r.read_full(100) == synth.block_bytes(4701, 0, 5) and r.pos() == 5 and r.read(1) == b""
+            bs, n = (1 << 20) + 4096, 3 * ((1 << 20) + 4096) + 777
+            model, data = _model_for(4702, n, bs, RM.ClientConf(short_circuit=sc))
+            with fs.open("/edge/ragged") as r:
+                while True:
+                    c = r.read_chunk()
+                    assert c == model.blocking_read()
+                    if not c:
+                        break
+                assert r.pos() == n
+                # the last chunk of every block is short (4096 bytes past 8 x 128 KiB)
+                r.seek(bs - 4096)
+                assert len(r.read_chunk()) == 4096
+
+
+def test_write_path_hand_built_messages_then_read_back(cluster):
+    """worker_test.rs:49-176, write half: WriteBlock Open -> Running x N -> Complete built with the oracle codec against
+    the product worker; the block file lands in the reference layout; read back, write-side sum == read-side sum."""
+    w, d = cluster
+    chunk, count = 1024, 100
+    bid = layout.create_block_id(4800, 0)
+    s = socket.create_connection(("127.0.0.1", w.port))
+    rid, wsum, blob = 0x5566, 0, bytearray()
+    o = _rpc(s, W.request(80, W.REQ_OPEN, rid, 0, W.BlockWriteRequest(bid, 0, W.STORAGE_MEM, 1, 0, 1 << 20, False, "t", chunk).encode()))
+    assert o.is_success()
+    r = W.BlockWriteResponse.decode(o.header)
+    assert (r.id, r.path, r.off, r.block_size, r.storage_type) == (bid, None, 0, 1 << 20, W.STORAGE_MEM)
+    rng = np.random.default_rng(4)
+    for i in range(count):
+        data = rng.bytes(chunk)
+        m = _rpc(s, W.request(80, W.REQ_RUNNING, rid, i + 1, b"", data))
+        assert m.is_success() and m.seq_id == i + 1 and m.data == b""
+        wsum += zlib.crc32(data)
+        blob += data
+    # a flush header must not seek; a seek header rewrites in place; out-of-range writes are error responses
+    assert _rpc(s, W.request(80, W.REQ_RUNNING, rid, count + 1, W.DataHeaderProto(5, True, False).encode())).is_success()
+    patch = b"PATCHED!"
+    assert _rpc(s, W.request(80, W.REQ_RUNNING, rid, count + 2, W.DataHeaderProto(10, False, False).encode(), patch)).is_success()
+    blob[10:18] = patch
+    e = _rpc(s, W.request(80, W.REQ_RUNNING, rid, count + 3, W.DataHeaderProto((1 << 20) - 4, False, False).encode(), b"12345678"))
+    assert e.resp_status == W.RESP_ERROR and "exceeds block size" in W.decode_error(e.data)[1]
+    e = _rpc(s, W.request(80, W.REQ_RUNNING, rid + 1, count + 4, b"", b"x"))
+    assert "Request id mismatch" in W.decode_error(e.data)[1]
+    c = _rpc(s, W.request(80, W.REQ_COMPLETE, rid, count + 5, W.BlockWriteRequest(bid, len(blob), W.STORAGE_MEM, 1, len(blob), 1 << 20, False, "t", 0).encode()))
+    assert c.is_success()
+    path = layout.block_path(str(d / "mem" / "curvine"), bid)
+    assert open(path, "rb").read() == bytes(blob)
+    # read it back through ReadBlock
+    o = _rpc(s, W.request(81, W.REQ_OPEN, 9, 0, W.BlockReadRequest(bid, 0, len(blob), chunk).encode()))
+    assert W.BlockReadResponse.decode(o.header).len == len(blob)
+    got = bytearray()
+    for i in range(count):
+        got += _rpc(s, W.request(81, W.REQ_RUNNING, 9, i + 1)).data
+    assert bytes(got) == bytes(blob)
+    # cancel removes the block
+    bid2 = layout.create_block_id(4800, 1)
+    assert _rpc(s, W.request(80, W.REQ_OPEN, 77, 0, W.BlockWriteRequest(bid2, 0, 0, 1, 0, 4096, False, "t", 1024).encode())).is_success()
+    assert _rpc(s, W.request(80, W.REQ_RUNNING, 77, 1, b"", b"abc")).is_success()
+    assert _rpc(s, W.request(80, W.REQ_CANCEL, 77, 2, W.BlockWriteRequest(bid2, 3, 0, 1, 3, 4096, False, "t", 0).encode())).is_success()
+    e = _rpc(s, W.request(81, W.REQ_OPEN, 9, 0, W.BlockReadRequest(bid2, 0, 3, 1024).encode()))
+    assert e.resp_status == W.RESP_ERROR
+    e = _rpc(s, W.request(80, W.REQ_OPEN, 78, 0, W.BlockWriteRequest(bid2, 0, 0, 1, 8192, 4096, False, "t", 1024).encode()))
+    assert "Invalid write offset" in W.decode_error(e.data)[1]
+    s.close()
+
+
+def test_writer_then_reader_checksums_agree(cluster):
+    """block_test.rs:209-226 discipline through the product's own writer: write 10240 x 1 KiB + a tail with 1 MiB blocks,
+    read back in 1 KiB calls; lengths and sum-crc equal; the manifest carries the write-time per-block CRCs."""
+    w, _ = cluster
+    rng = np.random.default_rng(9)
+    with F.CurvineFileSystem(F.client_conf(short_circuit=False, read_chunk_size="64KB")) as fs:
+        wr = fs.create("/w/f1", 4900, 1 << 20, w.port, chunk_size=65536)
+        data, wsum = bytearray(), 0
+        for _ in range(10240):
+            rec = rng.bytes(1024)
+            wr.write(rec)
+            wsum += zlib.crc32(rec)
+            data += rec
+        tail = b"timestamp-1234567"
+        wr.write(tail)
+        data += tail
+        man = wr.complete()
+        blocks = [l.split() for l in man.splitlines() if l.startswith("block ")]
+        assert len(blocks) == 11 and int(blocks[-1][2]) == len(tail)
+        assert [int(b[4], 16) for b in blocks] == [zlib.crc32(bytes(data[i << 20:(i + 1) << 20])) for i in range(11)]
+        assert [int(b[5], 16) for b in blocks] == [clib.crc(1, bytes(data[i << 20:(i + 1) << 20])) for i in range(11)]
+        r = fs.open("/w/f1")  # registered in the namespace by complete()
+        assert r.len() == len(data)
+        rsum, total = 0, 0
+        while True:
+            b = r.read(1024)
+            if not b:
+                break
+            total += len(b)
+            if total <= 10240 * 1024:
+                rsum += zlib.crc32(b)
+        assert total == len(data) and rsum == wsum
+        r.seek(0)
+        assert r.read_full(len(data)) == bytes(data)
+        r.complete()
+        # cancel: nothing registered
+        wr = fs.create("/w/f2", 4901, 1 << 20, w.port)
+        wr.write(b"abc")
+        wr.complete(cancel=True)
+        with pytest.raises(F.FsError):
+            fs.open("/w/f2")

@@ -256,3 +256,23 @@ def test_gather_shards_p2p_local_pointers(cuda, world):
     dst = torch.zeros(file_len, dtype=torch.uint8, device=cuda)
     K.gather_shards_p2p([s.data_ptr() for s in shards], bs, nb, file_len, dst)
     assert dst.cpu().numpy().tobytes() == data.tobytes()
+
+
+def test_unpack_rejects_oversized_and_negative_frames(cuda):
+    """decode_protocol limits (rpc_message.rs:329-334): data_len < 0 and > 16 MiB are flagged by K2's prefix check."""
+    import struct
+    import torch
+    from curvine_b200 import kernels as K
+    from curvine_b200._lib import CvFrameDesc
+    payload = _rand(4096, 3)
+    good = W.encode(W.success(W.request(81, W.REQ_RUNNING, 9, 1), b"", payload.tobytes()))
+    too_big = bytearray(good)
+    too_big[0:4] = struct.pack(">i", 18 + (16 << 20) + 1)
+    negative = bytearray(good)
+    negative[0:4] = struct.pack(">i", 17)
+    wire = np.frombuffer(bytes(good) + bytes(too_big) + bytes(negative), dtype=np.uint8).copy()
+    descs = [CvFrameDesc(i * len(good), i * 4096, 4096, 0, 9, 1, 0, 81, 0x03) for i in range(3)]
+    dst = torch.zeros(3 * 4096, dtype=torch.uint8, device=cuda)
+    _, err = K.unpack_frames(_to_dev(wire, cuda), K.frame_descs_to_device(descs, cuda), 3, 1, dst, 0, 3 * 4096)
+    e = K.u32(err)
+    assert e[0] == 0 and e[1] & 0x40 and e[1] & 0x01 and e[2] & 0x40 and e[2] & 0x01

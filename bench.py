@@ -138,7 +138,7 @@ def make_cluster(args, rank, world, dist, gib_total):
         base = args.dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
         d = tempfile.mkdtemp(prefix="cvbench_", dir=base)
         w = F.MiniWorker(["[MEM]" + d], hostname="localhost")
-        if world > 1:  # mem tier placed NUMA-locally to the GPU that will ingest each block (b % world)
+        if args.impl == "ours":  # mem tier placed NUMA-locally to the GPU that will ingest each block (b % world)
             from curvine_b200 import _lib
             _lib.lib().cv_synth_set_shard_world(world)
         t0 = time.time()

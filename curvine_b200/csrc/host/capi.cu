@@ -500,7 +500,7 @@ int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, i
                              int32_t mode, int32_t hole_every, int32_t threads, const char* worker_hostname, char** manifest_out) {
     API_GUARD_BEGIN
     std::vector<std::vector<int>> node_cpus;
-    if (g_synth_shard_world > 1) node_cpus = gpu_node_cpus();
+    if (g_synth_shard_world >= 1) node_cpus = gpu_node_cpus();
     if (block_size <= 0 || len < 0) return fail(Err(kInvalidFileSize, "bad file or block size"));
     const int64_t nb = (len + block_size - 1) / block_size;
     FileBlocks fb;

@@ -138,7 +138,7 @@ int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, i
                              int32_t storage_type, int32_t mode, int32_t hole_every, int32_t threads,
                              const char* worker_hostname, char** manifest_out);
 /* NUMA-aware mem-tier placement for round-robin shards: after cv_synth_set_shard_world(G), block b of newly created
- * files is first-touched on the NUMA node of GPU b % G (0 or 1 turns it off). */
+ * files is first-touched on the NUMA node of GPU b % G (G = 1: everything next to GPU 0; 0 turns it off). */
 int64_t cv_synth_set_shard_world(int32_t shard_world);
 /* fill buf with block `block_index` of file `file_id` (mode 0 generator) */
 void cv_synth_block(uint64_t file_id, uint64_t block_index, uint8_t* buf, size_t len);

@@ -349,27 +349,78 @@ __device__ __forceinline__ uint32_t walk_segment(const uint8_t* src, uint8_t* ds
         if (lane < nv) vr = ld_stream(sp + R * 32);
     } else {
         const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15u);
-        const uint8_t* s = src + lane * 16u;
         uint4* dp = reinterpret_cast<uint4*>(dst) + lane;
-        uint32_t j = 0;
-        for (; j + 2 <= R; j += 2) {  // 2 rows in flight per lane (4 rows measured slower: K3 4.4 -> 2.7 TB/s)
-            const uint4 v0 = load_shifted(s + (j + 0) * 512u, sh);
-            const uint4 v1 = load_shifted(s + (j + 1) * 512u, sh);
-            dp[(j + 0) * 32] = v0;
-            dp[(j + 1) * 32] = v1;
-            if (CRC) {
-                CV_STEP(v0);
-                CV_STEP(v1);
+        if (sh == 0) {  // source and destination share their 16-byte phase: one load per vector
+            const uint4* sp = reinterpret_cast<const uint4*>(src) + lane;
+            uint32_t j = 0;
+            for (; j + 2 <= R; j += 2) {
+                const uint4 v0 = ld_plain(sp + (j + 0) * 32);
+                const uint4 v1 = ld_plain(sp + (j + 1) * 32);
+                dp[(j + 0) * 32] = v0;
+                dp[(j + 1) * 32] = v1;
+                if (CRC) {
+                    CV_STEP(v0);
+                    CV_STEP(v1);
+                }
             }
-        }
-        for (; j < R; j++) {
-            const uint4 v = load_shifted(s + j * 512u, sh);
-            dp[j * 32] = v;
-            if (CRC) CV_STEP(v);
-        }
-        if (lane < nv) {
-            vr = load_shifted(s + R * 512u, sh);
-            dp[R * 32] = vr;
+            for (; j < R; j++) {
+                const uint4 v = ld_plain(sp + j * 32);
+                dp[j * 32] = v;
+                if (CRC) CV_STEP(v);
+            }
+            if (lane < nv) {
+                vr = ld_plain(sp + R * 32);
+                dp[R * 32] = vr;
+            }
+        } else {
+            // Shifted source (every frame payload: 22-byte prefixes put it 6, 12, 2, 8, ... bytes off the destination's
+            // phase).  Each ALIGNED source vector is loaded exactly once; the 16 output bytes of a lane straddle its own
+            // vector and its right neighbour's, which arrives by warp shuffle (lane 31 takes lane 0's vector of the NEXT
+            // row, which is prefetched anyway).
+            const uint4* bp = reinterpret_cast<const uint4*>(src - sh) + lane;
+            const uint32_t nvec = (L >> 4) + 1;  // aligned vectors that hold the L bytes
+            const uint32_t rows = R + (nv ? 1u : 0u);
+            const uint32_t q = sh >> 2, r8 = (sh & 3u) * 8u;
+            const uint4 zero = make_uint4(0, 0, 0, 0);
+            const uint32_t from = (lane + 1) & 31;
+            uint4 ra = lane < nvec ? ld_plain(bp) : zero;
+            uint4 rb = 32 + lane < nvec ? ld_plain(bp + 32) : zero;
+            for (uint32_t j = 0; j < rows; j++) {
+                const uint4 rc = (j + 2) * 32 + lane < nvec ? ld_plain(bp + (j + 2) * 32) : zero;  // prefetch two rows ahead
+                const uint4 give = lane == 0 ? rb : ra;
+                uint4 nb;
+                nb.x = __shfl_sync(0xffffffffu, give.x, from);
+                nb.y = __shfl_sync(0xffffffffu, give.y, from);
+                nb.z = __shfl_sync(0xffffffffu, give.z, from);
+                nb.w = __shfl_sync(0xffffffffu, give.w, from);
+                uint4 v;
+                switch (q) {
+                    case 0:
+                        v.x = __funnelshift_r(ra.x, ra.y, r8), v.y = __funnelshift_r(ra.y, ra.z, r8);
+                        v.z = __funnelshift_r(ra.z, ra.w, r8), v.w = __funnelshift_r(ra.w, nb.x, r8);
+                        break;
+                    case 1:
+                        v.x = __funnelshift_r(ra.y, ra.z, r8), v.y = __funnelshift_r(ra.z, ra.w, r8);
+                        v.z = __funnelshift_r(ra.w, nb.x, r8), v.w = __funnelshift_r(nb.x, nb.y, r8);
+                        break;
+                    case 2:
+                        v.x = __funnelshift_r(ra.z, ra.w, r8), v.y = __funnelshift_r(ra.w, nb.x, r8);
+                        v.z = __funnelshift_r(nb.x, nb.y, r8), v.w = __funnelshift_r(nb.y, nb.z, r8);
+                        break;
+                    default:
+                        v.x = __funnelshift_r(ra.w, nb.x, r8), v.y = __funnelshift_r(nb.x, nb.y, r8);
+                        v.z = __funnelshift_r(nb.y, nb.z, r8), v.w = __funnelshift_r(nb.z, nb.w, r8);
+                        break;
+                }
+                if (j < R) {
+                    dp[j * 32] = v;
+                    if (CRC) CV_STEP(v);
+                } else if (lane < nv) {
+                    dp[j * 32] = v;
+                    vr = v;
+                }
+                ra = rb, rb = rc;
+            }
         }
     }
     if (!CRC) return 0;

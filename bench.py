@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--verify-batch", type=int, default=16)
     ap.add_argument("--copy-group", type=int, default=8)
     ap.add_argument("--copy-streams", type=int, default=1)
+    ap.add_argument("--numa-node", type=int, default=-1, help="-1 bind fetch threads to the GPU's node, -2 no binding")
     ap.add_argument("--zero-copy", type=int, default=1, help="short-circuit: DMA from registered mmaps of the mem-tier block files")
     ap.add_argument("--also-pread", action="store_true", help="additionally report e2e over the pinned-ring (pread) path")
     ap.add_argument("--gpu-chunk", default="4MB")
@@ -163,9 +164,9 @@ def client_conf(args, sc, device, threads, slots, zero_copy=None, copy_group=Non
     from curvine_b200 import fs as F
     zc = args.zero_copy if zero_copy is None else zero_copy
     b200 = ('device = %d\nfetch_threads = %d\npinned_slots = %d\nverify_poly = %d\nverify = true\nverify_batch = %d\ncopy_group = %d\ngpu_chunk_size = "%s"\n'
-            'zero_copy = %s\nregister_cache = "%dGB"\ncopy_streams = %d\n'
+            'zero_copy = %s\nregister_cache = "%dGB"\ncopy_streams = %d\nnuma_node = %d\n'
             % (device, threads, slots, args.poly, args.verify_batch, args.copy_group if copy_group is None else copy_group, args.gpu_chunk,
-               "true" if zc else "false", int(args.gib_per_gpu * 1.5) + 1, args.copy_streams))
+               "true" if zc else "false", int(args.gib_per_gpu * 1.5) + 1, args.copy_streams, args.numa_node))
     return F.client_conf(hostname="localhost", short_circuit=sc, b200=b200)
 
 

@@ -208,8 +208,8 @@ class GpuIngest {
         CU_TRY(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
         reg.capacity = c.zero_copy ? static_cast<size_t>(std::max<int64_t>(c.register_cache, 0)) : 0;
         // CPUs of the GPU's NUMA node: pinned pages and fetch threads stay next to the PCIe root
-        int node = c.numa_node;
-        if (node < 0) {
+        int node = c.numa_node;  // -1: the GPU's node (auto); -2: do not bind the fetch threads
+        if (node == -1) {
             char bus[64] = {0};
             if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) == cudaSuccess) {
                 for (char* p = bus; *p; p++) *p = static_cast<char>(tolower(*p));

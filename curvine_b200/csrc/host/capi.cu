@@ -49,7 +49,6 @@ struct cv_reader {
     std::string path;
     std::unique_ptr<FsReader> host;
     std::unique_ptr<GpuFsReader> dev;
-    std::vector<int64_t> fuse_segs;
 };
 
 struct cv_writer {

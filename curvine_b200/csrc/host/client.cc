@@ -206,36 +206,6 @@ Err BlockClient::rpc(const Protocol& req, const std::string& header, Protocol* r
     return Err::ok();
 }
 
-Err BlockClient::rpc_into(const Protocol& req, const std::string& header, uint8_t* dst, size_t cap, size_t* n) {
-    CV_RETURN_IF_ERR(send_request(req, header));
-    Protocol resp;
-    std::string rh;
-    CV_RETURN_IF_ERR(recv_response_head(&resp, &rh));
-    if (!resp.is_success() || static_cast<size_t>(resp.data_len) > cap) {
-        std::string body(static_cast<size_t>(resp.data_len), '\0');
-        if (resp.data_len && recv_exact(fd_, &body[0], body.size())) {
-            broken = true;
-            return Err::io("connection closed");
-        }
-        if (!resp.is_success()) return decode_error_body(reinterpret_cast<const uint8_t*>(body.data()), body.size());
-        broken = true;
-        return Err::common("response payload larger than the receive buffer");
-    }
-    if (resp.data_len) {
-        Err e = recv_exact(fd_, dst, static_cast<size_t>(resp.data_len));
-        if (e) {
-            broken = true;
-            return e;
-        }
-    }
-    if (Err e = check_echo(req, resp)) {
-        broken = true;
-        return e;
-    }
-    *n = static_cast<size_t>(resp.data_len);
-    return Err::ok();
-}
-
 static Protocol request_proto(int8_t status, int64_t req_id, int32_t seq_id) {
     Protocol p;
     p.code = kCodeReadBlock, p.req_status = status, p.resp_status = kRespUndefined, p.req_id = req_id, p.seq_id = seq_id;

@@ -92,8 +92,6 @@ class BlockClient {
     const WorkerAddress& addr() const { return addr_; }
     // send one request frame, receive one response frame (heartbeats skipped), check echoes, map error responses
     Err rpc(const Protocol& req, const std::string& header, Protocol* resp, std::string* resp_header, std::string* resp_data);
-    // like rpc but the payload is received straight into `dst` (cap bytes); *n = payload length
-    Err rpc_into(const Protocol& req, const std::string& header, uint8_t* dst, size_t cap, size_t* n);
     Err open_block(const ClientConf& conf, const ExtendedBlock& b, int64_t off, int64_t len, int64_t req_id, int32_t seq_id, bool short_circuit,
                    int64_t chunk_size, BlockReadResponse* out);
     Err read_commit(const ExtendedBlock& b, int64_t req_id, int32_t seq_id);

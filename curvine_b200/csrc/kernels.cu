@@ -279,35 +279,6 @@ __device__ __forceinline__ uint4 ld_plain(const uint4* p) {
     return r;
 }
 
-// 16 source bytes starting at the (possibly unaligned) address s; sh = s & 15 is warp-uniform.
-__device__ __forceinline__ uint4 load_shifted(const uint8_t* s, uint32_t sh) {
-    const uint4* p = reinterpret_cast<const uint4*>(s - sh);
-    const uint4 A = ld_plain(p);
-    if (sh == 0) return A;
-    const uint4 B = ld_plain(p + 1);
-    const uint32_t r8 = (sh & 3u) * 8u;
-    uint4 o;
-    switch (sh >> 2) {
-        case 0:
-            o.x = __funnelshift_r(A.x, A.y, r8), o.y = __funnelshift_r(A.y, A.z, r8);
-            o.z = __funnelshift_r(A.z, A.w, r8), o.w = __funnelshift_r(A.w, B.x, r8);
-            break;
-        case 1:
-            o.x = __funnelshift_r(A.y, A.z, r8), o.y = __funnelshift_r(A.z, A.w, r8);
-            o.z = __funnelshift_r(A.w, B.x, r8), o.w = __funnelshift_r(B.x, B.y, r8);
-            break;
-        case 2:
-            o.x = __funnelshift_r(A.z, A.w, r8), o.y = __funnelshift_r(A.w, B.x, r8);
-            o.z = __funnelshift_r(B.x, B.y, r8), o.w = __funnelshift_r(B.y, B.z, r8);
-            break;
-        default:
-            o.x = __funnelshift_r(A.w, B.x, r8), o.y = __funnelshift_r(B.x, B.y, r8);
-            o.z = __funnelshift_r(B.y, B.z, r8), o.w = __funnelshift_r(B.z, B.w, r8);
-            break;
-    }
-    return o;
-}
-
 #define CV_STEP(v)                       \
     do {                                 \
         a0 = mul_row(a0, tl) ^ (v).x;    \

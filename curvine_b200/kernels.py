@@ -37,7 +37,7 @@ def crc_blocks(data: torch.Tensor, offs, lens, poly=POLY_IEEE, stream=None, out=
     offs_t = offs if isinstance(offs, torch.Tensor) else torch.tensor(np.asarray(offs, dtype=np.uint64).view(np.int64), device=dev)
     lens_t = lens if isinstance(lens, torch.Tensor) else torch.tensor(np.asarray(lens, dtype=np.uint64).view(np.int64), device=dev)
     n = offs_t.numel()
-    total = int(lens_t.sum().item()) if not isinstance(lens, torch.Tensor) or True else 0
+    total = int(lens_t.sum().item())
     if out is None:
         out = torch.empty(n, dtype=torch.int32, device=dev)
     check(_lib.lib().cvk_crc_blocks(ctypes.c_void_p(data.data_ptr() + base_offset), _ptr(offs_t), _ptr(lens_t), n, poly,

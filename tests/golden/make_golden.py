@@ -47,6 +47,12 @@ def main():
         "block_crc32c": C.crc32c(blk),
         "bench_sum_crc32_128k": C.bench_checksum(blk, 131072),
         "synth_block_1001_0_first32": blk[:32].hex(),
+        "write_open_request": W.encode(W.request(W.RPC_CODE_WRITE_BLOCK, W.REQ_OPEN, 0x0102030405060708, 0,
+                                                 W.BlockWriteRequest(block_id, 0, W.STORAGE_MEM, 1, 0, 4 << 20, False, "cv", 131072).encode())).hex(),
+        "write_open_response": W.encode(W.success(W.request(W.RPC_CODE_WRITE_BLOCK, W.REQ_OPEN, 0x0102030405060708, 0),
+                                                  W.BlockWriteResponse(block_id, None, 0, 4 << 20, W.STORAGE_MEM).encode())).hex(),
+        "write_complete_request": W.encode(W.request(W.RPC_CODE_WRITE_BLOCK, W.REQ_COMPLETE, 0x0102030405060708, 33,
+                                                     W.BlockWriteRequest(block_id, 4 << 20, W.STORAGE_MEM, 1, 4 << 20, 4 << 20, False, "cv", 0).encode())).hex(),
         "crc_check": {"input": "123456789", "crc32": C.CHECK_IEEE, "crc32c": C.CHECK_CASTAGNOLI},
     }
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "wire_vectors.json")

@@ -40,6 +40,21 @@ def test_golden_wire_vectors_appendix_a():
     assert layout.block_path("/data/curvine", bid) == GOLD["block_path"]
 
 
+def test_golden_write_protocol_vectors():
+    """WriteBlock (80) frames: BlockWriteRequest embeds ExtendedBlockProto (worker.proto:10-18, common.proto:98-104)."""
+    bid = GOLD["block_id"]
+    req = W.BlockWriteRequest(bid, 0, W.STORAGE_MEM, 1, 0, 4 << 20, False, "cv", 131072)
+    enc = W.encode(W.request(80, W.REQ_OPEN, 0x0102030405060708, 0, req.encode()))
+    assert enc.hex() == GOLD["write_open_request"]
+    assert W.BlockWriteRequest.decode(req.encode()) == req
+    assert enc[8] == 80 and enc[9] == 0xF2
+    rsp = W.BlockWriteResponse(bid, None, 0, 4 << 20, W.STORAGE_MEM)
+    assert W.BlockWriteResponse.decode(rsp.encode()) == rsp
+    assert W.encode(W.success(W.request(80, W.REQ_OPEN, 0x0102030405060708, 0), rsp.encode())).hex() == GOLD["write_open_response"]
+    # required string client_name is emitted even when empty (prost: required fields always encoded)
+    assert W.BlockWriteRequest(1, 0, 0, 1, 0, 1, False, "", 1).encode().endswith(bytes([0x2a, 0x00, 0x30, 0x01]))
+
+
 def test_frame_roundtrip_and_limits():
     rng = np.random.default_rng(0)
     for hl, dl in [(0, 0), (5, 0), (0, 1), (13, 131072), (29, 777)]:

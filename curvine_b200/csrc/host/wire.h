@@ -26,7 +26,9 @@ enum ResponseStatus : int8_t { kRespUndefined = -1, kRespSuccess = 0, kRespError
 // StorageTypeProto (common.proto:9-16)
 enum StorageType : int32_t { kStorageMem = 0, kStorageSsd = 1, kStorageHdd = 2, kStorageUfs = 3, kStorageDisk = 4, kStorageSpdkDisk = 5 };
 
-inline int8_t status_encode(int8_t req, int8_t resp) { return static_cast<int8_t>(req | static_cast<int8_t>(resp << 4)); }
+inline int8_t status_encode(int8_t req, int8_t resp) {
+    return static_cast<int8_t>(static_cast<uint8_t>(req) | static_cast<uint8_t>(static_cast<uint8_t>(resp) << 4));
+}
 inline void status_decode(int8_t v, int8_t* req, int8_t* resp) {
     int8_t r = v & 0x0f, s = static_cast<int8_t>(v >> 4);
     *req = (r >= 0 && r <= 5) ? r : kReqUndefined;

@@ -174,7 +174,7 @@ def run_e2e(fs, path, rank, world, dst, shard_bytes, steps, warmup, dist):
     """-> (per-step ms list over timed steps, stats of the last step)."""
     import torch
     stream = torch.cuda.current_stream().cuda_stream
-    times, stats, last = [], None, None
+    times, warm, stats, last = [], [], None, None
     for it in range(warmup + steps):
         barrier(dist)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -192,8 +192,8 @@ def run_e2e(fs, path, rank, world, dst, shard_bytes, steps, warmup, dist):
         assert bad == 0, "CRC mismatch in %d blocks" % bad
         assert got == shard_bytes and ver == shard_bytes // BLOCK, (got, ver)
         last = s
-        if it >= warmup:
-            times.append(a.elapsed_time(b))
+        (times if it >= warmup else warm).append(a.elapsed_time(b))
+    run_e2e.warmup_ms = warm
     return times, stats, last
 
 
@@ -245,6 +245,7 @@ def main():
         # ---- e2e: host buffers -> HBM through the C ABI
         t_a = sampler.mark()
         e2e_ms, stats, sum_crc = run_e2e(fs, "/bench/file", rank, world, dst, shard_bytes, args.steps, args.warmup, dist)
+        e2e_warm_ms = list(run_e2e.warmup_ms)  # step 0 is cold: it also mmaps + cudaHostRegisters every block file
         t_b = sampler.mark()
         # ---- value: same verify pass, bytes already in HBM (what landed in the last e2e step)
         blocks = np.arange(rank, nb_total, world, dtype=np.int64)
@@ -360,6 +361,7 @@ def main():
                            "l2": "inputs (16 GiB per GPU) are larger than L2; no flush needed", "host_cpus": ncpu},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) if world == 1 else shard_bytes * world,
                         "d2h_bytes_per_step": 4 * (my_blocks + 4) * world, "ms_per_step": e2e_step_ms, "best_ms": e2e_best_ms, "timed_steps_ms": e2e_ms,
+                        "warmup_steps_ms": e2e_warm_ms, "cold_first_step_GBps": total_bytes / e2e_warm_ms[0] / 1e6 if e2e_warm_ms else None,
                         "per_gpu_GBps": e2e_val / world, "frac_of_pcie_gen5_x16_raw_63GBps": e2e_val / world / pcie_raw,
                         "frac_of_measured_h2d_55.6GBps": e2e_val / world / 55.6,
                         "last_step_fetch_thread_sec": stats["fetch_sec"], "last_step_wall_sec": stats["wall_sec"],

@@ -2,6 +2,7 @@
 
 #include <errno.h>
 #include <fcntl.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -327,6 +328,10 @@ Err BlockReader::open_adapter(int64_t off) {
         }
         ctx_->release(std::move(client_));  // BlockReaderLocal keeps no connection; complete() acquires a new one
         kind_ = kLocal;
+        struct statfs sfs;
+        const bool tmpfs = fstatfs(fd_, &sfs) == 0 && sfs.f_type == 0x01021994;  // sys_libc.rs:320-339
+        ra_enabled_ = ctx_->conf.client.enable_read_ahead && !tmpfs && block_.len >= 256 * 1024;
+        last_ahead_ = -1;
     } else {
         kind_ = kRemote;
     }
@@ -347,6 +352,12 @@ Err BlockReader::read_once(std::string* buf) {
             buf->assign(static_cast<size_t>(want), '\0');
             break;
         case kLocal: {
+            // CacheManager::read_ahead (orpc/src/sys/cache_manager.rs:99-147, block_reader_local.rs:113-126): hint the next
+            // read_ahead_len bytes once the cursor passed half of the previous window; never on tmpfs or small files
+            if (ra_enabled_ && (last_ahead_ < 0 || pos_ >= last_ahead_ + ctx_->conf.client.read_ahead_len / 2)) {
+                posix_fadvise(fd_, pos_, ctx_->conf.client.read_ahead_len, POSIX_FADV_WILLNEED);
+                last_ahead_ = pos_;
+            }
             buf->resize(static_cast<size_t>(want));
             int64_t got = 0;
             while (got < want) {

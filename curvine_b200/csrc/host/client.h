@@ -161,6 +161,8 @@ class BlockReader {
     bool pending_seek_ = false;
     // local
     int fd_ = -1;
+    bool ra_enabled_ = false;
+    int64_t last_ahead_ = -1;
 };
 
 // ------------------------------------------------------------------ file-level reader

@@ -383,6 +383,26 @@ int64_t cv_worker_stop(cv_worker* w) {
     API_GUARD_END
 }
 
+int64_t cv_worker_hbm_load(cv_worker* w, int64_t block_id, int32_t device) {
+    API_GUARD_BEGIN
+    BlockMeta m;
+    API_TRY(w->w.store().get_block(block_id, &m));
+    std::ifstream f(m.path, std::ios::binary);
+    if (!f) return fail(Err::io("open " + m.path));
+    std::vector<char> buf(static_cast<size_t>(m.len));
+    f.read(buf.data(), static_cast<std::streamsize>(buf.size()));
+    if (f.gcount() != static_cast<std::streamsize>(buf.size())) return fail(Err::io("short read of " + m.path));
+    API_TRY(w->w.hbm().load(block_id, buf.data(), m.len, device));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_worker_hbm_stats(cv_worker* w, int64_t out[3]) {
+    WorkerMetrics& m = w->w.metrics();
+    out[0] = static_cast<int64_t>(w->w.hbm().size()), out[1] = m.read_blocks_hbm, out[2] = m.hbm_packed_bytes;
+    return ok();
+}
+
 int64_t cv_worker_metrics(cv_worker* w, int64_t out[6]) {
     WorkerMetrics& m = w->w.metrics();
     out[0] = m.read_bytes, out[1] = m.read_time_us, out[2] = m.read_count, out[3] = m.read_blocks_local, out[4] = m.read_blocks_remote;

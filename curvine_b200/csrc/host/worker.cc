@@ -44,7 +44,14 @@ Err ReadHandler::open(const RpcRequest& req, RpcResponse* resp) {
     const bool short_circuit = c.short_circuit && meta.storage_type != kStorageSpdkDisk;
     close_fd(fd_);
     fd_ = -1;
-    if (!short_circuit) {
+    from_hbm_ = !short_circuit && hbm_ && hbm_->get(c.id, &hbm_block_);
+    if (from_hbm_) {
+        // the block is resident in HBM: pack the whole response stream on the GPU now (K4), serve Running requests from it
+        len_ = hbm_block_.len, pos_ = c.off, next_seq_ = req.proto.seq_id + 1;
+        CV_RETURN_IF_ERR(hbm_->pack(hbm_block_, c.off, len_ - c.off, c.chunk_size, req.proto.req_id, next_seq_, &packed_));
+        metrics_->read_blocks_hbm++;
+        metrics_->hbm_packed_bytes += len_ - c.off;
+    } else if (!short_circuit) {
         fd_ = ::open(meta.path.c_str(), O_RDONLY | O_CLOEXEC);
         if (fd_ < 0) return Err::io(str_printf("open %s: %s", meta.path.c_str(), strerror(errno)));
         struct stat st;
@@ -59,7 +66,7 @@ Err ReadHandler::open(const RpcRequest& req, RpcResponse* resp) {
     ctx_ = c;
     ctx_req_id_ = req.proto.req_id;
     has_ctx_ = true;
-    (short_circuit ? metrics_->read_blocks_local : metrics_->read_blocks_remote)++;
+    if (!from_hbm_) (short_circuit ? metrics_->read_blocks_local : metrics_->read_blocks_remote)++;
     BlockReadResponse r;
     r.id = c.id, r.len = meta.len, r.has_path = short_circuit, r.path = meta.path, r.storage_type = meta.storage_type;
     resp->proto = response_proto(req.proto, kRespSuccess);
@@ -77,6 +84,30 @@ void ReadHandler::read_ahead() {
 }
 
 Err ReadHandler::read(const RpcRequest& req, RpcResponse* resp) {
+    if (from_hbm_ && has_ctx_) {
+        if (!req.header.empty()) {  // seek: re-pack from the new offset
+            DataHeaderProto h;
+            CV_RETURN_IF_ERR(DataHeaderProto::decode(reinterpret_cast<const uint8_t*>(req.header.data()), req.header.size(), &h));
+            if (h.offset != pos_) {
+                if (h.offset < 0 || h.offset > len_) return Err::io("seek out of range");
+                pos_ = h.offset;
+                CV_RETURN_IF_ERR(hbm_->pack(hbm_block_, pos_, len_ - pos_, ctx_.chunk_size, ctx_req_id_, req.proto.seq_id, &packed_));
+            }
+        }
+        const int64_t chunk = std::min<int64_t>(ctx_.chunk_size, len_ - pos_);
+        if (chunk <= 0) return Err::common(str_printf("offset exceeds file length, length=%lld, offset=%lld", (long long)len_, (long long)pos_));
+        const int64_t f = (pos_ - packed_.off0) / packed_.chunk;
+        uint8_t* frame = packed_.wire + f * (kProtocolSize + packed_.chunk);
+        // the prefix was packed with the expected echoes; patch them if this request carries different ones
+        if (static_cast<int32_t>(get_be32(frame + 18)) != req.proto.seq_id) put_be32(frame + 18, static_cast<uint32_t>(req.proto.seq_id));
+        if (static_cast<int64_t>(get_be64(frame + 10)) != req.proto.req_id) put_be64(frame + 10, static_cast<uint64_t>(req.proto.req_id));
+        resp->proto = response_proto(req.proto, kRespSuccess);
+        resp->raw = frame, resp->raw_len = static_cast<size_t>(kProtocolSize + chunk);
+        pos_ += chunk;
+        metrics_->read_bytes += chunk;
+        metrics_->read_count++;
+        return Err::ok();
+    }
     if (fd_ < 0) return Err::common("self.file is none");
     if (!has_ctx_) return Err::common("self.context is none");
     if (!req.header.empty()) {
@@ -304,13 +335,18 @@ void Worker::serve(int fd) {
         } else {
             whandler.reset();
             // worker_handler.rs:71-88: a fresh handler unless this is a Running message for the live one
-            if (!handler || req.proto.req_status != kReqRunning) handler.reset(new ReadHandler(&store_, &metrics_, enable_send_file_));
+            if (!handler || req.proto.req_status != kReqRunning) handler.reset(new ReadHandler(&store_, &metrics_, enable_send_file_, &hbm_));
             e = handler->handle(req, &resp);
         }
         if (e) {  // block_handler.rs:57-60 -> msg.error_ext(&e)
             resp = RpcResponse();
             resp.proto = response_proto(req.proto, kRespError);
             resp.data = encode_error_body(e.kind, e.msg);
+        }
+        if (!e && resp.raw) {  // a GPU-packed frame: prefix and payload already in wire order
+            if (send_all(fd, resp.raw, resp.raw_len)) return;
+            if (req.proto.req_status == kReqCancel || req.proto.req_status == kReqComplete) handler.reset(), whandler.reset();
+            continue;
         }
         resp.proto.header_len = static_cast<int32_t>(resp.header.size());
         resp.proto.data_len = resp.file_fd >= 0 ? resp.file_len : static_cast<int32_t>(resp.data.size());

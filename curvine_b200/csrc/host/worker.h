@@ -15,6 +15,7 @@
 #include <thread>
 
 #include "block_store.h"
+#include "hbm_tier.h"
 #include "wire.h"
 
 namespace cv {
@@ -22,6 +23,7 @@ namespace cv {
 struct WorkerMetrics {  // worker_metrics.rs:25-44
     std::atomic<int64_t> read_bytes{0}, read_time_us{0}, read_count{0}, read_blocks_local{0}, read_blocks_remote{0};
     std::atomic<int64_t> write_bytes{0}, write_time_us{0}, write_count{0}, write_blocks{0};
+    std::atomic<int64_t> read_blocks_hbm{0}, hbm_packed_bytes{0};
 };
 
 // One request message as received from the socket.
@@ -36,6 +38,8 @@ struct RpcResponse {
     Protocol proto;
     std::string header;
     std::string data;   // inline payload (errors, pread mode)
+    const uint8_t* raw = nullptr;  // a ready-made wire image (prefix + payload, packed on the GPU): sent verbatim
+    size_t raw_len = 0;
     int file_fd = -1;   // sendfile region when >= 0
     int64_t file_off = 0;
     int32_t file_len = 0;
@@ -44,7 +48,8 @@ struct RpcResponse {
 
 class ReadHandler {
    public:
-    ReadHandler(BlockStore* store, WorkerMetrics* m, bool enable_send_file) : store_(store), metrics_(m), enable_send_file_(enable_send_file) {}
+    ReadHandler(BlockStore* store, WorkerMetrics* m, bool enable_send_file, const HbmTier* hbm = nullptr)
+        : store_(store), metrics_(m), enable_send_file_(enable_send_file), hbm_(hbm) {}
     ~ReadHandler();
     Err handle(const RpcRequest& req, RpcResponse* resp);
 
@@ -63,6 +68,12 @@ class ReadHandler {
     int64_t pos_ = 0, len_ = 0, last_ahead_ = -1;
     bool is_tmpfs_ = false;
     std::string path_;
+    // HBM tier: the whole response stream of this read, packed by K4 at Open
+    const HbmTier* hbm_ = nullptr;
+    bool from_hbm_ = false;
+    HbmBlock hbm_block_;
+    PackedStream packed_;
+    int32_t next_seq_ = 1;
 };
 
 // Write-side mirror: WriteBlock = 80, Open{BlockWriteRequest} -> Running{payload, optional
@@ -97,12 +108,14 @@ class Worker {
     void stop();
     int port() const { return port_; }
     BlockStore& store() { return store_; }
+    HbmTier& hbm() { return hbm_; }
     WorkerMetrics& metrics() { return metrics_; }
 
    private:
     void accept_loop();
     void serve(int fd);
     BlockStore store_;
+    HbmTier hbm_;
     WorkerMetrics metrics_;
     int listen_fd_ = -1;
     int port_ = 0;

@@ -49,6 +49,15 @@ class MiniWorker:
         _lib.lib().cv_free(out)
         return text
 
+    def hbm_load(self, block_id: int, device: int = 0):
+        """HBM tier: make a finalized block resident in device memory; remote reads are then served from HBM (K4-packed frames)."""
+        _check(_lib.lib().cv_worker_hbm_load(self._h, block_id, device))
+
+    def hbm_stats(self) -> dict:
+        a = (ctypes.c_int64 * 3)()
+        _check(_lib.lib().cv_worker_hbm_stats(self._h, a))
+        return dict(zip(["resident_blocks", "reads_from_hbm", "packed_bytes"], a))
+
     def metrics(self) -> dict:
         a = (ctypes.c_int64 * 6)()
         _check(_lib.lib().cv_worker_metrics(self._h, a))

@@ -128,6 +128,11 @@ int64_t cv_writer_close(cv_writer* w, int32_t cancel, char** manifest_out);
 /* ---- fixture: in-process worker over a BlockStore directory tree + synthetic files */
 int64_t cv_worker_start(const char* conf_toml, cv_worker** out, int32_t* port);
 int64_t cv_worker_stop(cv_worker* w);
+/* HBM as a worker tier ("next" row 8f-2): copy a finalized block into device memory; from then on REMOTE reads of it are
+ * served from HBM as frames packed on the GPU (K4) -- the block file is no longer touched.
+ * stats: out[0]=resident blocks [1]=reads served from HBM [2]=payload bytes packed by K4. */
+int64_t cv_worker_hbm_load(cv_worker* w, int64_t block_id, int32_t device);
+int64_t cv_worker_hbm_stats(cv_worker* w, int64_t out[3]);
 /* out[0]=read_bytes [1]=read_time_us [2]=read_count [3]=read_blocks{local} [4]=read_blocks{remote} [5]=num_blocks */
 int64_t cv_worker_metrics(cv_worker* w, int64_t out[6]);
 /* Write `len` bytes of synthetic content as blocks of `block_size` into the worker's BlockStore (reference

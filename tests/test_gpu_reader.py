@@ -328,3 +328,33 @@ def test_write_device_then_read_device_roundtrip(cuda, cluster):
             assert bad == 0 and ver == len(blocks) and torch.equal(dst, src)
             assert s == int(clib.crc_blocks(1, host, bs).astype(np.uint64).sum())
             r.complete()
+
+
+def test_hbm_tier_serves_gpu_packed_frames(cuda, cluster):
+    """HBM as a worker tier: blocks made resident in device memory are served to remote readers as frames packed on the
+    GPU (K4).  The block files are DELETED first, so every byte must come from HBM; host reader (reference chunking,
+    seeks) and GPU reader (pipelined requests, K2 unpack + CRC) both get the oracle's bytes."""
+    import torch
+    w, d = cluster
+    bs, n, ino = 1 << 20, (4 << 20) + 4321, 7400
+    man = w.create_file("/hbm", ino, n, bs)
+    want = synth.file_bytes(ino, n, bs)
+    for i in range(5):
+        w.hbm_load(layout.create_block_id(ino, i), 0)
+        os.remove(layout.block_path(str(d / "mem" / "curvine"), layout.create_block_id(ino, i)))
+    assert w.hbm_stats()["resident_blocks"] >= 5
+    with F.CurvineFileSystem(_conf(False, 1, "128KB")) as fs:  # remote (framed) reads
+        fs.load_namespace(man)
+        r = fs.open("/hbm")
+        assert r.read_full(n) == want  # host path: 128 KiB ping-pong chunks out of the packed stream
+        r.seek(bs + 777)  # mid-block seek -> DataHeaderProto.offset -> re-pack from the new offset
+        assert r.read_full(300000) == want[bs + 777:bs + 777 + 300000]
+        dst = _dev_buf(n, cuda)
+        r.seek(0)
+        assert r.read_device(dst.data_ptr(), n, 0) == n
+        s, bad, ver = r.verify()
+        torch.cuda.synchronize()
+        assert bad == 0 and ver == 5 and dst.cpu().numpy().tobytes() == want
+        r.complete()
+    st = w.hbm_stats()
+    assert st["reads_from_hbm"] >= 10 and st["packed_bytes"] >= 2 * n

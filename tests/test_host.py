@@ -437,3 +437,46 @@ def test_writer_then_reader_checksums_agree(cluster):
         wr.complete(cancel=True)
         with pytest.raises(F.FsError):
             fs.open("/w/f2")
+
+
+def test_random_op_sequences_match_reader_model(cluster):
+    """Property test (hypothesis): arbitrary interleavings of read / read_full / read_chunk / seek / fuse_read give the
+    same bytes, the same short reads and the same pos() as the oracle's model of the reference reader stack, for
+    striped (read_parallel 3) and plain readers, short-circuit and framed."""
+    from hypothesis import given, settings, strategies as st
+    w, _ = cluster
+    bs, n, ino = 1 << 20, (6 << 20) + 4097, 5000
+    man = w.create_file("/prop", ino, n, bs)
+    op = st.one_of(
+        st.tuples(st.just("read"), st.integers(0, 300000)),
+        st.tuples(st.just("read_full"), st.integers(0, 700000)),
+        st.tuples(st.just("chunk"), st.just(0)),
+        st.tuples(st.just("seek"), st.integers(0, n + 10)),
+        st.tuples(st.just("fuse"), st.integers(0, n), st.integers(0, 400000)),
+    )
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.lists(op, min_size=1, max_size=25), st.booleans(), st.sampled_from([(64, 4, 1), (64, 2, 3), (128, 8, 1)]))
+    def run(ops, sc, shape):
+        chunk_kb, chunk_num, parallel = shape
+        conf = F.client_conf(short_circuit=sc, read_chunk_size="%dKB" % chunk_kb, read_chunk_num=chunk_num, read_parallel=parallel)
+        model, data = _model_for(ino, n, bs, RM.ClientConf(read_chunk_size=chunk_kb * 1024, read_chunk_num=chunk_num, read_parallel=parallel, short_circuit=sc))
+        with F.CurvineFileSystem(conf) as fs:
+            fs.load_namespace(man)
+            r = fs.open("/prop")
+            for o in ops:
+                if o[0] == "read":
+                    assert r.read(o[1]) == model.read(o[1])
+                elif o[0] == "read_full":
+                    assert r.read_full(o[1]) == model.read_full(o[1])
+                elif o[0] == "chunk":
+                    assert r.read_chunk() == model.blocking_read()
+                elif o[0] == "seek":
+                    r.seek(o[1])
+                    model.seek(o[1])
+                else:
+                    assert r.fuse_read(o[1], o[2]) == model.fuse_read(o[1], o[2])
+                assert r.pos() == model.pos
+            r.complete()
+
+    run()

@@ -220,6 +220,24 @@ class CurvineFileSystem:
         _check(_lib.lib().cv_open(self._h, path.encode(), ctypes.byref(h), ctypes.byref(n)))
         return Reader(h)
 
+    def read_to_tensor(self, path: str, device=None, verify: bool = True):
+        """Binding convenience: the whole file as a uint8 CUDA tensor (DLPack-exportable), CRC-verified
+        on the GPU.  Replaces curvinefs' copy-and-decode read (curvine-libsdk/python/curvinefs/curvineReader.py:17-49)."""
+        import torch
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        r = self.open(path)
+        try:
+            out = torch.empty(r.len(), dtype=torch.uint8, device=dev)
+            if r.len():
+                got = r.read_device(out.data_ptr(), r.len(), torch.cuda.current_stream(dev).cuda_stream)
+                assert got == r.len()
+            _, bad, _ = r.verify()
+            if verify and bad:
+                raise FsError(12, "%d blocks of %s failed CRC verification" % (bad, path))  # AbnormalData
+            return out
+        finally:
+            r.complete()
+
     def read_many_device(self, paths, d_ptr: int, dst_offs, cap: int, stream: int = 0):
         """Small-file batching: every file of ``paths`` lands at d_ptr + dst_offs[i] in one pipelined pass.
         -> (total_bytes, sum_crc, n_bad, n_verified)."""

@@ -358,3 +358,16 @@ def test_hbm_tier_serves_gpu_packed_frames(cuda, cluster):
         r.complete()
     st = w.hbm_stats()
     assert st["reads_from_hbm"] >= 10 and st["packed_bytes"] >= 2 * n
+
+
+def test_read_to_tensor_binding(cuda, cluster):
+    import torch
+    w, _ = cluster
+    n, ino = (3 << 20) + 77, 7500
+    man = w.create_file("/t2t", ino, n, 1 << 20)
+    with F.CurvineFileSystem(_conf(True)) as fs:
+        fs.load_namespace(man)
+        t = fs.read_to_tensor("/t2t")
+        assert t.is_cuda and t.dtype == torch.uint8 and t.numel() == n
+        assert t.cpu().numpy().tobytes() == synth.file_bytes(ino, n, 1 << 20)
+        assert torch.utils.dlpack.from_dlpack(torch.utils.dlpack.to_dlpack(t)).data_ptr() == t.data_ptr()

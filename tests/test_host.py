@@ -480,3 +480,28 @@ def test_random_op_sequences_match_reader_model(cluster):
             r.complete()
 
     run()
+
+
+@pytest.mark.parametrize("sc", [True, False])
+def test_config_c1_shape_cpu_reader_end_to_end(cluster, sc):
+    """BASELINE config C1: single 64 MiB file, 1 MiB blocks, mem-tier local worker, CPU reader end to end (plumbing, no
+    GPU): bytes == generator, curvine-bench checksum (sum of crc32 over 128 KiB read_full buffers) == oracle."""
+    w, _ = cluster
+    n, bs, ino = 64 << 20, 1 << 20, 5100
+    man = w.create_file("/c1cpu", ino, n, bs)
+    want = synth.file_bytes(ino, n, bs)
+    with F.CurvineFileSystem(F.client_conf(short_circuit=sc)) as fs:
+        fs.load_namespace(man)
+        with fs.open("/c1cpu") as r:
+            cks, total = 0, 0
+            while True:
+                b = r.read_full(128 * 1024)
+                if not b:
+                    break
+                assert b == want[total:total + len(b)]
+                cks += zlib.crc32(b)
+                total += len(b)
+            assert total == n and r.pos() == n
+    assert cks == clib.bench_checksum(want, 128 * 1024)
+    m = w.metrics()
+    assert (m["read_blocks_local"] if sc else m["read_blocks_remote"]) >= 64

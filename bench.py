@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--verify-batch", type=int, default=16)
     ap.add_argument("--copy-group", type=int, default=8)
     ap.add_argument("--copy-streams", type=int, default=1)
+    ap.add_argument("--register-threads", type=int, default=8, help="background registrar threads (0 = register inline on first touch)")
     ap.add_argument("--numa-node", type=int, default=-1, help="-1 bind fetch threads to the GPU's node, -2 no binding")
     ap.add_argument("--zero-copy", type=int, default=1, help="short-circuit: DMA from registered mmaps of the mem-tier block files")
     ap.add_argument("--also-pread", action="store_true", help="additionally report e2e over the pinned-ring (pread) path")
@@ -164,9 +165,9 @@ def client_conf(args, sc, device, threads, slots, zero_copy=None, copy_group=Non
     from curvine_b200 import fs as F
     zc = args.zero_copy if zero_copy is None else zero_copy
     b200 = ('device = %d\nfetch_threads = %d\npinned_slots = %d\nverify_poly = %d\nverify = true\nverify_batch = %d\ncopy_group = %d\ngpu_chunk_size = "%s"\n'
-            'zero_copy = %s\nregister_cache = "%dGB"\ncopy_streams = %d\nnuma_node = %d\n'
+            'zero_copy = %s\nregister_cache = "%dGB"\ncopy_streams = %d\nnuma_node = %d\nregister_threads = %d\n'
             % (device, threads, slots, args.poly, args.verify_batch, args.copy_group if copy_group is None else copy_group, args.gpu_chunk,
-               "true" if zc else "false", int(args.gib_per_gpu * 1.5) + 1, args.copy_streams, args.numa_node))
+               "true" if zc else "false", int(args.gib_per_gpu * 1.5) + 1, args.copy_streams, args.numa_node, args.register_threads))
     return F.client_conf(hostname="localhost", short_circuit=sc, b200=b200)
 
 
@@ -357,7 +358,7 @@ def main():
                 "config": {"workload": "C2: 16 GiB synthetic file per GPU, 4 MiB blocks, mem-tier (tmpfs) BlockStore, "
                                        "blocks round-robin across GPUs (C3 shape at N=8), on-GPU CRC-%s verify" % ("32C" if args.poly else "32"),
                            "file_bytes": total_bytes, "block_bytes": BLOCK, "blocks_per_gpu": my_blocks, "read_path": args.mode, "zero_copy": bool(args.zero_copy and args.mode == "short_circuit"),
-                           "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch, "copy_group": args.copy_group,
+                           "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch, "copy_group": args.copy_group, "register_threads": args.register_threads,
                            "l2": "inputs (16 GiB per GPU) are larger than L2; no flush needed", "host_cpus": ncpu},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) if world == 1 else shard_bytes * world,
                         "d2h_bytes_per_step": 4 * (my_blocks + 4) * world, "ms_per_step": e2e_step_ms, "best_ms": e2e_best_ms, "timed_steps_ms": e2e_ms,

@@ -112,6 +112,13 @@ int64_t cv_fs_close(cv_fs* fs) {
     API_GUARD_END
 }
 
+int64_t cv_fs_wait_registered(cv_fs* fs) {
+    API_GUARD_BEGIN
+    gpu_ingest_wait_registered(fs->ctx.get());
+    return ok();
+    API_GUARD_END
+}
+
 int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]) {
     out[0] = fs->ctx->read_bytes.load(), out[1] = fs->ctx->read_time_us.load();
     return ok();

@@ -8,7 +8,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <deque>
 #include <list>
+#include <set>
 
 #include <fstream>
 
@@ -67,7 +69,6 @@ class RegCache {
         std::vector<std::shared_ptr<RegMapping>> evicted;  // destroyed outside the lock
         {
             std::lock_guard<std::mutex> lk(mu_);
-            misses++;
             if (capacity == 0) return;
             lru_.emplace_front(m->key, m);
             map_[m->key] = lru_.begin();
@@ -152,6 +153,90 @@ static bool stat_stamps(const std::vector<std::string>& paths, std::vector<uint6
     return true;
 }
 
+// Background registration: a cache miss does not stall the read.  The foreground moves the group through the pinned
+// ring right away (cold pass at ring speed) while a few registrar threads mmap + cudaHostRegister the same files so that
+// the NEXT pass over them is zero-copy.
+class Registrar {
+   public:
+    struct Job {
+        std::string key;
+        std::vector<std::string> paths;
+        std::vector<int64_t> lens;
+    };
+    void start(int threads, int device, RegCache* cache, std::vector<int> cpus) {
+        device_ = device, cache_ = cache, cpus_ = std::move(cpus);
+        for (int t = 0; t < threads; t++) threads_.emplace_back([this] { loop(); });
+    }
+    void submit(Job j) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (stop_ || unsupported.load() || !pending_keys_.insert(j.key).second) return;
+        q_.push_back(std::move(j));
+        cv_.notify_one();
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            q_.clear();
+            cv_.notify_all();
+        }
+        for (auto& t : threads_) t.join();
+        threads_.clear();
+    }
+    void drain() {  // wait until the queue is empty and no registration is in flight
+        std::unique_lock<std::mutex> lk(mu_);
+        idle_cv_.wait(lk, [&] { return (q_.empty() && busy_ == 0) || stop_; });
+    }
+    std::atomic<bool> unsupported{false};
+    std::atomic<uint64_t> registered{0};
+
+   private:
+    void loop() {
+        if (!cpus_.empty()) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            for (int c : cpus_) CPU_SET(c, &set);
+            sched_setaffinity(0, sizeof(set), &set);
+        }
+        cudaSetDevice(device_);
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (stop_) return;
+                j = std::move(q_.front());
+                q_.pop_front();
+                busy_++;
+            }
+            std::shared_ptr<RegMapping> m;
+            std::vector<uint64_t> stamps;
+            Err e = map_and_register(j.paths, j.lens, &m, &stamps);
+            if (!e) {
+                m->key = j.key;
+                cache_->insert(m);
+                registered++;
+            } else if (e.kind == kUnsupported) {
+                unsupported.store(true);
+            }
+            std::lock_guard<std::mutex> lk(mu_);
+            pending_keys_.erase(j.key);
+            busy_--;
+            if (q_.empty() && busy_ == 0) idle_cv_.notify_all();
+        }
+    }
+    int device_ = 0;
+    RegCache* cache_ = nullptr;
+    std::vector<int> cpus_;
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_, idle_cv_;
+    std::deque<Job> q_;
+    std::set<std::string> pending_keys_;
+    int busy_ = 0;
+    bool stop_ = false;
+};
+
 // ------------------------------------------------------------------ GpuIngest: ring + streams
 
 class GpuIngest {
@@ -175,6 +260,8 @@ class GpuIngest {
     size_t h_result_cap = 0;
     GpuFsReader* pending_owner = nullptr;  // reader whose results still sit in h_result
     RegCache reg;
+    Registrar registrar;
+    bool register_inline = false;
 
     Err ensure_tables(size_t tables_bytes, size_t result_bytes) {
         if (tables_bytes > d_tables_cap) {
@@ -207,6 +294,7 @@ class GpuIngest {
         CU_TRY(cudaStreamCreateWithFlags(&vstream, cudaStreamNonBlocking));
         CU_TRY(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
         reg.capacity = c.zero_copy ? static_cast<size_t>(std::max<int64_t>(c.register_cache, 0)) : 0;
+        register_inline = c.register_threads <= 0 || reg.capacity == 0;
         // CPUs of the GPU's NUMA node: pinned pages and fetch threads stay next to the PCIe root
         int node = c.numa_node;  // -1: the GPU's node (auto); -2: do not bind the fetch threads
         if (node == -1) {
@@ -233,6 +321,7 @@ class GpuIngest {
                 }
             }
         }
+        if (c.zero_copy && !register_inline) registrar.start(c.register_threads, device, &reg, cpus);
         return Err::ok();
     }
 
@@ -273,6 +362,7 @@ class GpuIngest {
     }
 
     ~GpuIngest() {
+        registrar.stop();
         cudaSetDevice(device);
         cudaDeviceSynchronize();
         reg.clear();
@@ -303,6 +393,16 @@ GpuIngest* gpu_ingest_get(FsContext* ctx, Err* err) {
     }
     g_ingests[ctx] = g;
     return g;
+}
+
+void gpu_ingest_wait_registered(FsContext* ctx) {
+    GpuIngest* g = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ing_mu);
+        auto it = g_ingests.find(ctx);
+        if (it != g_ingests.end()) g = it->second;
+    }
+    if (g) g->registrar.drain();
 }
 
 void gpu_ingest_release(FsContext* ctx) {
@@ -763,21 +863,65 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                     lens[j - j0] = lb.block.len;
                 }
                 std::shared_ptr<RegMapping> m;
+                bool via_ring = false;
                 if (!e) {
                     std::string key;
                     for (const auto& p : paths) key += p, key += '|';
                     std::vector<uint64_t> stamps;
                     if (stat_stamps(paths, &stamps)) m = G.reg.find(key, stamps);
-                    if (!m) {
-                        e = map_and_register(paths, lens, &m, &stamps);
-                        if (!e) {
-                            m->key = key;
-                            G.reg.insert(m);
+                    if (!m) G.reg.misses++;
+                    if (!m && G.registrar.unsupported.load()) e = Err(kUnsupported, "cudaHostRegister of file mappings is not supported here");
+                    if (!m && !e) {
+                        if (G.register_inline) {
+                            e = map_and_register(paths, lens, &m, &stamps);
+                            if (!e) {
+                                m->key = key;
+                                G.reg.insert(m);
+                            }
+                        } else {  // cold group: register it in the background for the next pass, move it through the ring now
+                            G.registrar.submit(Registrar::Job{key, paths, lens});
+                            via_ring = true;
                         }
                     }
                 }
                 cudaError_t ce = cudaSuccess;
-                if (!e) {
+                if (!e && via_ring) {
+                    e = ensure_ring();
+                    uint8_t* hs = G.pinned + ss * k * G.slot_bytes;
+                    bool contiguous = true;
+                    for (size_t j = j0 + 1; j < j1; j++) contiguous = contiguous && jobs[j].dst_off == jobs[j - 1].dst_off + jobs[j - 1].n;
+                    if (contiguous && static_cast<size_t>(jobs[j1 - 1].dst_off + jobs[j1 - 1].n - jobs[j0].dst_off) > k * G.slot_bytes) contiguous = false;
+                    for (size_t j = j0; j < j1 && !e && ce == cudaSuccess; j++) {
+                        const size_t in_slot = contiguous ? static_cast<size_t>(jobs[j].dst_off - jobs[j0].dst_off) : (j - j0) * G.slot_bytes;
+                        const int fd = ::open(paths[j - j0].c_str(), O_RDONLY | O_CLOEXEC);
+                        if (fd < 0) {
+                            e = Err::io(str_printf("open %s: %s", paths[j - j0].c_str(), strerror(errno)));
+                            break;
+                        }
+                        int64_t got = 0;
+                        while (got < jobs[j].n) {
+                            const ssize_t r = pread(fd, hs + in_slot + got, static_cast<size_t>(jobs[j].n - got), jobs[j].block_off + got);
+                            if (r < 0 && errno == EINTR) continue;
+                            if (r <= 0) {
+                                e = Err::io(str_printf("read block file: %s", r == 0 ? "unexpected eof" : strerror(errno)));
+                                break;
+                            }
+                            got += r;
+                        }
+                        ::close(fd);
+                        if (!e && !contiguous) {
+                            ce = cudaMemcpyAsync(d_dst + jobs[j].dst_off, hs + in_slot, static_cast<size_t>(jobs[j].n), cudaMemcpyHostToDevice, cs);
+                            h2d[static_cast<size_t>(t)] += static_cast<size_t>(jobs[j].n);
+                        }
+                    }
+                    if (!e && contiguous && ce == cudaSuccess) {
+                        const size_t extent = static_cast<size_t>(jobs[j1 - 1].dst_off + jobs[j1 - 1].n - jobs[j0].dst_off);
+                        ce = cudaMemcpyAsync(d_dst + jobs[j0].dst_off, hs, extent, cudaMemcpyHostToDevice, cs);
+                        h2d[static_cast<size_t>(t)] += extent;
+                    }
+                    if (!e && ce == cudaSuccess) ce = cudaEventRecord(G.copy_ev[ss], cs);
+                    for (size_t j = j0; j < j1 && !e; j++) e = conn->read_commit((*jobs[j].lb).block, rids[j - j0], 1);
+                } else if (!e) {
                     // one copy when the group is whole blocks landing back to back, else one per job
                     bool whole = true;
                     for (size_t j = j0; j < j1; j++) {

@@ -97,5 +97,6 @@ class GpuFsReader {
 // one per (process, device): pinned ring, device staging ring, streams, events
 GpuIngest* gpu_ingest_get(FsContext* ctx, Err* err);
 void gpu_ingest_release(FsContext* ctx);
+void gpu_ingest_wait_registered(FsContext* ctx);  // block until the background registrar is idle
 
 }  // namespace cv

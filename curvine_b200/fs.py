@@ -220,6 +220,10 @@ class CurvineFileSystem:
         _check(_lib.lib().cv_open(self._h, path.encode(), ctypes.byref(h), ctypes.byref(n)))
         return Reader(h)
 
+    def wait_registered(self):
+        """Block until the background registrar of the zero-copy mem tier is idle (optional; reads never wait for it)."""
+        _check(_lib.lib().cv_fs_wait_registered(self._h))
+
     def read_to_tensor(self, path: str, device=None, verify: bool = True):
         """Binding convenience: the whole file as a uint8 CUDA tensor (DLPack-exportable), CRC-verified
         on the GPU.  Replaces curvinefs' copy-and-decode read (curvine-libsdk/python/curvinefs/curvineReader.py:17-49)."""

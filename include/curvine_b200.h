@@ -64,6 +64,9 @@ int64_t cv_fs_new_from_string(const char* conf_toml, cv_fs** out);
 int64_t cv_fs_load_namespace(cv_fs* fs, const char* manifest_path);
 int64_t cv_fs_load_namespace_string(cv_fs* fs, const char* manifest_text);
 int64_t cv_fs_close(cv_fs* fs);
+/* Zero-copy mem tier: block until the background registrar (mmap + cudaHostRegister of block files seen by earlier
+ * device reads) is idle.  Optional; reads never wait for it -- unregistered blocks go through the pinned ring. */
+int64_t cv_fs_wait_registered(cv_fs* fs);
 /* client metrics (client_metrics.rs:24-35): out[0]=read_bytes out[1]=read_time_us */
 int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]);
 

@@ -47,6 +47,7 @@ def _declare(L):
     vp, u8p, u32, u64, i = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
     L.cvk_init.argtypes, L.cvk_init.restype = [i], i
     L.cvk_launch_count.argtypes, L.cvk_launch_count.restype = [], u64
+    L.cvk_tune.argtypes, L.cvk_tune.restype = [i, i], i
     L.cvk_profile_enable.argtypes, L.cvk_profile_enable.restype = [i], i
     L.cvk_profile_collect.argtypes, L.cvk_profile_collect.restype = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u32)], i
     L.cvk_crc_blocks.argtypes, L.cvk_crc_blocks.restype = [u8p, vp, vp, u32, i, u64, vp, vp], i
@@ -110,12 +111,13 @@ def _declare(L):
 class CvReadStats(ctypes.Structure):
     _fields_ = [("bytes", ctypes.c_uint64), ("blocks", ctypes.c_uint64), ("verified", ctypes.c_uint64),
                 ("h2d_bytes", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("fetch_sec", ctypes.c_double),
-                ("wall_sec", ctypes.c_double), ("reg_hits", ctypes.c_uint64), ("reg_misses", ctypes.c_uint64)]
+                ("wall_sec", ctypes.c_double), ("reg_hits", ctypes.c_uint64), ("reg_misses", ctypes.c_uint64),
+                ("ring_alloc_sec", ctypes.c_double)]
 
 
 # every symbol include/*.h declares (tests check the .so exports all of them)
 EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_unpack_frames", "cvk_expand_streams", "cvk_gather_pages",
-           "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_gather_shards_p2p", "cvk_launch_count", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
+           "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_gather_shards_p2p", "cvk_launch_count", "cvk_tune", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
            "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_wait_registered", "cv_fs_metrics",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device",

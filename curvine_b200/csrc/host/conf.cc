@@ -152,6 +152,7 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "zero_copy") b.zero_copy = as_bool(v);
             else if (k == "register_cache") e = as_size(v, &b.register_cache);
             else if (k == "register_threads") b.register_threads = static_cast<int>(as_int(v));
+            else if (k == "register_when_idle") b.register_when_idle = as_bool(v);
         }
         if (e) return e.ctx("conf key " + k);
     }

@@ -155,7 +155,10 @@ static bool stat_stamps(const std::vector<std::string>& paths, std::vector<uint6
 
 // Background registration: a cache miss does not stall the read.  The foreground moves the group through the pinned
 // ring right away (cold pass at ring speed) while a few registrar threads mmap + cudaHostRegister the same files so that
-// the NEXT pass over them is zero-copy.
+// the NEXT pass over them is zero-copy.  cudaHostRegister pins 4 KiB pages at ~13-26 GB/s on the B200 box and
+// serialises with copy enqueues inside the driver, so by default (`register_when_idle`) the registrar threads yield to
+// reads in flight: `hold` counts them, and a registrar only starts a new group while it is zero (or while a caller is
+// blocked in drain()).
 class Registrar {
    public:
     struct Job {
@@ -163,8 +166,8 @@ class Registrar {
         std::vector<std::string> paths;
         std::vector<int64_t> lens;
     };
-    void start(int threads, int device, RegCache* cache, std::vector<int> cpus) {
-        device_ = device, cache_ = cache, cpus_ = std::move(cpus);
+    void start(int threads, int device, RegCache* cache, std::vector<int> cpus, const std::atomic<int>* hold) {
+        device_ = device, cache_ = cache, cpus_ = std::move(cpus), hold_ = hold;
         for (int t = 0; t < threads; t++) threads_.emplace_back([this] { loop(); });
     }
     void submit(Job j) {
@@ -185,7 +188,13 @@ class Registrar {
     }
     void drain() {  // wait until the queue is empty and no registration is in flight
         std::unique_lock<std::mutex> lk(mu_);
+        draining_++;
         idle_cv_.wait(lk, [&] { return (q_.empty() && busy_ == 0) || stop_; });
+        draining_--;
+    }
+    size_t backlog() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return q_.size() + static_cast<size_t>(busy_);
     }
     std::atomic<bool> unsupported{false};
     std::atomic<uint64_t> registered{0};
@@ -205,6 +214,11 @@ class Registrar {
                 std::unique_lock<std::mutex> lk(mu_);
                 cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
                 if (stop_) return;
+                if (hold_ && hold_->load(std::memory_order_acquire) > 0 && draining_ == 0) {  // a read is in flight: stay out of its way
+                    lk.unlock();
+                    usleep(300);
+                    continue;
+                }
                 j = std::move(q_.front());
                 q_.pop_front();
                 busy_++;
@@ -233,8 +247,9 @@ class Registrar {
     std::condition_variable cv_, idle_cv_;
     std::deque<Job> q_;
     std::set<std::string> pending_keys_;
-    int busy_ = 0;
+    int busy_ = 0, draining_ = 0;
     bool stop_ = false;
+    const std::atomic<int>* hold_ = nullptr;
 };
 
 // ------------------------------------------------------------------ GpuIngest: ring + streams
@@ -262,6 +277,8 @@ class GpuIngest {
     RegCache reg;
     Registrar registrar;
     bool register_inline = false;
+    std::atomic<int> reads_in_flight{0};  // run_jobs calls between entry and return (the registrar yields to them)
+    double ring_alloc_sec = 0;            // time spent allocating the pinned ring (one-off per context and slot size)
 
     Err ensure_tables(size_t tables_bytes, size_t result_bytes) {
         if (tables_bytes > d_tables_cap) {
@@ -321,7 +338,7 @@ class GpuIngest {
                 }
             }
         }
-        if (c.zero_copy && !register_inline) registrar.start(c.register_threads, device, &reg, cpus);
+        if (c.zero_copy && !register_inline) registrar.start(c.register_threads, device, &reg, cpus, c.register_when_idle ? &reads_in_flight : nullptr);
         return Err::ok();
     }
 
@@ -341,16 +358,18 @@ class GpuIngest {
             if (d_stage) cudaFree(d_stage);
             pinned = nullptr, d_stage = nullptr, d_stage_bytes = 0;
             slot_bytes = need_slot_bytes;
-            // allocate (and first-touch) the ring from a thread bound to the GPU's node
+            // allocate the ring from a thread bound to the GPU's node (the driver allocates and pins the pages in that
+            // thread's context, so they land on its node; no extra first-touch pass)
             Err err;
+            const double t0 = now_sec();
             std::thread t([&] {
                 bind_thread();
                 cudaSetDevice(device);
                 cudaError_t e = cudaHostAlloc(&pinned, slot_bytes * nslots, cudaHostAllocDefault);
                 if (e != cudaSuccess) err = Err::io(str_printf("cudaHostAlloc(%zu): %s", slot_bytes * nslots, cudaGetErrorString(e)));
-                else memset(pinned, 0, slot_bytes * nslots);
             });
             t.join();
+            ring_alloc_sec += now_sec() - t0;
             if (err) return err;
         }
         if (framed && d_stage_bytes < slot_bytes * nslots) {
@@ -696,6 +715,11 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     if (J == 0) return Err::ok();
     const double t_start = now_sec();
     GpuIngest& G = *ing_;
+    struct InFlight {
+        std::atomic<int>& n;
+        explicit InFlight(std::atomic<int>& c) : n(c) { n.fetch_add(1, std::memory_order_acq_rel); }
+        ~InFlight() { n.fetch_sub(1, std::memory_order_acq_rel); }
+    } in_flight(G.reads_in_flight);
     std::lock_guard<std::mutex> call_lock(G.mu);
     CU_TRY(cudaSetDevice(G.device));
     {
@@ -1091,6 +1115,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     for (int t = 0; t < T_threads; t++) stats_.fetch_sec += fetch_sec[static_cast<size_t>(t)], stats_.h2d_bytes += h2d[static_cast<size_t>(t)];
     stats_.wall_sec += now_sec() - t_start;
     stats_.reg_hits = G.reg.hits.load(), stats_.reg_misses = G.reg.misses.load();
+    stats_.ring_alloc_sec = G.ring_alloc_sec;
     return Err::ok();
 }
 

@@ -27,6 +27,7 @@ struct GpuReadStats {
     uint64_t reg_hits = 0, reg_misses = 0;  // registered-mapping cache (zero-copy path), context-wide
     double fetch_sec = 0;       // summed over fetch threads: time inside pread/recv
     double wall_sec = 0;
+    double ring_alloc_sec = 0;  // context-wide: one-off pinned-ring allocation time
 };
 
 // Round-robin shard of a file: block b -> rank b % world (the analogue of slice_id % read_parallel,

@@ -279,6 +279,39 @@ __device__ __forceinline__ uint4 ld_plain(const uint4* p) {
     return r;
 }
 
+// One output vector of a shifted walk: 16 bytes starting Q words + r8 bits into the 8-word window [ra | nb].
+template <int Q>
+__device__ __forceinline__ uint4 shift_window(const uint4& ra, const uint4& nb, uint32_t r8) {
+    uint4 v;
+    if (Q == 0) {
+        v.x = __funnelshift_r(ra.x, ra.y, r8), v.y = __funnelshift_r(ra.y, ra.z, r8);
+        v.z = __funnelshift_r(ra.z, ra.w, r8), v.w = __funnelshift_r(ra.w, nb.x, r8);
+    } else if (Q == 1) {
+        v.x = __funnelshift_r(ra.y, ra.z, r8), v.y = __funnelshift_r(ra.z, ra.w, r8);
+        v.z = __funnelshift_r(ra.w, nb.x, r8), v.w = __funnelshift_r(nb.x, nb.y, r8);
+    } else if (Q == 2) {
+        v.x = __funnelshift_r(ra.z, ra.w, r8), v.y = __funnelshift_r(ra.w, nb.x, r8);
+        v.z = __funnelshift_r(nb.x, nb.y, r8), v.w = __funnelshift_r(nb.y, nb.z, r8);
+    } else {
+        v.x = __funnelshift_r(ra.w, nb.x, r8), v.y = __funnelshift_r(nb.x, nb.y, r8);
+        v.z = __funnelshift_r(nb.y, nb.z, r8), v.w = __funnelshift_r(nb.z, nb.w, r8);
+    }
+    return v;
+}
+
+// The right neighbour's aligned vector (lane 31 takes `wrap`, the first vector of the following row, from lane 0).
+// Only the words the window for Q reaches are exchanged.
+template <int Q>
+__device__ __forceinline__ uint4 take_right(const uint4& own, const uint4& wrap, uint32_t lane) {
+    const uint32_t from = (lane + 1) & 31;
+    uint4 nb = make_uint4(0, 0, 0, 0);
+    nb.x = __shfl_sync(0xffffffffu, lane == 0 ? wrap.x : own.x, from);
+    if (Q >= 1) nb.y = __shfl_sync(0xffffffffu, lane == 0 ? wrap.y : own.y, from);
+    if (Q >= 2) nb.z = __shfl_sync(0xffffffffu, lane == 0 ? wrap.z : own.z, from);
+    if (Q >= 3) nb.w = __shfl_sync(0xffffffffu, lane == 0 ? wrap.w : own.w, from);
+    return nb;
+}
+
 #define CV_STEP(v)                       \
     do {                                 \
         a0 = mul_row(a0, tl) ^ (v).x;    \
@@ -287,20 +320,106 @@ __device__ __forceinline__ uint4 ld_plain(const uint4* p) {
         a3 = mul_row(a3, tl) ^ (v).w;    \
     } while (0)
 
+struct Chains {
+    uint32_t a0, a1, a2, a3;
+    uint4 vr;  // the partial last row's vector (zero when the lane has none)
+};
+
+// Shifted source (every frame payload: 22-byte prefixes put it 6, 12, 2, 8, ... bytes off the destination's phase).
+// Each ALIGNED source vector is loaded exactly once; the 16 output bytes of a lane straddle its own vector and its
+// right neighbour's, which arrives by warp shuffle.  Rows go in tiles of T: T row loads plus one single-lane load (the
+// vector that follows the tile, needed by lane 31 of its last row) are issued back to back, so a warp keeps T*512 bytes
+// in flight; rows of a tile are independent of each other.  Q = word part of the shift (template: the window
+// selection and the number of shuffles are resolved at compile time), r8 = its bit part.
+template <bool CRC, int T, int Q>
+__device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane, uint32_t tl, Chains& c) {
+    const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint4* bp = reinterpret_cast<const uint4*>(src - sh) + lane;
+    uint4* dp = reinterpret_cast<uint4*>(dst) + lane;
+    const uint32_t R = L >> 9, nv = (L & 511u) >> 4;
+    const uint32_t nvec = (L >> 4) + 1;  // aligned vectors that hold the L bytes
+    const uint32_t rows = R + (nv ? 1u : 0u);
+    const uint32_t r8 = (sh & 3u) * 8u;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    uint32_t a0 = c.a0, a1 = c.a1, a2 = c.a2, a3 = c.a3;
+    uint32_t j = 0;
+    for (; j + T <= R; j += T) {  // whole tiles: every vector touched (incl. the one after the tile) is < nvec
+        uint4 ra[T];
+#pragma unroll
+        for (int k = 0; k < T; k++) ra[k] = ld_plain(bp + (j + k) * 32);
+        uint4 ex = zero;
+        if (lane == 0) ex = ld_plain(bp + (j + T) * 32);
+#pragma unroll
+        for (int k = 0; k < T; k++) {
+            const uint4 nb = take_right<Q>(ra[k], k + 1 < T ? ra[(k + 1) % T] : ex, lane);
+            const uint4 v = shift_window<Q>(ra[k], nb, r8);
+            dp[(j + k) * 32] = v;
+            if (CRC) CV_STEP(v);
+        }
+    }
+    for (; j < rows; j++) {  // leftover rows, bounds-checked
+        const uint4 ra = j * 32 + lane < nvec ? ld_plain(bp + j * 32) : zero;
+        uint4 ex = zero;
+        if (lane == 0 && (j + 1) * 32 < nvec) ex = ld_plain(bp + (j + 1) * 32);
+        const uint4 nb = take_right<Q>(ra, ex, lane);
+        const uint4 v = shift_window<Q>(ra, nb, r8);
+        if (j < R) {
+            dp[j * 32] = v;
+            if (CRC) CV_STEP(v);
+        } else if (lane < nv) {
+            dp[j * 32] = v;
+            c.vr = v;
+        }
+    }
+    c.a0 = a0, c.a1 = a1, c.a2 = a2, c.a3 = a3;
+}
+
+// Source and destination share their 16-byte phase: one load and one store per vector, tiles of T rows.
+template <bool CRC, int T>
+__device__ __forceinline__ void walk_aligned_copy(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane, uint32_t tl, Chains& c) {
+    const uint4* sp = reinterpret_cast<const uint4*>(src) + lane;
+    uint4* dp = reinterpret_cast<uint4*>(dst) + lane;
+    const uint32_t R = L >> 9, nv = (L & 511u) >> 4;
+    uint32_t a0 = c.a0, a1 = c.a1, a2 = c.a2, a3 = c.a3;
+    uint32_t j = 0;
+    for (; j + T <= R; j += T) {
+        uint4 v[T];
+#pragma unroll
+        for (int k = 0; k < T; k++) v[k] = ld_plain(sp + (j + k) * 32);
+#pragma unroll
+        for (int k = 0; k < T; k++) {
+            dp[(j + k) * 32] = v[k];
+            if (CRC) CV_STEP(v[k]);
+        }
+    }
+    for (; j < R; j++) {
+        const uint4 v = ld_plain(sp + j * 32);
+        dp[j * 32] = v;
+        if (CRC) CV_STEP(v);
+    }
+    if (lane < nv) {
+        c.vr = ld_plain(sp + R * 32);
+        dp[R * 32] = c.vr;
+    }
+    c.a0 = a0, c.a1 = a1, c.a2 = a2, c.a3 = a3;
+}
+
 // One warp walks L bytes (multiple of 16) starting at src (dst is 16-byte aligned when DST; src is 16-byte
-// aligned when !DST).  Returns the segment's raw CRC in every lane (0 when !CRC).
-template <bool CRC, bool DST>
+// aligned when !DST).  Returns the segment's raw CRC in every lane (0 when !CRC).  T = rows per tile of the DST walks.
+template <bool CRC, bool DST, int T>
 __device__ __forceinline__ uint32_t walk_segment(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane,
                                                  const uint32_t* smem, uint32_t poly) {
     const uint32_t tl = static_cast<uint32_t>(__cvta_generic_to_shared(smem)) + lane * 4u;
     const uint32_t* t0 = smem + kTmWords;
     const uint32_t* xp128 = t0 + 256;
-    const uint32_t R = L >> 9;
     const uint32_t nv = (L & 511u) >> 4;
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    uint4 vr = make_uint4(0, 0, 0, 0);
+    Chains c;
+    c.a0 = c.a1 = c.a2 = c.a3 = 0;
+    c.vr = make_uint4(0, 0, 0, 0);
 
     if (!DST) {
+        const uint32_t R = L >> 9;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         const uint4* sp = reinterpret_cast<const uint4*>(src) + lane;
         uint32_t j = 0;
         for (; j + 4 <= R; j += 4) {
@@ -317,87 +436,25 @@ __device__ __forceinline__ uint32_t walk_segment(const uint8_t* src, uint8_t* ds
             const uint4 v = ld_stream(sp + j * 32);
             CV_STEP(v);
         }
-        if (lane < nv) vr = ld_stream(sp + R * 32);
+        if (lane < nv) c.vr = ld_stream(sp + R * 32);
+        c.a0 = a0, c.a1 = a1, c.a2 = a2, c.a3 = a3;
     } else {
         const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15u);
-        uint4* dp = reinterpret_cast<uint4*>(dst) + lane;
-        if (sh == 0) {  // source and destination share their 16-byte phase: one load per vector
-            const uint4* sp = reinterpret_cast<const uint4*>(src) + lane;
-            uint32_t j = 0;
-            for (; j + 2 <= R; j += 2) {
-                const uint4 v0 = ld_plain(sp + (j + 0) * 32);
-                const uint4 v1 = ld_plain(sp + (j + 1) * 32);
-                dp[(j + 0) * 32] = v0;
-                dp[(j + 1) * 32] = v1;
-                if (CRC) {
-                    CV_STEP(v0);
-                    CV_STEP(v1);
-                }
-            }
-            for (; j < R; j++) {
-                const uint4 v = ld_plain(sp + j * 32);
-                dp[j * 32] = v;
-                if (CRC) CV_STEP(v);
-            }
-            if (lane < nv) {
-                vr = ld_plain(sp + R * 32);
-                dp[R * 32] = vr;
-            }
+        if (sh == 0) {
+            walk_aligned_copy<CRC, T>(src, dst, L, lane, tl, c);
         } else {
-            // Shifted source (every frame payload: 22-byte prefixes put it 6, 12, 2, 8, ... bytes off the destination's
-            // phase).  Each ALIGNED source vector is loaded exactly once; the 16 output bytes of a lane straddle its own
-            // vector and its right neighbour's, which arrives by warp shuffle (lane 31 takes lane 0's vector of the NEXT
-            // row, which is prefetched anyway).
-            const uint4* bp = reinterpret_cast<const uint4*>(src - sh) + lane;
-            const uint32_t nvec = (L >> 4) + 1;  // aligned vectors that hold the L bytes
-            const uint32_t rows = R + (nv ? 1u : 0u);
-            const uint32_t q = sh >> 2, r8 = (sh & 3u) * 8u;
-            const uint4 zero = make_uint4(0, 0, 0, 0);
-            const uint32_t from = (lane + 1) & 31;
-            uint4 ra = lane < nvec ? ld_plain(bp) : zero;
-            uint4 rb = 32 + lane < nvec ? ld_plain(bp + 32) : zero;
-            for (uint32_t j = 0; j < rows; j++) {
-                const uint4 rc = (j + 2) * 32 + lane < nvec ? ld_plain(bp + (j + 2) * 32) : zero;  // prefetch two rows ahead
-                const uint4 give = lane == 0 ? rb : ra;
-                uint4 nb;
-                nb.x = __shfl_sync(0xffffffffu, give.x, from);
-                nb.y = __shfl_sync(0xffffffffu, give.y, from);
-                nb.z = __shfl_sync(0xffffffffu, give.z, from);
-                nb.w = __shfl_sync(0xffffffffu, give.w, from);
-                uint4 v;
-                switch (q) {
-                    case 0:
-                        v.x = __funnelshift_r(ra.x, ra.y, r8), v.y = __funnelshift_r(ra.y, ra.z, r8);
-                        v.z = __funnelshift_r(ra.z, ra.w, r8), v.w = __funnelshift_r(ra.w, nb.x, r8);
-                        break;
-                    case 1:
-                        v.x = __funnelshift_r(ra.y, ra.z, r8), v.y = __funnelshift_r(ra.z, ra.w, r8);
-                        v.z = __funnelshift_r(ra.w, nb.x, r8), v.w = __funnelshift_r(nb.x, nb.y, r8);
-                        break;
-                    case 2:
-                        v.x = __funnelshift_r(ra.z, ra.w, r8), v.y = __funnelshift_r(ra.w, nb.x, r8);
-                        v.z = __funnelshift_r(nb.x, nb.y, r8), v.w = __funnelshift_r(nb.y, nb.z, r8);
-                        break;
-                    default:
-                        v.x = __funnelshift_r(ra.w, nb.x, r8), v.y = __funnelshift_r(nb.x, nb.y, r8);
-                        v.z = __funnelshift_r(nb.y, nb.z, r8), v.w = __funnelshift_r(nb.z, nb.w, r8);
-                        break;
-                }
-                if (j < R) {
-                    dp[j * 32] = v;
-                    if (CRC) CV_STEP(v);
-                } else if (lane < nv) {
-                    dp[j * 32] = v;
-                    vr = v;
-                }
-                ra = rb, rb = rc;
+            switch (sh >> 2) {  // warp-uniform
+                case 0: walk_shifted<CRC, T, 0>(src, dst, L, lane, tl, c); break;
+                case 1: walk_shifted<CRC, T, 1>(src, dst, L, lane, tl, c); break;
+                case 2: walk_shifted<CRC, T, 2>(src, dst, L, lane, tl, c); break;
+                default: walk_shifted<CRC, T, 3>(src, dst, L, lane, tl, c); break;
             }
         }
     }
     if (!CRC) return 0;
     // lane fold: rows weigh x^(128*(31-lane+nv)), the partial row x^(128*(nv-1-lane))
-    uint32_t t = gf_mul(raw_vec(a0, a1, a2, a3, t0), xp128[31u - lane + nv], poly);
-    if (lane < nv) t ^= gf_mul(raw_vec(vr.x, vr.y, vr.z, vr.w, t0), xp128[nv - 1u - lane], poly);
+    uint32_t t = gf_mul(raw_vec(c.a0, c.a1, c.a2, c.a3, t0), xp128[31u - lane + nv], poly);
+    if (lane < nv) t ^= gf_mul(raw_vec(c.vr.x, c.vr.y, c.vr.z, c.vr.w, t0), xp128[nv - 1u - lane], poly);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) t ^= __shfl_xor_sync(0xffffffffu, t, d);
     return t;
@@ -438,7 +495,7 @@ __device__ __forceinline__ uint32_t advance_piece(const uint32_t* prefix, uint32
     }
 }
 
-template <bool CRC, bool DST>
+template <bool CRC, bool DST, int T>
 __global__ void __launch_bounds__(1024, 1)
     walk_kernel(const Piece* __restrict__ pieces, uint32_t n_pieces, const uint32_t* __restrict__ prefix,
                 uint32_t seg_shift, const CrcConsts* __restrict__ cc, uint32_t* __restrict__ partial,
@@ -474,7 +531,7 @@ __global__ void __launch_bounds__(1024, 1)
             L = rem < (1ull << seg_shift) ? static_cast<uint32_t>(rem) : (1u << seg_shift);
         }
         const uint32_t raw =
-            walk_segment<CRC, DST>(pc.src + g.head + seg_off, DST ? pc.dst + g.head + seg_off : nullptr, L, lane, smem, poly);
+            walk_segment<CRC, DST, T>(pc.src + g.head + seg_off, DST ? pc.dst + g.head + seg_off : nullptr, L, lane, smem, poly);
         if (CRC && lane == 0) partial[u] = raw;
         if (s == 0 && g.head && lane == 1) {
             const uint32_t r = walk_bytes<CRC, DST>(pc.src, pc.dst, g.head, t0);
@@ -602,8 +659,10 @@ static int ensure_device(int* dev_out) {
         g_consts[dev][pid] = d;
     }
     CV_TRY(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     g_ready[dev] = true;
     return 0;
 }
@@ -672,6 +731,28 @@ struct WalkTimer {
         g_prof_events.emplace_back(a, b);
     }
 };
+// Rows per tile of the DST walkers (cvk_tune; defaults chosen from the kbench sweep in profiles/).
+static std::atomic<int> g_tile_crc_dst{4}, g_tile_copy{4};
+
+static void launch_walk_crc_dst(int dev, cudaStream_t st, const Piece* pieces, uint32_t n, const uint32_t* prefix, uint32_t seg_shift,
+                                const CrcConsts* cc, uint32_t* partial, uint32_t cap, uint32_t* headraw, uint32_t* tailraw) {
+    const dim3 grid(g_sm_count[dev]), block(1024);
+    switch (g_tile_crc_dst.load(std::memory_order_relaxed)) {
+        case 1: walk_kernel<true, true, 1><<<grid, block, kSmemBytes, st>>>(pieces, n, prefix, seg_shift, cc, partial, cap, headraw, tailraw); break;
+        case 2: walk_kernel<true, true, 2><<<grid, block, kSmemBytes, st>>>(pieces, n, prefix, seg_shift, cc, partial, cap, headraw, tailraw); break;
+        default: walk_kernel<true, true, 4><<<grid, block, kSmemBytes, st>>>(pieces, n, prefix, seg_shift, cc, partial, cap, headraw, tailraw); break;
+    }
+}
+
+// copy-only walk: no shared memory, one CTA per SM (the kernels need > 32 registers, so two 1024-thread CTAs never fit)
+static void launch_walk_copy(int dev, cudaStream_t st, const Piece* pieces, uint32_t n, const uint32_t* prefix, uint32_t seg_shift,
+                             uint32_t* partial, uint32_t cap, uint32_t* headraw, uint32_t* tailraw) {
+    const dim3 grid(g_sm_count[dev]), block(1024);
+    switch (g_tile_copy.load(std::memory_order_relaxed)) {
+        case 2: walk_kernel<false, true, 2><<<grid, block, 0, st>>>(pieces, n, prefix, seg_shift, nullptr, partial, cap, headraw, tailraw); break;
+        default: walk_kernel<false, true, 4><<<grid, block, 0, st>>>(pieces, n, prefix, seg_shift, nullptr, partial, cap, headraw, tailraw); break;
+    }
+}
 static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace cv
@@ -688,6 +769,13 @@ int cvk_init(int device) {
     const int rc = ensure_device(&dev);
     if (device != cur) cudaSetDevice(cur);
     return rc;
+}
+
+int cvk_tune(int what, int value) {
+    if (what == 0 && (value == 1 || value == 2 || value == 4)) g_tile_crc_dst.store(value);
+    else if (what == 1 && (value == 2 || value == 4)) g_tile_copy.store(value);
+    else return int(cudaErrorInvalidValue);
+    return 0;
 }
 
 uint64_t cvk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -734,7 +822,7 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
     scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
     {
         WalkTimer wt(st);
-        walk_kernel<true, false><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.pieces, n, w.prefix, seg_shift, cc,
+        walk_kernel<true, false, 4><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.pieces, n, w.prefix, seg_shift, cc,
                                                                             w.partial, w.partial_cap, w.headraw, w.tailraw);
     }
     fold_blocks_kernel<false><<<cdiv(uint64_t(n) * 32, 256), 256, 0, st>>>(w.pieces, w.prefix, nullptr, nullptr, n, n, seg_shift,
@@ -790,8 +878,7 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
     if (d_block_crc) {
         {
             WalkTimer wt(st);
-            walk_kernel<true, true><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(
-                w.pieces, n_frames, w.prefix, seg_shift, cc, w.partial, w.partial_cap, w.headraw, w.tailraw);
+            launch_walk_crc_dst(dev, st, w.pieces, n_frames, w.prefix, seg_shift, cc, w.partial, w.partial_cap, w.headraw, w.tailraw);
         }
         mark_block_ranges_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_desc, n_frames, n_blocks, w.first, w.last);
         fold_blocks_kernel<true><<<cdiv(uint64_t(n_blocks) * 32, 256), 256, 0, st>>>(
@@ -799,8 +886,7 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
             w.partial, w.headraw, w.tailraw, d_block_crc);
         count_launch(3);
     } else {
-        walk_kernel<false, true><<<g_sm_count[dev] * 2, 1024, 0, st>>>(w.pieces, n_frames, w.prefix, seg_shift, cc,
-                                                                       w.partial, w.partial_cap, w.headraw, w.tailraw);
+        launch_walk_copy(dev, st, w.pieces, n_frames, w.prefix, seg_shift, w.partial, w.partial_cap, w.headraw, w.tailraw);
         count_launch();
     }
     CV_TRY(cudaGetLastError());
@@ -823,8 +909,7 @@ int cvk_pack_frames(const uint8_t* d_src, const CvFrameDesc* d_desc, uint32_t n_
 
 static int copy_pieces(Workspace& w, uint32_t n, uint32_t seg_shift, int dev, cudaStream_t st) {
     scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
-    walk_kernel<false, true><<<g_sm_count[dev] * 2, 1024, 0, st>>>(w.pieces, n, w.prefix, seg_shift, nullptr,
-                                                                   w.partial, w.partial_cap, w.headraw, w.tailraw);
+    launch_walk_copy(dev, st, w.pieces, n, w.prefix, seg_shift, w.partial, w.partial_cap, w.headraw, w.tailraw);
     count_launch(2);
     CV_TRY(cudaGetLastError());
     CV_TRY(cudaFreeAsync(w.base, st));

@@ -65,7 +65,9 @@ int64_t cv_fs_load_namespace(cv_fs* fs, const char* manifest_path);
 int64_t cv_fs_load_namespace_string(cv_fs* fs, const char* manifest_text);
 int64_t cv_fs_close(cv_fs* fs);
 /* Zero-copy mem tier: block until the background registrar (mmap + cudaHostRegister of block files seen by earlier
- * device reads) is idle.  Optional; reads never wait for it -- unregistered blocks go through the pinned ring. */
+ * device reads) is idle.  Optional; reads never wait for it -- unregistered blocks go through the pinned ring, and by
+ * default ([b200] register_when_idle = true) the registrar only works while no device read is in flight, so a cold
+ * pass runs at pinned-ring speed and later passes over the same blocks are zero-copy. */
 int64_t cv_fs_wait_registered(cv_fs* fs);
 /* client metrics (client_metrics.rs:24-35): out[0]=read_bytes out[1]=read_time_us */
 int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]);
@@ -111,6 +113,7 @@ typedef struct CvReadStats {
     uint64_t bytes, blocks, verified, h2d_bytes, kernel_launches;
     double fetch_sec, wall_sec;
     uint64_t reg_hits, reg_misses; /* registered-mapping cache of the zero-copy path */
+    double ring_alloc_sec;         /* one-off pinned-ring allocation time of the context (first cold read pays it) */
 } CvReadStats;
 int64_t cv_device_stats(cv_reader* r, CvReadStats* out);
 

@@ -25,10 +25,11 @@ def _dev_buf(n, cuda):
     return torch.full((n,), 0xA5, dtype=torch.uint8, device=cuda)
 
 
-def _conf(sc, poly=1, chunk="4MB", threads=4, batch=4, zero_copy=False, copy_group=2, register_threads=0):
+def _conf(sc, poly=1, chunk="4MB", threads=4, batch=4, zero_copy=False, copy_group=2, register_threads=0, register_when_idle=True):
     return F.client_conf(short_circuit=sc, b200='verify_poly = %d\ngpu_chunk_size = "%s"\nfetch_threads = %d\nverify_batch = %d\npinned_slots = 12\n'
-                         'zero_copy = %s\ncopy_group = %d\nregister_cache = "48MB"\nregister_threads = %d\n'
-                         % (poly, chunk, threads, batch, "true" if zero_copy else "false", copy_group, register_threads))
+                         'zero_copy = %s\ncopy_group = %d\nregister_cache = "48MB"\nregister_threads = %d\nregister_when_idle = %s\n'
+                         % (poly, chunk, threads, batch, "true" if zero_copy else "false", copy_group, register_threads,
+                            "true" if register_when_idle else "false"))
 
 
 @pytest.mark.parametrize("sc,chunk", [(True, "4MB"), (False, "128KB"), (False, "1MB"), (False, "4MB")])
@@ -193,18 +194,20 @@ def test_fuse_shaped_device_read_scatters_into_pages(cuda, cluster):
         r.complete()
 
 
-@pytest.mark.parametrize("copy_group,register_threads", [(1, 0), (4, 0), (4, 2)])
-def test_zero_copy_registered_mappings(cuda, cluster, copy_group, register_threads):
+@pytest.mark.parametrize("copy_group,register_threads,when_idle", [(1, 0, True), (4, 0, True), (4, 2, True), (2, 2, False)])
+def test_zero_copy_registered_mappings(cuda, cluster, copy_group, register_threads, when_idle):
     """Mem-tier zero-copy: DMA straight from cudaHostRegister'ed mmaps of the block files.  Same bytes, same CRCs;
     in-place corruption and file replacement are both seen (mappings revalidated by inode/size/mtime); the LRU
     (48 MB here, file 64 MiB) evicts without breaking anything."""
     import torch
     w, d = cluster
     n, bs, ino = (64 << 20) - 4096 * 3 - 5, 1 << 20, 7040 + copy_group + 10 * register_threads
+    idle_bg = register_threads > 0 and when_idle  # registrar yields to reads in flight: the first pass is ring-only
     man = w.create_file("/zc%d" % copy_group, ino, n, bs)
     want = bytearray(synth.file_bytes(ino, n, bs))
     nb = (n + bs - 1) // bs
-    with F.CurvineFileSystem(_conf(True, 1, zero_copy=True, copy_group=copy_group, register_threads=register_threads)) as fs:
+    with F.CurvineFileSystem(_conf(True, 1, zero_copy=True, copy_group=copy_group, register_threads=register_threads,
+                                   register_when_idle=when_idle)) as fs:
         fs.load_namespace(man)
         for rep in range(3):
             fs.wait_registered()  # background mode: rep 0 goes through the ring while the registrar maps the files
@@ -217,6 +220,8 @@ def test_zero_copy_registered_mappings(cuda, cluster, copy_group, register_threa
             assert dst[:n].cpu().numpy().tobytes() == bytes(want) and (dst[n:] == 0xA5).all()
             st = r.device_stats()
             assert st["reg_misses"] > 0, "the registered-mapping path did not run (silent fallback to the pinned ring)"
+            if rep == 0 and idle_bg:
+                assert st["reg_hits"] == 0, "idle-priority registrar ran during the cold pass"
             if rep == 2:
                 assert st["reg_hits"] > 0, "no read was served from a registered mapping"
             r.complete()

@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--verify-batch", type=int, default=16)
     ap.add_argument("--copy-group", type=int, default=8)
     ap.add_argument("--copy-streams", type=int, default=1)
-    ap.add_argument("--register-threads", type=int, default=8, help="background registrar threads (0 = register inline on first touch)")
+    ap.add_argument("--register-threads", type=int, default=16, help="background registrar threads (0 = register inline on first touch)")
     ap.add_argument("--numa-node", type=int, default=-1, help="-1 bind fetch threads to the GPU's node, -2 no binding")
     ap.add_argument("--register-when-idle", type=int, default=1, help="1: registrar threads yield to reads in flight (cold pass at ring speed); 0: register concurrently")
     ap.add_argument("--zero-copy", type=int, default=1, help="short-circuit: DMA from registered mmaps of the mem-tier block files")

@@ -46,7 +46,7 @@ struct B200Conf {
     int64_t gpu_chunk_size = 4 << 20;  // Running-request chunk for the framed GPU path (<= 16 MiB frame cap)
     bool zero_copy = false;       // short-circuit reads: DMA straight from cudaHostRegister'ed mmaps of the block files
     int64_t register_cache = 64ll << 30;  // bytes of registered mappings kept across calls (LRU)
-    int register_threads = 8;     // background registrar threads (a cold group goes through the pinned ring meanwhile); 0 = register inline
+    int register_threads = 16;    // background registrar threads (a cold group goes through the pinned ring meanwhile); 0 = register inline
     bool register_when_idle = true;  // registrar threads yield to reads in flight (a cold pass runs at ring speed; mappings are
                                      // registered between reads); false = register concurrently with the cold pass
     int numa_node = -1;           // bind fetch threads to this node's CPUs (-1: the GPU's node if discoverable, -2: no binding)

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -52,6 +53,19 @@ __device__ __forceinline__ Geom piece_geom(const Piece& p, uint32_t seg_shift) {
     g.units = p.len ? (g.nseg ? g.nseg : 1u) : 0u;
     return g;
 }
+
+// One unit of walker work, expanded from (pieces, prefix) by expand_units_kernel so that the walker reads ONE 32-byte
+// record per unit -- at an address it knows a whole unit ahead, so the record is prefetched behind the current walk
+// instead of a chain of dependent lookups (prefix search -> piece -> geometry) stalling the warp at every unit boundary.
+struct __align__(16) Unit {
+    const uint8_t* src;  // first body byte of the segment (piece.src + head + segment offset)
+    uint8_t* dst;        // 16-byte aligned when the walk stores; nullptr otherwise
+    uint32_t L;          // body bytes in this segment (multiple of 16; 0 for a piece shorter than one vector)
+    uint32_t piece;
+    uint32_t head;       // > 0 on the first unit of a piece with head bytes (they sit right before src)
+    uint32_t tail;       // > 0 on the last unit of a piece with tail bytes (they sit right behind src + L)
+};
+static_assert(sizeof(Unit) == 32, "Unit is two 16-byte vectors");
 
 // ------------------------------------------------------------------ piece preparation kernels
 
@@ -231,6 +245,9 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* count
 constexpr uint32_t kTmWords = 4 * 256 * 32;  // replicated x^4096 tables: [table][byte][lane]
 constexpr uint32_t kSmemWords = kTmWords + 256 + 64 + 16;
 constexpr uint32_t kSmemBytes = kSmemWords * 4;
+constexpr int kStageCrc = 6;    // row slots per warp of the staged CRC+copy walk (tables 129 KB + 32 x 6 x 512 B = 225 KB of 227)
+constexpr int kStageCopy = 12;  // ... of the staged copy-only walk (32 x 12 x 512 B = 192 KB)
+static_assert(kSmemBytes % 16 == 0, "stage slots must be 16-byte aligned");
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     uint4 r;
@@ -277,6 +294,18 @@ __device__ __forceinline__ uint4 ld_plain(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+}
+
+// streaming (no L1 allocation) coherent load for local sources of the DST walks: rows are read once, and pending L1
+// line allocations cap how many rows a CTA can keep in flight
+__device__ __forceinline__ uint4 ld_plain_na(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+template <bool NA>
+__device__ __forceinline__ uint4 ld_src(const uint4* p) {
+    return NA ? ld_plain_na(p) : ld_plain(p);
 }
 
 // One output vector of a shifted walk: 16 bytes starting Q words + r8 bits into the 8-word window [ra | nb].
@@ -331,7 +360,7 @@ struct Chains {
 // vector that follows the tile, needed by lane 31 of its last row) are issued back to back, so a warp keeps T*512 bytes
 // in flight; rows of a tile are independent of each other.  Q = word part of the shift (template: the window
 // selection and the number of shuffles are resolved at compile time), r8 = its bit part.
-template <bool CRC, int T, int Q>
+template <bool CRC, int T, int Q, bool NA>
 __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane, uint32_t tl, Chains& c) {
     const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15u);
     const uint4* bp = reinterpret_cast<const uint4*>(src - sh) + lane;
@@ -346,9 +375,9 @@ __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, u
     for (; j + T <= R; j += T) {  // whole tiles: every vector touched (incl. the one after the tile) is < nvec
         uint4 ra[T];
 #pragma unroll
-        for (int k = 0; k < T; k++) ra[k] = ld_plain(bp + (j + k) * 32);
+        for (int k = 0; k < T; k++) ra[k] = ld_src<NA>(bp + (j + k) * 32);
         uint4 ex = zero;
-        if (lane == 0) ex = ld_plain(bp + (j + T) * 32);
+        if (lane == 0) ex = ld_src<NA>(bp + (j + T) * 32);
 #pragma unroll
         for (int k = 0; k < T; k++) {
             const uint4 nb = take_right<Q>(ra[k], k + 1 < T ? ra[(k + 1) % T] : ex, lane);
@@ -358,9 +387,9 @@ __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, u
         }
     }
     for (; j < rows; j++) {  // leftover rows, bounds-checked
-        const uint4 ra = j * 32 + lane < nvec ? ld_plain(bp + j * 32) : zero;
+        const uint4 ra = j * 32 + lane < nvec ? ld_src<NA>(bp + j * 32) : zero;
         uint4 ex = zero;
-        if (lane == 0 && (j + 1) * 32 < nvec) ex = ld_plain(bp + (j + 1) * 32);
+        if (lane == 0 && (j + 1) * 32 < nvec) ex = ld_src<NA>(bp + (j + 1) * 32);
         const uint4 nb = take_right<Q>(ra, ex, lane);
         const uint4 v = shift_window<Q>(ra, nb, r8);
         if (j < R) {
@@ -375,7 +404,7 @@ __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, u
 }
 
 // Source and destination share their 16-byte phase: one load and one store per vector, tiles of T rows.
-template <bool CRC, int T>
+template <bool CRC, int T, bool NA>
 __device__ __forceinline__ void walk_aligned_copy(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane, uint32_t tl, Chains& c) {
     const uint4* sp = reinterpret_cast<const uint4*>(src) + lane;
     uint4* dp = reinterpret_cast<uint4*>(dst) + lane;
@@ -385,7 +414,7 @@ __device__ __forceinline__ void walk_aligned_copy(const uint8_t* src, uint8_t* d
     for (; j + T <= R; j += T) {
         uint4 v[T];
 #pragma unroll
-        for (int k = 0; k < T; k++) v[k] = ld_plain(sp + (j + k) * 32);
+        for (int k = 0; k < T; k++) v[k] = ld_src<NA>(sp + (j + k) * 32);
 #pragma unroll
         for (int k = 0; k < T; k++) {
             dp[(j + k) * 32] = v[k];
@@ -393,22 +422,86 @@ __device__ __forceinline__ void walk_aligned_copy(const uint8_t* src, uint8_t* d
         }
     }
     for (; j < R; j++) {
-        const uint4 v = ld_plain(sp + j * 32);
+        const uint4 v = ld_src<NA>(sp + j * 32);
         dp[j * 32] = v;
         if (CRC) CV_STEP(v);
     }
     if (lane < nv) {
-        c.vr = ld_plain(sp + R * 32);
+        c.vr = ld_src<NA>(sp + R * 32);
         dp[R * 32] = c.vr;
+    }
+    c.a0 = a0, c.a1 = a1, c.a2 = a2, c.a3 = a3;
+}
+
+// ---- shared-memory staged DST walk (cp.async): rows in flight live in shared memory, not in registers.
+// Every warp owns S row slots of 512 bytes.  Lane l copies its aligned source vector of row r into slot r % S with a
+// 16-byte cp.async (L2 only), one commit group per row; the consumer side waits until rows j and j+1 have landed
+// (wait_group S-2), reads its own vector and its right neighbour's (lane 31: lane 0 of the following row) back with two
+// LDS.128, funnel-shifts the 16 output bytes together, stores them and feeds the CRC chains, then refills the slot with
+// row j+S.  A warp so keeps S-1 rows (CRC+copy: 5 x 512 B, copy-only: 11 x 512 B) in flight all the time, independent of
+// the 64-register budget of the 1024-thread CTA.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+
+template <bool CRC, int Q, int S>
+__device__ __forceinline__ void walk_staged(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane, uint32_t tl, Chains& c,
+                                            uint32_t stage) {
+    if (L == 0) return;
+    const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint4* bp = reinterpret_cast<const uint4*>(src - sh) + lane;
+    uint4* dp = reinterpret_cast<uint4*>(dst) + lane;
+    const uint32_t R = L >> 9, nv = (L & 511u) >> 4;
+    const uint32_t nvec = (L >> 4) + (sh ? 1u : 0u);  // aligned vectors that hold the L bytes
+    const uint32_t rows = R + (nv ? 1u : 0u);
+    const uint32_t r8 = (sh & 3u) * 8u;
+    const uint32_t mine = stage + lane * 16u;
+    const uint32_t right = stage + ((lane + 1u) & 31u) * 16u;
+    uint32_t a0 = c.a0, a1 = c.a1, a2 = c.a2, a3 = c.a3;
+#pragma unroll
+    for (int r = 0; r < S; r++) {
+        if (r * 32u + lane < nvec) cp_async16(mine + r * 512u, bp + r * 32);
+        cp_async_commit();
+    }
+    uint32_t slot = 0;  // slot of row j
+    for (uint32_t j = 0; j < rows; j++) {
+        cp_async_wait<S - 2>();  // groups 0 .. j+1 done: rows j and j+1 are in shared memory (this lane's part)
+        __syncwarp();            // ... and every other lane's
+        const uint32_t nslot = slot + 1 == S ? 0u : slot + 1;
+        const uint4 ra = lds128(mine + slot * 512u);
+        const uint4 nb = lds128(right + (lane == 31 ? nslot : slot) * 512u);
+        const uint4 v = shift_window<Q>(ra, nb, r8);
+        if (j < R) {
+            dp[j * 32] = v;
+            if (CRC) CV_STEP(v);
+        } else if (lane < nv) {
+            dp[j * 32] = v;
+            c.vr = v;
+        }
+        __syncwarp();  // all lanes are done with slot `slot` before it is refilled
+        const uint32_t nr = j + S;
+        if (nr * 32u + lane < nvec) cp_async16(mine + slot * 512u, bp + nr * 32);
+        cp_async_commit();
+        slot = nslot;
     }
     c.a0 = a0, c.a1 = a1, c.a2 = a2, c.a3 = a3;
 }
 
 // One warp walks L bytes (multiple of 16) starting at src (dst is 16-byte aligned when DST; src is 16-byte
 // aligned when !DST).  Returns the segment's raw CRC in every lane (0 when !CRC).  T = rows per tile of the DST walks.
-template <bool CRC, bool DST, int T>
+template <bool CRC, bool DST, int T, bool NA, int S>
 __device__ __forceinline__ uint32_t walk_segment(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane,
-                                                 const uint32_t* smem, uint32_t poly) {
+                                                 const uint32_t* smem, uint32_t poly, uint32_t stage) {
     const uint32_t tl = static_cast<uint32_t>(__cvta_generic_to_shared(smem)) + lane * 4u;
     const uint32_t* t0 = smem + kTmWords;
     const uint32_t* xp128 = t0 + 256;
@@ -440,14 +533,21 @@ __device__ __forceinline__ uint32_t walk_segment(const uint8_t* src, uint8_t* ds
         c.a0 = a0, c.a1 = a1, c.a2 = a2, c.a3 = a3;
     } else {
         const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15u);
-        if (sh == 0) {
-            walk_aligned_copy<CRC, T>(src, dst, L, lane, tl, c);
+        if (S > 0) {
+            switch (sh >> 2) {  // warp-uniform; sh == 0 runs as Q = 0 with a zero bit shift
+                case 0: walk_staged<CRC, 0, S ? S : 2>(src, dst, L, lane, tl, c, stage); break;
+                case 1: walk_staged<CRC, 1, S ? S : 2>(src, dst, L, lane, tl, c, stage); break;
+                case 2: walk_staged<CRC, 2, S ? S : 2>(src, dst, L, lane, tl, c, stage); break;
+                default: walk_staged<CRC, 3, S ? S : 2>(src, dst, L, lane, tl, c, stage); break;
+            }
+        } else if (sh == 0) {
+            walk_aligned_copy<CRC, T, NA>(src, dst, L, lane, tl, c);
         } else {
             switch (sh >> 2) {  // warp-uniform
-                case 0: walk_shifted<CRC, T, 0>(src, dst, L, lane, tl, c); break;
-                case 1: walk_shifted<CRC, T, 1>(src, dst, L, lane, tl, c); break;
-                case 2: walk_shifted<CRC, T, 2>(src, dst, L, lane, tl, c); break;
-                default: walk_shifted<CRC, T, 3>(src, dst, L, lane, tl, c); break;
+                case 0: walk_shifted<CRC, T, 0, NA>(src, dst, L, lane, tl, c); break;
+                case 1: walk_shifted<CRC, T, 1, NA>(src, dst, L, lane, tl, c); break;
+                case 2: walk_shifted<CRC, T, 2, NA>(src, dst, L, lane, tl, c); break;
+                default: walk_shifted<CRC, T, 3, NA>(src, dst, L, lane, tl, c); break;
             }
         }
     }
@@ -495,13 +595,45 @@ __device__ __forceinline__ uint32_t advance_piece(const uint32_t* prefix, uint32
     }
 }
 
-template <bool CRC, bool DST, int T>
+template <bool DST>
+__global__ void expand_units_kernel(const Piece* __restrict__ pieces, uint32_t n_pieces, const uint32_t* __restrict__ prefix,
+                                    uint32_t seg_shift, Unit* __restrict__ units, uint32_t cap) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= min(__ldg(prefix + n_pieces), cap)) return;
+    const uint32_t p = find_piece(prefix, n_pieces, u);
+    const Piece pc = pieces[p];
+    const Geom g = piece_geom<DST>(pc, seg_shift);
+    const uint32_t s = u - __ldg(prefix + p);
+    const uint64_t seg_off = uint64_t(s) << seg_shift;
+    Unit un;
+    un.L = 0;
+    if (s < g.nseg) {
+        const uint64_t rem = g.body - seg_off;
+        un.L = rem < (1ull << seg_shift) ? static_cast<uint32_t>(rem) : (1u << seg_shift);
+    }
+    un.src = pc.src + g.head + seg_off;
+    un.dst = DST ? pc.dst + g.head + seg_off : nullptr;
+    un.piece = p;
+    un.head = s == 0 ? g.head : 0u;
+    un.tail = s + 1 == g.units ? g.tail : 0u;
+    units[u] = un;
+}
+
+__device__ __forceinline__ Unit ld_unit(const Unit* p) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    Unit un;
+    un.src = reinterpret_cast<const uint8_t*>(uint64_t(a.x) | (uint64_t(a.y) << 32));
+    un.dst = reinterpret_cast<uint8_t*>(uint64_t(a.z) | (uint64_t(a.w) << 32));
+    un.L = b.x, un.piece = b.y, un.head = b.z, un.tail = b.w;
+    return un;
+}
+
+template <bool CRC, bool DST, int T, bool NA, int S = 0>
 __global__ void __launch_bounds__(1024, 1)
-    walk_kernel(const Piece* __restrict__ pieces, uint32_t n_pieces, const uint32_t* __restrict__ prefix,
-                uint32_t seg_shift, const CrcConsts* __restrict__ cc, uint32_t* __restrict__ partial,
-                uint32_t partial_cap, uint32_t* __restrict__ headraw, uint32_t* __restrict__ tailraw) {
+    walk_kernel(const Unit* __restrict__ units, const uint32_t* __restrict__ total_units, const CrcConsts* __restrict__ cc,
+                uint32_t* __restrict__ partial, uint32_t partial_cap, uint32_t* __restrict__ headraw, uint32_t* __restrict__ tailraw) {
     extern __shared__ uint32_t smem[];
-    const uint32_t total = min(__ldg(prefix + n_pieces), partial_cap);
+    const uint32_t total = min(__ldg(total_units), partial_cap);
     const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
     const uint32_t u0 = min(total, blockIdx.x * per), u1 = min(total, u0 + per);
     if (u0 >= u1) return;
@@ -518,30 +650,22 @@ __global__ void __launch_bounds__(1024, 1)
     }
     const uint32_t* t0 = smem + kTmWords;
     if (u0 + warp >= u1) return;
-    uint32_t p = find_piece(prefix, n_pieces, u0 + warp);
+    // staged walks: this warp's S row slots sit behind the tables (CRC) or at the start of shared memory (copy-only)
+    const uint32_t stage = static_cast<uint32_t>(__cvta_generic_to_shared(smem)) + (CRC ? kSmemBytes : 0u) + warp * (S * 512u);
+    Unit cur = ld_unit(units + u0 + warp);
     for (uint32_t u = u0 + warp; u < u1; u += 32) {
-        p = advance_piece(prefix, n_pieces, p, u, lane);
-        const Piece pc = pieces[p];
-        const Geom g = piece_geom<DST>(pc, seg_shift);
-        const uint32_t s = u - __ldg(prefix + p);
-        const uint64_t seg_off = uint64_t(s) << seg_shift;
-        uint32_t L = 0;
-        if (s < g.nseg) {
-            const uint64_t rem = g.body - seg_off;
-            L = rem < (1ull << seg_shift) ? static_cast<uint32_t>(rem) : (1u << seg_shift);
-        }
-        const uint32_t raw =
-            walk_segment<CRC, DST, T>(pc.src + g.head + seg_off, DST ? pc.dst + g.head + seg_off : nullptr, L, lane, smem, poly);
+        const Unit nxt = ld_unit(units + (u + 32 < u1 ? u + 32 : u));  // next unit's record travels behind this walk
+        const uint32_t raw = walk_segment<CRC, DST, T, NA, S>(cur.src, cur.dst, cur.L, lane, smem, poly, stage);
         if (CRC && lane == 0) partial[u] = raw;
-        if (s == 0 && g.head && lane == 1) {
-            const uint32_t r = walk_bytes<CRC, DST>(pc.src, pc.dst, g.head, t0);
-            if (CRC) headraw[p] = r;
+        if (cur.head && lane == 1) {
+            const uint32_t r = walk_bytes<CRC, DST>(cur.src - cur.head, DST ? cur.dst - cur.head : nullptr, cur.head, t0);
+            if (CRC) headraw[cur.piece] = r;
         }
-        if (s + 1 == g.units && g.tail && lane == 2) {
-            const uint64_t o = g.head + g.body;
-            const uint32_t r = walk_bytes<CRC, DST>(pc.src + o, DST ? pc.dst + o : nullptr, g.tail, t0);
-            if (CRC) tailraw[p] = r;
+        if (cur.tail && lane == 2) {
+            const uint32_t r = walk_bytes<CRC, DST>(cur.src + cur.L, DST ? cur.dst + cur.L : nullptr, cur.tail, t0);
+            if (CRC) tailraw[cur.piece] = r;
         }
+        cur = nxt;
     }
 }
 
@@ -611,10 +735,15 @@ __global__ void verify_crcs_kernel(const uint32_t* crc, const uint32_t* expect, 
 // ------------------------------------------------------------------ host side
 
 static std::atomic<uint64_t> g_launches{0};
+// Tuning of the DST walkers (cvk_tune; defaults chosen from the kbench sweep in profiles/): rows per tile, whether local
+// sources are read with L1::no_allocate, and register-tiled vs shared-memory staged walks.
+static std::atomic<int> g_tile_crc_dst{4}, g_tile_copy{2}, g_src_na{0};
+static std::atomic<bool> g_staged{false};  // cvk_tune(3, 1) / CVK_STAGED=1: shared-memory staged (cp.async) DST walks for local sources
 static std::mutex g_mu;
 constexpr int kMaxDev = 16;
 static CrcConsts* g_consts[kMaxDev][2];
 static int g_sm_count[kMaxDev];
+static cudaMemPool_t g_pool[kMaxDev];  // workspace pool that keeps its memory across synchronisation points
 static bool g_ready[kMaxDev];
 
 #define CV_TRY(x)                             \
@@ -659,10 +788,27 @@ static int ensure_device(int* dev_out) {
         g_consts[dev][pid] = d;
     }
     CV_TRY(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    {
+        // Per-launch workspaces come from a private stream-ordered pool with an unlimited release threshold.  The default
+        // pool hands its memory back to the driver at every synchronisation point (threshold 0), so a caller that syncs
+        // between calls (every verify batch does) would pay a fresh physical allocation in front of each launch train.
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        CV_TRY(cudaMemPoolCreate(&g_pool[dev], &props));
+        uint64_t keep = ~0ull;
+        CV_TRY(cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4, false, kStageCrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + kStageCrc * 512 * 32));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<false, true, 2, false, kStageCopy>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageCopy * 512 * 32));
+    if (const char* e = getenv("CVK_STAGED")) g_staged.store(atoi(e) != 0);
     g_ready[dev] = true;
     return 0;
 }
@@ -678,12 +824,13 @@ static uint32_t pick_seg_shift(uint64_t total_bytes, int sm_count) {
 
 struct Workspace {
     Piece* pieces;
+    Unit* units;
     uint32_t *counts, *prefix, *headraw, *tailraw, *partial, *first, *last;
     uint32_t partial_cap;
     void* base;
 };
 
-static int ws_alloc(Workspace* w, uint32_t n_pieces, uint32_t n_blocks, uint64_t total_bytes, uint32_t seg_shift,
+static int ws_alloc(Workspace* w, int dev, uint32_t n_pieces, uint32_t n_blocks, uint64_t total_bytes, uint32_t seg_shift,
                     cudaStream_t st) {
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     const uint64_t cap64 = uint64_t(n_pieces) + (total_bytes >> seg_shift) + 1;
@@ -692,10 +839,12 @@ static int ws_alloc(Workspace* w, uint32_t n_pieces, uint32_t n_blocks, uint64_t
     const size_t s_n = up(4 * (size_t(n_pieces) + 1));
     const size_t s_part = up(4 * size_t(w->partial_cap));
     const size_t s_blk = up(4 * (size_t(n_blocks) + 1));
-    const size_t total = s_pieces + 4 * s_n + s_part + 2 * s_blk;
-    CV_TRY(cudaMallocAsync(&w->base, total, st));
+    const size_t s_units = up(sizeof(Unit) * size_t(w->partial_cap));
+    const size_t total = s_pieces + s_units + 4 * s_n + s_part + 2 * s_blk;
+    CV_TRY(cudaMallocFromPoolAsync(&w->base, total, g_pool[dev], st));
     uint8_t* p = static_cast<uint8_t*>(w->base);
     w->pieces = reinterpret_cast<Piece*>(p), p += s_pieces;
+    w->units = reinterpret_cast<Unit*>(p), p += s_units;
     w->counts = reinterpret_cast<uint32_t*>(p), p += s_n;
     w->prefix = reinterpret_cast<uint32_t*>(p), p += s_n;
     w->headraw = reinterpret_cast<uint32_t*>(p), p += s_n;
@@ -731,28 +880,48 @@ struct WalkTimer {
         g_prof_events.emplace_back(a, b);
     }
 };
-// Rows per tile of the DST walkers (cvk_tune; defaults chosen from the kbench sweep in profiles/).
-static std::atomic<int> g_tile_crc_dst{4}, g_tile_copy{4};
+#define CV_WALK_ARGS w.units, w.prefix + n, cc, w.partial, w.partial_cap, w.headraw, w.tailraw
+// (pieces, prefix) -> one 32-byte record per unit; every walker launch is preceded by this
+template <bool DST>
+static void launch_expand(const Workspace& w, uint32_t n, uint32_t seg_shift, cudaStream_t st) {
+    expand_units_kernel<DST><<<cdiv(w.partial_cap, 256), 256, 0, st>>>(w.pieces, n, w.prefix, seg_shift, w.units, w.partial_cap);
+}
 
-static void launch_walk_crc_dst(int dev, cudaStream_t st, const Piece* pieces, uint32_t n, const uint32_t* prefix, uint32_t seg_shift,
-                                const CrcConsts* cc, uint32_t* partial, uint32_t cap, uint32_t* headraw, uint32_t* tailraw) {
+static void launch_walk_crc_dst(int dev, cudaStream_t st, const Workspace& w, uint32_t n, const CrcConsts* cc) {
     const dim3 grid(g_sm_count[dev]), block(1024);
-    switch (g_tile_crc_dst.load(std::memory_order_relaxed)) {
-        case 1: walk_kernel<true, true, 1><<<grid, block, kSmemBytes, st>>>(pieces, n, prefix, seg_shift, cc, partial, cap, headraw, tailraw); break;
-        case 2: walk_kernel<true, true, 2><<<grid, block, kSmemBytes, st>>>(pieces, n, prefix, seg_shift, cc, partial, cap, headraw, tailraw); break;
-        default: walk_kernel<true, true, 4><<<grid, block, kSmemBytes, st>>>(pieces, n, prefix, seg_shift, cc, partial, cap, headraw, tailraw); break;
+    const bool na = g_src_na.load(std::memory_order_relaxed) != 0;
+    if (g_staged.load(std::memory_order_relaxed)) {
+        walk_kernel<true, true, 4, false, kStageCrc><<<grid, block, kSmemBytes + kStageCrc * 512 * 32, st>>>(CV_WALK_ARGS);
+        return;
+    }
+    if (g_tile_crc_dst.load(std::memory_order_relaxed) == 2) {
+        if (na) walk_kernel<true, true, 2, true><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
+        else walk_kernel<true, true, 2, false><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
+    } else {
+        if (na) walk_kernel<true, true, 4, true><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
+        else walk_kernel<true, true, 4, false><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
     }
 }
 
-// copy-only walk: no shared memory, one CTA per SM (the kernels need > 32 registers, so two 1024-thread CTAs never fit)
-static void launch_walk_copy(int dev, cudaStream_t st, const Piece* pieces, uint32_t n, const uint32_t* prefix, uint32_t seg_shift,
-                             uint32_t* partial, uint32_t cap, uint32_t* headraw, uint32_t* tailraw) {
+// copy-only walk: no shared memory, one CTA per SM (the kernels need > 32 registers, so two 1024-thread CTAs never fit).
+// peer = some source may be another GPU's HBM mapped over NVLink: plain coherent loads only.
+static void launch_walk_copy(int dev, cudaStream_t st, const Workspace& w, uint32_t n, bool peer = false) {
     const dim3 grid(g_sm_count[dev]), block(1024);
-    switch (g_tile_copy.load(std::memory_order_relaxed)) {
-        case 2: walk_kernel<false, true, 2><<<grid, block, 0, st>>>(pieces, n, prefix, seg_shift, nullptr, partial, cap, headraw, tailraw); break;
-        default: walk_kernel<false, true, 4><<<grid, block, 0, st>>>(pieces, n, prefix, seg_shift, nullptr, partial, cap, headraw, tailraw); break;
+    const CrcConsts* cc = nullptr;
+    const bool na = !peer && g_src_na.load(std::memory_order_relaxed) != 0;
+    if (!peer && g_staged.load(std::memory_order_relaxed)) {
+        walk_kernel<false, true, 2, false, kStageCopy><<<grid, block, kStageCopy * 512 * 32, st>>>(CV_WALK_ARGS);
+        return;
+    }
+    if (g_tile_copy.load(std::memory_order_relaxed) == 4) {
+        if (na) walk_kernel<false, true, 4, true><<<grid, block, 0, st>>>(CV_WALK_ARGS);
+        else walk_kernel<false, true, 4, false><<<grid, block, 0, st>>>(CV_WALK_ARGS);
+    } else {
+        if (na) walk_kernel<false, true, 2, true><<<grid, block, 0, st>>>(CV_WALK_ARGS);
+        else walk_kernel<false, true, 2, false><<<grid, block, 0, st>>>(CV_WALK_ARGS);
     }
 }
+#undef CV_WALK_ARGS
 static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace cv
@@ -772,8 +941,10 @@ int cvk_init(int device) {
 }
 
 int cvk_tune(int what, int value) {
-    if (what == 0 && (value == 1 || value == 2 || value == 4)) g_tile_crc_dst.store(value);
+    if (what == 0 && (value == 2 || value == 4)) g_tile_crc_dst.store(value);
     else if (what == 1 && (value == 2 || value == 4)) g_tile_copy.store(value);
+    else if (what == 2 && (value == 0 || value == 1)) g_src_na.store(value);
+    else if (what == 3 && (value == 0 || value == 1)) g_staged.store(value != 0);
     else return int(cudaErrorInvalidValue);
     return 0;
 }
@@ -816,19 +987,20 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t seg_shift = pick_seg_shift(total_bytes, g_sm_count[dev]);
     Workspace w;
-    if (int rc = ws_alloc(&w, n, n, total_bytes, seg_shift, st)) return rc;
+    if (int rc = ws_alloc(&w, dev, n, n, total_bytes, seg_shift, st)) return rc;
     const CrcConsts* cc = g_consts[dev][poly];
     prep_blocks_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_base, d_off, d_len, n, seg_shift, w.pieces, w.counts);
     scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
+    launch_expand<false>(w, n, seg_shift, st);
     {
         WalkTimer wt(st);
-        walk_kernel<true, false, 4><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.pieces, n, w.prefix, seg_shift, cc,
-                                                                            w.partial, w.partial_cap, w.headraw, w.tailraw);
+        walk_kernel<true, false, 4, false><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.units, w.prefix + n, cc, w.partial, w.partial_cap,
+                                                                                       w.headraw, w.tailraw);
     }
     fold_blocks_kernel<false><<<cdiv(uint64_t(n) * 32, 256), 256, 0, st>>>(w.pieces, w.prefix, nullptr, nullptr, n, n, seg_shift,
                                                                            gf_xpow(8ull << seg_shift, poly_of(poly)), cc,
                                                                            w.partial, w.headraw, w.tailraw, d_crc_out);
-    count_launch(4);
+    count_launch(5);
     CV_TRY(cudaGetLastError());
     CV_TRY(cudaFreeAsync(w.base, st));
     return 0;
@@ -865,7 +1037,7 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t seg_shift = pick_seg_shift(total_bytes, g_sm_count[dev]);
     Workspace w;
-    if (int rc = ws_alloc(&w, n_frames, n_blocks, total_bytes, seg_shift, st)) return rc;
+    if (int rc = ws_alloc(&w, dev, n_frames, n_blocks, total_bytes, seg_shift, st)) return rc;
     const CrcConsts* cc = g_consts[dev][poly];
     if (pack)
         prep_pack_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_in, d_desc, n_frames, d_out, seg_shift, w.pieces,
@@ -874,11 +1046,12 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
         prep_unpack_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_in, d_desc, n_frames, d_out, seg_shift, w.pieces,
                                                                 w.counts, d_err_flags);
     scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n_frames, w.prefix);
-    count_launch(2);
+    launch_expand<true>(w, n_frames, seg_shift, st);
+    count_launch(3);
     if (d_block_crc) {
         {
             WalkTimer wt(st);
-            launch_walk_crc_dst(dev, st, w.pieces, n_frames, w.prefix, seg_shift, cc, w.partial, w.partial_cap, w.headraw, w.tailraw);
+            launch_walk_crc_dst(dev, st, w, n_frames, cc);
         }
         mark_block_ranges_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_desc, n_frames, n_blocks, w.first, w.last);
         fold_blocks_kernel<true><<<cdiv(uint64_t(n_blocks) * 32, 256), 256, 0, st>>>(
@@ -886,7 +1059,7 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
             w.partial, w.headraw, w.tailraw, d_block_crc);
         count_launch(3);
     } else {
-        launch_walk_copy(dev, st, w.pieces, n_frames, w.prefix, seg_shift, w.partial, w.partial_cap, w.headraw, w.tailraw);
+        launch_walk_copy(dev, st, w, n_frames);
         count_launch();
     }
     CV_TRY(cudaGetLastError());
@@ -907,10 +1080,11 @@ int cvk_pack_frames(const uint8_t* d_src, const CvFrameDesc* d_desc, uint32_t n_
                          stream);
 }
 
-static int copy_pieces(Workspace& w, uint32_t n, uint32_t seg_shift, int dev, cudaStream_t st) {
+static int copy_pieces(Workspace& w, uint32_t n, uint32_t seg_shift, int dev, cudaStream_t st, bool peer = false) {
     scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
-    launch_walk_copy(dev, st, w.pieces, n, w.prefix, seg_shift, w.partial, w.partial_cap, w.headraw, w.tailraw);
-    count_launch(2);
+    launch_expand<true>(w, n, seg_shift, st);
+    launch_walk_copy(dev, st, w, n, peer);
+    count_launch(3);
     CV_TRY(cudaGetLastError());
     CV_TRY(cudaFreeAsync(w.base, st));
     return 0;
@@ -925,7 +1099,7 @@ int cvk_gather_pages(const uint8_t* d_src, const CvSeg* d_segs, uint32_t n, uint
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t seg_shift = pick_seg_shift(total_bytes, g_sm_count[dev]);
     Workspace w;
-    if (int rc = ws_alloc(&w, n, 0, total_bytes, seg_shift, st)) return rc;
+    if (int rc = ws_alloc(&w, dev, n, 0, total_bytes, seg_shift, st)) return rc;
     prep_segs_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_src, d_segs, n, d_dst, seg_shift, w.pieces, w.counts);
     count_launch();
     return copy_pieces(w, n, seg_shift, dev, st);
@@ -942,7 +1116,7 @@ int cvk_deinterleave_blocks(const uint8_t* d_gathered, uint64_t shard_stride, ui
     const uint32_t seg_shift = pick_seg_shift(file_len, g_sm_count[dev]);
     Workspace w;
     const uint32_t n = uint32_t(n_blocks);
-    if (int rc = ws_alloc(&w, n, 0, file_len, seg_shift, st)) return rc;
+    if (int rc = ws_alloc(&w, dev, n, 0, file_len, seg_shift, st)) return rc;
     prep_deinterleave_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_gathered, shard_stride, world, block_size, n_blocks,
                                                            file_len, d_dst, seg_shift, w.pieces, w.counts);
     count_launch();
@@ -960,7 +1134,7 @@ int cvk_gather_shards_p2p(const uint8_t* const* shard_ptrs, uint32_t world, uint
     const uint32_t seg_shift = pick_seg_shift(file_len, g_sm_count[dev]);
     Workspace w;
     const uint32_t n = uint32_t(n_blocks);
-    if (int rc = ws_alloc(&w, n, 64, file_len, seg_shift, st)) return rc;  // w.first doubles as the pointer table (>= 64*8 bytes)
+    if (int rc = ws_alloc(&w, dev, n, 64, file_len, seg_shift, st)) return rc;  // w.first doubles as the pointer table (>= 64*8 bytes)
     static_assert(sizeof(uint8_t*) == 8, "64-bit pointers");
     // kernels on this device read the peers' HBM directly: make sure peer access (this device -> owner) is enabled in the
     // primary context (idempotent; another runtime instance in the process may or may not have done it already)
@@ -980,7 +1154,7 @@ int cvk_gather_shards_p2p(const uint8_t* const* shard_ptrs, uint32_t world, uint
     CV_TRY(cudaStreamSynchronize(st));  // shard_ptrs is the caller's (pageable) array
     prep_gather_shards_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_ptrs, world, block_size, n_blocks, file_len, d_dst, seg_shift, w.pieces, w.counts);
     count_launch();
-    return copy_pieces(w, n, seg_shift, dev, st);
+    return copy_pieces(w, n, seg_shift, dev, st, true);
 }
 
 }  // extern "C"

@@ -436,15 +436,20 @@ def cpu_run(state, n_total, sc, parallel, limit, checksum=1):
 
 def cpu_baseline(state, n_total, sc):
     """The reference's CPU read path (oracle port: per-chunk ping-pong / pread, memcpy, PCLMUL crc32 on the caller
-    thread) on a bounded sample of the same file, with the reference's default read_parallel for this file size."""
+    thread) on a bounded sample of the same file, with the reference's default read_parallel for this file size:
+    whole-file passes (or a prefix when one pass would take too long) repeated for about 12 s of CPU work."""
     from oracle import clib
     par = clib.reference_read_parallel(n_total)
-    pilot, _, _, _, _ = cpu_run(state, n_total, sc, par, 1 << 30)
+    pilot, _, _, _, _ = cpu_run(state, n_total, sc, par, 1 << 30)  # also the warm-up pass
     sample = int(min(n_total, max(1 << 30, pilot * 1e9 * 12))) // BLOCK * BLOCK
-    v, threads, got, cks, dt = cpu_run(state, n_total, sc, par, sample)
-    return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "first %.1f GiB of the same file, read_parallel=%d (reference default for this size), 128 KiB chunks and buffers, "
-                      "%s, crc32 (PCLMUL) on the caller thread; %.1f s" % (got / 2 ** 30, par, "short-circuit pread" if sc else "framed over loopback TCP", dt)}
+    passes, got_total, dt_total, threads = 0, 0, 0.0, 0
+    while dt_total < 12.0 and passes < 16:
+        v, threads, got, cks, dt = cpu_run(state, n_total, sc, par, sample)
+        passes, got_total, dt_total = passes + 1, got_total + got, dt_total + dt
+    return {"value": got_total / dt_total / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d pass(es) over the first %.1f GiB of the same file, read_parallel=%d (reference default for this size), 128 KiB chunks and "
+                      "buffers, %s, crc32 (PCLMUL) on the caller thread; %.1f s of wall time"
+                      % (passes, sample / 2 ** 30, par, "short-circuit pread" if sc else "framed over loopback TCP", dt_total)}
 
 
 def main_reference(args):

@@ -204,38 +204,60 @@ __global__ void mark_block_ranges_kernel(const CvFrameDesc* desc, uint32_t n, ui
     if (i == n - 1 || desc[i + 1].block != b) last[b] = i + 1;
 }
 
-// exclusive prefix sum of counts[0..n) into prefix[0..n]; single CTA (n is a frame/block count, not bytes)
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* counts, uint32_t n, uint32_t* prefix) {
+// exclusive prefix sum of counts[0..n) into prefix[0..n]; single CTA (n is a frame/block/page count, not bytes).
+// Tiles of 4096 elements: every thread takes one 16-byte vector of four counts (coalesced), the tile is scanned with
+// warp shuffles + one shared-memory hop, and the next tile's vector is already in flight while the current one is
+// scanned.  256 Ki page descriptors (a 1 GiB FUSE-shaped gather) scan in ~64 tile steps.
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ prefix) {
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
+    __shared__ uint32_t tile_total;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (n + 1023) / 1024;
-    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
-    uint32_t incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_sums[lane], wi = w;
+    auto load4 = [&](uint32_t base) -> uint4 {  // counts[base .. base+3], zero past n (counts is 256-byte aligned)
+        if (base + 4 <= n) return __ldg(reinterpret_cast<const uint4*>(counts + base));
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (base < n) v.x = __ldg(counts + base);
+        if (base + 1 < n) v.y = __ldg(counts + base + 1);
+        if (base + 2 < n) v.z = __ldg(counts + base + 2);
+        return v;
+    };
+    uint32_t carry = 0;
+    uint4 nxt = load4(tid * 4);
+    for (uint32_t t0 = 0; t0 < n; t0 += 4096) {
+        const uint4 c = nxt;
+        const uint32_t base = t0 + tid * 4;
+        if (t0 + 4096 < n) nxt = load4(base + 4096);
+        const uint32_t sum = c.x + c.y + c.z + c.w;
+        uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
         }
-        warp_sums[lane] = wi - w;  // exclusive
-        if (lane == 31) carry = wi;
-    }
-    __syncthreads();
-    uint32_t run = warp_sums[warp] + incl - sum;
-    for (uint32_t i = lo; i < hi; i++) {
-        prefix[i] = run;
-        run += counts[i];
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = warp_sums[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += t;
+            }
+            warp_sums[lane] = wi - w;  // exclusive
+            if (lane == 31) tile_total = wi;
+        }
+        __syncthreads();
+        const uint32_t e0 = carry + warp_sums[warp] + incl - sum;  // exclusive prefix of this thread's first element
+        const uint4 o = make_uint4(e0, e0 + c.x, e0 + c.x + c.y, e0 + c.x + c.y + c.z);
+        if (base + 4 <= n) {
+            *reinterpret_cast<uint4*>(prefix + base) = o;
+        } else {
+            if (base < n) prefix[base] = o.x;
+            if (base + 1 < n) prefix[base + 1] = o.y;
+            if (base + 2 < n) prefix[base + 2] = o.z;
+        }
+        carry += tile_total;
+        __syncthreads();  // warp_sums / tile_total are rewritten by the next tile
     }
     if (tid == 0) prefix[n] = carry;
 }

@@ -199,6 +199,31 @@ def test_gather_pages(cuda):
     assert dst.cpu().numpy().tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("n_segs", [4095, 4096, 4097, 13001])
+def test_many_small_pieces_multi_tile_scan(cuda, n_segs):
+    """More pieces than one scan tile (4096): FUSE-shaped scatter of thousands of tiny pages, and the CRC of
+    thousands of small blocks -- the prefix sum over piece unit counts spans several tiles, zero-length pieces included."""
+    import torch
+    from curvine_b200 import kernels as K
+    rng = np.random.default_rng(n_segs)
+    src = _rand(1 << 20, 12)
+    lens = rng.choice([0, 1, 7, 16, 33, 100, 257, 4096], size=n_segs)
+    sos = rng.integers(0, len(src) - 4096, size=n_segs)
+    segs, pos = [], 0
+    for so, n in zip(sos, lens):
+        segs.append((int(so), pos, int(n)))
+        pos += int(n) + int(rng.integers(0, 3))
+    want = np.zeros(pos + 16, dtype=np.uint8)
+    for so, do, n in segs:
+        want[do:do + n] = src[so:so + n]
+    d_src = _to_dev(src, cuda)
+    dst = torch.zeros(pos + 16, dtype=torch.uint8, device=cuda)
+    K.gather_pages(d_src, K.segs_to_device(segs, cuda), len(segs), int(lens.sum()), dst)
+    assert dst.cpu().numpy().tobytes() == want.tobytes()
+    got = K.u32(K.crc_blocks(d_src, [int(x) for x in sos], [int(x) for x in lens], 1))
+    assert got.tolist() == [clib.crc(1, src[o:o + n]) for o, n in zip(sos, lens)]
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_deinterleave_blocks(cuda, world):
     import torch

@@ -318,18 +318,6 @@ __device__ __forceinline__ uint4 ld_plain(const uint4* p) {
     return r;
 }
 
-// streaming (no L1 allocation) coherent load for local sources of the DST walks: rows are read once, and pending L1
-// line allocations cap how many rows a CTA can keep in flight
-__device__ __forceinline__ uint4 ld_plain_na(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-template <bool NA>
-__device__ __forceinline__ uint4 ld_src(const uint4* p) {
-    return NA ? ld_plain_na(p) : ld_plain(p);
-}
-
 // One output vector of a shifted walk: 16 bytes starting Q words + r8 bits into the 8-word window [ra | nb].
 template <int Q>
 __device__ __forceinline__ uint4 shift_window(const uint4& ra, const uint4& nb, uint32_t r8) {
@@ -382,7 +370,7 @@ struct Chains {
 // vector that follows the tile, needed by lane 31 of its last row) are issued back to back, so a warp keeps T*512 bytes
 // in flight; rows of a tile are independent of each other.  Q = word part of the shift (template: the window
 // selection and the number of shuffles are resolved at compile time), r8 = its bit part.
-template <bool CRC, int T, int Q, bool NA>
+template <bool CRC, int T, int Q>
 __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane, uint32_t tl, Chains& c) {
     const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15u);
     const uint4* bp = reinterpret_cast<const uint4*>(src - sh) + lane;
@@ -397,9 +385,9 @@ __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, u
     for (; j + T <= R; j += T) {  // whole tiles: every vector touched (incl. the one after the tile) is < nvec
         uint4 ra[T];
 #pragma unroll
-        for (int k = 0; k < T; k++) ra[k] = ld_src<NA>(bp + (j + k) * 32);
+        for (int k = 0; k < T; k++) ra[k] = ld_plain(bp + (j + k) * 32);
         uint4 ex = zero;
-        if (lane == 0) ex = ld_src<NA>(bp + (j + T) * 32);
+        if (lane == 0) ex = ld_plain(bp + (j + T) * 32);
 #pragma unroll
         for (int k = 0; k < T; k++) {
             const uint4 nb = take_right<Q>(ra[k], k + 1 < T ? ra[(k + 1) % T] : ex, lane);
@@ -409,9 +397,9 @@ __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, u
         }
     }
     for (; j < rows; j++) {  // leftover rows, bounds-checked
-        const uint4 ra = j * 32 + lane < nvec ? ld_src<NA>(bp + j * 32) : zero;
+        const uint4 ra = j * 32 + lane < nvec ? ld_plain(bp + j * 32) : zero;
         uint4 ex = zero;
-        if (lane == 0 && (j + 1) * 32 < nvec) ex = ld_src<NA>(bp + (j + 1) * 32);
+        if (lane == 0 && (j + 1) * 32 < nvec) ex = ld_plain(bp + (j + 1) * 32);
         const uint4 nb = take_right<Q>(ra, ex, lane);
         const uint4 v = shift_window<Q>(ra, nb, r8);
         if (j < R) {
@@ -426,7 +414,7 @@ __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, u
 }
 
 // Source and destination share their 16-byte phase: one load and one store per vector, tiles of T rows.
-template <bool CRC, int T, bool NA>
+template <bool CRC, int T>
 __device__ __forceinline__ void walk_aligned_copy(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane, uint32_t tl, Chains& c) {
     const uint4* sp = reinterpret_cast<const uint4*>(src) + lane;
     uint4* dp = reinterpret_cast<uint4*>(dst) + lane;
@@ -436,7 +424,7 @@ __device__ __forceinline__ void walk_aligned_copy(const uint8_t* src, uint8_t* d
     for (; j + T <= R; j += T) {
         uint4 v[T];
 #pragma unroll
-        for (int k = 0; k < T; k++) v[k] = ld_src<NA>(sp + (j + k) * 32);
+        for (int k = 0; k < T; k++) v[k] = ld_plain(sp + (j + k) * 32);
 #pragma unroll
         for (int k = 0; k < T; k++) {
             dp[(j + k) * 32] = v[k];
@@ -444,12 +432,12 @@ __device__ __forceinline__ void walk_aligned_copy(const uint8_t* src, uint8_t* d
         }
     }
     for (; j < R; j++) {
-        const uint4 v = ld_src<NA>(sp + j * 32);
+        const uint4 v = ld_plain(sp + j * 32);
         dp[j * 32] = v;
         if (CRC) CV_STEP(v);
     }
     if (lane < nv) {
-        c.vr = ld_src<NA>(sp + R * 32);
+        c.vr = ld_plain(sp + R * 32);
         dp[R * 32] = c.vr;
     }
     c.a0 = a0, c.a1 = a1, c.a2 = a2, c.a3 = a3;
@@ -521,7 +509,7 @@ __device__ __forceinline__ void walk_staged(const uint8_t* src, uint8_t* dst, ui
 
 // One warp walks L bytes (multiple of 16) starting at src (dst is 16-byte aligned when DST; src is 16-byte
 // aligned when !DST).  Returns the segment's raw CRC in every lane (0 when !CRC).  T = rows per tile of the DST walks.
-template <bool CRC, bool DST, int T, bool NA, int S>
+template <bool CRC, bool DST, int T, int S>
 __device__ __forceinline__ uint32_t walk_segment(const uint8_t* src, uint8_t* dst, uint32_t L, uint32_t lane,
                                                  const uint32_t* smem, uint32_t poly, uint32_t stage) {
     const uint32_t tl = static_cast<uint32_t>(__cvta_generic_to_shared(smem)) + lane * 4u;
@@ -563,13 +551,13 @@ __device__ __forceinline__ uint32_t walk_segment(const uint8_t* src, uint8_t* ds
                 default: walk_staged<CRC, 3, S ? S : 2>(src, dst, L, lane, tl, c, stage); break;
             }
         } else if (sh == 0) {
-            walk_aligned_copy<CRC, T, NA>(src, dst, L, lane, tl, c);
+            walk_aligned_copy<CRC, T>(src, dst, L, lane, tl, c);
         } else {
             switch (sh >> 2) {  // warp-uniform
-                case 0: walk_shifted<CRC, T, 0, NA>(src, dst, L, lane, tl, c); break;
-                case 1: walk_shifted<CRC, T, 1, NA>(src, dst, L, lane, tl, c); break;
-                case 2: walk_shifted<CRC, T, 2, NA>(src, dst, L, lane, tl, c); break;
-                default: walk_shifted<CRC, T, 3, NA>(src, dst, L, lane, tl, c); break;
+                case 0: walk_shifted<CRC, T, 0>(src, dst, L, lane, tl, c); break;
+                case 1: walk_shifted<CRC, T, 1>(src, dst, L, lane, tl, c); break;
+                case 2: walk_shifted<CRC, T, 2>(src, dst, L, lane, tl, c); break;
+                default: walk_shifted<CRC, T, 3>(src, dst, L, lane, tl, c); break;
             }
         }
     }
@@ -650,7 +638,7 @@ __device__ __forceinline__ Unit ld_unit(const Unit* p) {
     return un;
 }
 
-template <bool CRC, bool DST, int T, bool NA, int S = 0>
+template <bool CRC, bool DST, int T, int S = 0>
 __global__ void __launch_bounds__(1024, 1)
     walk_kernel(const Unit* __restrict__ units, const uint32_t* __restrict__ total_units, const CrcConsts* __restrict__ cc,
                 uint32_t* __restrict__ partial, uint32_t partial_cap, uint32_t* __restrict__ headraw, uint32_t* __restrict__ tailraw) {
@@ -677,7 +665,7 @@ __global__ void __launch_bounds__(1024, 1)
     Unit cur = ld_unit(units + u0 + warp);
     for (uint32_t u = u0 + warp; u < u1; u += 32) {
         const Unit nxt = ld_unit(units + (u + 32 < u1 ? u + 32 : u));  // next unit's record travels behind this walk
-        const uint32_t raw = walk_segment<CRC, DST, T, NA, S>(cur.src, cur.dst, cur.L, lane, smem, poly, stage);
+        const uint32_t raw = walk_segment<CRC, DST, T, S>(cur.src, cur.dst, cur.L, lane, smem, poly, stage);
         if (CRC && lane == 0) partial[u] = raw;
         if (cur.head && lane == 1) {
             const uint32_t r = walk_bytes<CRC, DST>(cur.src - cur.head, DST ? cur.dst - cur.head : nullptr, cur.head, t0);
@@ -757,9 +745,9 @@ __global__ void verify_crcs_kernel(const uint32_t* crc, const uint32_t* expect, 
 // ------------------------------------------------------------------ host side
 
 static std::atomic<uint64_t> g_launches{0};
-// Tuning of the DST walkers (cvk_tune; defaults chosen from the kbench sweep in profiles/): rows per tile, whether local
-// sources are read with L1::no_allocate, and register-tiled vs shared-memory staged walks.
-static std::atomic<int> g_tile_crc_dst{4}, g_tile_copy{2}, g_src_na{0};
+// Tuning of the DST walkers (cvk_tune; defaults chosen from the kbench sweeps in profiles/): rows per tile, and
+// register-tiled vs shared-memory staged walks.  (An L1::no_allocate load flavour was swept too: no gain, removed.)
+static std::atomic<int> g_tile_crc_dst{4}, g_tile_copy{2};
 static std::atomic<bool> g_staged{false};  // cvk_tune(3, 1) / CVK_STAGED=1: shared-memory staged (cp.async) DST walks for local sources
 static std::mutex g_mu;
 constexpr int kMaxDev = 16;
@@ -823,13 +811,11 @@ static int ensure_device(int* dev_out) {
         uint64_t keep = ~0ull;
         CV_TRY(cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4, false, kStageCrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + kStageCrc * 512 * 32));
-    CV_TRY(cudaFuncSetAttribute(walk_kernel<false, true, 2, false, kStageCopy>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageCopy * 512 * 32));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<true, true, 4, kStageCrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + kStageCrc * 512 * 32));
+    CV_TRY(cudaFuncSetAttribute(walk_kernel<false, true, 2, kStageCopy>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageCopy * 512 * 32));
     if (const char* e = getenv("CVK_STAGED")) g_staged.store(atoi(e) != 0);
     g_ready[dev] = true;
     return 0;
@@ -911,37 +897,25 @@ static void launch_expand(const Workspace& w, uint32_t n, uint32_t seg_shift, cu
 
 static void launch_walk_crc_dst(int dev, cudaStream_t st, const Workspace& w, uint32_t n, const CrcConsts* cc) {
     const dim3 grid(g_sm_count[dev]), block(1024);
-    const bool na = g_src_na.load(std::memory_order_relaxed) != 0;
-    if (g_staged.load(std::memory_order_relaxed)) {
-        walk_kernel<true, true, 4, false, kStageCrc><<<grid, block, kSmemBytes + kStageCrc * 512 * 32, st>>>(CV_WALK_ARGS);
-        return;
-    }
-    if (g_tile_crc_dst.load(std::memory_order_relaxed) == 2) {
-        if (na) walk_kernel<true, true, 2, true><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
-        else walk_kernel<true, true, 2, false><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
-    } else {
-        if (na) walk_kernel<true, true, 4, true><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
-        else walk_kernel<true, true, 4, false><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
-    }
+    if (g_staged.load(std::memory_order_relaxed))
+        walk_kernel<true, true, 4, kStageCrc><<<grid, block, kSmemBytes + kStageCrc * 512 * 32, st>>>(CV_WALK_ARGS);
+    else if (g_tile_crc_dst.load(std::memory_order_relaxed) == 2)
+        walk_kernel<true, true, 2><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
+    else
+        walk_kernel<true, true, 4><<<grid, block, kSmemBytes, st>>>(CV_WALK_ARGS);
 }
 
 // copy-only walk: no shared memory, one CTA per SM (the kernels need > 32 registers, so two 1024-thread CTAs never fit).
-// peer = some source may be another GPU's HBM mapped over NVLink: plain coherent loads only.
+// peer = some source may be another GPU's HBM mapped over NVLink: register-tiled walk with plain coherent loads only.
 static void launch_walk_copy(int dev, cudaStream_t st, const Workspace& w, uint32_t n, bool peer = false) {
     const dim3 grid(g_sm_count[dev]), block(1024);
     const CrcConsts* cc = nullptr;
-    const bool na = !peer && g_src_na.load(std::memory_order_relaxed) != 0;
-    if (!peer && g_staged.load(std::memory_order_relaxed)) {
-        walk_kernel<false, true, 2, false, kStageCopy><<<grid, block, kStageCopy * 512 * 32, st>>>(CV_WALK_ARGS);
-        return;
-    }
-    if (g_tile_copy.load(std::memory_order_relaxed) == 4) {
-        if (na) walk_kernel<false, true, 4, true><<<grid, block, 0, st>>>(CV_WALK_ARGS);
-        else walk_kernel<false, true, 4, false><<<grid, block, 0, st>>>(CV_WALK_ARGS);
-    } else {
-        if (na) walk_kernel<false, true, 2, true><<<grid, block, 0, st>>>(CV_WALK_ARGS);
-        else walk_kernel<false, true, 2, false><<<grid, block, 0, st>>>(CV_WALK_ARGS);
-    }
+    if (!peer && g_staged.load(std::memory_order_relaxed))
+        walk_kernel<false, true, 2, kStageCopy><<<grid, block, kStageCopy * 512 * 32, st>>>(CV_WALK_ARGS);
+    else if (g_tile_copy.load(std::memory_order_relaxed) == 4)
+        walk_kernel<false, true, 4><<<grid, block, 0, st>>>(CV_WALK_ARGS);
+    else
+        walk_kernel<false, true, 2><<<grid, block, 0, st>>>(CV_WALK_ARGS);
 }
 #undef CV_WALK_ARGS
 static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -965,7 +939,6 @@ int cvk_init(int device) {
 int cvk_tune(int what, int value) {
     if (what == 0 && (value == 2 || value == 4)) g_tile_crc_dst.store(value);
     else if (what == 1 && (value == 2 || value == 4)) g_tile_copy.store(value);
-    else if (what == 2 && (value == 0 || value == 1)) g_src_na.store(value);
     else if (what == 3 && (value == 0 || value == 1)) g_staged.store(value != 0);
     else return int(cudaErrorInvalidValue);
     return 0;
@@ -1016,7 +989,7 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
     launch_expand<false>(w, n, seg_shift, st);
     {
         WalkTimer wt(st);
-        walk_kernel<true, false, 4, false><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.units, w.prefix + n, cc, w.partial, w.partial_cap,
+        walk_kernel<true, false, 4><<<g_sm_count[dev], 1024, kSmemBytes, st>>>(w.units, w.prefix + n, cc, w.partial, w.partial_cap,
                                                                                        w.headraw, w.tailraw);
     }
     fold_blocks_kernel<false><<<cdiv(uint64_t(n) * 32, 256), 256, 0, st>>>(w.pieces, w.prefix, nullptr, nullptr, n, n, seg_shift,

@@ -144,10 +144,10 @@ int cvk_gather_shards_p2p(const uint8_t* const* shard_ptrs, uint32_t world, uint
 int cvk_profile_enable(int on);
 int cvk_profile_collect(double* walk_ms_total, uint32_t* walk_launches);
 
-/* Tuning hook for the DST row walkers: rows per tile (= 512-byte rows a warp keeps in flight).
- * what 0: CRC+copy walkers (K2/K4), value in {2,4}; what 1: copy-only walker (K3/deinterleave/P2P gather), value in
- * {2,4}; what 2: read local sources with L1::no_allocate (1) or plain loads (0, default); what 3: shared-memory staged
- * (cp.async) DST walks (1) or register-tiled ones (0, default).  Process-wide; results are identical for every setting (tools/kbench.py sweeps it). */
+/* Tuning hook for the DST row walkers.  what 0: rows per tile (= 512-byte rows a warp keeps in flight in registers) of
+ * the CRC+copy walkers (K2/K4), value in {2,4}; what 1: of the copy-only walker (K3/deinterleave/P2P gather), value in
+ * {2,4}; what 3: shared-memory staged (cp.async) DST walks (1) or register-tiled ones (0, default; CVK_STAGED=1 in the
+ * environment flips the default).  Process-wide; results are identical for every setting (tools/kbench.py sweeps it). */
 int cvk_tune(int what, int value);
 
 /* Number of kernel launches issued by this library in this process (bench.py's gpu_launches claim). */

@@ -82,8 +82,6 @@ def main():
     def tune(which, tc, na, stg):
         if tc:
             _lib.check(_lib.lib().cvk_tune(which, tc))
-        if na is not None:
-            _lib.check(_lib.lib().cvk_tune(2, na))
         if stg is not None:
             _lib.check(_lib.lib().cvk_tune(3, stg))
         return ("_staged" if stg else "_T%d_na%d" % (tc, na)) if a.sweep else ""

@@ -401,6 +401,8 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "walk_kernel<CRC,!DST> (K1 CRC verify)",
                              "achieved": shard_bytes / walk_avg_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
                              "frac": shard_bytes / walk_avg_ms / 1e6 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                             "note": "K1 only reads (N bytes in, 4 bytes per block out) while the peak is a read+write copy rate, so frac can exceed 1; "
+                                     "a bare read-only kernel in the same layout measured 7,150 GB/s on this GPU (profiles/r01_pattern_probe.txt)",
                              "algorithmic_bytes_per_launch": shard_bytes, "avg_launch_ms": walk_avg_ms, "launches_timed": int(walk_n.value)},
                 "clocks": sampler.summary(t_c, t_d),
                 "clocks_e2e": sampler.summary(t_a, t_b),

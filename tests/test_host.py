@@ -40,6 +40,16 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
 
 
+def test_tuning_hook_validates_its_arguments_without_a_gpu():
+    """cvk_tune only flips process-wide launch choices: legal values are accepted, everything else is cudaErrorInvalidValue (1)."""
+    L = _lib.lib()
+    for what, value in ((0, 2), (0, 4), (1, 4), (1, 2), (3, 1), (3, 0)):
+        assert L.cvk_tune(what, value) == 0
+    for what, value in ((0, 3), (1, 8), (2, 1), (3, 2), (9, 0)):
+        assert L.cvk_tune(what, value) == 1
+    assert L.cvk_tune(0, 4) == 0 and L.cvk_tune(1, 2) == 0 and L.cvk_tune(3, 0) == 0  # back to the defaults
+
+
 def test_host_crc_and_generator_match_oracle():
     L = _lib.lib()
     rng = np.random.default_rng(0)

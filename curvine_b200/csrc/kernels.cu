@@ -864,6 +864,13 @@ static int ws_alloc(Workspace* w, int dev, uint32_t n_pieces, uint32_t n_blocks,
     return 0;
 }
 
+// end of a launch train: report the first launch error (if any) and hand the workspace back to the pool either way
+static int ws_finish(Workspace& w, cudaStream_t st) {
+    const cudaError_t launch = cudaGetLastError();
+    const cudaError_t freed = cudaFreeAsync(w.base, st);
+    return int(launch != cudaSuccess ? launch : freed);
+}
+
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return uint32_t((a + b - 1) / b); }
 
 // optional timing of the dominant (walk) kernel: events on the launching stream, summed by cvk_profile_collect
@@ -996,9 +1003,7 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
                                                                            gf_xpow(8ull << seg_shift, poly_of(poly)), cc,
                                                                            w.partial, w.headraw, w.tailraw, d_crc_out);
     count_launch(5);
-    CV_TRY(cudaGetLastError());
-    CV_TRY(cudaFreeAsync(w.base, st));
-    return 0;
+    return ws_finish(w, st);
 }
 
 int cvk_verify_crcs(const uint32_t* d_crc, const uint32_t* d_expect, uint32_t n, uint32_t* d_n_bad,
@@ -1057,9 +1062,7 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
         launch_walk_copy(dev, st, w, n_frames);
         count_launch();
     }
-    CV_TRY(cudaGetLastError());
-    CV_TRY(cudaFreeAsync(w.base, st));
-    return 0;
+    return ws_finish(w, st);
 }
 
 int cvk_unpack_frames(const uint8_t* d_wire, const CvFrameDesc* d_desc, uint32_t n_frames, uint32_t n_blocks,
@@ -1080,9 +1083,7 @@ static int copy_pieces(Workspace& w, uint32_t n, uint32_t seg_shift, int dev, cu
     launch_expand<true>(w, n, seg_shift, st);
     launch_walk_copy(dev, st, w, n, peer);
     count_launch(3);
-    CV_TRY(cudaGetLastError());
-    CV_TRY(cudaFreeAsync(w.base, st));
-    return 0;
+    return ws_finish(w, st);
 }
 
 int cvk_gather_pages(const uint8_t* d_src, const CvSeg* d_segs, uint32_t n, uint64_t total_bytes, uint8_t* d_dst,
@@ -1145,8 +1146,12 @@ int cvk_gather_shards_p2p(const uint8_t* const* shard_ptrs, uint32_t world, uint
         cudaGetLastError();
     }
     const uint8_t** d_ptrs = reinterpret_cast<const uint8_t**>(w.first);
-    CV_TRY(cudaMemcpyAsync(d_ptrs, shard_ptrs, sizeof(uint8_t*) * world, cudaMemcpyHostToDevice, st));
-    CV_TRY(cudaStreamSynchronize(st));  // shard_ptrs is the caller's (pageable) array
+    cudaError_t ce = cudaMemcpyAsync(d_ptrs, shard_ptrs, sizeof(uint8_t*) * world, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // shard_ptrs is the caller's (pageable) array
+    if (ce != cudaSuccess) {
+        cudaFreeAsync(w.base, st);
+        return int(ce);
+    }
     prep_gather_shards_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_ptrs, world, block_size, n_blocks, file_len, d_dst, seg_shift, w.pieces, w.counts);
     count_launch();
     return copy_pieces(w, n, seg_shift, dev, st, true);

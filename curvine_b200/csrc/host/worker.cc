@@ -267,10 +267,10 @@ Err Worker::start(const std::vector<std::string>& data_dirs, const std::string& 
 void Worker::stop() {
     if (listen_fd_ < 0) return;
     stopping_ = true;
-    ::shutdown(listen_fd_, SHUT_RDWR);
+    ::shutdown(listen_fd_, SHUT_RDWR);  // wakes accept(); the descriptor stays valid (and ours) until the accept thread is gone
+    if (accept_thread_.joinable()) accept_thread_.join();
     close_fd(listen_fd_);
     listen_fd_ = -1;
-    if (accept_thread_.joinable()) accept_thread_.join();
     {
         std::lock_guard<std::mutex> lk(conn_mu_);
         for (int fd : conn_fds_) ::shutdown(fd, SHUT_RDWR);

@@ -247,7 +247,8 @@ Err FsContext::acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClie
         }
     }
     int fd = -1;
-    CV_RETURN_IF_ERR(tcp_connect(addr.ip_addr.empty() ? addr.hostname : addr.ip_addr, static_cast<int>(addr.rpc_port), &fd));
+    CV_RETURN_IF_ERR(tcp_connect(addr.ip_addr.empty() ? addr.hostname : addr.ip_addr, static_cast<int>(addr.rpc_port), &fd, conf.client.conn_timeout_ms,
+                                 conf.client.data_timeout_ms));
     out->reset(new BlockClient(fd, addr));
     return Err::ok();
 }

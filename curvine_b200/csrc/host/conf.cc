@@ -129,6 +129,9 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "large_file_size") e = as_size(v, &cl.large_file_size);
             else if (k == "max_read_parallel") cl.max_read_parallel = as_int(v);
             else if (k == "sequential_read_threshold") cl.sequential_read_threshold = as_int(v);
+            else if (k == "conn_timeout_ms") cl.conn_timeout_ms = as_int(v);
+            else if (k == "rpc_timeout_ms") cl.rpc_timeout_ms = as_int(v);
+            else if (k == "data_timeout_ms") cl.data_timeout_ms = as_int(v);
             else if (k == "enable_block_conn_pool") cl.enable_block_conn_pool = as_bool(v);
             else if (k == "block_conn_idle_size") cl.block_conn_idle_size = as_int(v);
             else if (k == "hostname") cl.hostname = unquote(v);

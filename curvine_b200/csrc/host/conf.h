@@ -27,6 +27,9 @@ struct ClientConf {
     int64_t large_file_size = 10ll << 30;
     int64_t max_read_parallel = 8;
     int64_t sequential_read_threshold = 7;
+    int64_t conn_timeout_ms = 30 * 1000;   // client_conf.rs:361 (connect), :363 (every block RPC: data_timeout_ms)
+    int64_t rpc_timeout_ms = 120 * 1000;   // parsed for compatibility; block RPCs use data_timeout_ms (block_client.rs:56)
+    int64_t data_timeout_ms = 120 * 1000;
     bool enable_block_conn_pool = true;
     int64_t block_conn_idle_size = 128;
     std::string hostname;  // CURVINE_CLIENT_HOSTNAME override; default gethostname()

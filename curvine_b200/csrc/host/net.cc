@@ -1,7 +1,10 @@
 #include "net.h"
 
+#include <algorithm>
 #include <arpa/inet.h>
 #include <errno.h>
+#include <fcntl.h>
+#include <poll.h>
 #include <netdb.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
@@ -43,16 +46,48 @@ static Err resolve(const std::string& host, int port, sockaddr_in* sa) {
     return Err::ok();
 }
 
-Err tcp_connect(const std::string& host, int port, int* fd_out) {
+Err tcp_connect(const std::string& host, int port, int* fd_out, int64_t conn_timeout_ms, int64_t io_timeout_ms) {
     sockaddr_in sa;
     CV_RETURN_IF_ERR(resolve(host, port, &sa));
     const int fd = socket(AF_INET, SOCK_STREAM, 0);
     if (fd < 0) return Err::io(str_printf("socket: %s", strerror(errno)));
     set_sock_opts(fd);
-    if (connect(fd, reinterpret_cast<sockaddr*>(&sa), sizeof(sa)) != 0) {
+    int rc;
+    if (conn_timeout_ms > 0) {  // non-blocking connect + poll, then back to blocking
+        const int fl = fcntl(fd, F_GETFL, 0);
+        fcntl(fd, F_SETFL, fl | O_NONBLOCK);
+        rc = connect(fd, reinterpret_cast<sockaddr*>(&sa), sizeof(sa));
+        if (rc != 0 && errno == EINPROGRESS) {
+            pollfd pf{fd, POLLOUT, 0};
+            int pr;
+            do pr = poll(&pf, 1, static_cast<int>(std::min<int64_t>(conn_timeout_ms, 0x7fffffff)));
+            while (pr < 0 && errno == EINTR);
+            if (pr == 0) {
+                ::close(fd);
+                return Err::io(str_printf("connect %s:%d: timed out after %lld ms", host.c_str(), port, (long long)conn_timeout_ms));
+            }
+            int soerr = 0;
+            socklen_t sl = sizeof(soerr);
+            getsockopt(fd, SOL_SOCKET, SO_ERROR, &soerr, &sl);
+            rc = soerr == 0 ? 0 : -1;
+            errno = soerr;
+        }
+        const int e = errno;
+        fcntl(fd, F_SETFL, fl);
+        errno = e;
+    } else {
+        rc = connect(fd, reinterpret_cast<sockaddr*>(&sa), sizeof(sa));
+    }
+    if (rc != 0) {
         const int e = errno;
         ::close(fd);
         return Err::io(str_printf("connect %s:%d: %s", host.c_str(), port, strerror(e)));
+    }
+    if (io_timeout_ms > 0) {
+        timeval tv;
+        tv.tv_sec = static_cast<time_t>(io_timeout_ms / 1000), tv.tv_usec = static_cast<suseconds_t>((io_timeout_ms % 1000) * 1000);
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+        setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
     }
     *fd_out = fd;
     return Err::ok();
@@ -84,6 +119,7 @@ Err send_all(int fd, const void* buf, size_t n) {
         const ssize_t w = ::send(fd, p, n, MSG_NOSIGNAL);
         if (w < 0) {
             if (errno == EINTR) continue;
+            if (errno == EAGAIN || errno == EWOULDBLOCK) return Err::io("send: timed out");  // SO_SNDTIMEO elapsed
             return Err::io(str_printf("send: %s", strerror(errno)));
         }
         p += w, n -= static_cast<size_t>(w);
@@ -98,6 +134,7 @@ Err recv_exact(int fd, void* buf, size_t n) {
         if (r == 0) return Err::io("connection closed");
         if (r < 0) {
             if (errno == EINTR) continue;
+            if (errno == EAGAIN || errno == EWOULDBLOCK) return Err::io("recv: timed out");  // SO_RCVTIMEO elapsed
             return Err::io(str_printf("recv: %s", strerror(errno)));
         }
         p += r, n -= static_cast<size_t>(r);

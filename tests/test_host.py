@@ -326,6 +326,58 @@ def test_replica_failover_on_read_error(tmp_path):
         w2.stop()
 
 
+def test_hung_worker_times_out_with_an_io_error(cluster):
+    """client_conf.rs:361-363 + block_client.rs:56,88-95: every block RPC runs under data_timeout_ms; an elapsed timer
+    is io::ErrorKind::TimedOut -> FsError::IO (orpc/src/io/io_error.rs:148-153).  A worker that accepts the connection
+    and never answers must therefore surface as kind IO after about data_timeout_ms, not hang the reader; a worker
+    address nothing listens on fails the connect.  The hung connection must not go back to the pool."""
+    import socket
+    import threading
+    import time
+    w, _ = cluster
+    man = w.create_file("/hung", 4650, 1 << 20, 1 << 20)
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(8)
+    held = []
+    stop = threading.Event()
+
+    def black_hole():
+        srv.settimeout(0.1)
+        while not stop.is_set():
+            try:
+                held.append(srv.accept()[0])  # accept, read nothing, answer nothing
+            except OSError:
+                pass
+
+    t = threading.Thread(target=black_hole, daemon=True)
+    t.start()
+    try:
+        man2 = man.replace(":%d:" % w.port, ":%d:" % srv.getsockname()[1])
+        for sc in (True, False):
+            with F.CurvineFileSystem(F.client_conf(short_circuit=sc, extra_client="data_timeout_ms = 300\nconn_timeout_ms = 1000")) as fs:
+                fs.load_namespace(man2)
+                r = fs.open("/hung")
+                t0 = time.time()
+                with pytest.raises(F.FsError) as ei:
+                    r.read(10)
+                dt = time.time() - t0
+                assert ei.value.kind == 1 and "timed out" in ei.value.msg, (ei.value.kind, ei.value.msg)
+                assert 0.25 <= dt < 5.0, dt
+                with pytest.raises(F.FsError):  # the broken connection was dropped: a second attempt times out again, it does not
+                    r.read(10)                  # read a stale answer off a pooled socket
+        # the same file through the real worker still reads fine with the short timeouts
+        with F.CurvineFileSystem(F.client_conf(short_circuit=False, extra_client="data_timeout_ms = 300")) as fs:
+            fs.load_namespace(man)
+            assert fs.open("/hung").read_full(1 << 20) == synth.file_bytes(4650, 1 << 20, 1 << 20)
+    finally:
+        stop.set()
+        t.join()
+        for c in held:
+            c.close()
+        srv.close()
+
+
 def test_empty_and_ragged_files(cluster):
     """Edge shapes: empty file; file shorter than a chunk; block size that is not a multiple of the chunk size
     (chunks restart at every block: local_file.rs:103-117, fs_reader_base.rs:181-204)."""

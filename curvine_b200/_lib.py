@@ -70,6 +70,7 @@ def _declare(L):
     L.cv_fs_close.argtypes, L.cv_fs_close.restype = [vp], i64
     L.cv_fs_wait_registered.argtypes, L.cv_fs_wait_registered.restype = [vp], i64
     L.cv_fs_metrics.argtypes, L.cv_fs_metrics.restype = [vp, cp(i64)], i64
+    L.cv_fs_pool_stats.argtypes, L.cv_fs_pool_stats.restype = [vp, cp(i64)], i64
     L.cv_open.argtypes, L.cv_open.restype = [vp, c, cp(vp), cp(i64)], i64
     L.cv_read.argtypes, L.cv_read.restype = [vp, cp(vp), cp(i64)], i64
     L.cv_read_buf.argtypes, L.cv_read_buf.restype = [vp, vp, i64, cp(i64)], i64
@@ -118,7 +119,7 @@ class CvReadStats(ctypes.Structure):
 # every symbol include/*.h declares (tests check the .so exports all of them)
 EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_unpack_frames", "cvk_expand_streams", "cvk_gather_pages",
            "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_gather_shards_p2p", "cvk_launch_count", "cvk_tune", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
-           "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_wait_registered", "cv_fs_metrics",
+           "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_wait_registered", "cv_fs_metrics", "cv_fs_pool_stats",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device",
            "cv_verify", "cv_device_stats", "cv_writer_open", "cv_write", "cv_write_device", "cv_writer_close", "cv_worker_start", "cv_worker_stop", "cv_worker_hbm_load", "cv_worker_hbm_stats", "cv_worker_metrics",

@@ -124,6 +124,11 @@ int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]) {
     return ok();
 }
 
+int64_t cv_fs_pool_stats(cv_fs* fs, int64_t out[3]) {
+    fs->ctx->pool_stats(out);
+    return ok();
+}
+
 int64_t cv_open(cv_fs* fs, const char* path, cv_reader** out, int64_t* len) {
     API_GUARD_BEGIN
     std::unique_ptr<cv_reader> r(new cv_reader());

@@ -236,28 +236,49 @@ Err BlockClient::read_commit(const ExtendedBlock& b, int64_t req_id, int32_t seq
 
 FsContext::~FsContext() = default;
 
+static int64_t now_ms() { return static_cast<int64_t>(now_sec() * 1000.0); }
+
 Err FsContext::acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClient>* out) {
     if (conf.client.enable_block_conn_pool) {
+        std::vector<std::unique_ptr<BlockClient>> expired;  // closed outside the lock
         std::lock_guard<std::mutex> lk(mu_);
         auto& v = idle_[addr.str()];
-        if (!v.empty()) {
-            *out = std::move(v.back());  // LIFO
+        const int64_t now = now_ms();
+        while (!v.empty()) {
+            std::unique_ptr<BlockClient> c = std::move(v.back());  // LIFO
             v.pop_back();
-            return Err::ok();
+            idle_total_--;
+            if (now - c->idle_since_ms < conf.client.block_conn_idle_time_ms) {
+                *out = std::move(c);
+                return Err::ok();
+            }
+            expired.push_back(std::move(c));
+            conns_expired_++;
         }
     }
     int fd = -1;
     CV_RETURN_IF_ERR(tcp_connect(addr.ip_addr.empty() ? addr.hostname : addr.ip_addr, static_cast<int>(addr.rpc_port), &fd, conf.client.conn_timeout_ms,
                                  conf.client.data_timeout_ms));
     out->reset(new BlockClient(fd, addr));
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        conns_opened_++;
+    }
     return Err::ok();
 }
 
 void FsContext::release(std::unique_ptr<BlockClient> c) {
     if (!c || c->broken || !conf.client.enable_block_conn_pool) return;
     std::lock_guard<std::mutex> lk(mu_);
-    auto& v = idle_[c->addr().str()];
-    if (static_cast<int64_t>(v.size()) < conf.client.block_conn_idle_size) v.push_back(std::move(c));
+    if (idle_total_ >= conf.client.block_conn_idle_size) return;  // pool full: the connection is closed
+    c->idle_since_ms = now_ms();
+    idle_[c->addr().str()].push_back(std::move(c));
+    idle_total_++;
+}
+
+void FsContext::pool_stats(int64_t out[3]) {
+    std::lock_guard<std::mutex> lk(mu_);
+    out[0] = idle_total_, out[1] = conns_opened_, out[2] = conns_expired_;
 }
 
 // ------------------------------------------------------------------ BlockReader

@@ -98,6 +98,7 @@ class BlockClient {
     Err send_request(const Protocol& req, const std::string& header);
     Err recv_response_head(Protocol* resp, std::string* resp_header);  // prefix + header; payload left on the socket
     bool broken = false;
+    int64_t idle_since_ms = 0;  // set when the connection goes back to the pool (BlockClient::uptime, block_client.rs:47,80-86)
 
    private:
     int fd_;
@@ -110,7 +111,9 @@ class FsContext {
     ~FsContext();
     ClusterConf conf;
     Namespace ns;
-    // block_client_pool.rs: LIFO idle connections per worker, at most block_conn_idle_size
+    // block_client_pool.rs:102-160: LIFO idle connections per worker; at most block_conn_idle_size idle connections over all
+    // workers (a connection returned to a full pool is closed); a pooled connection idle for block_conn_idle_time or longer
+    // is dropped when acquire meets it
     Err acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClient>* out);
     void release(std::unique_ptr<BlockClient> c);
     bool is_local_worker(const WorkerAddress& addr) const { return addr.hostname == conf.client.hostname; }
@@ -121,6 +124,10 @@ class FsContext {
    private:
     std::mutex mu_;
     std::unordered_map<std::string, std::vector<std::unique_ptr<BlockClient>>> idle_;
+    int64_t idle_total_ = 0;  // cur_idle_size
+    int64_t conns_opened_ = 0, conns_expired_ = 0;
+   public:
+    void pool_stats(int64_t out[3]);  // idle now (BlockClientPool::idle_conn), connections opened so far, pooled connections dropped as expired
 };
 
 // ------------------------------------------------------------------ block readers

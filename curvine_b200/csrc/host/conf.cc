@@ -61,6 +61,33 @@ static std::string unquote(const std::string& v) {
     return v;
 }
 
+Err parse_duration_ms(const std::string& in, int64_t* out) {
+    std::string s;
+    for (char c : in) s += static_cast<char>(tolower(static_cast<unsigned char>(c)));
+    size_t a = 0, b = s.size();
+    while (a < b && isspace(static_cast<unsigned char>(s[a]))) a++;
+    while (b > a && isspace(static_cast<unsigned char>(s[b - 1]))) b--;
+    s = s.substr(a, b - a);
+    size_t k = 0;
+    while (k < s.size() && (isdigit(static_cast<unsigned char>(s[k])) || s[k] == '.' || s[k] == 'e' || s[k] == '-' || s[k] == '+')) k++;
+    const std::string num = s.substr(0, k);
+    std::string unit = s.substr(k);
+    while (!unit.empty() && isspace(static_cast<unsigned char>(unit.front()))) unit.erase(unit.begin());
+    double mult;
+    if (unit == "s" || unit == "second") mult = 1000.0;
+    else if (unit == "m" || unit == "minute") mult = 60.0 * 1000;
+    else if (unit == "h" || unit == "hour") mult = 3600.0 * 1000;
+    else if (unit == "d" || unit == "day") mult = 86400.0 * 1000;
+    else if (unit == "ms" || unit.empty()) mult = 1.0;
+    else return Err::common("valid duration " + s + ", only d, h, m, s, ms are supported");
+    if (num.empty()) return Err::common("invalid duration string: " + s);
+    char* end = nullptr;
+    const double v = strtod(num.c_str(), &end);
+    if (end == num.c_str() || *end != '\0' || v < 0) return Err::common("invalid duration string: " + s);
+    *out = static_cast<int64_t>(v * mult);
+    return Err::ok();
+}
+
 static Err as_size(const std::string& v, int64_t* out) { return parse_byte_size(unquote(v), out); }
 static bool as_bool(const std::string& v) { return unquote(v) == "true" || unquote(v) == "1"; }
 static int64_t as_int(const std::string& v) { return strtoll(unquote(v).c_str(), nullptr, 10); }
@@ -134,6 +161,7 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "data_timeout_ms") cl.data_timeout_ms = as_int(v);
             else if (k == "enable_block_conn_pool") cl.enable_block_conn_pool = as_bool(v);
             else if (k == "block_conn_idle_size") cl.block_conn_idle_size = as_int(v);
+            else if (k == "block_conn_idle_time") e = parse_duration_ms(unquote(v), &cl.block_conn_idle_time_ms);
             else if (k == "hostname") cl.hostname = unquote(v);
         } else if (section == "worker") {
             if (k == "data_dir") c->worker_dirs = as_list(v);

@@ -31,7 +31,8 @@ struct ClientConf {
     int64_t rpc_timeout_ms = 120 * 1000;   // parsed for compatibility; block RPCs use data_timeout_ms (block_client.rs:56)
     int64_t data_timeout_ms = 120 * 1000;
     bool enable_block_conn_pool = true;
-    int64_t block_conn_idle_size = 128;
+    int64_t block_conn_idle_size = 128;       // idle connections kept by the pool, over ALL workers (block_client_pool.rs:147-155)
+    int64_t block_conn_idle_time_ms = 60000;  // "block_conn_idle_time", DurationUnit string, default "60s" (client_conf.rs:412-413)
     std::string hostname;  // CURVINE_CLIENT_HOSTNAME override; default gethostname()
     Err init();            // client_conf.rs:228-281
 };
@@ -71,5 +72,7 @@ struct ClusterConf {
 
 // "128KB" -> 131072; plain integers pass through
 Err parse_byte_size(const std::string& s, int64_t* out);
+// DurationUnit::from_str (orpc/src/common/duration_unit.rs:66-108): "60s" "5m" "2h" "1d" "250ms" "250" (= ms) "1.5s" -> milliseconds
+Err parse_duration_ms(const std::string& s, int64_t* out);
 
 }  // namespace cv

@@ -264,6 +264,12 @@ class CurvineFileSystem:
         _check(_lib.lib().cv_fs_metrics(self._h, a))
         return {"read_bytes": a[0], "read_time_us": a[1]}
 
+    def pool_stats(self) -> dict:
+        """Block connection pool: idle connections now, connections opened so far, pooled connections dropped as expired."""
+        a = (ctypes.c_int64 * 3)()
+        _check(_lib.lib().cv_fs_pool_stats(self._h, a))
+        return {"idle": a[0], "opened": a[1], "expired": a[2]}
+
     def close(self):
         if self._h:
             h, self._h = self._h, None

@@ -71,6 +71,9 @@ int64_t cv_fs_close(cv_fs* fs);
 int64_t cv_fs_wait_registered(cv_fs* fs);
 /* client metrics (client_metrics.rs:24-35): out[0]=read_bytes out[1]=read_time_us */
 int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]);
+/* block connection pool (block_client_pool.rs:102-168): out[0]=idle connections now (idle_conn), out[1]=connections opened so far,
+ * out[2]=pooled connections dropped because they sat idle for block_conn_idle_time or longer */
+int64_t cv_fs_pool_stats(cv_fs* fs, int64_t out[3]);
 
 /* ---- reader */
 int64_t cv_open(cv_fs* fs, const char* path, cv_reader** out, int64_t* len);

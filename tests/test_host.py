@@ -270,6 +270,60 @@ def test_conf_parsing_matches_reference_rules():
         F.CurvineFileSystem('[client]\nread_chunk_size = "64XB"\n')
 
 
+def test_duration_strings_and_block_conn_pool_semantics(cluster):
+    """block_client_pool.rs:102-168 + client_conf.rs:406-413 + duration_unit.rs:66-108: connections are reused LIFO per worker;
+    the pool keeps at most block_conn_idle_size idle connections over all workers (extra ones are closed on release); a pooled
+    connection that sat idle for block_conn_idle_time or longer is dropped at the next acquire."""
+    import time
+    w, _ = cluster
+    man = "".join(w.create_file("/pool/f%d" % i, 4800 + i, 1 << 20, 1 << 18) for i in range(3))  # 3 files x 4 blocks
+
+    def read_all(fs, name):
+        r = fs.open(name)
+        got = r.read_full(1 << 20)
+        r.complete()
+        return got
+
+    for bad in ("10x", "abc", "-5s"):
+        with pytest.raises(F.FsError):
+            F.CurvineFileSystem('[client]\nblock_conn_idle_time = "%s"\n' % bad)
+    for ok in ("60s", "5m", "2h", "1d", "250ms", "250", "1.5s"):
+        F.CurvineFileSystem('[client]\nblock_conn_idle_time = "%s"\n' % ok).close()
+    # reuse: sequential block readers of one file and of the next file share one pooled connection
+    with F.CurvineFileSystem(F.client_conf(short_circuit=False)) as fs:
+        fs.load_namespace(man)
+        assert read_all(fs, "/pool/f0") == synth.file_bytes(4800, 1 << 20, 1 << 18)
+        read_all(fs, "/pool/f1")
+        st = fs.pool_stats()
+        # (the reader opens block k+1 while block k's reader is still alive, so two connections alternate for any number of blocks)
+        assert 1 <= st["opened"] <= 2 and st["idle"] == st["opened"] and st["expired"] == 0, st
+    # global idle cap: 4 parallel sub-readers open 4 connections, only block_conn_idle_size = 2 stay pooled
+    with F.CurvineFileSystem(F.client_conf(short_circuit=False, read_parallel=4, read_chunk_size="64KB", read_chunk_num=1,
+                                           extra_client="block_conn_idle_size = 2")) as fs:
+        fs.load_namespace(man)
+        read_all(fs, "/pool/f2")
+        st = fs.pool_stats()
+        assert st["opened"] >= 2 and st["idle"] <= 2, st
+    # idle-time expiry: the pooled connection is 80 ms old when the next reader asks, the limit is 50 ms -> dropped, a new one opened
+    with F.CurvineFileSystem(F.client_conf(short_circuit=False, extra_client='block_conn_idle_time = "50ms"')) as fs:
+        fs.load_namespace(man)
+        read_all(fs, "/pool/f0")
+        st0 = fs.pool_stats()
+        assert st0["idle"] == st0["opened"] >= 1 and st0["expired"] == 0, st0
+        time.sleep(0.08)
+        r = fs.open("/pool/f1")
+        r.read(10)
+        st = fs.pool_stats()
+        assert st["expired"] == st0["idle"] and st["opened"] == st0["opened"] + 1, (st0, st)  # every stale one met was dropped
+        r.complete()
+    # pool disabled: nothing is kept
+    with F.CurvineFileSystem(F.client_conf(short_circuit=False, extra_client="enable_block_conn_pool = false")) as fs:
+        fs.load_namespace(man)
+        read_all(fs, "/pool/f0")
+        st = fs.pool_stats()
+        assert st["idle"] == 0 and st["opened"] == 4, st  # one connection per block reader
+
+
 def test_storage_tier_selection(cluster):
     """storage policy: blocks go to a dir of the file's storage type, falling back to Disk dirs (policy.rs:56-105)."""
     w, d = cluster

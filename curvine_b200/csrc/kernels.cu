@@ -1,7 +1,7 @@
 // sm_100a kernels for the Curvine sequential block-read path + their extern "C" launchers
 // (declared in include/curvine_b200_kernels.h, which cites the reference code each one replaces).
 //
-// This is a byte-stream / integer path: no tensor cores.  Design (see DESIGN.md §4):
+// This is a byte-stream / integer path: no tensor cores.  Design (see DESIGN.md §3):
 //   * CRC is linear over GF(2).  Each warp owns a contiguous *segment* and walks it in 512-byte rows
 //     (one coalesced 16-byte vector per lane).  Every lane keeps 4 independent 32-bit Horner chains
 //     (one per word of its vector): a <- a * x^4096 (+) w.  The multiply by the row constant x^4096 is
@@ -12,7 +12,9 @@
 //     applies init/xorout, so results are bit-identical to crc32fast / zlib (or CRC-32C).
 //   * The same row walker optionally stores the (re-aligned) vectors to a destination, which gives the
 //     fused frame-unpack+gather+CRC (K2), frame-pack+CRC (K4) and page scatter/gather (K3) kernels.
-// Persistent launch: one 1024-thread CTA per SM (148 on B200), contiguous unit ranges per CTA.
+// Launch train of one call: prep_* (piece geometry) -> scan_counts (prefix sum of per-piece unit counts) -> expand_units
+// (one 32-byte record per unit) -> walk_kernel (persistent: one 1024-thread CTA per SM, 148 on B200, contiguous unit range per
+// CTA, a warp per unit) -> fold_blocks (unit partials -> one CRC per block).  Workspaces come from a private memory pool.
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -592,17 +594,6 @@ __device__ __forceinline__ uint32_t find_piece(const uint32_t* prefix, uint32_t 
             hi = mid;
     }
     return lo;
-}
-
-__device__ __forceinline__ uint32_t advance_piece(const uint32_t* prefix, uint32_t n, uint32_t p, uint32_t u,
-                                                  uint32_t lane) {
-    for (;;) {
-        const uint32_t idx = p + 1 + lane;
-        const uint32_t v = (idx <= n) ? __ldg(prefix + idx) : 0xffffffffu;
-        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, u >= v));
-        p += cnt;
-        if (cnt < 32) return p;
-    }
 }
 
 template <bool DST>

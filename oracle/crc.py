@@ -128,6 +128,20 @@ def crc_raw(data: bytes, poly: int) -> int:
     return r
 
 
+def python_bench_checksum(thread_streams) -> int:
+    """The reference's PYTHON bench figure (curvine-libsdk/python/test/curvineBench.py:30-52): every thread keeps ONE running
+    ``zlib.crc32(data, running)`` over all the buffers it moves (i.e. the CRC-32 of the concatenation of its buffers), and the
+    per-thread values are folded in thread order with ``zlib.crc32(value.to_bytes(4, "big"), acc)``.
+    ``thread_streams``: one iterable of buffers per thread."""
+    acc = 0
+    for bufs in thread_streams:
+        run = 0
+        for b in bufs:
+            run = zlib.crc32(b, run)
+        acc = zlib.crc32((run & 0xFFFFFFFF).to_bytes(4, "big"), acc)
+    return acc & 0xFFFFFFFF
+
+
 def crc_combine(crc_a: int, crc_b: int, len_b: int, poly: int) -> int:
     """CRC(A||B) from CRC(A), CRC(B), len(B) -- zlib's crc32_combine restated."""
     return gf_mul(crc_a, gf_xpow(8 * len_b, poly), poly) ^ crc_b

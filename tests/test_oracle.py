@@ -117,6 +117,32 @@ def test_bench_checksum_semantics():
     assert clib.bench_checksum(synth.block_bytes(1001, 0, 4 << 20), 131072) == GOLD["bench_sum_crc32_128k"]
 
 
+def test_python_bench_checksum_chaining_equals_block_combine():
+    """curvineBench.py:30-52 chains zlib.crc32 across buffers; the product never chains -- it CRCs pieces independently (per
+    warp segment on the GPU, per block on the host) and combines them with x^(8*len) multipliers.  Same numbers: the reference's
+    own Python tool is therefore a second in-tree anchor (next to crc32fast) for CRC-32 == zlib and for the combine algebra."""
+    from curvine_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(11)
+    bufs = [rng.integers(0, 256, size=n, dtype=np.uint8).tobytes() for n in (131072, 131072, 5, 0, 4097, 131072 - 1)]
+    chained = 0
+    for b in bufs:
+        chained = zlib.crc32(b, chained)
+    assert chained == zlib.crc32(b"".join(bufs))
+    # combine of independent per-buffer CRCs (oracle restatement, and the product's host CRC feeding the same algebra)
+    acc = 0
+    for b in bufs:
+        c_or = C.crc32(b)
+        arr = np.frombuffer(b, dtype=np.uint8)
+        c_host = L.cv_host_crc(0, arr.ctypes.data if len(b) else None, len(b))
+        assert c_or == c_host == zlib.crc32(b)
+        acc = C.crc_combine(acc, c_or, len(b), C.POLY_IEEE)
+    assert acc == chained
+    # two "threads": the tool's fold of per-thread values
+    want = zlib.crc32(zlib.crc32(b"".join(bufs[3:])).to_bytes(4, "big"), zlib.crc32(zlib.crc32(b"".join(bufs[:3])).to_bytes(4, "big"), 0))
+    assert C.python_bench_checksum([bufs[:3], bufs[3:]]) == want
+
+
 def test_block_id_and_layout():
     """inode_id.rs:100-118 + block_meta.rs:199-237."""
     rng = np.random.default_rng(3)

@@ -8,6 +8,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# Test infrastructure: tests/test_ingest_pipeline_cpu.py re-runs the GPU reader tests in a SUBPROCESS against the mock
+# library of tests/mock_cuda (the C++ host side built against a host-memory stand-in for the CUDA runtime, CPU stand-ins
+# for the cvk_* launchers), so the ingest pipeline's host logic is exercised on machines without a GPU.  Only that
+# subprocess sets this variable; the product (curvine_b200/) has no knob that loads anything but its own library.
+MOCK_LIB = os.environ.get("CV_TEST_MOCK_CUDA_LIB", "")
+if MOCK_LIB:
+    from curvine_b200 import _lib as _cv_lib
+    _cv_lib.LIB_PATH = MOCK_LIB
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
@@ -15,6 +25,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def cuda():
     import torch
+    if MOCK_LIB:  # "device memory" is host memory here: CPU tensors, no streams to wait for
+        import types
+        torch.cuda.synchronize = lambda *a, **k: None
+        torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0, synchronize=lambda: None)
+        torch.cuda.current_device = lambda: 0
+        return torch.device("cpu")
     if not torch.cuda.is_available():
         pytest.fail("this test is marked gpu but no CUDA device is visible")
     torch.cuda.set_device(0)

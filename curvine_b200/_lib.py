@@ -113,7 +113,7 @@ class CvReadStats(ctypes.Structure):
     _fields_ = [("bytes", ctypes.c_uint64), ("blocks", ctypes.c_uint64), ("verified", ctypes.c_uint64),
                 ("h2d_bytes", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("fetch_sec", ctypes.c_double),
                 ("wall_sec", ctypes.c_double), ("reg_hits", ctypes.c_uint64), ("reg_misses", ctypes.c_uint64),
-                ("ring_alloc_sec", ctypes.c_double)]
+                ("ring_alloc_sec", ctypes.c_double), ("reg_rejected", ctypes.c_uint64), ("reg_bytes", ctypes.c_uint64)]
 
 
 # every symbol include/*.h declares (tests check the .so exports all of them)

@@ -325,6 +325,7 @@ int64_t cv_device_stats(cv_reader* r, CvReadStats* out) {
     out->kernel_launches = s.kernel_launches, out->fetch_sec = s.fetch_sec, out->wall_sec = s.wall_sec;
     out->reg_hits = s.reg_hits, out->reg_misses = s.reg_misses;
     out->ring_alloc_sec = s.ring_alloc_sec;
+    out->reg_rejected = s.reg_rejected, out->reg_bytes = s.reg_bytes;
     return ok();
 }
 

@@ -182,6 +182,7 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "numa_node") b.numa_node = static_cast<int>(as_int(v));
             else if (k == "zero_copy") b.zero_copy = as_bool(v);
             else if (k == "register_cache") e = as_size(v, &b.register_cache);
+            else if (k == "register_min_age") e = parse_duration_ms(unquote(v), &b.register_min_age_ms);
             else if (k == "register_threads") b.register_threads = static_cast<int>(as_int(v));
             else if (k == "register_when_idle") b.register_when_idle = as_bool(v);
         }

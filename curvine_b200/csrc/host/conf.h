@@ -50,6 +50,8 @@ struct B200Conf {
     int64_t gpu_chunk_size = 4 << 20;  // Running-request chunk for the framed GPU path (<= 16 MiB frame cap)
     bool zero_copy = false;       // short-circuit reads: DMA straight from cudaHostRegister'ed mmaps of the block files
     int64_t register_cache = 64ll << 30;  // bytes of registered mappings kept across calls (LRU)
+    int64_t register_min_age_ms = 5000;   // "register_min_age" (duration string): a cached mapping used more recently than this is not
+                                          // displaced by a newcomer (scan resistance); 0 = plain LRU
     int register_threads = 16;    // background registrar threads (a cold group goes through the pinned ring meanwhile); 0 = register inline
     bool register_when_idle = true;  // registrar threads yield to reads in flight (a cold pass runs at ring speed; mappings are
                                      // registered between reads); false = register concurrently with the cold pass

@@ -34,14 +34,21 @@ namespace cv {
 //
 // A mem-tier block file lives in tmpfs page-cache pages.  Instead of pread()ing it into a pinned slot (one CPU copy
 // per byte), map the block files of one copy group back to back into a reserved VA range, cudaHostRegister the range
-// once, and let the copy engine DMA straight out of the page cache.  Mappings are cached (LRU by bytes) and
-// revalidated by (inode, size, mtime) on every use; block files are write-once in Curvine.
+// once, and let the copy engine DMA straight out of the page cache.  Mappings are cached (LRU by bytes, never more than
+// `register_cache` bytes registered through the cache) and revalidated by (inode, size, mtime) on every use; block files
+// are write-once in Curvine.
+// Admission is scan-resistant: a new mapping only displaces mappings that nobody is using AND that have not been used for
+// `register_min_age` (default 5 s); otherwise the newcomer is not cached (its group keeps going through the pinned ring).
+// With plain LRU a sequential re-read of a file larger than the cache finds every group evicted just before it gets there
+// -- 0 hits while paying registration every pass; with this rule the first cache-full of groups stays registered and a
+// cyclic scan hits cache/working-set of the time, while a working set that moved away ages out after register_min_age.
 struct RegMapping {
     std::string key;
     uint8_t* base = nullptr;
     size_t bytes = 0;     // registered extent (page-rounded)
     std::vector<uint64_t> stamps;  // inode, size, mtime_ns per member file
     bool registered = false;
+    double last_used = 0;  // now_sec() of the last find() hit or the insertion (under RegCache's lock)
     ~RegMapping() {
         if (registered) cudaHostUnregister(base);
         if (base) munmap(base, bytes);
@@ -50,38 +57,68 @@ struct RegMapping {
 
 class RegCache {
    public:
-    size_t capacity = 0;  // bytes; 0 disables caching (mappings live for one call)
+    size_t capacity = 0;   // bytes; 0 disables caching (mappings live for one call)
+    double min_age_sec = 5.0;  // a mapping used more recently than this is not displaced by a newcomer
     std::shared_ptr<RegMapping> find(const std::string& key, const std::vector<uint64_t>& stamps) {
+        std::shared_ptr<RegMapping> stale;  // destroyed (unregistered, unmapped) outside the lock
         std::lock_guard<std::mutex> lk(mu_);
         auto it = map_.find(key);
         if (it == map_.end()) return nullptr;
         if (it->second->second->stamps != stamps) {  // file replaced: drop the stale mapping
-            bytes_ -= it->second->second->bytes;
+            stale = it->second->second;
+            bytes_ -= stale->bytes;
             lru_.erase(it->second);
             map_.erase(it);
             return nullptr;
         }
         lru_.splice(lru_.begin(), lru_, it->second);
+        it->second->second->last_used = now_sec();
         hits++;
         return it->second->second;
     }
-    void insert(const std::shared_ptr<RegMapping>& m) {
+    // -> true when the mapping was admitted.  A rejected mapping stays valid for the caller's own use and goes away with it.
+    bool insert(const std::shared_ptr<RegMapping>& m) {
         std::vector<std::shared_ptr<RegMapping>> evicted;  // destroyed outside the lock
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            if (capacity == 0) return;
-            lru_.emplace_front(m->key, m);
-            map_[m->key] = lru_.begin();
-            bytes_ += m->bytes;
-            while (bytes_ > capacity && lru_.size() > 1) {
-                auto& back = lru_.back();
-                if (back.second.use_count() > 1) break;  // still referenced by a call in flight
-                bytes_ -= back.second->bytes;
-                evicted.push_back(back.second);
-                map_.erase(back.first);
-                lru_.pop_back();
-            }
+        std::lock_guard<std::mutex> lk(mu_);
+        if (capacity == 0 || m->bytes > capacity) return false;
+        auto dup = map_.find(m->key);
+        if (dup != map_.end()) {  // same group registered twice (two contexts' worth of threads raced): the newer one wins
+            bytes_ -= dup->second->second->bytes;
+            evicted.push_back(dup->second->second);
+            lru_.erase(dup->second);
+            map_.erase(dup);
         }
+        const double now = now_sec();
+        // make room from the cold end; stop at the first entry that is in use or still young
+        while (bytes_ + m->bytes > capacity && !lru_.empty()) {
+            auto& back = lru_.back();
+            if (back.second.use_count() > 1 || now - back.second->last_used < min_age_sec) break;
+            bytes_ -= back.second->bytes;
+            evicted.push_back(back.second);
+            map_.erase(back.first);
+            lru_.pop_back();
+        }
+        if (bytes_ + m->bytes > capacity) {
+            rejected++;
+            return false;
+        }
+        m->last_used = now;
+        lru_.emplace_front(m->key, m);
+        map_[m->key] = lru_.begin();
+        bytes_ += m->bytes;
+        return true;
+    }
+    // would insert() admit a mapping of `bytes` right now?  (asked BEFORE paying for mmap + cudaHostRegister)
+    bool can_admit(size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (capacity == 0 || bytes > capacity) return false;
+        size_t room = capacity - std::min(capacity, bytes_);
+        const double now = now_sec();
+        for (auto it = lru_.rbegin(); room < bytes && it != lru_.rend(); ++it) {
+            if (it->second.use_count() > 1 || now - it->second->last_used < min_age_sec) break;
+            room += it->second->bytes;
+        }
+        return room >= bytes;
     }
     void clear() {
         std::lock_guard<std::mutex> lk(mu_);
@@ -89,7 +126,11 @@ class RegCache {
         lru_.clear();
         bytes_ = 0;
     }
-    std::atomic<uint64_t> hits{0}, misses{0};
+    size_t bytes() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return bytes_;
+    }
+    std::atomic<uint64_t> hits{0}, misses{0}, rejected{0};
 
    private:
     std::mutex mu_;
@@ -225,11 +266,12 @@ class Registrar {
             }
             std::shared_ptr<RegMapping> m;
             std::vector<uint64_t> stamps;
-            Err e = map_and_register(j.paths, j.lens, &m, &stamps);
+            size_t job_bytes = 0;
+            for (int64_t l : j.lens) job_bytes += (static_cast<size_t>(l) + 4095) / 4096 * 4096;
+            Err e = cache_->can_admit(job_bytes) ? map_and_register(j.paths, j.lens, &m, &stamps) : Err(kCommon, "registration cache is full");
             if (!e) {
                 m->key = j.key;
-                cache_->insert(m);
-                registered++;
+                if (cache_->insert(m)) registered++;
             } else if (e.kind == kUnsupported) {
                 unsupported.store(true);
             }
@@ -311,6 +353,7 @@ class GpuIngest {
         CU_TRY(cudaStreamCreateWithFlags(&vstream, cudaStreamNonBlocking));
         CU_TRY(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
         reg.capacity = c.zero_copy ? static_cast<size_t>(std::max<int64_t>(c.register_cache, 0)) : 0;
+        reg.min_age_sec = static_cast<double>(std::max<int64_t>(c.register_min_age_ms, 0)) / 1000.0;
         register_inline = c.register_threads <= 0 || reg.capacity == 0;
         // CPUs of the GPU's NUMA node: pinned pages and fetch threads stay next to the PCIe root
         int node = c.numa_node;  // -1: the GPU's node (auto); -2: do not bind the fetch threads
@@ -896,7 +939,14 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                     if (!m) G.reg.misses++;
                     if (!m && G.registrar.unsupported.load()) e = Err(kUnsupported, "cudaHostRegister of file mappings is not supported here");
                     if (!m && !e) {
-                        if (G.register_inline) {
+                        size_t group_bytes = 0;
+                        for (int64_t l : lens) group_bytes += (static_cast<size_t>(l) + 4095) / 4096 * 4096;
+                        if (G.reg.capacity > 0 && !G.reg.can_admit(group_bytes)) {
+                            // the cache is full of mappings in use or used moments ago (a scan larger than the cache): registering
+                            // this group would be paid for and thrown away -- it goes through the ring, now and next time
+                            G.reg.rejected++;
+                            via_ring = true;
+                        } else if (G.register_inline) {
                             e = map_and_register(paths, lens, &m, &stamps);
                             if (!e) {
                                 m->key = key;
@@ -1115,6 +1165,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     for (int t = 0; t < T_threads; t++) stats_.fetch_sec += fetch_sec[static_cast<size_t>(t)], stats_.h2d_bytes += h2d[static_cast<size_t>(t)];
     stats_.wall_sec += now_sec() - t_start;
     stats_.reg_hits = G.reg.hits.load(), stats_.reg_misses = G.reg.misses.load();
+    stats_.reg_rejected = G.reg.rejected.load(), stats_.reg_bytes = G.reg.bytes();
     stats_.ring_alloc_sec = G.ring_alloc_sec;
     return Err::ok();
 }

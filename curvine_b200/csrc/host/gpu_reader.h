@@ -25,6 +25,8 @@ struct GpuReadStats {
     uint64_t h2d_bytes = 0;     // bytes moved by cudaMemcpyAsync (payload, + prefixes when framed)
     uint64_t kernel_launches = 0;
     uint64_t reg_hits = 0, reg_misses = 0;  // registered-mapping cache (zero-copy path), context-wide
+    uint64_t reg_rejected = 0;              // mappings not admitted because the cache was full of in-use or recently used ones
+    uint64_t reg_bytes = 0;                 // bytes registered through the cache right now (<= register_cache)
     double fetch_sec = 0;       // summed over fetch threads: time inside pread/recv
     double wall_sec = 0;
     double ring_alloc_sec = 0;  // context-wide: one-off pinned-ring allocation time

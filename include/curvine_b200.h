@@ -117,6 +117,8 @@ typedef struct CvReadStats {
     double fetch_sec, wall_sec;
     uint64_t reg_hits, reg_misses; /* registered-mapping cache of the zero-copy path */
     double ring_alloc_sec;         /* one-off pinned-ring allocation time of the context (first cold read pays it) */
+    uint64_t reg_rejected;         /* mappings not admitted: the cache was full of in-use or recently used ones */
+    uint64_t reg_bytes;            /* bytes registered through the cache right now (<= register_cache) */
 } CvReadStats;
 int64_t cv_device_stats(cv_reader* r, CvReadStats* out);
 

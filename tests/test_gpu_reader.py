@@ -259,6 +259,36 @@ def test_zero_copy_registered_mappings(cuda, cluster, copy_group, register_threa
         r.complete()
 
 
+@pytest.mark.parametrize("min_age,want_hits", [("5s", 16), ("0ms", 0)])
+def test_registration_cache_is_scan_resistant(cuda, cluster, min_age, want_hits):
+    """A file twice the size of the registration cache, re-read sequentially in quarter-file calls.  Plain LRU
+    (register_min_age = 0) evicts every group just before the scan comes back to it: 0 hits, registration paid every pass.
+    The default admission rule keeps the first cache-full of groups registered (recently used mappings are not displaced by
+    newcomers, the rest of the file keeps going through the pinned ring): half the groups hit on every later pass, and the
+    cache never holds more than register_cache bytes.  Bytes and CRCs are the same either way."""
+    import torch
+    w, _ = cluster
+    n, bs, ino = 32 << 20, 1 << 20, 7300 + want_hits
+    man = w.create_file("/scan%d" % want_hits, ino, n, bs)
+    want = synth.file_bytes(ino, n, bs)
+    conf = _conf(True, 1, zero_copy=True, copy_group=2, register_threads=0, register_cache="16MB").rstrip("\n") + '\nregister_min_age = "%s"\n' % min_age
+    with F.CurvineFileSystem(conf) as fs:
+        fs.load_namespace(man)
+        for rep in range(3):
+            r = fs.open("/scan%d" % want_hits)
+            dst = _dev_buf(n, cuda)
+            for q in range(4):
+                assert r.read_device(dst.data_ptr() + q * (n // 4), n // 4, torch.cuda.current_stream().cuda_stream) == n // 4
+                assert r.verify()[1] == 0  # also releases the mappings this call held
+            torch.cuda.synchronize()
+            assert dst.cpu().numpy().tobytes() == want
+            st = r.device_stats()
+            r.complete()
+        assert st["reg_hits"] == want_hits, st
+        assert st["reg_bytes"] <= 16 << 20, st
+        assert (st["reg_rejected"] > 0) == (want_hits > 0), st
+
+
 @pytest.mark.parametrize("zero_copy", [False, True])
 def test_read_many_small_files_in_one_pass(cuda, cluster, zero_copy):
     """C5 batching: many single-block files in one pipelined call; bytes, CRC sum and verify count match the oracle."""

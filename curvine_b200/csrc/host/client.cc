@@ -1,6 +1,9 @@
 #include "client.h"
 
 #include <errno.h>
+#include <sys/socket.h>
+
+#include <errno.h>
 #include <fcntl.h>
 #include <sys/vfs.h>
 #include <unistd.h>
@@ -238,6 +241,15 @@ FsContext::~FsContext() = default;
 
 static int64_t now_ms() { return static_cast<int64_t>(now_sec() * 1000.0); }
 
+// A pooled connection whose peer went away (worker restarted, idle timeout on the server side) has a FIN or RST queued: a
+// non-blocking peek sees it without consuming anything.  An idle healthy connection has nothing to read (EAGAIN); bytes nobody
+// asked for mean the stream is out of step.  Either way the connection is not handed out again.
+static bool pooled_connection_is_usable(int fd) {
+    char b;
+    const ssize_t r = ::recv(fd, &b, 1, MSG_PEEK | MSG_DONTWAIT);
+    return r < 0 && (errno == EAGAIN || errno == EWOULDBLOCK);
+}
+
 Err FsContext::acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClient>* out) {
     if (conf.client.enable_block_conn_pool) {
         std::vector<std::unique_ptr<BlockClient>> expired;  // closed outside the lock
@@ -248,7 +260,7 @@ Err FsContext::acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClie
             std::unique_ptr<BlockClient> c = std::move(v.back());  // LIFO
             v.pop_back();
             idle_total_--;
-            if (now - c->idle_since_ms < conf.client.block_conn_idle_time_ms) {
+            if (now - c->idle_since_ms < conf.client.block_conn_idle_time_ms && pooled_connection_is_usable(c->fd())) {
                 *out = std::move(c);
                 return Err::ok();
             }

@@ -324,6 +324,36 @@ def test_duration_strings_and_block_conn_pool_semantics(cluster):
         assert st["idle"] == 0 and st["opened"] == 4, st  # one connection per block reader
 
 
+def test_pooled_connections_to_a_restarted_worker_are_not_reused(tmp_path):
+    """A worker restart leaves the client's pooled sockets with a FIN queued.  The pool checks a connection (non-blocking
+    peek) before handing it out, so the first read after the restart opens a fresh connection instead of failing on a dead
+    one (the reference only has the 60 s idle expiry for this; every stale connection there costs one failed read)."""
+    d = tmp_path / "w"
+    n, ino = (3 << 20) + 7, 4900
+    w = F.MiniWorker(["[MEM]" + str(d)])
+    try:
+        man = w.create_file("/restart", ino, n, 1 << 20)
+        want = synth.file_bytes(ino, n, 1 << 20)
+        for sc in (False, True):
+            with F.CurvineFileSystem(F.client_conf(short_circuit=sc)) as fs:
+                fs.load_namespace(man)
+                r = fs.open("/restart")
+                assert r.read_full(n) == want
+                r.complete()
+                st0 = fs.pool_stats()
+                assert st0["idle"] >= 1
+                port = w.port
+                w.stop()
+                w = F.MiniWorker(["[MEM]" + str(d)], port=port)
+                r = fs.open("/restart")
+                assert r.read_full(n) == want
+                r.complete()
+                st = fs.pool_stats()
+                assert st["expired"] >= 1 and st["opened"] > st0["opened"], (st0, st)
+    finally:
+        w.stop()
+
+
 def test_storage_tier_selection(cluster):
     """storage policy: blocks go to a dir of the file's storage type, falling back to Disk dirs (policy.rs:56-105)."""
     w, d = cluster

@@ -259,89 +259,6 @@ def test_zero_copy_registered_mappings(cuda, cluster, copy_group, register_threa
         r.complete()
 
 
-@pytest.mark.parametrize("min_age,want_hits", [("5s", 16), ("0ms", 0)])
-def test_registration_cache_is_scan_resistant(cuda, cluster, min_age, want_hits):
-    """A file twice the size of the registration cache, re-read sequentially in quarter-file calls.  Plain LRU
-    (register_min_age = 0) evicts every group just before the scan comes back to it: 0 hits, registration paid every pass.
-    The default admission rule keeps the first cache-full of groups registered (recently used mappings are not displaced by
-    newcomers, the rest of the file keeps going through the pinned ring): half the groups hit on every later pass, and the
-    cache never holds more than register_cache bytes.  Bytes and CRCs are the same either way."""
-    import torch
-    w, _ = cluster
-    n, bs, ino = 32 << 20, 1 << 20, 7300 + want_hits
-    man = w.create_file("/scan%d" % want_hits, ino, n, bs)
-    want = synth.file_bytes(ino, n, bs)
-    conf = _conf(True, 1, zero_copy=True, copy_group=2, register_threads=0, register_cache="16MB").rstrip("\n") + '\nregister_min_age = "%s"\n' % min_age
-    with F.CurvineFileSystem(conf) as fs:
-        fs.load_namespace(man)
-        for rep in range(3):
-            r = fs.open("/scan%d" % want_hits)
-            dst = _dev_buf(n, cuda)
-            for q in range(4):
-                assert r.read_device(dst.data_ptr() + q * (n // 4), n // 4, torch.cuda.current_stream().cuda_stream) == n // 4
-                assert r.verify()[1] == 0  # also releases the mappings this call held
-            torch.cuda.synchronize()
-            assert dst.cpu().numpy().tobytes() == want
-            st = r.device_stats()
-            r.complete()
-        assert st["reg_hits"] == want_hits, st
-        assert st["reg_bytes"] <= 16 << 20, st
-        assert (st["reg_rejected"] > 0) == (want_hits > 0), st
-
-
-@pytest.mark.parametrize("sc", [True, False])
-def test_device_read_fails_over_to_the_next_replica_and_reports_dead_workers(cuda, tmp_path_factory, sc):
-    """block_reader.rs:217-254 for the device path: a block whose first replica does not answer is fetched from the next one
-    (every fetch thread fails over on its own); when no replica answers the call fails with kind IO -- no hang, no partial
-    success -- and the same filesystem handle works again once a worker is back."""
-    import shutil
-    import torch
-    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
-    root = __import__("pathlib").Path(__import__("tempfile").mkdtemp(prefix="cvha", dir=base))
-    d1, d2 = root / "w1", root / "w2"
-    n, bs, ino = (12 << 20) + 333, 1 << 20, 7400 + int(sc)
-    w1 = F.MiniWorker(["[MEM]" + str(d1)])
-    w2 = None
-    try:
-        man = w1.create_file("/ha", ino, n, bs)
-        shutil.copytree(str(d1), str(d2))
-        w2 = F.MiniWorker(["[MEM]" + str(d2)])  # rescans active/ on start
-        want = synth.file_bytes(ino, n, bs)
-        man2 = "\n".join(l + ",localhost:%d:2" % w2.port if l.startswith("block ") else l for l in man.splitlines())
-        w1.stop()  # the first replica of every block is gone before the read starts
-        with F.CurvineFileSystem(_conf(sc, 1, "256KB", threads=4)) as fs:
-            fs.load_namespace(man2)
-            r = fs.open("/ha")
-            dst = _dev_buf(n, cuda)
-            assert r.read_device(dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
-            s, bad, ver = r.verify()
-            torch.cuda.synchronize()
-            assert bad == 0 and ver == (n + bs - 1) // bs and dst.cpu().numpy().tobytes() == want
-            r.complete()
-            assert w2.metrics()["read_blocks_local" if sc else "read_blocks_remote"] >= ver
-            # now nobody answers
-            w2.stop()
-            r = fs.open("/ha")
-            with pytest.raises(F.FsError) as ei:
-                r.read_device(dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
-            assert ei.value.kind == 1, (ei.value.kind, ei.value.msg)
-            r.complete()
-            # a worker comes back on the second replica's address: the handle recovers (broken connections were not pooled)
-            w2 = F.MiniWorker(["[MEM]" + str(d2)], port=w2.port)
-            r = fs.open("/ha")
-            dst2 = _dev_buf(n, cuda)
-            assert r.read_device(dst2.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
-            assert r.verify()[1] == 0
-            torch.cuda.synchronize()
-            assert dst2.cpu().numpy().tobytes() == want
-            r.complete()
-    finally:
-        w1.stop()
-        if w2 is not None:
-            w2.stop()
-        shutil.rmtree(str(root), ignore_errors=True)
-
-
 @pytest.mark.parametrize("zero_copy", [False, True])
 def test_read_many_small_files_in_one_pass(cuda, cluster, zero_copy):
     """C5 batching: many single-block files in one pipelined call; bytes, CRC sum and verify count match the oracle."""

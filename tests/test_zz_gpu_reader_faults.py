@@ -1,0 +1,224 @@
+"""Fault injection and cache-policy checks of the GPU reader through the C ABI (dead workers, fail-over, recovery, registration cache
+admission).  Collected last (zz) so the established parity suites run first; runs on a B200 (`-m gpu`) and, through
+tests/test_ingest_pipeline_cpu.py, against the mock runtime on CPU."""
+import os
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from curvine_b200 import fs as F
+from oracle import clib, layout, synth
+from test_gpu_reader import _conf, _dev_buf, cluster  # noqa: F401  (same fixtures and knobs as the parity suite)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("min_age,want_hits", [("60s", 16), ("0ms", 0)])
+def test_registration_cache_is_scan_resistant(cuda, cluster, min_age, want_hits):
+    """A file twice the size of the registration cache, re-read sequentially in quarter-file calls.  Plain LRU
+    (register_min_age = 0) evicts every group just before the scan comes back to it: 0 hits, registration paid every pass.
+    The default admission rule keeps the first cache-full of groups registered (recently used mappings are not displaced by
+    newcomers, the rest of the file keeps going through the pinned ring): half the groups hit on every later pass, and the
+    cache never holds more than register_cache bytes.  Bytes and CRCs are the same either way."""
+    import torch
+    w, _ = cluster
+    n, bs, ino = 32 << 20, 1 << 20, 7300 + want_hits
+    man = w.create_file("/scan%d" % want_hits, ino, n, bs)
+    want = synth.file_bytes(ino, n, bs)
+    conf = _conf(True, 1, zero_copy=True, copy_group=2, register_threads=0, register_cache="16MB").rstrip("\n") + '\nregister_min_age = "%s"\n' % min_age
+    with F.CurvineFileSystem(conf) as fs:
+        fs.load_namespace(man)
+        for rep in range(3):
+            r = fs.open("/scan%d" % want_hits)
+            dst = _dev_buf(n, cuda)
+            for q in range(4):
+                assert r.read_device(dst.data_ptr() + q * (n // 4), n // 4, torch.cuda.current_stream().cuda_stream) == n // 4
+                assert r.verify()[1] == 0  # also releases the mappings this call held
+            torch.cuda.synchronize()
+            assert dst.cpu().numpy().tobytes() == want
+            st = r.device_stats()
+            r.complete()
+        assert st["reg_hits"] == want_hits, st
+        assert st["reg_bytes"] <= 16 << 20, st
+        assert (st["reg_rejected"] > 0) == (want_hits > 0), st
+
+
+@pytest.mark.parametrize("sc", [True, False])
+def test_device_read_fails_over_to_the_next_replica_and_reports_dead_workers(cuda, tmp_path_factory, sc):
+    """block_reader.rs:217-254 for the device path: a block whose first replica does not answer is fetched from the next one
+    (every fetch thread fails over on its own); when no replica answers the call fails with kind IO -- no hang, no partial
+    success -- and the same filesystem handle works again once a worker is back."""
+    import shutil
+    import torch
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    root = __import__("pathlib").Path(__import__("tempfile").mkdtemp(prefix="cvha", dir=base))
+    d1, d2 = root / "w1", root / "w2"
+    n, bs, ino = (12 << 20) + 333, 1 << 20, 7400 + int(sc)
+    w1 = F.MiniWorker(["[MEM]" + str(d1)])
+    w2 = None
+    try:
+        man = w1.create_file("/ha", ino, n, bs)
+        shutil.copytree(str(d1), str(d2))
+        w2 = F.MiniWorker(["[MEM]" + str(d2)])  # rescans active/ on start
+        want = synth.file_bytes(ino, n, bs)
+        man2 = "\n".join(l + ",localhost:%d:2" % w2.port if l.startswith("block ") else l for l in man.splitlines())
+        w1.stop()  # the first replica of every block is gone before the read starts
+        with F.CurvineFileSystem(_conf(sc, 1, "256KB", threads=4)) as fs:
+            fs.load_namespace(man2)
+            r = fs.open("/ha")
+            dst = _dev_buf(n, cuda)
+            assert r.read_device(dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
+            s, bad, ver = r.verify()
+            torch.cuda.synchronize()
+            assert bad == 0 and ver == (n + bs - 1) // bs and dst.cpu().numpy().tobytes() == want
+            r.complete()
+            assert w2.metrics()["read_blocks_local" if sc else "read_blocks_remote"] >= ver
+            # now nobody answers
+            w2.stop()
+            r = fs.open("/ha")
+            with pytest.raises(F.FsError) as ei:
+                r.read_device(dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+            assert ei.value.kind == 1, (ei.value.kind, ei.value.msg)
+            r.complete()
+            # a worker comes back on the second replica's address: the handle recovers (broken connections were not pooled)
+            w2 = F.MiniWorker(["[MEM]" + str(d2)], port=w2.port)
+            r = fs.open("/ha")
+            dst2 = _dev_buf(n, cuda)
+            assert r.read_device(dst2.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
+            assert r.verify()[1] == 0
+            torch.cuda.synchronize()
+            assert dst2.cpu().numpy().tobytes() == want
+            r.complete()
+    finally:
+        w1.stop()
+        if w2 is not None:
+            w2.stop()
+        shutil.rmtree(str(root), ignore_errors=True)
+
+
+
+
+@pytest.mark.parametrize("sc", [True, False])
+def test_worker_dying_in_the_middle_of_a_device_read_fails_the_call_cleanly(cuda, sc):
+    """The only replica goes away while fetch threads are in flight: the call must come back (no thread stuck on a ring slot or
+    a socket) with an error, or complete if it had already fetched everything; afterwards the same handle reads the file again
+    from a restarted worker, bit-exact."""
+    import shutil
+    import torch
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    root = __import__("pathlib").Path(__import__("tempfile").mkdtemp(prefix="cvdie", dir=base))
+    n, bs, ino = 96 << 20, 1 << 20, 7500 + int(sc)
+    w = F.MiniWorker(["[MEM]" + str(root / "w")])
+    try:
+        man = w.create_file("/die", ino, n, bs)
+        want = synth.file_bytes(ino, n, bs)
+        port = w.port
+        with F.CurvineFileSystem(_conf(sc, 1, "256KB", threads=4, batch=4)) as fs:
+            fs.load_namespace(man)
+            dst = _dev_buf(n, cuda)
+            out = {}
+
+            def reader():
+                r = fs.open("/die")
+                try:
+                    out["got"] = r.read_device(dst.data_ptr(), n, 0)
+                    out["verify"] = r.verify()
+                except F.FsError as e:
+                    out["err"] = e
+                finally:
+                    try:
+                        r.complete()
+                    except F.FsError as e:  # the pending results of a failed call may surface here
+                        out.setdefault("err", e)
+
+            t = threading.Thread(target=reader)
+            t.start()
+            time.sleep(0.02)
+            w.stop()
+            t.join(timeout=60)
+            assert not t.is_alive(), "device read still blocked 60 s after its worker went away"
+            assert ("err" in out) or out.get("got") == n, out
+            if "err" in out:
+                assert out["err"].kind in (1, 10000), (out["err"].kind, out["err"].msg)
+            w = F.MiniWorker(["[MEM]" + str(root / "w")], port=port)
+            r = fs.open("/die")
+            dst2 = _dev_buf(n, cuda)
+            assert r.read_device(dst2.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
+            s, bad, ver = r.verify()
+            torch.cuda.synchronize()
+            assert bad == 0 and ver == n // bs and dst2.cpu().numpy().tobytes() == want
+            r.complete()
+    finally:
+        w.stop()
+        shutil.rmtree(str(root), ignore_errors=True)
+
+
+def test_two_threads_read_different_files_through_one_handle(cuda, cluster):
+    """lib_filesystem.rs:25-40: a filesystem handle is shareable between threads (a reader handle is not).  Two threads, two
+    readers, one context: the device reads serialise inside the library; both files land bit-exact with the right CRC sums."""
+    import torch
+    w, _ = cluster
+    bs = 1 << 20
+    specs = [("/mt_a", 7601, (24 << 20) + 11), ("/mt_b", 7602, (17 << 20) + 4097)]
+    man = "".join(w.create_file(p, ino, n, bs) for p, ino, n in specs)
+    with F.CurvineFileSystem(_conf(True, 1, zero_copy=True, copy_group=2, register_threads=2, register_cache="128MB")) as fs:
+        fs.load_namespace(man)
+        res, errs = {}, []
+
+        def run(p, ino, n):
+            try:
+                want = synth.file_bytes(ino, n, bs)
+                for rep in range(3):
+                    r = fs.open(p)
+                    dst = _dev_buf(n + 32, cuda)
+                    assert r.read_device(dst.data_ptr(), n, 0) == n
+                    s, bad, ver = r.verify()
+                    torch.cuda.synchronize()
+                    assert bad == 0 and ver == (n + bs - 1) // bs
+                    assert dst[:n].cpu().numpy().tobytes() == want and (dst[n:] == 0xA5).all()
+                    assert s == int(clib.crc_blocks(1, np.frombuffer(want, dtype=np.uint8), bs).astype(np.uint64).sum())
+                    r.complete()
+                res[p] = True
+            except Exception as e:  # noqa: BLE001
+                errs.append((p, repr(e)))
+
+        ts = [threading.Thread(target=run, args=sp) for sp in specs]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=120)
+        assert not errs and len(res) == 2, errs
+
+
+@pytest.mark.parametrize("sc", [True, False])
+def test_vanished_block_file_and_bad_arguments(cuda, cluster, sc):
+    """A block file that disappeared after the manifest was written: the worker answers Open with an error (remote) or the
+    client cannot read the path it was given (short-circuit) -> the call fails with a reference error kind, names the block, and
+    leaves the handle usable.  A negative seek and a destination that is not device memory are refused up front."""
+    import torch
+    w, d = cluster
+    n, bs, ino = 6 << 20, 1 << 20, 7700 + int(sc)
+    man = w.create_file("/gone%d" % sc, ino, n, bs) + w.create_file("/fine%d" % sc, ino + 50, n, bs)
+    os.remove(layout.block_path(str(d / "mem" / "curvine"), layout.create_block_id(ino, 3)))
+    with F.CurvineFileSystem(_conf(sc)) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/gone%d" % sc)
+        dst = _dev_buf(n, cuda)
+        with pytest.raises(F.FsError) as ei:
+            r.read_device(dst.data_ptr(), n, 0)
+            r.verify()
+        assert ei.value.kind in (1, 10000), (ei.value.kind, ei.value.msg)
+        with pytest.raises(F.FsError):
+            r.seek(-1)
+        try:
+            r.complete()
+        except F.FsError:
+            pass
+        r = fs.open("/fine%d" % sc)
+        assert r.read_device(dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
+        assert r.verify()[1:] == (0, n // bs)
+        torch.cuda.synchronize()
+        assert dst.cpu().numpy().tobytes() == synth.file_bytes(ino + 50, n, bs)
+        r.complete()

@@ -22,3 +22,41 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 2 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_own_arm_control_flow_and_json_line_on_the_mock_runtime():
+    """bench.py's own arm (context warm-up read, cold pass, registration wait, timed e2e steps, HBM-resident value steps,
+    roofline, cpu_baseline) executed end to end without a GPU: tests/mock_cuda/run_bench_on_mock.py swaps in the mock library and
+    tells torch that "cuda" tensors are CPU tensors.  Checks the control flow and the contract of the printed line; every number
+    in it is meaningless here and is looked at only for type and bookkeeping (bytes per step, launch counts, cache counters)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_cuda"))
+    try:
+        import build as mock_build
+    finally:
+        sys.path.pop(0)
+    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=mock_build.build())
+    gib, steps, warmup = 0.25, 2, 2
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "run_bench_on_mock.py"), "--gib-per-gpu", str(gib), "--steps", str(steps),
+                        "--warmup", str(warmup)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    n = int(gib * (1 << 30))
+    blocks = n // (4 << 20)
+    assert "impl" not in d and d["metric"] == "sequential read GB/s into HBM (CRC-verified)" and d["unit"] == "GB/s"
+    assert d["n_gpus"] == 1 and d["steps"] == steps and d["warmup"] == warmup and d["higher_is_better"] is True
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "u8" and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and "workload" in d["config"] and "model" not in d["config"]
+    e = d["e2e"]
+    assert e["unit"] == "GB/s" and e["value"] > 0 and e["h2d_bytes_per_step"] == n and e["d2h_bytes_per_step"] == 4 * (blocks + 4)
+    assert len(e["timed_steps_ms"]) == steps and len(e["warmup_steps_ms"]) == warmup and e["registration_ms"] is not None
+    groups = blocks // 8  # copy_group = 8; + 2 groups of the context warm-up file
+    assert e["registered_mapping_cache"] == {"hits": groups * (steps + warmup - 1), "misses": groups + 2}
+    assert d["gpu_launches"] == 6 * steps  # prep, scan, expand, walk, fold + compare per HBM-resident step
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["algorithmic_bytes_per_launch"] == n and r["launches_timed"] == steps
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "note" in r
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["unit"] == "GB/s" and c["value"] > 0 and c["cores"] >= 2 and "pass" in c["sample"]

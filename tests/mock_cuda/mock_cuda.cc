@@ -83,7 +83,7 @@ cudaError_t cudaMemsetAsync(void* dst, int v, size_t n, cudaStream_t) {
     return cudaSuccess;
 }
 cudaError_t cudaSetDevice(int dev) {
-    if (dev != 0) return cudaErrorInvalidDevice;
+    if (dev < 0 || dev >= 8) return cudaErrorInvalidDevice;  // eight pretend devices, all the same host memory
     t_device = dev;
     return cudaSuccess;
 }
@@ -92,7 +92,7 @@ cudaError_t cudaGetDevice(int* dev) {
     return cudaSuccess;
 }
 cudaError_t cudaGetDeviceCount(int* n) {
-    *n = 1;
+    *n = 8;
     return cudaSuccess;
 }
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
@@ -131,7 +131,7 @@ cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes* a, const void
         return x < it->first + it->second;
     };
     a->type = (inside(g_pinned) || inside(g_registered)) ? cudaMemoryTypeHost : cudaMemoryTypeDevice;
-    a->device = 0;
+    a->device = t_device;  // "device memory" belongs to whichever device the asking thread has selected
     a->devicePointer = const_cast<void*>(p), a->hostPointer = nullptr;
     return cudaSuccess;
 }

@@ -51,5 +51,10 @@ torch.cuda.set_device = lambda *a, **k: None
 torch.cuda.current_device = lambda: 0
 torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0, synchronize=lambda: None)
 
+import torch.distributed as _dist  # noqa: E402
+
+_init_pg = _dist.init_process_group
+_dist.init_process_group = lambda backend=None, **kw: _init_pg("gloo", **{k: v for k, v in kw.items() if k != "device_id"})  # gloo stands in for NCCL
+
 sys.argv = [os.path.join(ROOT, "bench.py")] + sys.argv[1:]
 runpy.run_path(os.path.join(ROOT, "bench.py"), run_name="__main__")

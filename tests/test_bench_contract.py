@@ -60,3 +60,31 @@ def test_own_arm_control_flow_and_json_line_on_the_mock_runtime():
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["unit"] == "GB/s" and c["value"] > 0 and c["cores"] >= 2 and "pass" in c["sample"]
+
+
+def test_own_arm_two_ranks_on_the_mock_runtime():
+    """The N>1 launch the driver uses (torch.distributed.run, one rank per GPU) with world_size 2 on CPU: gloo stands in for NCCL, the
+    mock runtime for the GPUs.  Rank 0 hosts the worker and generates the 2 x 0.25 GiB file, the manifest is broadcast, every rank
+    reads its round-robin shard, timings are max-reduced, rank 0 prints the one line."""
+    import socket
+    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_cuda"))
+    try:
+        import build as mock_build
+    finally:
+        sys.path.pop(0)
+    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=mock_build.build(), OMP_NUM_THREADS="1")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(ROOT, "tests", "mock_cuda", "run_bench_on_mock.py"), "--gpus", "2", "--gib-per-gpu", "0.25", "--steps", "2", "--warmup", "2"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, p.stdout[-2000:]
+    d = json.loads(lines[0])
+    n = 2 * int(0.25 * (1 << 30))
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["config"]["file_bytes"] == n and d["config"]["blocks_per_gpu"] == n // (4 << 20) // 2
+    assert d["e2e"]["h2d_bytes_per_step"] == n and d["e2e"]["value"] > 0 and d["value"] > 0
+    assert "cpu_baseline" not in d  # rank 0 at N=1 only

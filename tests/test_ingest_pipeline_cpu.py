@@ -31,3 +31,17 @@ def test_gpu_reader_suite_against_the_mock_runtime():
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
     assert m and int(m.group(1)) >= 37, tail
+
+
+def test_device_reader_releases_every_device_and_pinned_allocation_and_registration():
+    """tests/mock_cuda/leak_check.py: mixed workload over four pipeline configurations incl. failed and abandoned reads and a device
+    write; after every cv_fs_close the mock runtime must hold no device allocation, no pinned allocation and no registered range."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_cuda"))
+    try:
+        import build as mock_build
+    finally:
+        sys.path.pop(0)
+    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=mock_build.build())
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "leak_check.py")], cwd=ROOT, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "leak check ok" in r.stdout, r.stdout[-3000:]

@@ -381,6 +381,7 @@ int64_t cv_worker_start(const char* conf_toml, cv_worker** out, int32_t* port) {
     API_TRY(ClusterConf::from_string(conf_toml ? conf_toml : "", &c));
     std::unique_ptr<cv_worker> w(new cv_worker());
     w->hostname = c.worker_hostname;
+    w->w.hbm().configure(c.worker_hbm_capacity, c.worker_hbm_promote_after, c.worker_hbm_device);
     API_TRY(w->w.start(c.worker_dirs, c.cluster_id, "", c.worker_port, c.worker_enable_send_file));
     if (port) *port = w->w.port();
     *out = w.release();
@@ -414,6 +415,11 @@ int64_t cv_worker_hbm_load(cv_worker* w, int64_t block_id, int32_t device) {
 int64_t cv_worker_hbm_stats(cv_worker* w, int64_t out[3]) {
     WorkerMetrics& m = w->w.metrics();
     out[0] = static_cast<int64_t>(w->w.hbm().size()), out[1] = m.read_blocks_hbm, out[2] = m.hbm_packed_bytes;
+    return ok();
+}
+
+int64_t cv_worker_hbm_tier(cv_worker* w, int64_t out[6]) {
+    w->w.hbm().stats(out);
     return ok();
 }
 

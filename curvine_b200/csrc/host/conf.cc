@@ -168,6 +168,9 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "hostname") c->worker_hostname = unquote(v);
             else if (k == "rpc_port") c->worker_port = static_cast<int>(as_int(v));
             else if (k == "enable_send_file") c->worker_enable_send_file = as_bool(v);
+            else if (k == "hbm_capacity") e = as_size(v, &c->worker_hbm_capacity);
+            else if (k == "hbm_promote_after") c->worker_hbm_promote_after = static_cast<int>(as_int(v));
+            else if (k == "hbm_device") c->worker_hbm_device = static_cast<int>(as_int(v));
         } else if (section == "b200") {
             B200Conf& b = c->b200;
             if (k == "device") b.device = static_cast<int>(as_int(v));

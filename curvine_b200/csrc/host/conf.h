@@ -67,6 +67,9 @@ struct ClusterConf {
     std::string worker_hostname = "localhost";
     int worker_port = 0;
     bool worker_enable_send_file = true;
+    int64_t worker_hbm_capacity = 0;     // [worker] hbm_capacity: bytes of device memory the HBM tier may hold (0 = unbounded, manual loads)
+    int worker_hbm_promote_after = 0;    // [worker] hbm_promote_after: framed reads of a block before it is loaded into the tier (0 = never)
+    int worker_hbm_device = 0;           // [worker] hbm_device
 
     static Err from_file(const std::string& path, ClusterConf* out);
     static Err from_string(const std::string& toml, ClusterConf* out);

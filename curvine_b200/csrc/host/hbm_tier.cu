@@ -19,32 +19,93 @@ PackedStream::~PackedStream() {
     if (wire) cudaFreeHost(wire);
 }
 
-HbmTier::~HbmTier() {
-    for (auto& kv : blocks_) {
-        cudaSetDevice(kv.second.device);
-        cudaFree(kv.second.d_ptr);
-    }
+HbmBuf::~HbmBuf() {
+    if (!d_ptr) return;
+    cudaSetDevice(device);
+    cudaFree(d_ptr);
+}
+
+void HbmTier::configure(int64_t capacity_bytes, int promote_after, int device) {
+    std::lock_guard<std::mutex> lk(mu_);
+    capacity_ = std::max<int64_t>(capacity_bytes, 0), promote_after_ = std::max(promote_after, 0), device_ = device;
 }
 
 Err HbmTier::load(int64_t block_id, const void* host_bytes, int64_t len, int device) {
-    CUH_TRY(cudaSetDevice(device));
-    HbmBlock b;
-    b.len = len, b.device = device;
-    CUH_TRY(cudaMalloc(&b.d_ptr, static_cast<size_t>(std::max<int64_t>(len, 1))));
-    CUH_TRY(cudaMemcpy(b.d_ptr, host_bytes, static_cast<size_t>(len), cudaMemcpyHostToDevice));
+    std::vector<HbmBlock> dropped;  // released outside the lock (cudaFree)
+    {
+        // make room first: never hold more than `capacity` bytes, not even transiently
+        std::lock_guard<std::mutex> lk(mu_);
+        auto old = blocks_.find(block_id);
+        if (old != blocks_.end()) {  // re-load: the old copy leaves the table (readers of it keep it alive)
+            bytes_ -= old->second.buf->len;
+            dropped.push_back(old->second.buf);
+            lru_.erase(old->second.pos);
+            blocks_.erase(old);
+        }
+        if (capacity_ > 0) {
+            if (len > capacity_) {
+                refused_++;
+                return Err::common(str_printf("block of %lld bytes exceeds the HBM tier capacity %lld", (long long)len, (long long)capacity_));
+            }
+            auto it = lru_.end();
+            while (bytes_ + len > capacity_ && it != lru_.begin()) {
+                --it;  // walk from the cold end, skipping blocks somebody is reading
+                auto e = blocks_.find(*it);
+                if (e->second.buf.use_count() > 1) continue;
+                bytes_ -= e->second.buf->len;
+                dropped.push_back(e->second.buf);
+                blocks_.erase(e);
+                it = lru_.erase(it);
+                evictions_++;
+            }
+            if (bytes_ + len > capacity_) {
+                refused_++;
+                return Err::common("the HBM tier is full of blocks that are being read");
+            }
+        }
+        bytes_ += len;  // reserved
+    }
+    dropped.clear();
+    auto fail = [&](Err e) {
+        std::lock_guard<std::mutex> lk(mu_);
+        bytes_ -= len;
+        return e;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(Err::io("cudaSetDevice failed"));
+    std::shared_ptr<HbmBuf> b(new HbmBuf());
+    b->len = len, b->device = device;
+    cudaError_t ce = cudaMalloc(&b->d_ptr, static_cast<size_t>(std::max<int64_t>(len, 1)));
+    if (ce == cudaSuccess) ce = cudaMemcpy(b->d_ptr, host_bytes, static_cast<size_t>(len), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) return fail(Err::io(str_printf("HBM tier load: %s", cudaGetErrorString(ce))));
     std::lock_guard<std::mutex> lk(mu_);
-    auto it = blocks_.find(block_id);
-    if (it != blocks_.end()) cudaFree(it->second.d_ptr);
-    blocks_[block_id] = b;
+    auto dup = blocks_.find(block_id);
+    if (dup != blocks_.end()) {  // two loads of one id raced: the later one wins
+        bytes_ -= dup->second.buf->len;
+        lru_.erase(dup->second.pos);
+        blocks_.erase(dup);
+    }
+    lru_.push_front(block_id);
+    blocks_[block_id] = Entry{b, lru_.begin()};
+    remote_reads_.erase(block_id);
     return Err::ok();
 }
 
-bool HbmTier::get(int64_t block_id, HbmBlock* out) const {
+bool HbmTier::get(int64_t block_id, HbmBlock* out) {
     std::lock_guard<std::mutex> lk(mu_);
     auto it = blocks_.find(block_id);
     if (it == blocks_.end()) return false;
-    *out = it->second;
+    lru_.splice(lru_.begin(), lru_, it->second.pos);
+    *out = it->second.buf;
     return true;
+}
+
+bool HbmTier::should_promote(int64_t block_id) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (promote_after_ <= 0) return false;
+    int& n = remote_reads_[block_id];
+    if (n >= promote_after_) return true;
+    n++;
+    return false;
 }
 
 size_t HbmTier::size() const {
@@ -52,7 +113,14 @@ size_t HbmTier::size() const {
     return blocks_.size();
 }
 
-Err HbmTier::pack(const HbmBlock& b, int64_t off, int64_t n, int64_t chunk, int64_t req_id, int32_t first_seq, PackedStream* out) const {
+void HbmTier::stats(int64_t out[6]) const {
+    std::lock_guard<std::mutex> lk(mu_);
+    out[0] = static_cast<int64_t>(blocks_.size()), out[1] = bytes_, out[2] = capacity_;
+    out[3] = evictions_.load(), out[4] = promotions_.load(), out[5] = refused_.load();
+}
+
+Err HbmTier::pack(const HbmBlock& blk, int64_t off, int64_t n, int64_t chunk, int64_t req_id, int32_t first_seq, PackedStream* out) const {
+    const HbmBuf& b = *blk;
     CUH_TRY(cudaSetDevice(b.device));
     const uint32_t nf = static_cast<uint32_t>((n + chunk - 1) / chunk);
     const size_t wire_bytes = static_cast<size_t>(n) + size_t(nf) * kProtocolSize;

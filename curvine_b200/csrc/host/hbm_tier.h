@@ -6,6 +6,8 @@
 // RpcFrame::send (orpc/src/handler/rpc_frame.rs:205-220); the tier sits beside Mem/Ssd/Hdd
 // (curvine-common/src/state/storage_info.rs:36-49).
 #pragma once
+#include <atomic>
+#include <list>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
@@ -14,11 +16,16 @@
 
 namespace cv {
 
-struct HbmBlock {
+// One resident block.  Shared ownership: the tier's table holds one reference, every open read context that serves from the block
+// holds another, so an eviction (or a re-load of the same id) while a reader is packing frames from it only drops the table's
+// reference -- the device memory goes away with the last reader.
+struct HbmBuf {
     uint8_t* d_ptr = nullptr;
     int64_t len = 0;
     int device = 0;
+    ~HbmBuf();
 };
+using HbmBlock = std::shared_ptr<const HbmBuf>;
 
 // The packed response stream of one block read: frame f = wire + f*(22+chunk), carries min(chunk, remaining) bytes.
 struct PackedStream {
@@ -31,18 +38,39 @@ struct PackedStream {
     ~PackedStream();
 };
 
+// Admission / eviction (the tier sits beside Mem/Ssd/Hdd; the reference's tiers are capacity-bounded directories chosen by
+// storage policy, worker/storage/policy.rs:56-105 -- here the policy is LRU over resident blocks):
+//   capacity      bytes of HBM the tier may hold; 0 = unbounded (blocks stay until the worker stops)
+//   load()        admits a block, evicting least-recently-read blocks nobody is reading until it fits; a block larger than the
+//                 capacity, or one that does not fit because everything resident is being read, is refused (kind Common)
+//   promote_after a block read remotely (framed) this many times from its file is loaded on the next remote Open and that very read
+//                 is served from HBM; 0 = manual loads only
 class HbmTier {
    public:
-    ~HbmTier();
+    void configure(int64_t capacity_bytes, int promote_after, int device);
     Err load(int64_t block_id, const void* host_bytes, int64_t len, int device);
-    bool get(int64_t block_id, HbmBlock* out) const;
+    bool get(int64_t block_id, HbmBlock* out);  // LRU touch
+    // a remote read of a block that is not resident is about to be served from its file: true = promote it first
+    bool should_promote(int64_t block_id);
+    int device() const { return device_; }
     size_t size() const;
+    void stats(int64_t out[6]) const;  // resident blocks, resident bytes, capacity, evictions, promotions, refused loads
+    void note_promotion() { promotions_++; }
     // K4 over [off, off+n) of a resident block: prefixes (code 81, status Running|Success, req_id, seq first_seq..) + payload
     Err pack(const HbmBlock& b, int64_t off, int64_t n, int64_t chunk, int64_t req_id, int32_t first_seq, PackedStream* out) const;
 
    private:
     mutable std::mutex mu_;
-    std::unordered_map<int64_t, HbmBlock> blocks_;
+    std::list<int64_t> lru_;  // front = most recently read
+    struct Entry {
+        HbmBlock buf;
+        std::list<int64_t>::iterator pos;
+    };
+    std::unordered_map<int64_t, Entry> blocks_;
+    std::unordered_map<int64_t, int> remote_reads_;  // non-resident blocks: framed reads served from the file so far
+    int64_t capacity_ = 0, bytes_ = 0;
+    int promote_after_ = 0, device_ = 0;
+    std::atomic<int64_t> evictions_{0}, promotions_{0}, refused_{0};
 };
 
 }  // namespace cv

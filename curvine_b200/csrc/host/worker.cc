@@ -44,10 +44,29 @@ Err ReadHandler::open(const RpcRequest& req, RpcResponse* resp) {
     const bool short_circuit = c.short_circuit && meta.storage_type != kStorageSpdkDisk;
     close_fd(fd_);
     fd_ = -1;
+    hbm_block_.reset();
     from_hbm_ = !short_circuit && hbm_ && hbm_->get(c.id, &hbm_block_);
+    if (!from_hbm_ && !short_circuit && hbm_ && hbm_->should_promote(c.id)) {
+        // read often enough from its file: load it into the HBM tier now (evicting colder blocks) and serve this read from there;
+        // a refusal (tier full of blocks being read, block larger than the tier) just leaves the block where it is
+        std::vector<char> buf(static_cast<size_t>(meta.len));
+        const int pfd = ::open(meta.path.c_str(), O_RDONLY | O_CLOEXEC);
+        bool ok = pfd >= 0;
+        for (size_t got = 0; ok && got < buf.size();) {
+            const ssize_t r = pread(pfd, buf.data() + got, buf.size() - got, static_cast<off_t>(got));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) ok = false;
+            else got += static_cast<size_t>(r);
+        }
+        close_fd(pfd);
+        if (ok && !hbm_->load(c.id, buf.data(), meta.len, hbm_->device()) && hbm_->get(c.id, &hbm_block_)) {
+            hbm_->note_promotion();
+            from_hbm_ = true;
+        }
+    }
     if (from_hbm_) {
         // the block is resident in HBM: pack the whole response stream on the GPU now (K4), serve Running requests from it
-        len_ = hbm_block_.len, pos_ = c.off, next_seq_ = req.proto.seq_id + 1;
+        len_ = hbm_block_->len, pos_ = c.off, next_seq_ = req.proto.seq_id + 1;
         CV_RETURN_IF_ERR(hbm_->pack(hbm_block_, c.off, len_ - c.off, c.chunk_size, req.proto.req_id, next_seq_, &packed_));
         metrics_->read_blocks_hbm++;
         metrics_->hbm_packed_bytes += len_ - c.off;
@@ -147,6 +166,7 @@ Err ReadHandler::complete(const RpcRequest& req, RpcResponse* resp) {
         return Err::common(str_printf("Request id mismatch, expected %lld, actual %lld", (long long)ctx_req_id_, (long long)req.proto.req_id));
     close_fd(fd_);
     fd_ = -1;
+    hbm_block_.reset();  // the read context's reference on the resident block
     resp->proto = response_proto(req.proto, kRespSuccess);
     return Err::ok();
 }

@@ -48,7 +48,7 @@ struct RpcResponse {
 
 class ReadHandler {
    public:
-    ReadHandler(BlockStore* store, WorkerMetrics* m, bool enable_send_file, const HbmTier* hbm = nullptr)
+    ReadHandler(BlockStore* store, WorkerMetrics* m, bool enable_send_file, HbmTier* hbm = nullptr)
         : store_(store), metrics_(m), enable_send_file_(enable_send_file), hbm_(hbm) {}
     ~ReadHandler();
     Err handle(const RpcRequest& req, RpcResponse* resp);
@@ -69,7 +69,7 @@ class ReadHandler {
     bool is_tmpfs_ = false;
     std::string path_;
     // HBM tier: the whole response stream of this read, packed by K4 at Open
-    const HbmTier* hbm_ = nullptr;
+    HbmTier* hbm_ = nullptr;
     bool from_hbm_ = false;
     HbmBlock hbm_block_;
     PackedStream packed_;

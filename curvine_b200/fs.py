@@ -29,9 +29,9 @@ class MiniWorker:
     """In-process worker over a BlockStore directory tree (fixture; worker_test.rs:35-48 analogue)."""
 
     def __init__(self, data_dirs: List[str], cluster_id: str = "curvine", hostname: str = "localhost",
-                 enable_send_file: bool = True, port: int = 0):
-        conf = 'cluster_id = "%s"\n[worker]\ndata_dir = [%s]\nhostname = "%s"\nrpc_port = %d\nenable_send_file = %s\n' % (
-            cluster_id, ", ".join('"%s"' % d for d in data_dirs), hostname, port, "true" if enable_send_file else "false")
+                 enable_send_file: bool = True, port: int = 0, extra_worker: str = ""):
+        conf = 'cluster_id = "%s"\n[worker]\ndata_dir = [%s]\nhostname = "%s"\nrpc_port = %d\nenable_send_file = %s\n%s\n' % (
+            cluster_id, ", ".join('"%s"' % d for d in data_dirs), hostname, port, "true" if enable_send_file else "false", extra_worker)
         self.hostname = hostname
         self._h = ctypes.c_void_p()
         p = ctypes.c_int32()
@@ -57,6 +57,12 @@ class MiniWorker:
         a = (ctypes.c_int64 * 3)()
         _check(_lib.lib().cv_worker_hbm_stats(self._h, a))
         return dict(zip(["resident_blocks", "reads_from_hbm", "packed_bytes"], a))
+
+    def hbm_tier(self) -> dict:
+        """HBM tier occupancy and policy counters ([worker] hbm_capacity / hbm_promote_after / hbm_device)."""
+        a = (ctypes.c_int64 * 6)()
+        _check(_lib.lib().cv_worker_hbm_tier(self._h, a))
+        return dict(zip(["resident_blocks", "resident_bytes", "capacity", "evictions", "promotions", "refused"], a))
 
     def metrics(self) -> dict:
         a = (ctypes.c_int64 * 6)()

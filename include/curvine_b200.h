@@ -144,6 +144,10 @@ int64_t cv_worker_stop(cv_worker* w);
  * stats: out[0]=resident blocks [1]=reads served from HBM [2]=payload bytes packed by K4. */
 int64_t cv_worker_hbm_load(cv_worker* w, int64_t block_id, int32_t device);
 int64_t cv_worker_hbm_stats(cv_worker* w, int64_t out[3]);
+/* HBM tier occupancy and policy counters ([worker] hbm_capacity / hbm_promote_after / hbm_device): out[0]=resident blocks,
+ * out[1]=resident bytes, out[2]=capacity (0 = unbounded), out[3]=evictions (LRU, never a block that is being read),
+ * out[4]=promotions (blocks loaded because they were read remotely hbm_promote_after times), out[5]=refused loads */
+int64_t cv_worker_hbm_tier(cv_worker* w, int64_t out[6]);
 /* out[0]=read_bytes [1]=read_time_us [2]=read_count [3]=read_blocks{local} [4]=read_blocks{remote} [5]=num_blocks */
 int64_t cv_worker_metrics(cv_worker* w, int64_t out[6]);
 /* Write `len` bytes of synthetic content as blocks of `block_size` into the worker's BlockStore (reference

@@ -68,6 +68,19 @@ def main():
                 fs.close()
                 after = counters()
                 assert after["device_allocs"] == 0 and after["pinned_allocs"] == 0 and after["registered_ranges"] == 0, (conf_kw, mid, after)
+            # HBM tier: two resident blocks (one re-loaded, one evicted by capacity would need a conf; here: manual loads), framed read, then the
+            # worker goes away with them
+            from oracle import layout
+            for i in (0, 1, 1):
+                w.hbm_load(layout.create_block_id(8001, i), 0)
+            assert counters()["device_allocs"] == 2
+            fs = F.CurvineFileSystem(F.client_conf(short_circuit=False))
+            fs.load_namespace(man)
+            r = fs.open("/a")
+            assert r.read_full(3 << 20) == want[:3 << 20]
+            r.complete()
+            fs.close()
+            assert w.hbm_stats()["reads_from_hbm"] >= 2
             # write path: device bytes -> worker -> read back
             fs = F.CurvineFileSystem(F.client_conf(short_circuit=False))
             src = np.frombuffer(synth.file_bytes(8200, 3 << 20, 1 << 20), dtype=np.uint8).copy()

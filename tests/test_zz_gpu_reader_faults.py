@@ -222,3 +222,95 @@ def test_vanished_block_file_and_bad_arguments(cuda, cluster, sc):
         torch.cuda.synchronize()
         assert dst.cpu().numpy().tobytes() == synth.file_bytes(ino + 50, n, bs)
         r.complete()
+
+
+def _own_worker(extra_worker):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    root = __import__("pathlib").Path(__import__("tempfile").mkdtemp(prefix="cvhbm", dir=base))
+    return F.MiniWorker(["[MEM]" + str(root / "mem")], extra_worker=extra_worker), root
+
+
+def test_hbm_tier_capacity_lru_eviction_and_blocks_being_read():
+    """[worker] hbm_capacity: the tier never holds more than its capacity; loads evict the least recently READ block nobody is
+    reading; a block with an open read context survives its own eviction (the context keeps the device memory alive) and keeps
+    serving the right bytes; evicted blocks are served from their files again; a block larger than the tier is refused."""
+    import shutil
+    bs, ino = 1 << 20, 7800
+    w, root = _own_worker('hbm_capacity = "3MB"')
+    try:
+        n = 6 * bs
+        man = w.create_file("/t", ino, n, bs) + w.create_file("/big", ino + 1, 4 << 20, 4 << 20)
+        want = synth.file_bytes(ino, n, bs)
+        ids = [layout.create_block_id(ino, i) for i in range(6)]
+        for i in range(3):
+            w.hbm_load(ids[i], 0)
+        t = w.hbm_tier()
+        assert t["resident_blocks"] == 3 and t["resident_bytes"] == 3 * bs and t["capacity"] == 3 << 20 and t["evictions"] == 0
+        with F.CurvineFileSystem(F.client_conf(short_circuit=False, read_chunk_size="64KB")) as fs:
+            fs.load_namespace(man)
+            r0 = fs.open("/t")
+            assert r0.read(1000) == want[:1000]  # block 0 now has an open read context served from HBM (and is the most recently read)
+            hbm_reads = w.hbm_stats()["reads_from_hbm"]
+            assert hbm_reads >= 1
+            w.hbm_load(ids[3], 0)  # evicts block 1 (coldest that nobody reads)
+            w.hbm_load(ids[4], 0)  # evicts block 2
+            t = w.hbm_tier()
+            assert t["resident_blocks"] == 3 and t["evictions"] == 2 and t["resident_bytes"] == 3 * bs, t
+            w.hbm_load(ids[5], 0)  # block 0 is the coldest but is being read: block 3 goes instead
+            t = w.hbm_tier()
+            assert t["evictions"] == 3 and t["resident_bytes"] <= 3 << 20, t
+            assert r0.read_full(n) == want[1000:]  # the open context on block 0 kept working; blocks 1-3 came from files, 4-5 from HBM
+            r0.complete()
+            with pytest.raises(F.FsError):
+                w.hbm_load(layout.create_block_id(ino + 1, 0), 0)  # 4 MiB block, 3 MB tier
+            assert w.hbm_tier()["refused"] == 1
+            r = fs.open("/t")
+            assert r.read_full(n) == want
+            r.complete()
+        assert w.hbm_stats()["reads_from_hbm"] > hbm_reads
+    finally:
+        w.stop()
+        shutil.rmtree(str(root), ignore_errors=True)
+
+
+def test_hbm_tier_promotes_blocks_that_are_read_remotely(cuda):
+    """[worker] hbm_promote_after = 2: the third framed read of a block loads it into the tier and is itself served from HBM
+    (frames packed by K4); short-circuit reads never count; bytes are identical before and after; the device reader sees the
+    same CRCs through K2."""
+    import shutil
+    import torch
+    bs, ino, n = 1 << 20, 7900, (3 << 20) + 99
+    w, root = _own_worker('hbm_promote_after = 2\nhbm_capacity = "64MB"')
+    try:
+        man = w.create_file("/p", ino, n, bs)
+        want = synth.file_bytes(ino, n, bs)
+        with F.CurvineFileSystem(_conf(False, 1, "256KB")) as fs:
+            fs.load_namespace(man)
+            for rep in range(2):
+                r = fs.open("/p")
+                assert r.read_full(n) == want
+                r.complete()
+                assert w.hbm_tier()["promotions"] == 0 and w.hbm_stats()["reads_from_hbm"] == 0
+            r = fs.open("/p")
+            dst = _dev_buf(n, cuda)
+            assert r.read_device(dst.data_ptr(), n, 0) == n  # third remote read of every block: promoted, served from HBM
+            s, bad, ver = r.verify()
+            torch.cuda.synchronize()
+            assert bad == 0 and ver == 4 and dst.cpu().numpy().tobytes() == want
+            r.complete()
+            t = w.hbm_tier()
+            assert t["promotions"] == 4 and t["resident_blocks"] == 4 and t["resident_bytes"] == n, t
+            assert w.hbm_stats()["reads_from_hbm"] == 4
+            r = fs.open("/p")
+            assert r.read_full(n) == want
+            r.complete()
+            assert w.hbm_stats()["reads_from_hbm"] == 8 and w.hbm_tier()["promotions"] == 4
+        with F.CurvineFileSystem(_conf(True, 1)) as fs:  # short-circuit readers go to the file, resident or not
+            fs.load_namespace(man)
+            r = fs.open("/p")
+            assert r.read_full(n) == want
+            r.complete()
+            assert w.hbm_stats()["reads_from_hbm"] == 8
+    finally:
+        w.stop()
+        shutil.rmtree(str(root), ignore_errors=True)

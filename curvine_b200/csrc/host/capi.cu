@@ -30,6 +30,11 @@ static int64_t ok() { return 0; }
         Err e__ = (expr);         \
         if (e__) return fail(e__); \
     } while (0)
+// every handle / required out-pointer is checked before it is touched: a NULL comes back as -(Common) with a message, never a crash
+#define API_NEED(x)                                                          \
+    do {                                                                     \
+        if (!(x)) return fail(Err::common("null argument: " #x));           \
+    } while (0)
 #define API_GUARD_BEGIN try {
 #define API_GUARD_END                                                     \
     }                                                                     \
@@ -67,6 +72,7 @@ void cv_free(void* p) { free(p); }
 
 int64_t cv_fs_new_from_string(const char* conf_toml, cv_fs** out) {
     API_GUARD_BEGIN
+    API_NEED(out);
     ClusterConf c;
     API_TRY(ClusterConf::from_string(conf_toml ? conf_toml : "", &c));
     std::unique_ptr<cv_fs> fs(new cv_fs());
@@ -79,6 +85,7 @@ int64_t cv_fs_new_from_string(const char* conf_toml, cv_fs** out) {
 
 int64_t cv_fs_new(const char* conf_path, cv_fs** out) {
     API_GUARD_BEGIN
+    API_NEED(out);
     ClusterConf c;
     API_TRY(ClusterConf::from_file(conf_path ? conf_path : "", &c));
     std::unique_ptr<cv_fs> fs(new cv_fs());
@@ -91,6 +98,8 @@ int64_t cv_fs_new(const char* conf_path, cv_fs** out) {
 
 int64_t cv_fs_load_namespace(cv_fs* fs, const char* manifest_path) {
     API_GUARD_BEGIN
+    API_NEED(fs);
+    API_NEED(manifest_path);
     API_TRY(fs->ctx->ns.load(manifest_path));
     return ok();
     API_GUARD_END
@@ -98,6 +107,8 @@ int64_t cv_fs_load_namespace(cv_fs* fs, const char* manifest_path) {
 
 int64_t cv_fs_load_namespace_string(cv_fs* fs, const char* text) {
     API_GUARD_BEGIN
+    API_NEED(fs);
+    API_NEED(text);
     API_TRY(fs->ctx->ns.load_string(text));
     return ok();
     API_GUARD_END
@@ -114,23 +125,31 @@ int64_t cv_fs_close(cv_fs* fs) {
 
 int64_t cv_fs_wait_registered(cv_fs* fs) {
     API_GUARD_BEGIN
+    API_NEED(fs);
     gpu_ingest_wait_registered(fs->ctx.get());
     return ok();
     API_GUARD_END
 }
 
 int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]) {
+    API_NEED(fs);
+    API_NEED(out);
     out[0] = fs->ctx->read_bytes.load(), out[1] = fs->ctx->read_time_us.load();
     return ok();
 }
 
 int64_t cv_fs_pool_stats(cv_fs* fs, int64_t out[3]) {
+    API_NEED(fs);
+    API_NEED(out);
     fs->ctx->pool_stats(out);
     return ok();
 }
 
 int64_t cv_open(cv_fs* fs, const char* path, cv_reader** out, int64_t* len) {
     API_GUARD_BEGIN
+    API_NEED(fs);
+    API_NEED(path);
+    API_NEED(out);
     std::unique_ptr<cv_reader> r(new cv_reader());
     r->fs = fs, r->path = path;
     API_TRY(FsReader::open(fs->ctx.get(), path, &r->host));
@@ -142,6 +161,9 @@ int64_t cv_open(cv_fs* fs, const char* path, cv_reader** out, int64_t* len) {
 
 int64_t cv_read(cv_reader* r, const uint8_t** ptr, int64_t* len) {
     API_GUARD_BEGIN
+    API_NEED(r);
+    API_NEED(ptr);
+    API_NEED(len);
     API_TRY(r->host->read_chunk(ptr, len, -1));
     return ok();
     API_GUARD_END
@@ -149,6 +171,8 @@ int64_t cv_read(cv_reader* r, const uint8_t** ptr, int64_t* len) {
 
 int64_t cv_read_buf(cv_reader* r, uint8_t* buf, int64_t cap, int64_t* n) {
     API_GUARD_BEGIN
+    API_NEED(r);
+    API_NEED(n);
     API_TRY(r->host->read(buf, cap, n));
     return ok();
     API_GUARD_END
@@ -156,6 +180,8 @@ int64_t cv_read_buf(cv_reader* r, uint8_t* buf, int64_t cap, int64_t* n) {
 
 int64_t cv_read_full(cv_reader* r, uint8_t* buf, int64_t cap, int64_t* n) {
     API_GUARD_BEGIN
+    API_NEED(r);
+    API_NEED(n);
     API_TRY(r->host->read_full(buf, cap, n));
     return ok();
     API_GUARD_END
@@ -164,6 +190,7 @@ int64_t cv_read_full(cv_reader* r, uint8_t* buf, int64_t cap, int64_t* n) {
 int64_t cv_fuse_read(cv_reader* r, int64_t pos, int64_t len, uint8_t* buf, int64_t* n, int64_t* seg_lens, int32_t max_segs,
                      int32_t* n_segs) {
     API_GUARD_BEGIN
+    API_NEED(r);
     API_TRY(r->host->seek(pos));
     int64_t remaining = len, off = 0;
     int32_t segs = 0;
@@ -184,14 +211,15 @@ int64_t cv_fuse_read(cv_reader* r, int64_t pos, int64_t len, uint8_t* buf, int64
 
 int64_t cv_seek(cv_reader* r, int64_t pos) {
     API_GUARD_BEGIN
+    API_NEED(r);
     API_TRY(r->host->seek(pos));
     return ok();
     API_GUARD_END
 }
 
-int64_t cv_pos(cv_reader* r) { return r->host->pos(); }
-int64_t cv_len(cv_reader* r) { return r->host->len(); }
-int64_t cv_chunk_size(cv_reader* r) { return r->host->chunk_size(); }
+int64_t cv_pos(cv_reader* r) { return r ? r->host->pos() : -int64_t(kCommon); }
+int64_t cv_len(cv_reader* r) { return r ? r->host->len() : -int64_t(kCommon); }
+int64_t cv_chunk_size(cv_reader* r) { return r ? r->host->chunk_size() : -int64_t(kCommon); }
 
 int64_t cv_close_reader(cv_reader* r) {
     API_GUARD_BEGIN
@@ -214,6 +242,8 @@ static Err ensure_dev(cv_reader* r) {
 
 int64_t cv_read_device(cv_reader* r, void* d_dst, int64_t cap, cv_stream_t stream, int64_t* nbytes) {
     API_GUARD_BEGIN
+    API_NEED(r);
+    API_NEED(nbytes);
     API_TRY(ensure_dev(r));
     API_TRY(r->dev->seek(r->host->pos()));
     int64_t n = 0;
@@ -227,6 +257,8 @@ int64_t cv_read_device(cv_reader* r, void* d_dst, int64_t cap, cv_stream_t strea
 int64_t cv_read_device_sharded(cv_reader* r, int32_t rank, int32_t world, void* d_dst, int64_t cap, cv_stream_t stream,
                                int64_t* nbytes) {
     API_GUARD_BEGIN
+    API_NEED(r);
+    API_NEED(nbytes);
     API_TRY(ensure_dev(r));
     int64_t n = 0;
     API_TRY(r->dev->read_device_sharded(rank, world, d_dst, cap, stream, &n));
@@ -238,6 +270,9 @@ int64_t cv_read_device_sharded(cv_reader* r, int32_t rank, int32_t world, void* 
 int64_t cv_read_many_device(cv_fs* fs, const char* const* paths, int32_t n, void* d_dst, const int64_t* dst_offs, int64_t cap, cv_stream_t stream,
                             uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified, int64_t* total_bytes) {
     API_GUARD_BEGIN
+    API_NEED(fs);
+    API_NEED(paths);
+    API_NEED(dst_offs);
     std::vector<std::string> ps;
     for (int32_t i = 0; i < n; i++) ps.emplace_back(paths[i]);
     uint64_t s = 0, v = 0;
@@ -255,6 +290,7 @@ int64_t cv_read_many_device(cv_fs* fs, const char* const* paths, int32_t n, void
 int64_t cv_shard_plan(cv_reader* r, int32_t rank, int32_t world, int64_t* block_index, int64_t* file_off, int64_t* len, int64_t* dst_off,
                       int32_t cap, int32_t* n, int64_t* total_bytes) {
     API_GUARD_BEGIN
+    API_NEED(r);
     std::vector<ShardJob> plan;
     int64_t total = 0;
     API_TRY(plan_shard(r->host->file_blocks(), rank, world, -1, &plan, &total));
@@ -273,6 +309,7 @@ int64_t cv_shard_plan(cv_reader* r, int32_t rank, int32_t world, int64_t* block_
 int64_t cv_fuse_read_device(cv_reader* r, int64_t pos, int64_t len, void* d_scratch, void* d_page_base, const uint64_t* page_offsets,
                             int32_t n_pages, int64_t page_size, cv_stream_t stream, int64_t* nbytes) {
     API_GUARD_BEGIN
+    API_NEED(r);
     API_TRY(ensure_dev(r));
     API_TRY(r->host->seek(pos));
     API_TRY(r->dev->seek(pos));
@@ -307,6 +344,10 @@ int64_t cv_fuse_read_device(cv_reader* r, int64_t pos, int64_t len, void* d_scra
 
 int64_t cv_verify(cv_reader* r, uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified) {
     API_GUARD_BEGIN
+    API_NEED(r);
+    API_NEED(sum_crc);
+    API_NEED(n_bad);
+    API_NEED(n_verified);
     uint64_t s = 0, v = 0;
     uint32_t b = 0;
     if (r->dev) API_TRY(r->dev->verify(&s, &b, &v));
@@ -318,6 +359,8 @@ int64_t cv_verify(cv_reader* r, uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_
 }
 
 int64_t cv_device_stats(cv_reader* r, CvReadStats* out) {
+    API_NEED(r);
+    API_NEED(out);
     memset(out, 0, sizeof(*out));
     if (!r->dev) return ok();
     const GpuReadStats& s = r->dev->stats();
@@ -334,6 +377,10 @@ int64_t cv_device_stats(cv_reader* r, CvReadStats* out) {
 int64_t cv_writer_open(cv_fs* fs, const char* path, int64_t inode_id, int64_t block_size, int32_t storage_type, const char* worker_host,
                        int32_t worker_port, int64_t chunk_size, cv_writer** out) {
     API_GUARD_BEGIN
+    API_NEED(fs);
+    API_NEED(path);
+    API_NEED(worker_host);
+    API_NEED(out);
     WorkerAddress a;
     a.worker_id = 1, a.hostname = worker_host, a.ip_addr = "127.0.0.1", a.rpc_port = static_cast<uint32_t>(worker_port);
     if (a.hostname != "localhost") a.ip_addr = a.hostname;
@@ -346,6 +393,7 @@ int64_t cv_writer_open(cv_fs* fs, const char* path, int64_t inode_id, int64_t bl
 
 int64_t cv_write(cv_writer* w, const uint8_t* buf, int64_t n) {
     API_GUARD_BEGIN
+    API_NEED(w);
     API_TRY(w->w->write(buf, n));
     return ok();
     API_GUARD_END
@@ -353,6 +401,7 @@ int64_t cv_write(cv_writer* w, const uint8_t* buf, int64_t n) {
 
 int64_t cv_write_device(cv_writer* w, const void* d_src, int64_t n, cv_stream_t stream) {
     API_GUARD_BEGIN
+    API_NEED(w);
     API_TRY(w->w->write_device(d_src, n, stream));
     return ok();
     API_GUARD_END
@@ -360,6 +409,7 @@ int64_t cv_write_device(cv_writer* w, const void* d_src, int64_t n, cv_stream_t 
 
 int64_t cv_writer_close(cv_writer* w, int32_t cancel, char** manifest_out) {
     API_GUARD_BEGIN
+    API_NEED(w);
     if (!w) return ok();
     Err e = cancel ? w->w->cancel() : w->w->complete();
     if (!e && manifest_out) {
@@ -377,6 +427,7 @@ int64_t cv_writer_close(cv_writer* w, int32_t cancel, char** manifest_out) {
 
 int64_t cv_worker_start(const char* conf_toml, cv_worker** out, int32_t* port) {
     API_GUARD_BEGIN
+    API_NEED(out);
     ClusterConf c;
     API_TRY(ClusterConf::from_string(conf_toml ? conf_toml : "", &c));
     std::unique_ptr<cv_worker> w(new cv_worker());
@@ -400,6 +451,7 @@ int64_t cv_worker_stop(cv_worker* w) {
 
 int64_t cv_worker_hbm_load(cv_worker* w, int64_t block_id, int32_t device) {
     API_GUARD_BEGIN
+    API_NEED(w);
     BlockMeta m;
     API_TRY(w->w.store().get_block(block_id, &m));
     std::ifstream f(m.path, std::ios::binary);
@@ -413,17 +465,23 @@ int64_t cv_worker_hbm_load(cv_worker* w, int64_t block_id, int32_t device) {
 }
 
 int64_t cv_worker_hbm_stats(cv_worker* w, int64_t out[3]) {
+    API_NEED(w);
+    API_NEED(out);
     WorkerMetrics& m = w->w.metrics();
     out[0] = static_cast<int64_t>(w->w.hbm().size()), out[1] = m.read_blocks_hbm, out[2] = m.hbm_packed_bytes;
     return ok();
 }
 
 int64_t cv_worker_hbm_tier(cv_worker* w, int64_t out[6]) {
+    API_NEED(w);
+    API_NEED(out);
     w->w.hbm().stats(out);
     return ok();
 }
 
 int64_t cv_worker_metrics(cv_worker* w, int64_t out[6]) {
+    API_NEED(w);
+    API_NEED(out);
     WorkerMetrics& m = w->w.metrics();
     out[0] = m.read_bytes, out[1] = m.read_time_us, out[2] = m.read_count, out[3] = m.read_blocks_local, out[4] = m.read_blocks_remote;
     out[5] = static_cast<int64_t>(w->w.store().num_blocks());
@@ -538,6 +596,9 @@ int64_t cv_synth_set_shard_world(int32_t shard_world) {
 int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, int64_t len, int64_t block_size, int32_t storage_type,
                              int32_t mode, int32_t hole_every, int32_t threads, const char* worker_hostname, char** manifest_out) {
     API_GUARD_BEGIN
+    API_NEED(w);
+    API_NEED(path);
+    API_NEED(manifest_out);
     std::vector<std::vector<int>> node_cpus;
     if (g_synth_shard_world >= 1) node_cpus = gpu_node_cpus();
     if (block_size <= 0 || len < 0) return fail(Err(kInvalidFileSize, "bad file or block size"));

@@ -40,6 +40,36 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
 
 
+def test_null_handles_and_out_pointers_are_errors_not_crashes():
+    """include/curvine_b200.h: entry points never throw or abort.  Every cv_* function called with NULL for every pointer argument
+    (and 0 for every integer) must come back -- with a negative ErrorKind where a handle or a required out-pointer is missing -- in a
+    subprocess, so a crash is a test failure and not the end of the test run."""
+    import subprocess
+    import sys
+    code = """
+import ctypes, sys
+sys.path.insert(0, %r)
+from curvine_b200 import _lib
+L = _lib.lib()
+bad = []
+for name in _lib.EXPORTS:
+    if not name.startswith("cv_"):
+        continue
+    fn = getattr(L, name)
+    args = []
+    for t in (fn.argtypes or []):
+        args.append(None if (t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or hasattr(t, "_type_") and isinstance(t._type_, type)) else 0)
+    rc = fn(*args)
+    if name in ("cv_open", "cv_read", "cv_seek", "cv_verify", "cv_read_device", "cv_fs_load_namespace_string", "cv_worker_hbm_load", "cv_writer_open",
+                "cv_write", "cv_device_stats", "cv_fs_pool_stats", "cv_worker_metrics", "cv_shard_plan", "cv_read_many_device") and not (isinstance(rc, int) and rc < 0):
+        bad.append((name, rc))
+print("survived", bad)
+assert not bad, bad
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "survived []" in r.stdout, (r.returncode, r.stdout[-1500:])
+
+
 def test_tuning_hook_validates_its_arguments_without_a_gpu():
     """cvk_tune only flips process-wide launch choices: legal values are accepted, everything else is cudaErrorInvalidValue (1)."""
     L = _lib.lib()

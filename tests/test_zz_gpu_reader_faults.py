@@ -314,3 +314,60 @@ def test_hbm_tier_promotes_blocks_that_are_read_remotely(cuda):
     finally:
         w.stop()
         shutil.rmtree(str(root), ignore_errors=True)
+
+
+@pytest.mark.parametrize("sc,zero_copy", [(True, False), (True, True), (False, False)])
+def test_thousands_of_small_blocks_cycle_the_ring_many_times(cuda, cluster, sc, zero_copy):
+    """3,000 blocks of 20 KiB + a ragged tail through a ring of a few slots: every super-slot is handed over hundreds of times
+    between fetch threads, the copy stream and the verifier (released/copied hand-shake, verify batches that straddle slot reuse)."""
+    import torch
+    w, _ = cluster
+    bs = 20 * 1024
+    n, ino = 3000 * bs + 777, 8300 + 2 * int(sc) + int(zero_copy)
+    man = w.create_file("/many%d%d" % (sc, zero_copy), ino, n, bs, threads=8)
+    want = synth.file_bytes(ino, n, bs)
+    with F.CurvineFileSystem(_conf(sc, 1, "8KB", threads=6, batch=5, zero_copy=zero_copy, copy_group=3, register_threads=2, register_cache="128MB")) as fs:
+        fs.load_namespace(man)
+        for rep in range(2):
+            r = fs.open("/many%d%d" % (sc, zero_copy))
+            dst = _dev_buf(n + 8, cuda)
+            assert r.read_device(dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
+            s, bad, ver = r.verify()
+            torch.cuda.synchronize()
+            assert bad == 0 and ver == 3001
+            assert dst[:n].cpu().numpy().tobytes() == want and (dst[n:] == 0xA5).all()
+            assert s == int(clib.crc_blocks(1, np.frombuffer(want, dtype=np.uint8), bs).astype(np.uint64).sum())
+            r.complete()
+            fs.wait_registered()
+
+
+def test_read_many_with_empty_files_holes_and_hundreds_of_files(cuda, cluster):
+    """cv_read_many_device over 300 files in one pass: lengths from 0 to a few blocks, some with hole blocks; every file lands at
+    its own offset, the CRC sum is the sum over all blocks that have a manifest CRC, nothing else in the destination is touched."""
+    import torch
+    w, _ = cluster
+    rng = np.random.default_rng(5)
+    bs = 64 * 1024
+    specs, mans, off, offs = [], [], 0, []
+    for i in range(300):
+        ln = int(rng.choice([0, 1, 4095, bs - 1, bs, bs + 1, 3 * bs + 17]))
+        hole = (i % 17 == 3 and ln > bs)
+        mans.append(w.create_file("/rm/f%d" % i, 8400 + i, ln, bs, mode=2 if hole else 0, hole_every=2 if hole else 0, threads=1))
+        data = bytearray(synth.file_bytes(8400 + i, ln, bs))
+        if hole:
+            for b in range(1, (ln + bs - 1) // bs, 2):
+                data[b * bs:(b + 1) * bs] = bytes(min(bs, ln - b * bs))
+        specs.append(bytes(data))
+        offs.append(off)
+        off += ln + int(rng.integers(0, 9))
+    with F.CurvineFileSystem(_conf(True, 1, threads=6, batch=7, copy_group=4)) as fs:
+        fs.load_namespace("".join(mans))
+        dst = _dev_buf(off + 64, cuda)
+        tot, s, bad, ver = fs.read_many_device(["/rm/f%d" % i for i in range(300)], dst.data_ptr(), offs, off + 64, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert tot == sum(len(x) for x in specs) and bad == 0
+        host = dst.cpu().numpy()
+        expect = np.full(off + 64, 0xA5, dtype=np.uint8)
+        for o, x in zip(offs, specs):
+            expect[o:o + len(x)] = np.frombuffer(x, dtype=np.uint8)
+        assert host.tobytes() == expect.tobytes()

@@ -30,7 +30,7 @@ def test_gpu_reader_suite_against_the_mock_runtime():
     tail = "\n".join(r.stdout.splitlines()[-25:])
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 43, tail
+    assert m and int(m.group(1)) >= 46, tail
 
 
 def test_device_reader_releases_every_device_and_pinned_allocation_and_registration():

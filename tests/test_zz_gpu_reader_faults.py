@@ -371,3 +371,47 @@ def test_read_many_with_empty_files_holes_and_hundreds_of_files(cuda, cluster):
         for o, x in zip(offs, specs):
             expect[o:o + len(x)] = np.frombuffer(x, dtype=np.uint8)
         assert host.tobytes() == expect.tobytes()
+
+
+@pytest.mark.parametrize("sc,zero_copy,seed", [(True, True, 1), (True, False, 2), (False, False, 3)])
+def test_random_mixed_host_and_device_op_sequences(cuda, cluster, sc, zero_copy, seed):
+    """Seeded random walks over one reader: seek / host read / device read of random sizes (block-crossing, past EOF, zero), host
+    and device reads sharing the one position (reader.rs:50-141 semantics for both).  Every step is checked against the file bytes;
+    verify() must never report a bad block."""
+    import torch
+    w, _ = cluster
+    bs = 256 * 1024
+    n, ino = 23 * bs + 12345, 8600 + seed
+    man = w.create_file("/walk%d" % seed, ino, n, bs)
+    want = synth.file_bytes(ino, n, bs)
+    rng = np.random.default_rng(seed)
+    with F.CurvineFileSystem(_conf(sc, 1, "64KB", threads=3, batch=3, zero_copy=zero_copy, copy_group=2, register_threads=1, register_cache="64MB")) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/walk%d" % seed)
+        pos = 0
+        for step in range(120):
+            op = rng.integers(0, 4)
+            if op == 0:
+                pos = int(rng.choice([0, n, n - 1, int(rng.integers(0, n)), int(rng.integers(0, n)), n + 5000]))
+                r.seek(pos)
+                assert r.pos() == pos
+            elif op == 1:
+                k = int(rng.choice([0, 1, 100, 65536, bs + 1, 3 * bs]))
+                got = r.read(k)
+                exp = want[pos:pos + k] if pos < n else b""
+                # Reader::read returns at most the current chunk: a prefix of the expectation, non-empty unless at EOF or k == 0
+                assert exp.startswith(got) and (len(got) > 0 or k == 0 or pos >= n), (step, pos, k, len(got))
+                pos += len(got)
+            else:
+                cap = int(rng.choice([0, 7, 4096, bs - 3, bs, 2 * bs + 11, 5 * bs]))
+                dst = _dev_buf(cap + 16, cuda)
+                got = r.read_device(dst.data_ptr(), cap, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                exp = want[pos:pos + cap] if pos < n else b""
+                assert got == len(exp), (step, pos, cap, got)
+                host = dst.cpu().numpy()
+                assert host[:got].tobytes() == exp and (host[got:] == 0xA5).all()
+                pos += got
+            assert r.pos() == pos
+        assert r.verify()[1] == 0
+        r.complete()

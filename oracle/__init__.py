@@ -2,8 +2,10 @@
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
 only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
-``--impl reference`` legs may import, link or execute it, and there only as the
-checker (or as the timed CPU baseline), never as the thing shipped.
+``--impl reference`` legs may import, link or execute it (plus the measurement
+scripts ``tools/c3_ssd_tier.py`` / ``tools/c5_smallfiles.py``, which time its CPU
+reader beside the GPU path exactly as bench.py's CPU-baseline leg does), and there
+only as the checker (or as the timed CPU baseline), never as the thing shipped.
 
 It is a *restatement* of the reference's algorithm for this path, written from
 the reference sources cited function by function (paths relative to

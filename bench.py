@@ -1,22 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- sequential read GB/s into HBM (CRC-verified), the metric BASELINE.json names.
 
-    python bench.py --gpus N --steps K --warmup W            # this implementation
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU read path (oracle port)
+    python bench.py --gpus N --steps K --warmup W                      # this implementation
+    python bench.py --impl reference --gpus N --steps K --warmup W     # the reference's CPU read path (oracle port)
+    python bench.py --config c4 --gpus N                               # model distribution: every GPU ends up with the whole file
     (N > 1: launched by torchrun, one rank per GPU)
 
-Workload (config C2 of BASELINE.json, scaled weakly: C3's shape at N=8): one synthetic file of N x 16 GiB in
-4 MiB blocks in a mem-tier (tmpfs) BlockStore served by an in-process worker; GPU g reads the blocks
-b % N == g (16 GiB per GPU).  A step = one full pass:
-  e2e    through the public C ABI (cv_open -> cv_read_device[_sharded] -> cv_verify -> cv_close_reader): block
-         files -> worker protocol -> pinned host ring -> cudaMemcpyAsync H2D -> on-GPU CRC-32C -> compare
-         with the manifest -> D2H of the per-block CRCs and the mismatch count.  Host buffers in, HBM out.
-  value  the same verify pass with the bytes already resident in HBM (K1 over every block + compare).
-Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
-Inputs (16 GiB per GPU) are >> L2 (126 MB), so no L2 flush is needed between iterations.
+Workload (config C2 of BASELINE.json per GPU, scaled weakly: C3's shape at N=8): synthetic files of N x 16 GiB in 4 MiB
+blocks in the worker's mem tier; GPU g reads the blocks b % N == g (16 GiB per GPU).  EVERY step reads a file that no client
+has read before: rank 0 writes a fresh file (new inode, new bytes) before the step and drops the one read two steps ago, all
+outside the timed region.  A step = one full pass through the public C ABI:
+    cv_open -> cv_read_device[_sharded] -> cv_verify -> cv_close_reader
+block locations -> worker Open/Complete RPCs per block -> DMA of the block bytes from host memory into HBM -> on-GPU CRC-32C
+(K1) -> compare with the manifest on the GPU -> D2H of the per-block CRCs and the mismatch count.  Host bytes in, HBM out.
+    value   the ingest rate of those steps, timed on the device from the first H2D copy to the verified result (CUDA events on the
+            calling stream around cv_read_device .. cv_verify), max over ranks
+    e2e     the same steps timed around the whole reader life cycle (cv_open .. cv_close_reader): what a caller sees
+Beside the headline (mem-ARENA tier: blocks are extents of segments the client pinned once at mount, arena.h) the line reports
+the same read over the reference's one-file-per-block mem tier through the pinned ring (`e2e_pread`), over TCP frames unpacked by
+K2 on the GPU (`e2e_framed`), a re-read of an already-read file (`e2e_reread`), the HBM-resident K1 verify rate (`resident_verify`,
+`roofline`) and the reference's CPU reader on the host cores (`cpu_baseline`).
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  Inputs (16 GiB per GPU per
+step, never the same bytes twice) are >> L2 (126 MB): no L2 flush needed.
 """
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import shutil
@@ -32,6 +41,8 @@ sys.path.insert(0, ROOT)
 METRIC = "sequential read GB/s into HBM (CRC-verified)"
 UNIT = "GB/s"
 BLOCK = 4 << 20
+PCIE_RAW = 63.0  # PCIe Gen5 x16 per direction, GB/s
+SEG = 1 << 30
 
 
 def parse():
@@ -40,22 +51,24 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"])
     ap.add_argument("--gib-per-gpu", type=float, default=16.0)
-    ap.add_argument("--mode", default="short_circuit", choices=["short_circuit", "framed"])
+    ap.add_argument("--mode", default="short_circuit", choices=["short_circuit", "framed"], help="read path of the headline steps")
+    ap.add_argument("--tier", default="arena", choices=["arena", "files"], help="mem tier of the headline steps: pinned-once arena (arena.h) or the reference's one file per block")
+    ap.add_argument("--pool", type=int, default=2, help="files kept alive at once; a step's file is dropped `pool` steps later")
     ap.add_argument("--fetch-threads", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--verify-batch", type=int, default=16)
     ap.add_argument("--copy-group", type=int, default=8)
     ap.add_argument("--copy-streams", type=int, default=1)
-    ap.add_argument("--register-threads", type=int, default=16, help="background registrar threads (0 = register inline on first touch)")
+    ap.add_argument("--register-threads", type=int, default=16)
+    ap.add_argument("--register-slice", default="256MB")
     ap.add_argument("--numa-node", type=int, default=-1, help="-1 bind fetch threads to the GPU's node, -2 no binding")
-    ap.add_argument("--register-when-idle", type=int, default=1, help="1: registrar threads yield to reads in flight (cold pass at ring speed); 0: register concurrently")
-    ap.add_argument("--zero-copy", type=int, default=1, help="short-circuit: DMA from registered mmaps of the mem-tier block files")
-    ap.add_argument("--also-pread", action="store_true", help="additionally report e2e over the pinned-ring (pread) path")
     ap.add_argument("--gpu-chunk", default="4MB")
+    ap.add_argument("--framed-threads", type=int, default=0)
     ap.add_argument("--poly", type=int, default=1)
+    ap.add_argument("--side-steps", type=int, default=2, help="timed steps of each side leg (reread / pread / framed); 0 skips them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--also-framed", action="store_true", help="additionally report e2e over the framed (TCP) path")
     ap.add_argument("--dir", default="")
     return ap.parse_args()
 
@@ -80,17 +93,14 @@ class ClockSampler:
         for line in self.p.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def mark(self):
-        return time.time()
-
     def stop(self):
         if self.p:
             self.p.terminate()
 
-    def summary(self, t0, t1):
+    def summary(self, windows):
         sm, mx, reasons = [], 0.0, set()
         for t, r in self.rows:
-            if len(r) < 8 or not (t0 <= t <= t1 + 0.2):
+            if len(r) < 8 or not any(t0 <= t <= t1 + 0.2 for t0, t1 in windows):
                 continue
             try:
                 sm.append(float(r[1]))
@@ -132,83 +142,6 @@ def barrier(dist, cuda=True):
         torch.cuda.synchronize()
 
 
-def make_cluster(args, rank, world, dist, gib_total):
-    """rank 0 hosts the worker + generates the file; everyone gets (manifest, port)."""
-    from curvine_b200 import fs as F
-    n = int(gib_total * (1 << 30)) // BLOCK * BLOCK
-    state = {}
-    if rank == 0:
-        base = args.dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
-        d = tempfile.mkdtemp(prefix="cvbench_", dir=base)
-        w = F.MiniWorker(["[MEM]" + d], hostname="localhost")
-        if args.impl == "ours":  # mem tier placed NUMA-locally to the GPU that will ingest each block (b % world)
-            from curvine_b200 import _lib
-            _lib.lib().cv_synth_set_shard_world(world)
-        t0 = time.time()
-        man = w.create_file("/bench/file", 4242, n, BLOCK, storage_type=0, threads=min(64, os.cpu_count() or 8))
-        # a second, small file: read once before the timed loop so that the context is warm (pinned ring allocated, worker
-        # connections open, kernels loaded) and step 0 measures a cold FILE, not a cold process
-        man_warm = w.create_file("/bench/ctxwarm", 4243, 16 * world * BLOCK, BLOCK, storage_type=0, threads=8)
-        state.update(dir=d, worker=w, gen_sec=time.time() - t0)
-        payload = [man, w.port, man_warm]
-    else:
-        payload = [None, None, None]
-    if dist is not None:
-        dist.broadcast_object_list(payload, src=0)
-    state.update(manifest=payload[0], port=payload[1], file_len=n, manifest_warm=payload[2])
-    return state
-
-
-def teardown(state):
-    if "worker" in state:
-        state["worker"].stop()
-        shutil.rmtree(state["dir"], ignore_errors=True)
-
-
-def client_conf(args, sc, device, threads, slots, zero_copy=None, copy_group=None):
-    from curvine_b200 import fs as F
-    zc = args.zero_copy if zero_copy is None else zero_copy
-    b200 = ('device = %d\nfetch_threads = %d\npinned_slots = %d\nverify_poly = %d\nverify = true\nverify_batch = %d\ncopy_group = %d\ngpu_chunk_size = "%s"\n'
-            'zero_copy = %s\nregister_cache = "%dGB"\ncopy_streams = %d\nnuma_node = %d\nregister_threads = %d\nregister_when_idle = %s\n'
-            % (device, threads, slots, args.poly, args.verify_batch, args.copy_group if copy_group is None else copy_group, args.gpu_chunk,
-               "true" if zc else "false", int(args.gib_per_gpu * 1.5) + 1, args.copy_streams, args.numa_node, args.register_threads, "true" if args.register_when_idle else "false"))
-    return F.client_conf(hostname="localhost", short_circuit=sc, b200=b200)
-
-
-def run_e2e(fs, path, rank, world, dst, shard_bytes, steps, warmup, dist, wait_registered=False):
-    """-> (per-step ms list over timed steps, stats of the last step)."""
-    import torch
-    stream = torch.cuda.current_stream().cuda_stream
-    times, warm, stats, last = [], [], None, None
-    run_e2e.registration_ms = None
-    for it in range(warmup + steps):
-        barrier(dist)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = fs.open(path)
-        if world == 1:
-            got = r.read_device(dst.data_ptr(), shard_bytes, stream)
-        else:
-            got = r.read_device_sharded(rank, world, dst.data_ptr(), shard_bytes, stream)
-        s, bad, ver = r.verify()  # blocks until the CRCs and the mismatch count are back on the host (D2H)
-        b.record()
-        b.synchronize()
-        stats = r.device_stats()
-        r.complete()
-        assert bad == 0, "CRC mismatch in %d blocks" % bad
-        assert got == shard_bytes and ver == shard_bytes // BLOCK, (got, ver)
-        last = s
-        (times if it >= warmup else warm).append(a.elapsed_time(b))
-        if it == 0 and wait_registered and warmup > 0:
-            # the cold pass went through the pinned ring; its block files are mmap'ed + cudaHostRegister'ed in the background
-            # while no read is in flight.  Let that finish here (untimed step gap) so the steady state is the zero-copy path.
-            t0 = time.time()
-            fs.wait_registered()
-            run_e2e.registration_ms = (time.time() - t0) * 1e3
-    run_e2e.warmup_ms = warm
-    return times, stats, last
-
-
 _REAL_STDOUT = None
 
 
@@ -226,11 +159,147 @@ def emit(obj):
     _REAL_STDOUT.flush()
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------ cluster (rank 0 hosts the workers and writes the files)
+
+class Cluster:
+    """Two in-process workers on rank 0: `arena` ([MEM] dirs kept as pinned-once arenas, one per GPU, each on its GPU's NUMA
+    node) and `files` (the reference layout: one tmpfs file per block).  Files are created on demand and dropped again."""
+
+    def __init__(self, args, rank, world, dist, shard_bytes, need_files_tier):
+        from curvine_b200 import _lib, fs as F
+        self.args, self.rank, self.world, self.dist, self.F = args, rank, world, dist, F
+        self.shard_bytes = shard_bytes
+        self.live = {}  # path -> (worker key, inode, blocks)
+        self.gen_sec = 0.0
+        payload = [None]
+        if rank == 0:
+            base = args.dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+            self.dir = tempfile.mkdtemp(prefix="cvbench_", dir=base)
+            L = _lib.lib()
+            nodes = [int(L.cv_gpu_numa_node(g)) for g in range(world)]
+            cap = (args.pool + 1) * shard_bytes + SEG + (64 << 20)  # pool + the file being written + quarantine slack
+            dirs = ["[MEM:%d]%s/arena%d" % (cap, self.dir, g) for g in range(world)]
+            t0 = time.time()
+            self.arena = F.MiniWorker(dirs, hostname="localhost",
+                                      extra_worker='mem_arena = true\narena_segment = "%d"\narena_numa = [%s]\narena_reuse_delay = "1s"\n'
+                                                   % (SEG, ", ".join(str(n) for n in nodes)))
+            self.arena_start_sec = time.time() - t0
+            self.files = F.MiniWorker(["[MEM]%s/files%d" % (self.dir, g) for g in range(world)], hostname="localhost") if need_files_tier else None
+            L.cv_synth_set_shard_world(world)  # block b -> dir b % world, first-touched on GPU (b % world)'s node
+            payload = [{"dir": self.dir, "arena_port": self.arena.port, "files_port": self.files.port if self.files else 0, "nodes": nodes,
+                        "arena_stats": self.arena.arena_stats(), "arena_start_sec": self.arena_start_sec}]
+        if dist is not None:
+            dist.broadcast_object_list(payload, src=0)
+        self.info = payload[0]
+        self.dir = self.info["dir"]
+
+    def create(self, tier, path, inode, nbytes):
+        """rank 0 writes the file; every rank gets the manifest text."""
+        payload = [None]
+        if self.rank == 0:
+            w = self.arena if tier == "arena" else self.files
+            t0 = time.time()
+            payload = [w.create_file(path, inode, nbytes, BLOCK, storage_type=0, threads=min(64, os.cpu_count() or 8))]
+            self.gen_sec += time.time() - t0
+            self.live[path] = (tier, inode, (nbytes + BLOCK - 1) // BLOCK)
+        if self.dist is not None:
+            self.dist.broadcast_object_list(payload, src=0)
+        return payload[0]
+
+    def drop(self, path):
+        if self.rank == 0 and path in self.live:
+            tier, inode, nb = self.live.pop(path)
+            (self.arena if tier == "arena" else self.files).delete_file(inode, nb)
+
+    def close(self):
+        if self.rank == 0:
+            from curvine_b200 import _lib
+            _lib.lib().cv_synth_set_shard_world(0)
+            self.arena.stop()
+            if self.files:
+                self.files.stop()
+            shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def client_conf(args, cluster, sc, device, threads, slots, rank, zero_copy=True, copy_group=None, chunk=None):
+    from curvine_b200 import fs as F
+    b200 = ('device = %d\nfetch_threads = %d\npinned_slots = %d\nverify_poly = %d\nverify = true\nverify_batch = %d\ncopy_group = %d\ngpu_chunk_size = "%s"\n'
+            'zero_copy = %s\nregister_threads = %d\nregister_cache = "%dGB"\ncopy_streams = %d\nnuma_node = %d\narena_preregister = ["%s/arena%d"]\n'
+            'arena_register_slice = "%s"\n'
+            % (device, threads, slots, args.poly, args.verify_batch, args.copy_group if copy_group is None else copy_group, chunk or args.gpu_chunk,
+               "true" if zero_copy else "false", args.register_threads, int(args.gib_per_gpu * 1.5) + 1, args.copy_streams, args.numa_node, cluster.dir, rank, args.register_slice))
+    return F.client_conf(hostname="localhost", short_circuit=sc, b200=b200)
+
+
+def timed_read(fs, path, rank, world, dst, shard_bytes, stream):
+    """One step through the C ABI.  -> (e2e_ms, ingest_ms, sum_crc, stats).  CUDA events on the calling stream; cv_verify blocks
+    until the CRCs and the mismatch count are back on the host, so the closing events are complete when they are read."""
+    import torch
+    a, a2, b2, b = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    a.record()
+    r = fs.open(path)
+    a2.record()
+    if world == 1:
+        got = r.read_device(dst.data_ptr(), shard_bytes, stream)
+    else:
+        got = r.read_device_sharded(rank, world, dst.data_ptr(), shard_bytes, stream)
+    s, bad, ver = r.verify()
+    b2.record()
+    stats = r.device_stats()
+    r.complete()
+    b.record()
+    b.synchronize()
+    assert bad == 0, "CRC mismatch in %d blocks of %s" % (bad, path)
+    assert got == shard_bytes and ver == shard_bytes // BLOCK, (got, ver, shard_bytes)
+    return a.elapsed_time(b), a2.elapsed_time(b2), s, stats
+
+
+def run_leg(name, cluster, fs, tier, args, rank, world, dist, dst, shard_bytes, steps, warmup, fresh, inode0, sampler=None):
+    """steps+warmup passes; fresh=True: every pass reads a file written just before it (never read by anyone), and the file of
+    `pool` passes ago is dropped; fresh=False: one file, read again and again.  -> dict(e2e_ms[], ingest_ms[], warm_ms[], stats)."""
+    import torch
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {"e2e_ms": [], "ingest_ms": [], "warm_e2e_ms": [], "windows": []}
+    paths = []
+    n_total = shard_bytes * world
+    for it in range(warmup + steps):
+        if fresh or it == 0:
+            path = "/bench/%s_%d" % (name, it)
+            fs.load_namespace(cluster.create(tier, path, inode0 + it, n_total))
+            paths.append(path)
+            if fresh and len(paths) > args.pool:
+                cluster.drop(paths.pop(0))
+        barrier(dist)
+        t0 = time.time()
+        e2e_ms, ing_ms, s, stats = timed_read(fs, paths[-1], rank, world, dst, shard_bytes, stream)
+        barrier(dist)
+        if it >= warmup:
+            out["e2e_ms"].append(e2e_ms)
+            out["ingest_ms"].append(ing_ms)
+            out["windows"].append((t0, time.time()))
+        else:
+            out["warm_e2e_ms"].append(e2e_ms)
+        out["stats"], out["sum_crc"] = stats, s
+    for p in paths:
+        cluster.drop(p)
+    return out
+
+
 def main():
     args = parse()
     quiet_stdout()
     if args.impl == "reference":
         return main_reference(args)
+    if args.config == "c4":
+        from tools import c4_allgather
+        return c4_allgather.main_bench(args, emit)
+    if args.config == "c5":
+        from tools import c5_smallfiles
+        return c5_smallfiles.main_bench(args, emit)
     import numpy as np
     import torch
     from curvine_b200 import _lib, fs as F, kernels as K
@@ -239,128 +308,101 @@ def main():
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
     L = _lib.lib()
     _lib.check(L.cvk_init(local), "cvk_init")
-    state = make_cluster(args, rank, world, dist, args.gib_per_gpu * world)
-    n_total = state["file_len"]
-    nb_total = n_total // BLOCK
-    my_blocks = len(range(rank, nb_total, world))
-    shard_bytes = my_blocks * BLOCK
+    shard_bytes = int(args.gib_per_gpu * (1 << 30)) // BLOCK * BLOCK
+    n_total = shard_bytes * world
+    my_blocks = shard_bytes // BLOCK
     ncpu = os.cpu_count() or 8
     threads = args.fetch_threads or max(4, min(16, ncpu // (2 * world)))
+    fthreads = args.framed_threads or max(4, min(24, ncpu // (2 * world)))
     slots = args.slots or (2 * args.verify_batch + threads + 8)
+    side = args.side_steps
+    cluster = Cluster(args, rank, world, dist, shard_bytes, need_files_tier=True)
     dst = torch.empty(shard_bytes, dtype=torch.uint8, device="cuda")
     sampler = ClockSampler(local)
     sampler.start()
     out = {}
     try:
-        fs = F.CurvineFileSystem(client_conf(args, args.mode == "short_circuit", local, threads, slots))
-        fs.load_namespace(state["manifest"])
-        fs.load_namespace(state["manifest_warm"])
-        # ---- context warm-up on the small file (untimed): ring allocation, worker connections, kernel module load
+        sc = args.mode == "short_circuit"
+        fs = F.CurvineFileSystem(client_conf(args, cluster, sc, local, threads, slots, rank))
+        # ---- mount: map + pin this rank's arena (off every read path), then one small read so the process is warm
         t0 = time.time()
-        r0 = fs.open("/bench/ctxwarm")
-        if world == 1:
-            r0.read_device(dst.data_ptr(), 16 * BLOCK, torch.cuda.current_stream().cuda_stream)
-        else:
-            r0.read_device_sharded(rank, world, dst.data_ptr(), 16 * BLOCK, torch.cuda.current_stream().cuda_stream)
-        _, bad0, _ = r0.verify()
-        ctx_stats = r0.device_stats()
-        r0.complete()
-        assert bad0 == 0
+        fs.preregister()
+        fs.wait_registered()
+        mount_ms = (time.time() - t0) * 1e3
+        arena0 = fs.arena_stats()
+        t0 = time.time()
+        fs.load_namespace(cluster.create(args.tier, "/bench/ctxwarm", 4100, 16 * world * BLOCK))
+        timed_read(fs, "/bench/ctxwarm", rank, world, dst, 16 * BLOCK, torch.cuda.current_stream().cuda_stream)
+        cluster.drop("/bench/ctxwarm")
         ctx_warm_ms = (time.time() - t0) * 1e3
-        # ---- e2e: host buffers -> HBM through the C ABI
-        t_a = sampler.mark()
-        zc_on = bool(args.zero_copy and args.mode == "short_circuit")
-        e2e_ms, stats, sum_crc = run_e2e(fs, "/bench/file", rank, world, dst, shard_bytes, args.steps, args.warmup, dist, wait_registered=zc_on)
-        e2e_warm_ms = list(run_e2e.warmup_ms)  # step 0 is the cold pass over the file (pinned ring; mappings not registered yet)
-        registration_ms = run_e2e.registration_ms
-        t_b = sampler.mark()
-        # ---- value: same verify pass, bytes already in HBM (what landed in the last e2e step)
-        blocks = np.arange(rank, nb_total, world, dtype=np.int64)
-        man_crc = {}
-        for line in state["manifest"].splitlines():
-            if line.startswith("block "):
-                f = line.split()
-                man_crc[int(f[1])] = (int(f[4], 16), int(f[5], 16))
-        # block_id = inode << 24 | seq (inode_id.rs:48-60)
-        exp = np.array([man_crc[(4242 << 24) | int(b)][1 if args.poly else 0] for b in blocks], dtype=np.uint32)
+        # ---- headline: every step reads a never-read file
+        launches0 = K.launch_count()
+        head = run_leg("fresh", cluster, fs, args.tier, args, rank, world, dist, dst, shard_bytes, args.steps, args.warmup, True, 5000)
+        launches = (K.launch_count() - launches0) * args.steps // max(1, args.steps + args.warmup)
+        arena1 = fs.arena_stats()
+        # ---- side legs
+        reread = pread = framed = None
+        if side > 0:
+            reread = run_leg("reread", cluster, fs, args.tier, args, rank, world, dist, dst, shard_bytes, side, 1, False, 6000)
+        # ---- resident verify (K1 over what the last step left in HBM) + roofline of K1
+        fs.load_namespace(cluster.create(args.tier, "/bench/resident", 4200, n_total))
+        _, _, sum_crc, _ = timed_read(fs, "/bench/resident", rank, world, dst, shard_bytes, torch.cuda.current_stream().cuda_stream)
+        
         d_off = torch.arange(my_blocks, dtype=torch.int64, device="cuda") * BLOCK
         d_len = torch.full((my_blocks,), BLOCK, dtype=torch.int64, device="cuda")
-        d_exp = torch.from_numpy(exp.view(np.int32)).cuda()
         d_crc = torch.empty(my_blocks, dtype=torch.int32, device="cuda")
-        d_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
         def resident_step():
             _lib.check(L.cvk_crc_blocks(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(d_off.data_ptr()), ctypes.c_void_p(d_len.data_ptr()),
                                         my_blocks, args.poly, shard_bytes, ctypes.c_void_p(d_crc.data_ptr()), stream), "cvk_crc_blocks")
-            _lib.check(L.cvk_verify_crcs(ctypes.c_void_p(d_crc.data_ptr()), ctypes.c_void_p(d_exp.data_ptr()), my_blocks,
-                                         ctypes.c_void_p(d_bad.data_ptr()), None, stream), "cvk_verify_crcs")
 
-        for _ in range(args.warmup):
+        for _ in range(3):
             resident_step()
         barrier(dist)
-        launches0 = K.launch_count()
         L.cvk_profile_enable(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_c = sampler.mark()
+        t_c = time.time()
         a.record()
-        for _ in range(args.steps):
+        for _ in range(5):
             resident_step()
         b.record()
         barrier(dist)
-        t_d = sampler.mark()
-        val_ms = a.elapsed_time(b) / args.steps
-        if os.environ.get("CVB_DEBUG"):
-            ev = []
-            for _ in range(3):
-                x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                t0 = time.time()
-                x.record()
-                resident_step()
-                y.record()
-                t1 = time.time()
-                y.synchronize()
-                ev.append((x.elapsed_time(y), (t1 - t0) * 1e3))
-            print("[debug rank %d] torch dev %d val_ms %.3f per-step (gpu_ms, host_enqueue_ms) %s" % (rank, torch.cuda.current_device(), val_ms, ev),
-                  file=sys.stderr, flush=True)
+        t_d = time.time()
+        res_ms = a.elapsed_time(b) / 5
         walk_ms, walk_n = ctypes.c_double(), ctypes.c_uint32()
         _lib.check(L.cvk_profile_collect(ctypes.byref(walk_ms), ctypes.byref(walk_n)), "cvk_profile_collect")
         L.cvk_profile_enable(0)
-        launches = K.launch_count() - launches0
-        assert int(d_bad.item()) == 0, "resident verify found mismatches"
-        assert int(d_crc.cpu().numpy().view(np.uint32).astype(np.uint64).sum()) == sum_crc
-
-        # ---- optional: e2e over the pinned-ring (pread) path and over the framed path
-        pread = None
-        if args.also_pread:
-            fs3 = F.CurvineFileSystem(client_conf(args, True, local, threads, slots, zero_copy=0, copy_group=1))
-            fs3.load_namespace(state["manifest"])
-            p_ms, p_stats, _ = run_e2e(fs3, "/bench/file", rank, world, dst, shard_bytes, max(2, args.steps // 2), 2, dist)
-            pread = (p_ms, p_stats)
-            fs3.close()
-        framed = None
-        if args.also_framed:
-            fs2 = F.CurvineFileSystem(client_conf(args, False, local, threads, slots))
-            fs2.load_namespace(state["manifest"])
-            f_ms, f_stats, _ = run_e2e(fs2, "/bench/file", rank, world, dst, shard_bytes, max(2, args.steps // 2), 1, dist)
-            framed = (f_ms, f_stats)
-            fs2.close()
+        assert int(d_crc.cpu().numpy().view(np.uint32).astype(np.uint64).sum()) == sum_crc, "resident K1 pass disagrees with the ingest's CRCs"
+        cluster.drop("/bench/resident")
         fs.close()
+        if side > 0:
+            # reference layout (one tmpfs file per block), never-read files, through the pinned ring
+            fs3 = F.CurvineFileSystem(client_conf(args, cluster, True, local, threads, slots, rank, zero_copy=False, copy_group=1))
+            pread = run_leg("pread", cluster, fs3, "files", args, rank, world, dist, dst, shard_bytes, side, 1, True, 7000)
+            fs3.close()
+            # TCP frames from the arena worker (send(2) out of its mapping), received verbatim, unpacked + CRC'd by K2
+            fs2 = F.CurvineFileSystem(client_conf(args, cluster, False, local, fthreads, 2 * args.verify_batch + fthreads + 8, rank))
+            framed = run_leg("framed", cluster, fs2, "arena", args, rank, world, dist, dst, shard_bytes, side, 1, True, 8000)
+            fs2.close()
 
         # ---- max over ranks
         def maxr(x):
-            if dist is None:
+            if dist is None or x is None:
                 return x
             t = torch.tensor([x], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
 
-        e2e_step_ms = maxr(sum(e2e_ms) / len(e2e_ms))
-        e2e_best_ms = maxr(min(e2e_ms))
-        val_ms = maxr(val_ms)
+        def mean(v):
+            return sum(v) / len(v) if v else None
+
+        e2e_ms = maxr(mean(head["e2e_ms"]))
+        ing_ms = maxr(mean(head["ingest_ms"]))
+        res_ms = maxr(res_ms)
         walk_avg_ms = maxr(walk_ms.value / max(1, walk_n.value))
-        framed_ms = maxr(sum(framed[0]) / len(framed[0])) if framed else None
-        pread_ms = maxr(sum(pread[0]) / len(pread[0])) if pread else None
+        side_ms = {k: maxr(mean(v["e2e_ms"])) if v else None for k, v in (("reread", reread), ("pread", pread), ("framed", framed))}
+        per_step_e2e = [maxr(x) for x in head["e2e_ms"]]
 
         if rank == 0:
             peaks = {}
@@ -369,57 +411,56 @@ def main():
             except Exception:
                 pass
             hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-            traffic = None
-            try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_ncu_summary.json"))).get("dram_bytes_per_launch_at_16GiB")
-            except Exception:
-                pass
-            total_bytes = n_total
-            pcie_raw = 63.0
-            e2e_val = total_bytes / e2e_step_ms / 1e6
+            gbps = lambda ms: n_total / ms / 1e6 if ms else None
+            e2e_val, ing_val = gbps(e2e_ms), gbps(ing_ms)
+            stats = head["stats"]
             out = {
-                "metric": METRIC, "value": total_bytes / val_ms / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": val_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "C2: 16 GiB synthetic file per GPU, 4 MiB blocks, mem-tier (tmpfs) BlockStore, "
-                                       "blocks round-robin across GPUs (C3 shape at N=8), on-GPU CRC-%s verify" % ("32C" if args.poly else "32"),
-                           "file_bytes": total_bytes, "block_bytes": BLOCK, "blocks_per_gpu": my_blocks, "read_path": args.mode, "zero_copy": bool(args.zero_copy and args.mode == "short_circuit"),
-                           "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch, "copy_group": args.copy_group, "register_threads": args.register_threads, "register_when_idle": bool(args.register_when_idle),
-                           "l2": "inputs (16 GiB per GPU) are larger than L2; no flush needed", "host_cpus": ncpu},
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) if world == 1 else shard_bytes * world,
-                        "d2h_bytes_per_step": 4 * (my_blocks + 4) * world, "ms_per_step": e2e_step_ms, "best_ms": e2e_best_ms, "timed_steps_ms": e2e_ms,
-                        "warmup_steps_ms": e2e_warm_ms, "cold_first_step_GBps": total_bytes / e2e_warm_ms[0] / 1e6 if e2e_warm_ms else None,
-                        "cold_note": "step 0 = first read of the file in a warm context (64 MiB read of another file first: %.0f ms, of which pinned-ring "
-                                     "allocation %.0f ms); cold blocks go through the pinned ring, then the registrar maps + cudaHostRegisters "
-                                     "them while no read is in flight (waited for once after step 0: registration_ms)" % (ctx_warm_ms, 1e3 * ctx_stats["ring_alloc_sec"]),
-                        "registration_ms": registration_ms, "context_warmup_ms": ctx_warm_ms,
-                        "per_gpu_GBps": e2e_val / world, "frac_of_pcie_gen5_x16_raw_63GBps": e2e_val / world / pcie_raw,
-                        "frac_of_measured_h2d_55.6GBps": e2e_val / world / 55.6,
-                        "last_step_fetch_thread_sec": stats["fetch_sec"], "last_step_wall_sec": stats["wall_sec"],
-                        "registered_mapping_cache": {"hits": stats["reg_hits"], "misses": stats["reg_misses"]}},
+                "metric": METRIC, "value": ing_val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ing_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "value_is": "device-timed ingest of never-read files: first H2D copy .. CRCs verified and back on the host (cv_read_device + cv_verify), max over ranks",
+                "config": {"workload": "C2 per GPU: %g GiB synthetic file per GPU per step, 4 MiB blocks, mem tier = %s, blocks round-robin across GPUs "
+                                       "(C3 shape at N=8), on-GPU CRC-%s verify; every step reads a file nobody has read before"
+                                       % (args.gib_per_gpu, "pinned-once arena (arena.h)" if args.tier == "arena" else "one tmpfs file per block", "32C" if args.poly else "32"),
+                           "file_bytes": n_total, "block_bytes": BLOCK, "blocks_per_gpu": my_blocks, "read_path": args.mode, "mem_tier": args.tier,
+                           "fresh_file_every_step": True, "file_pool": args.pool, "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch,
+                           "copy_group": args.copy_group, "arena_segment_bytes": SEG, "arena_register_slice": args.register_slice,
+                           "l2": "inputs (%g GiB per GPU per step, new bytes every step) are larger than L2; no flush needed" % args.gib_per_gpu, "host_cpus": ncpu},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) * world, "d2h_bytes_per_step": 4 * (my_blocks + 4) * world,
+                        "ms_per_step": e2e_ms, "timed_steps_ms": per_step_e2e, "warmup_steps_ms": head["warm_e2e_ms"],
+                        "what": "cv_open -> cv_read_device[_sharded] -> cv_verify -> cv_close_reader on a file written just before the step (never read), "
+                                "host memory in, HBM + CRCs out",
+                        "per_gpu_GBps": e2e_val / world, "frac_of_pcie_gen5_x16_raw_63GBps": e2e_val / world / PCIE_RAW,
+                        "last_step_fetch_thread_sec": stats["fetch_sec"], "last_step_wall_sec": stats["wall_sec"]},
+                "mount": {"arena_map_and_pin_ms": mount_ms, "pinned_bytes": arena0["pinned_bytes"], "segments": arena0["segments"],
+                          "pin_GBps": arena0["pinned_bytes"] / max(arena0["register_us"], 1) / 1e3, "context_warmup_ms": ctx_warm_ms,
+                          "worker_arena_create_populate_sec": cluster.info["arena_start_sec"],
+                          "note": "paid once per client context, before any read; segments pinned after the headline steps: %d (unchanged = no per-file registration)" % arena1["segments"]},
+                "arena_dma": {"block_jobs": arena1["dma_jobs"] - arena0["dma_jobs"], "bytes": arena1["dma_bytes"] - arena0["dma_bytes"],
+                              "registered_mapping_cache_hits": stats["reg_hits"], "pinned_ring_allocated": stats["ring_alloc_sec"] > 0},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "walk_kernel<CRC,!DST> (K1 CRC verify)",
-                             "achieved": shard_bytes / walk_avg_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": shard_bytes / walk_avg_ms / 1e6 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                             "note": "K1 only reads (N bytes in, 4 bytes per block out) while the peak is a read+write copy rate, so frac can exceed 1; "
-                                     "a bare read-only kernel in the same layout measured 7,150 GB/s on this GPU (profiles/r01_pattern_probe.txt)",
+                "resident_verify": {"value": gbps(res_ms), "unit": UNIT, "ms": res_ms, "what": "K1 + fold over the bytes already in HBM (no ingest): an HBM-bound kernel rate, not a read rate"},
+                "roofline": {"bound": "hbm", "kernel": "walk_kernel<CRC,!DST> (K1 CRC verify)", "achieved": shard_bytes / walk_avg_ms / 1e6, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": shard_bytes / walk_avg_ms / 1e6 / hbm_peak, "traffic": ncu_traffic(shard_bytes), "peak_source": peak_src,
+                             "note": "K1 only reads (N bytes in, 4 bytes per block out) while the peak is a read+write copy rate, so frac can exceed 1. The metric itself "
+                                     "is bound by PCIe ingest (e2e.frac_of_pcie_gen5_x16_raw_63GBps), under which K1 hides completely.",
                              "algorithmic_bytes_per_launch": shard_bytes, "avg_launch_ms": walk_avg_ms, "launches_timed": int(walk_n.value)},
-                "clocks": sampler.summary(t_c, t_d),
-                "clocks_e2e": sampler.summary(t_a, t_b),
-                "setup": {"file_gen_sec": state.get("gen_sec"), "sum_crc": sum_crc},
+                "clocks": sampler.summary(head["windows"]),
+                "clocks_resident": sampler.summary([(t_c, t_d)]),
+                "setup": {"file_gen_sec_total": cluster.gen_sec, "sum_crc_last": head["sum_crc"]},
             }
-            if pread_ms:
-                out["e2e_pread"] = {"value": total_bytes / pread_ms / 1e6, "unit": UNIT, "ms_per_step": pread_ms,
-                                    "note": "short-circuit via pread into the pinned ring (no registered mappings), copy_group=1",
-                                    "fetch_thread_sec": pread[1]["fetch_sec"]}
-            if framed_ms:
-                out["e2e_framed"] = {"value": total_bytes / framed_ms / 1e6, "unit": UNIT, "ms_per_step": framed_ms,
-                                     "h2d_bytes_per_step": int(framed[1]["h2d_bytes"]), "gpu_chunk": args.gpu_chunk}
+            for k, what in (("reread", "the same (already read) arena file again: same path as the headline, nothing is cached per file"),
+                            ("pread", "reference layout (one tmpfs file per block), never-read files: pread into the pinned ring, then H2D"),
+                            ("framed", "short_circuit = false: TCP frames from the arena worker received verbatim, H2D of the wire image, K2 validates every "
+                                       "prefix, gathers and CRCs (gpu_chunk %s, %d connections)" % (args.gpu_chunk, fthreads))):
+                if side_ms[k]:
+                    v = gbps(side_ms[k])
+                    out["e2e_" + k] = {"value": v, "unit": UNIT, "ms_per_step": side_ms[k], "per_gpu_GBps": v / world,
+                                       "frac_of_pcie_gen5_x16_raw_63GBps": v / world / PCIE_RAW, "steps": side, "what": what}
             if world == 1 and not args.no_cpu_baseline:
-                out["cpu_baseline"] = cpu_baseline(state, n_total, args.mode == "short_circuit")
+                out["cpu_baseline"] = cpu_baseline(cluster, args)
     finally:
         sampler.stop()
-        teardown(state)
+        cluster.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -427,75 +468,103 @@ def main():
         emit(out)
 
 
-def cpu_run(state, n_total, sc, parallel, limit, checksum=1):
+def ncu_traffic(shard_bytes):
+    """dram bytes per K1 launch from the committed `ncu --set full` capture -- only when that capture was taken from THIS kernels.cu
+    at this launch size; anything else reports null rather than a stale constant."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")))
+        sha = hashlib.sha256(open(os.path.join(ROOT, "curvine_b200", "csrc", "kernels.cu"), "rb").read()).hexdigest()
+        if rec.get("kernels_cu_sha256") == sha and rec.get("launch_bytes") == shard_bytes:
+            return rec.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    return None
+
+
+# ------------------------------------------------------------------ the reference's CPU read path (oracle port)
+
+def cpu_run(port, n_total, sc, parallel, limit, inode, checksum=1):
     from oracle import clib, layout
-    ids = [layout.create_block_id(4242, i) for i in range(n_total // BLOCK)]
+    ids = [layout.create_block_id(inode, i) for i in range(n_total // BLOCK)]
     t0 = time.time()
-    got, cks, threads = clib.cpu_read_file(state["port"], sc, n_total, BLOCK, ids, 131072, 8, parallel, 131072, limit, checksum)
+    got, cks, threads = clib.cpu_read_file(port, sc, n_total, BLOCK, ids, 131072, 8, parallel, 131072, limit, checksum)
     dt = time.time() - t0
     return got / dt / 1e9, threads, got, cks, dt
 
 
-def cpu_baseline(state, n_total, sc):
-    """The reference's CPU read path (oracle port: per-chunk ping-pong / pread, memcpy, PCLMUL crc32 on the caller
-    thread) on a bounded sample of the same file, with the reference's default read_parallel for this file size:
-    whole-file passes (or a prefix when one pass would take too long) repeated for about 12 s of CPU work."""
+def reference_policy(n_total):
+    """The reference stripes one file over min(max_read_parallel = 8, ceil(len / large_file_size = 10 GiB)) sub-readers
+    (read_detector.rs:130-135); both arms use this one policy."""
     from oracle import clib
-    par = clib.reference_read_parallel(n_total)
-    pilot, _, _, _, _ = cpu_run(state, n_total, sc, par, 1 << 30)  # also the warm-up pass
+    return clib.reference_read_parallel(n_total)
+
+
+def cpu_baseline(cluster, args):
+    """The reference's CPU read path (oracle port: per-chunk pread / ping-pong, memcpy, PCLMUL crc32 on the caller thread) on a
+    bounded sample of the same workload in the reference's own layout (one tmpfs file per block), with the reference's
+    read_parallel for this file size; whole-file passes repeated for about 12 s of CPU work."""
+    n_total = int(args.gib_per_gpu * (1 << 30)) // BLOCK * BLOCK
+    cluster.create("files", "/bench/cpu", 9100, n_total)
+    port = cluster.info["files_port"]
+    sc = args.mode == "short_circuit"
+    par = reference_policy(n_total)
+    pilot, _, _, _, _ = cpu_run(port, n_total, sc, par, 1 << 30, 9100)  # also the warm-up pass
     sample = int(min(n_total, max(1 << 30, pilot * 1e9 * 12))) // BLOCK * BLOCK
     passes, got_total, dt_total, threads = 0, 0, 0.0, 0
     while dt_total < 12.0 and passes < 16:
-        v, threads, got, cks, dt = cpu_run(state, n_total, sc, par, sample)
+        v, threads, got, cks, dt = cpu_run(port, n_total, sc, par, sample, 9100)
         passes, got_total, dt_total = passes + 1, got_total + got, dt_total + dt
+    cluster.drop("/bench/cpu")
     return {"value": got_total / dt_total / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d pass(es) over the first %.1f GiB of the same file, read_parallel=%d (reference default for this size), 128 KiB chunks and "
-                      "buffers, %s, crc32 (PCLMUL) on the caller thread; %.1f s of wall time"
-                      % (passes, sample / 2 ** 30, par, "short-circuit pread" if sc else "framed over loopback TCP", dt_total)}
+            "sample": "%d pass(es) over the first %.1f GiB of a %g GiB file in the reference layout, read_parallel=%d (reference default for this size), "
+                      "128 KiB chunks and buffers, %s, crc32 (PCLMUL) on the caller thread; %.1f s of wall time"
+                      % (passes, sample / 2 ** 30, n_total / 2 ** 30, par, "short-circuit pread" if sc else "framed over loopback TCP", dt_total)}
 
 
 def main_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  It is Rust and cannot be built in this
-    image, so this runs the oracle port (oracle/cpu_reader.c) against the same worker/BlockStore on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path.  It is Rust and cannot be built in this image
+    (no cargo/rustc), so this times the oracle port (oracle/cpu_reader.c) on the host cores, against a worker emulator that is
+    test infrastructure too (oracle/ref_worker.c: Open/Running/Complete over a reference-layout BlockStore written by the
+    oracle's own generator) -- nothing of the product library is on this path."""
     rank, world, local, dist = setup_dist(args)
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return
-    from oracle import clib
+    from oracle import clib, refworker
     gib = args.gib_per_gpu * args.gpus
-    st = make_cluster(args, 0, 1, None, gib)
-    n_total = st["file_len"]
+    n_total = int(gib * (1 << 30)) // BLOCK * BLOCK
     sc = args.mode == "short_circuit"
+    base = args.dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+    d = tempfile.mkdtemp(prefix="cvref_", dir=base)
+    w = None
     try:
-        # the reference can stripe one file over at most max_read_parallel=8 sub-readers (+1 caller thread);
-        # its default for this size is min(8, ceil(len / 10 GiB)).  Report the better of the two settings.
-        best = None
-        for par in sorted({clib.reference_read_parallel(n_total), 8}):
-            pilot, _, _, _, _ = cpu_run(st, n_total, sc, par, 1 << 30)
-            sample = int(min(n_total, max(1 << 30, pilot * 1e9 * 6))) // BLOCK * BLOCK
-            times = []
-            for it in range(args.warmup + args.steps):
-                v, threads, got, cks, dt = cpu_run(st, n_total, sc, par, sample)
-                if it >= args.warmup:
-                    times.append(dt)
-            ms = 1e3 * sum(times) / len(times)
-            val = sample / ms / 1e6
-            if best is None or val > best[0]:
-                best = (val, ms, threads, par, sample)
-        val, ms, threads, par, sample = best
+        w = refworker.RefWorker(d)
+        w.create_file(9200, n_total, BLOCK, threads=min(64, os.cpu_count() or 8))
+        par = reference_policy(n_total)
+        pilot, _, _, _, _ = cpu_run(w.port, n_total, sc, par, 1 << 30, 9200)
+        sample = int(min(n_total, max(1 << 30, pilot * 1e9 * 6))) // BLOCK * BLOCK
+        times = []
+        for it in range(args.warmup + args.steps):
+            v, threads, got, cks, dt = cpu_run(w.port, n_total, sc, par, sample, 9200)
+            if it >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * sum(times) / len(times)
+        val = sample / ms / 1e6
         out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-               "config": {"workload": "C2: %.0f GiB synthetic file, 4 MiB blocks, mem-tier (tmpfs) BlockStore; CPU reader, bytes land in host memory" % gib,
+               "config": {"workload": "C2 per GPU: %g GiB synthetic file, 4 MiB blocks, mem-tier (tmpfs, one file per block) BlockStore; CPU reader, bytes land in host memory" % gib,
                           "file_bytes": n_total, "block_bytes": BLOCK, "read_path": args.mode, "host_cpus": os.cpu_count()},
                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "each step reads the first %.1f GiB; read_parallel=%d, 128 KiB chunks/buffers, crc32 (PCLMUL) on the caller thread"
-                                          % (sample / 2 ** 30, par)},
+                                "sample": "each step reads the first %.1f GiB; read_parallel=%d (reference default for this size), 128 KiB chunks/buffers, "
+                                          "crc32 (PCLMUL) on the caller thread; worker = oracle/ref_worker.c" % (sample / 2 ** 30, par)},
                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
     finally:
-        teardown(st)
+        if w is not None:
+            w.stop()
+        shutil.rmtree(d, ignore_errors=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -15,14 +15,14 @@ class CvFrameDesc(ctypes.Structure):
     _fields_ = [("wire_off", ctypes.c_uint64), ("dst_off", ctypes.c_uint64), ("data_len", ctypes.c_uint32),
                 ("header_len", ctypes.c_uint32), ("req_id", ctypes.c_int64), ("seq_id", ctypes.c_int32),
                 ("block", ctypes.c_uint32), ("code", ctypes.c_uint8), ("status", ctypes.c_uint8),
-                ("pad_", ctypes.c_uint8 * 6)]
+                ("pad_", ctypes.c_uint8 * 2), ("tail_clip", ctypes.c_uint32)]
 
 
 class CvStreamDesc(ctypes.Structure):
     _fields_ = [("wire_off", ctypes.c_uint64), ("dst_off", ctypes.c_uint64), ("block_len", ctypes.c_uint64),
                 ("req_id", ctypes.c_int64), ("chunk_size", ctypes.c_uint32), ("first_seq_id", ctypes.c_int32),
                 ("block", ctypes.c_uint32), ("first_frame", ctypes.c_uint32), ("code", ctypes.c_uint8),
-                ("status", ctypes.c_uint8), ("pad_", ctypes.c_uint8 * 6)]
+                ("status", ctypes.c_uint8), ("pad_", ctypes.c_uint8 * 2), ("tail_clip", ctypes.c_uint32)]
 
 
 class CvSeg(ctypes.Structure):
@@ -52,6 +52,7 @@ def _declare(L):
     L.cvk_profile_collect.argtypes, L.cvk_profile_collect.restype = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u32)], i
     L.cvk_crc_blocks.argtypes, L.cvk_crc_blocks.restype = [u8p, vp, vp, u32, i, u64, vp, vp], i
     L.cvk_verify_crcs.argtypes, L.cvk_verify_crcs.restype = [vp, vp, u32, vp, vp, vp], i
+    L.cvk_verify_crcs_masked.argtypes, L.cvk_verify_crcs_masked.restype = [vp, vp, vp, u32, vp, vp, vp], i
     L.cvk_unpack_frames.argtypes, L.cvk_unpack_frames.restype = [u8p, vp, u32, u32, u8p, i, u64, vp, vp, vp], i
     L.cvk_expand_streams.argtypes, L.cvk_expand_streams.restype = [vp, u32, vp, u32, vp], i
     L.cvk_gather_pages.argtypes, L.cvk_gather_pages.restype = [u8p, vp, u32, u64, u8p, vp], i
@@ -69,6 +70,11 @@ def _declare(L):
     L.cv_fs_load_namespace_string.argtypes, L.cv_fs_load_namespace_string.restype = [vp, c], i64
     L.cv_fs_close.argtypes, L.cv_fs_close.restype = [vp], i64
     L.cv_fs_wait_registered.argtypes, L.cv_fs_wait_registered.restype = [vp], i64
+    L.cv_fs_preregister.argtypes, L.cv_fs_preregister.restype = [vp], i64
+    L.cv_fs_arena_stats.argtypes, L.cv_fs_arena_stats.restype = [vp, cp(u64)], i64
+    L.cv_synth_delete_file.argtypes, L.cv_synth_delete_file.restype = [vp, i64, i64], i64
+    L.cv_worker_arena_stats.argtypes, L.cv_worker_arena_stats.restype = [vp, cp(i64)], i64
+    L.cv_gpu_numa_node.argtypes, L.cv_gpu_numa_node.restype = [i32], i64
     L.cv_fs_metrics.argtypes, L.cv_fs_metrics.restype = [vp, cp(i64)], i64
     L.cv_fs_pool_stats.argtypes, L.cv_fs_pool_stats.restype = [vp, cp(i64)], i64
     L.cv_open.argtypes, L.cv_open.restype = [vp, c, cp(vp), cp(i64)], i64
@@ -118,9 +124,9 @@ class CvReadStats(ctypes.Structure):
 
 
 # every symbol include/*.h declares (tests check the .so exports all of them)
-EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_unpack_frames", "cvk_expand_streams", "cvk_gather_pages",
+EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_verify_crcs_masked", "cvk_unpack_frames", "cvk_expand_streams", "cvk_gather_pages",
            "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_gather_shards_p2p", "cvk_launch_count", "cvk_tune", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
-           "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_wait_registered", "cv_fs_metrics", "cv_fs_pool_stats",
+           "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_wait_registered", "cv_fs_preregister", "cv_fs_arena_stats", "cv_synth_delete_file", "cv_worker_arena_stats", "cv_gpu_numa_node", "cv_fs_metrics", "cv_fs_pool_stats",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device",
            "cv_verify", "cv_device_stats", "cv_writer_open", "cv_write", "cv_write_device", "cv_writer_close", "cv_worker_start", "cv_worker_stop", "cv_worker_hbm_load", "cv_worker_hbm_stats", "cv_worker_hbm_tier", "cv_worker_metrics",

@@ -2,8 +2,11 @@
 // every failure becomes -(ErrorKind) plus a thread-local message (cv_last_error).
 #include <cuda_runtime.h>
 #include <nmmintrin.h>
+#include <errno.h>
+#include <fcntl.h>
 #include <sched.h>
 #include <stdlib.h>
+#include <unistd.h>
 
 #include <fstream>
 #include <thread>
@@ -129,6 +132,21 @@ int64_t cv_fs_wait_registered(cv_fs* fs) {
     gpu_ingest_wait_registered(fs->ctx.get());
     return ok();
     API_GUARD_END
+}
+
+int64_t cv_fs_preregister(cv_fs* fs) {
+    API_GUARD_BEGIN
+    API_NEED(fs);
+    API_TRY(gpu_ingest_preregister(fs->ctx.get()));
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_fs_arena_stats(cv_fs* fs, uint64_t out[5]) {
+    API_NEED(fs);
+    API_NEED(out);
+    gpu_ingest_arena_stats(fs->ctx.get(), out);
+    return ok();
 }
 
 int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]) {
@@ -433,7 +451,9 @@ int64_t cv_worker_start(const char* conf_toml, cv_worker** out, int32_t* port) {
     std::unique_ptr<cv_worker> w(new cv_worker());
     w->hostname = c.worker_hostname;
     w->w.hbm().configure(c.worker_hbm_capacity, c.worker_hbm_promote_after, c.worker_hbm_device);
-    API_TRY(w->w.start(c.worker_dirs, c.cluster_id, "", c.worker_port, c.worker_enable_send_file));
+    ArenaOpts ao;
+    ao.enable = c.worker_mem_arena, ao.seg_bytes = c.worker_arena_segment, ao.numa = c.worker_arena_numa, ao.reuse_delay_ms = c.worker_arena_reuse_delay_ms;
+    API_TRY(w->w.start(c.worker_dirs, c.cluster_id, "", c.worker_port, c.worker_enable_send_file, ao));
     if (port) *port = w->w.port();
     *out = w.release();
     return ok();
@@ -485,6 +505,33 @@ int64_t cv_worker_metrics(cv_worker* w, int64_t out[6]) {
     WorkerMetrics& m = w->w.metrics();
     out[0] = m.read_bytes, out[1] = m.read_time_us, out[2] = m.read_count, out[3] = m.read_blocks_local, out[4] = m.read_blocks_remote;
     out[5] = static_cast<int64_t>(w->w.store().num_blocks());
+    return ok();
+}
+
+int64_t cv_synth_delete_file(cv_worker* w, int64_t inode_id, int64_t n_blocks) {
+    API_GUARD_BEGIN
+    API_NEED(w);
+    for (int64_t b = 0; b < n_blocks; b++) {
+        int64_t id = 0;
+        API_TRY(create_block_id(inode_id, b, &id));
+        w->w.hbm().evict(id);
+        w->w.store().remove_block(id);
+    }
+    return ok();
+    API_GUARD_END
+}
+
+int64_t cv_worker_arena_stats(cv_worker* w, int64_t out[5]) {
+    API_NEED(w);
+    API_NEED(out);
+    memset(out, 0, 5 * sizeof(int64_t));
+    double sec = 0;
+    for (const auto& d : w->w.store().dirs())
+        if (d.arena) {
+            out[0]++, out[1] += static_cast<int64_t>(d.arena->num_segments()), out[2] = d.arena->seg_bytes(), out[3] += d.arena->used_bytes();
+            sec += d.arena->populate_sec;
+        }
+    out[4] = static_cast<int64_t>(sec * 1e6);
     return ok();
 }
 
@@ -584,6 +631,20 @@ static std::vector<std::vector<int>> gpu_node_cpus() {
     return out;
 }
 
+// NUMA node of the PCIe root the device hangs off (-1 unknown): where its mem arena and fetch threads should live
+int64_t cv_gpu_numa_node(int32_t device) {
+    char bus[64] = {0};
+    int node = -1;
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* p = bus; *p; p++) *p = static_cast<char>(tolower(*p));
+    std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+    if (f) f >> node;
+    return node;
+}
+
 static int g_synth_shard_world = 0;
 
 // NUMA-aware mem-tier placement for round-robin shards: with shard_world = G, block b of files created afterwards is
@@ -620,6 +681,30 @@ int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, i
             c = static_cast<char>('a' + z % 26);
         }
     }
+    // Places first, in block order on this thread: in an arena dir consecutive blocks (of one placement class) get back-to-back
+    // extents, so a reader later moves a whole copy group with one DMA.  The bytes are then produced in parallel -- straight
+    // into the extent for arena dirs, through a buffer + write(2) for file dirs.
+    std::vector<BlockWriteTarget> targets(static_cast<size_t>(nb));
+    std::vector<uint8_t> is_hole(static_cast<size_t>(nb), 0);
+    for (int64_t b = 0; b < nb; b++) {
+        LocatedBlock& lb = fb.block_locs[static_cast<size_t>(b)];
+        int64_t id = 0;
+        API_TRY(create_block_id(inode_id, b, &id));
+        const int64_t blen = std::min(block_size, len - b * block_size);
+        lb.block.id = id, lb.block.len = blen, lb.block.storage_type = storage_type;
+        if (mode == 2 && hole_every > 0 && b % hole_every == hole_every - 1) {
+            lb.block.has_alloc_opts = true;  // allocated, never written, no location: BlockReaderHole
+            is_hole[static_cast<size_t>(b)] = 1;
+            continue;
+        }
+        Err e = w->w.store().reserve_block(id, blen, storage_type, g_synth_shard_world >= 1 ? static_cast<int>(b % g_synth_shard_world) : -1,
+                                           &targets[static_cast<size_t>(b)]);
+        if (e) {
+            for (int64_t x = 0; x < b; x++)
+                if (!is_hole[static_cast<size_t>(x)]) w->w.store().abort_block(fb.block_locs[static_cast<size_t>(x)].block.id, &targets[static_cast<size_t>(x)]);
+            return fail(e);
+        }
+    }
     std::atomic<int64_t> next{0};
     std::mutex emu;
     Err first;
@@ -629,7 +714,10 @@ int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, i
         for (;;) {
             const int64_t b = next.fetch_add(1);
             if (b >= nb) break;
-            const int64_t blen = std::min(block_size, len - b * block_size);
+            if (is_hole[static_cast<size_t>(b)]) continue;
+            LocatedBlock& lb = fb.block_locs[static_cast<size_t>(b)];
+            BlockWriteTarget& t = targets[static_cast<size_t>(b)];
+            const int64_t blen = lb.block.len;
             if (!node_cpus.empty()) {
                 const std::vector<int>& cpus = node_cpus[static_cast<size_t>(b % g_synth_shard_world) % node_cpus.size()];
                 if (!cpus.empty()) {
@@ -639,29 +727,30 @@ int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, i
                     sched_setaffinity(0, sizeof(set), &set);
                 }
             }
-            LocatedBlock& lb = fb.block_locs[static_cast<size_t>(b)];
-            int64_t id = 0;
-            Err e = create_block_id(inode_id, b, &id);
-            lb.block.id = id, lb.block.len = blen, lb.block.storage_type = storage_type;
-            if (!e && mode == 2 && hole_every > 0 && b % hole_every == hole_every - 1) {
-                lb.block.has_alloc_opts = true;  // allocated, never written, no location: BlockReaderHole
-                continue;
+            uint8_t* out = t.arena ? t.mem() : buf.data();
+            if (mode == 1)
+                for (int64_t o = 0; o < blen; o += static_cast<int64_t>(az.size()))
+                    memcpy(out + o, az.data(), static_cast<size_t>(std::min<int64_t>(static_cast<int64_t>(az.size()), blen - o)));
+            else
+                cv_synth_block(static_cast<uint64_t>(inode_id), static_cast<uint64_t>(b), out, static_cast<size_t>(blen));
+            lb.crc32 = cv_host_crc(0, out, static_cast<size_t>(blen));
+            lb.crc32c = cv_host_crc(1, out, static_cast<size_t>(blen));
+            lb.has_crc = true;
+            Err e;
+            if (!t.arena) {
+                const int fd = ::open(t.path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+                if (fd < 0) e = Err::io(str_printf("open %s: %s", t.path.c_str(), strerror(errno)));
+                for (int64_t done = 0; !e && done < blen;) {
+                    const ssize_t wr = ::write(fd, out + done, static_cast<size_t>(blen - done));
+                    if (wr < 0 && errno == EINTR) continue;
+                    if (wr <= 0) e = Err::io(str_printf("write %s: %s", t.path.c_str(), strerror(errno)));
+                    else done += wr;
+                }
+                if (fd >= 0) ::close(fd);
             }
-            if (!e) {
-                if (mode == 1)
-                    for (int64_t o = 0; o < blen; o += static_cast<int64_t>(az.size()))
-                        memcpy(&buf[static_cast<size_t>(o)], az.data(), static_cast<size_t>(std::min<int64_t>(static_cast<int64_t>(az.size()), blen - o)));
-                else
-                    cv_synth_block(static_cast<uint64_t>(inode_id), static_cast<uint64_t>(b), buf.data(), static_cast<size_t>(blen));
-                lb.crc32 = cv_host_crc(0, buf.data(), static_cast<size_t>(blen));
-                lb.crc32c = cv_host_crc(1, buf.data(), static_cast<size_t>(blen));
-                lb.has_crc = true;
-                std::string p;
-                e = w->w.store().put_block(id, buf.data(), blen, storage_type, &p);
-                BlockMeta m;
-                if (!e && !w->w.store().get_block(id, &m)) lb.block.storage_type = m.storage_type;
-                lb.locs.push_back(addr);
-            }
+            if (!e) e = w->w.store().commit_block(lb.block.id, &t, blen);
+            lb.block.storage_type = t.dir_storage_type;
+            lb.locs.push_back(addr);
             if (e) {
                 std::lock_guard<std::mutex> lk(emu);
                 if (!first) first = e;

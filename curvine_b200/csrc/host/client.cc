@@ -217,9 +217,10 @@ static Protocol request_proto(int8_t status, int64_t req_id, int32_t seq_id) {
 }
 
 Err BlockClient::open_block(const ClientConf& conf, const ExtendedBlock& b, int64_t off, int64_t len, int64_t req_id, int32_t seq_id,
-                            bool short_circuit, int64_t chunk_size, BlockReadResponse* out) {
+                            bool short_circuit, int64_t chunk_size, BlockReadResponse* out, bool accept_arena) {
     BlockReadRequest r;
     r.id = b.id, r.off = off, r.len = len, r.chunk_size = static_cast<int32_t>(chunk_size), r.short_circuit = short_circuit;
+    r.accept_arena = accept_arena && short_circuit;
     r.enable_read_ahead = conf.enable_read_ahead, r.read_ahead_len = conf.read_ahead_len, r.drop_cache_len = conf.drop_cache_len;
     Protocol resp;
     std::string rh, rd;
@@ -345,7 +346,7 @@ Err BlockReader::open_adapter(int64_t off) {
     pending_seek_ = false;
     CV_RETURN_IF_ERR(ctx_->acquire_read(loc, &client_));
     BlockReadResponse resp;
-    Err e = client_->open_block(ctx_->conf.client, block_, off, block_.len, req_id_, seq_id_, sc, chunk_size_, &resp);
+    Err e = client_->open_block(ctx_->conf.client, block_, off, block_.len, req_id_, seq_id_, sc, chunk_size_, &resp, ctx_->conf.b200.arena);
     if (e) {
         drop_adapter();
         return e;
@@ -362,6 +363,7 @@ Err BlockReader::open_adapter(int64_t off) {
         }
         ctx_->release(std::move(client_));  // BlockReaderLocal keeps no connection; complete() acquires a new one
         kind_ = kLocal;
+        base_off_ = resp.has_arena ? resp.arena_off : 0;  // arena block: the bytes start at arena_off inside the segment file
         struct statfs sfs;
         const bool tmpfs = fstatfs(fd_, &sfs) == 0 && sfs.f_type == 0x01021994;  // sys_libc.rs:320-339
         ra_enabled_ = ctx_->conf.client.enable_read_ahead && !tmpfs && block_.len >= 256 * 1024;
@@ -389,13 +391,13 @@ Err BlockReader::read_once(std::string* buf) {
             // CacheManager::read_ahead (orpc/src/sys/cache_manager.rs:99-147, block_reader_local.rs:113-126): hint the next
             // read_ahead_len bytes once the cursor passed half of the previous window; never on tmpfs or small files
             if (ra_enabled_ && (last_ahead_ < 0 || pos_ >= last_ahead_ + ctx_->conf.client.read_ahead_len / 2)) {
-                posix_fadvise(fd_, pos_, ctx_->conf.client.read_ahead_len, POSIX_FADV_WILLNEED);
+                posix_fadvise(fd_, base_off_ + pos_, ctx_->conf.client.read_ahead_len, POSIX_FADV_WILLNEED);
                 last_ahead_ = pos_;
             }
             buf->resize(static_cast<size_t>(want));
             int64_t got = 0;
             while (got < want) {
-                const ssize_t r = pread(fd_, &(*buf)[got], static_cast<size_t>(want - got), pos_ + got);
+                const ssize_t r = pread(fd_, &(*buf)[got], static_cast<size_t>(want - got), base_off_ + pos_ + got);
                 if (r < 0 && errno == EINTR) continue;
                 if (r <= 0) return Err::io(str_printf("read block file: %s", r == 0 ? "unexpected eof" : strerror(errno)));
                 got += r;

@@ -93,7 +93,7 @@ class BlockClient {
     // send one request frame, receive one response frame (heartbeats skipped), check echoes, map error responses
     Err rpc(const Protocol& req, const std::string& header, Protocol* resp, std::string* resp_header, std::string* resp_data);
     Err open_block(const ClientConf& conf, const ExtendedBlock& b, int64_t off, int64_t len, int64_t req_id, int32_t seq_id, bool short_circuit,
-                   int64_t chunk_size, BlockReadResponse* out);
+                   int64_t chunk_size, BlockReadResponse* out, bool accept_arena = false);
     Err read_commit(const ExtendedBlock& b, int64_t req_id, int32_t seq_id);
     Err send_request(const Protocol& req, const std::string& header);
     Err recv_response_head(Protocol* resp, std::string* resp_header);  // prefix + header; payload left on the socket
@@ -168,6 +168,7 @@ class BlockReader {
     bool pending_seek_ = false;
     // local
     int fd_ = -1;
+    int64_t base_off_ = 0;  // where the block starts inside fd_ (non-zero for a mem-arena extent)
     bool ra_enabled_ = false;
     int64_t last_ahead_ = -1;
 };

@@ -168,6 +168,12 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "hostname") c->worker_hostname = unquote(v);
             else if (k == "rpc_port") c->worker_port = static_cast<int>(as_int(v));
             else if (k == "enable_send_file") c->worker_enable_send_file = as_bool(v);
+            else if (k == "mem_arena") c->worker_mem_arena = as_bool(v);
+            else if (k == "arena_segment") e = as_size(v, &c->worker_arena_segment);
+            else if (k == "arena_numa") {
+                c->worker_arena_numa.clear();
+                for (const auto& x : as_list(v)) c->worker_arena_numa.push_back(static_cast<int>(as_int(x)));
+            } else if (k == "arena_reuse_delay") e = parse_duration_ms(unquote(v), &c->worker_arena_reuse_delay_ms);
             else if (k == "hbm_capacity") e = as_size(v, &c->worker_hbm_capacity);
             else if (k == "hbm_promote_after") c->worker_hbm_promote_after = static_cast<int>(as_int(v));
             else if (k == "hbm_device") c->worker_hbm_device = static_cast<int>(as_int(v));
@@ -188,6 +194,9 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "register_min_age") e = parse_duration_ms(unquote(v), &b.register_min_age_ms);
             else if (k == "register_threads") b.register_threads = static_cast<int>(as_int(v));
             else if (k == "register_when_idle") b.register_when_idle = as_bool(v);
+            else if (k == "arena") b.arena = as_bool(v);
+            else if (k == "arena_preregister") b.arena_dirs = as_list(v);
+            else if (k == "arena_register_slice") e = as_size(v, &b.arena_register_slice);
         }
         if (e) return e.ctx("conf key " + k);
     }

@@ -55,6 +55,12 @@ struct B200Conf {
     int register_threads = 16;    // background registrar threads (a cold group goes through the pinned ring meanwhile); 0 = register inline
     bool register_when_idle = true;  // registrar threads yield to reads in flight (a cold pass runs at ring speed; mappings are
                                      // registered between reads); false = register concurrently with the cold pass
+    bool arena = true;            // short-circuit Opens say accept_arena: arena-backed mem-tier blocks are DMA'd straight out of the
+                                  // worker's arena segments (arena.h), which this context maps and pins once per segment
+    std::vector<std::string> arena_dirs;  // "arena_preregister": worker data dirs (as in [worker] data_dir, tag optional) whose arena
+                                          // segments are mapped + pinned in the background from the first device read (or
+                                          // cv_fs_preregister) on -- off the read path; other segments are pinned when first met
+    int64_t arena_register_slice = 256ll << 20;  // one cudaHostRegister call covers this much of a segment (slices go to register_threads)
     int numa_node = -1;           // bind fetch threads to this node's CPUs (-1: the GPU's node if discoverable, -2: no binding)
 };
 
@@ -67,6 +73,10 @@ struct ClusterConf {
     std::string worker_hostname = "localhost";
     int worker_port = 0;
     bool worker_enable_send_file = true;
+    bool worker_mem_arena = false;             // [worker] mem_arena: every [MEM] data dir keeps its blocks in one arena (arena.h)
+    int64_t worker_arena_segment = 1ll << 30;  // [worker] arena_segment
+    std::vector<int> worker_arena_numa;        // [worker] arena_numa = [node per MEM dir]
+    int64_t worker_arena_reuse_delay_ms = 1000;  // [worker] arena_reuse_delay (duration string)
     int64_t worker_hbm_capacity = 0;     // [worker] hbm_capacity: bytes of device memory the HBM tier may hold (0 = unbounded, manual loads)
     int worker_hbm_promote_after = 0;    // [worker] hbm_promote_after: framed reads of a block before it is loaded into the tier (0 = never)
     int worker_hbm_device = 0;           // [worker] hbm_device

@@ -15,6 +15,7 @@
 #include <fstream>
 
 #include "../../../include/curvine_b200_kernels.h"
+#include "block_store.h"
 #include "net.h"
 
 namespace cv {
@@ -294,6 +295,179 @@ class Registrar {
     const std::atomic<int>* hold_ = nullptr;
 };
 
+// ------------------------------------------------------------------ mem-arena segments (pinned once, off the read path)
+//
+// An arena-backed worker (arena.h) keeps every mem-tier block as an extent of a few large tmpfs segment files.  A segment is
+// mapped and cudaHostRegister'ed ONCE per context -- in the background from the first device read on for the dirs named in
+// `[b200] arena_preregister`, on demand for any other segment an Open names -- and stays pinned until the context closes.
+// From then on every block in it, whatever file it belongs to and whenever it was written, is DMA'd straight out of the
+// segment: no per-file or per-block client state, so the first read of a file runs at the same rate as a re-read.
+// Registration is sliced (`arena_register_slice`) so that all registrar threads pin one segment together.
+struct ArenaSeg {
+    std::string path;
+    uint8_t* base = nullptr;
+    size_t bytes = 0, slice = 0;
+    uint64_t ino = 0;
+    std::vector<uint8_t> slice_registered;
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t slices_left = 0;
+    bool done = false;
+    Err err;
+    ~ArenaSeg() {
+        if (base) mprotect(base, bytes, PROT_READ | PROT_WRITE);
+        for (size_t i = 0; i < slice_registered.size(); i++)
+            if (slice_registered[i]) cudaHostUnregister(base + i * slice);
+        if (base) munmap(base, bytes);
+    }
+};
+
+class ArenaSegs {
+   public:
+    std::atomic<uint64_t> dma_jobs{0}, dma_bytes{0};  // block jobs / bytes moved straight out of a pinned segment
+    std::atomic<bool> unsupported{false};             // cudaHostRegister refuses these mappings: arena blocks go through the ring
+    double register_sec = 0;                          // wall time from the first slice queued to the last one pinned (under mu_)
+
+    void start(int threads, int device, std::vector<int> cpus, size_t slice) {
+        device_ = device, cpus_ = std::move(cpus), slice_ = std::max<size_t>(slice, 2 << 20) & ~size_t(4095);
+        for (int t = 0; t < std::max(1, threads); t++) threads_.emplace_back([this] { loop(); });
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            q_.clear();
+            cv_.notify_all();
+        }
+        for (auto& t : threads_) t.join();
+        threads_.clear();
+        std::lock_guard<std::mutex> lk(mu_);
+        segs_.clear();
+        retired_.clear();
+    }
+    // Every seg_* file under <data_dir>/<cluster_id>/arena is queued for mapping + pinning.  Returns immediately.
+    void preregister_dir(const std::string& arena_dir) {
+        for (int k = 0;; k++) {
+            const std::string p = str_printf("%s/seg_%04d", arena_dir.c_str(), k);
+            struct stat st;
+            if (stat(p.c_str(), &st) != 0) break;
+            std::shared_ptr<ArenaSeg> seg;
+            begin(p, &seg);
+        }
+    }
+    // The pinned mapping of segment `path` (blocks until it is fully registered; starts the registration if nobody has).
+    Err get(const std::string& path, std::shared_ptr<ArenaSeg>* out) {
+        std::shared_ptr<ArenaSeg> seg;
+        CV_RETURN_IF_ERR(begin(path, &seg));
+        std::unique_lock<std::mutex> lk(seg->mu);
+        seg->cv.wait(lk, [&] { return seg->done; });
+        if (seg->err) return seg->err;
+        *out = std::move(seg);
+        return Err::ok();
+    }
+    void drain() {  // wait until everything queued so far is pinned
+        std::vector<std::shared_ptr<ArenaSeg>> all;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (auto& kv : segs_) all.push_back(kv.second);
+        }
+        for (auto& seg : all) {
+            std::unique_lock<std::mutex> lk(seg->mu);
+            seg->cv.wait(lk, [&] { return seg->done; });
+        }
+    }
+    void stats(uint64_t* n_segs, uint64_t* bytes, double* sec) {
+        std::lock_guard<std::mutex> lk(mu_);
+        *n_segs = segs_.size(), *bytes = 0, *sec = register_sec;
+        for (auto& kv : segs_) *bytes += kv.second->err ? 0 : kv.second->bytes;
+    }
+
+   private:
+    Err begin(const std::string& path, std::shared_ptr<ArenaSeg>* out) {
+        struct stat st;
+        if (stat(path.c_str(), &st) != 0) return Err::io(str_printf("arena segment %s: %s", path.c_str(), strerror(errno)));
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = segs_.find(path);
+        if (it != segs_.end() && it->second->ino == static_cast<uint64_t>(st.st_ino) && it->second->bytes == static_cast<size_t>(st.st_size)) {
+            *out = it->second;
+            return Err::ok();
+        }
+        if (it != segs_.end()) retired_.push_back(it->second);  // the file was replaced (worker restarted on a fresh dir): copies may still be in flight
+        if (unsupported.load()) return Err(kUnsupported, "cudaHostRegister of arena segments is not supported here");
+        std::shared_ptr<ArenaSeg> seg(new ArenaSeg());
+        seg->path = path, seg->bytes = static_cast<size_t>(st.st_size), seg->ino = static_cast<uint64_t>(st.st_ino), seg->slice = slice_;
+        // cudaHostRegister needs a writable shared mapping (cudaHostRegisterReadOnly is refused on this platform); the mapping is
+        // write-protected again as soon as it is pinned
+        const int fd = ::open(path.c_str(), O_RDWR | O_CLOEXEC);
+        if (fd < 0) return Err(kUnsupported, str_printf("open %s read-write: %s", path.c_str(), strerror(errno)));
+        void* m = mmap(nullptr, seg->bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        ::close(fd);
+        if (m == MAP_FAILED) return Err::io(str_printf("mmap %s: %s", path.c_str(), strerror(errno)));
+        seg->base = static_cast<uint8_t*>(m);
+        const size_t n = (seg->bytes + slice_ - 1) / slice_;
+        seg->slice_registered.assign(n, 0);
+        seg->slices_left = n;
+        if (busy_ == 0 && q_.empty()) t_first_ = now_sec();
+        for (size_t i = 0; i < n; i++) q_.emplace_back(seg, i);
+        segs_[path] = seg;
+        cv_.notify_all();
+        *out = std::move(seg);
+        return Err::ok();
+    }
+    void loop() {
+        if (!cpus_.empty()) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            for (int c : cpus_) CPU_SET(c, &set);
+            sched_setaffinity(0, sizeof(set), &set);
+        }
+        cudaSetDevice(device_);
+        for (;;) {
+            std::pair<std::shared_ptr<ArenaSeg>, size_t> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (stop_) return;
+                job = std::move(q_.front());
+                q_.pop_front();
+                busy_++;
+            }
+            ArenaSeg& seg = *job.first;
+            const size_t off = job.second * seg.slice, len = std::min(seg.slice, seg.bytes - off);
+            const cudaError_t ce = cudaHostRegister(seg.base + off, len, cudaHostRegisterDefault);
+            if (ce != cudaSuccess) cudaGetLastError();
+            bool last = false;
+            {
+                std::lock_guard<std::mutex> lk(seg.mu);
+                if (ce == cudaSuccess) seg.slice_registered[job.second] = 1;
+                else if (!seg.err) seg.err = Err(kUnsupported, str_printf("cudaHostRegister(%s + %zu, %zu): %s", seg.path.c_str(), off, len, cudaGetErrorString(ce)));
+                last = --seg.slices_left == 0;
+                if (last) {
+                    if (!seg.err) mprotect(seg.base, seg.bytes, PROT_READ);  // pinned pages stay DMA-able; nothing in this process can scribble on them
+                    else unsupported.store(true);
+                    seg.done = true;
+                    seg.cv.notify_all();
+                }
+            }
+            std::lock_guard<std::mutex> lk(mu_);
+            busy_--;
+            if (busy_ == 0 && q_.empty()) register_sec += now_sec() - t_first_;
+        }
+    }
+    int device_ = 0;
+    size_t slice_ = 256 << 20;
+    std::vector<int> cpus_;
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::pair<std::shared_ptr<ArenaSeg>, size_t>> q_;
+    std::unordered_map<std::string, std::shared_ptr<ArenaSeg>> segs_;
+    std::vector<std::shared_ptr<ArenaSeg>> retired_;
+    int busy_ = 0;
+    double t_first_ = 0;
+    bool stop_ = false;
+};
+
 // ------------------------------------------------------------------ GpuIngest: ring + streams
 
 class GpuIngest {
@@ -318,6 +492,8 @@ class GpuIngest {
     GpuFsReader* pending_owner = nullptr;  // reader whose results still sit in h_result
     RegCache reg;
     Registrar registrar;
+    ArenaSegs arena;
+    cudaEvent_t entry_ev = nullptr;  // what the caller's stream had queued when a read started
     bool register_inline = false;
     std::atomic<int> reads_in_flight{0};  // run_jobs calls between entry and return (the registrar yields to them)
     double ring_alloc_sec = 0;            // time spent allocating the pinned ring (one-off per context and slot size)
@@ -352,6 +528,7 @@ class GpuIngest {
         for (auto& s : copy_streams) CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         CU_TRY(cudaStreamCreateWithFlags(&vstream, cudaStreamNonBlocking));
         CU_TRY(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&entry_ev, cudaEventDisableTiming));
         reg.capacity = c.zero_copy ? static_cast<size_t>(std::max<int64_t>(c.register_cache, 0)) : 0;
         reg.min_age_sec = static_cast<double>(std::max<int64_t>(c.register_min_age_ms, 0)) / 1000.0;
         register_inline = c.register_threads <= 0 || reg.capacity == 0;
@@ -382,6 +559,8 @@ class GpuIngest {
             }
         }
         if (c.zero_copy && !register_inline) registrar.start(c.register_threads, device, &reg, cpus, c.register_when_idle ? &reads_in_flight : nullptr);
+        if (c.zero_copy && c.arena) arena.start(std::max(1, c.register_threads), device, cpus, static_cast<size_t>(std::max<int64_t>(c.arena_register_slice, 0)));
+        else arena.unsupported.store(true);
         return Err::ok();
     }
 
@@ -427,6 +606,7 @@ class GpuIngest {
         registrar.stop();
         cudaSetDevice(device);
         cudaDeviceSynchronize();
+        arena.stop();
         reg.clear();
         if (pinned) cudaFreeHost(pinned);
         if (d_stage) cudaFree(d_stage);
@@ -437,6 +617,7 @@ class GpuIngest {
         for (auto s : copy_streams) cudaStreamDestroy(s);
         if (vstream) cudaStreamDestroy(vstream);
         if (done_ev) cudaEventDestroy(done_ev);
+        if (entry_ev) cudaEventDestroy(entry_ev);
     }
 };
 
@@ -454,7 +635,30 @@ GpuIngest* gpu_ingest_get(FsContext* ctx, Err* err) {
         return nullptr;
     }
     g_ingests[ctx] = g;
+    // the arenas named in the configuration are mapped + pinned from now on, in the background, off any read path
+    if (ctx->conf.b200.zero_copy && ctx->conf.b200.arena)
+        for (const std::string& spec : ctx->conf.b200.arena_dirs) {
+            StorageDir d;
+            if (parse_data_dir(spec, &d)) continue;
+            g->arena.preregister_dir((ctx->conf.cluster_id.empty() ? d.path : d.path + "/" + ctx->conf.cluster_id) + "/arena");
+        }
     return g;
+}
+
+Err gpu_ingest_preregister(FsContext* ctx) {
+    Err e;
+    gpu_ingest_get(ctx, &e);
+    return e;
+}
+
+void gpu_ingest_arena_stats(FsContext* ctx, uint64_t out[5]) {
+    memset(out, 0, 5 * sizeof(uint64_t));
+    std::lock_guard<std::mutex> lk(g_ing_mu);
+    auto it = g_ingests.find(ctx);
+    if (it == g_ingests.end()) return;
+    double sec = 0;
+    it->second->arena.stats(&out[0], &out[1], &sec);
+    out[2] = static_cast<uint64_t>(sec * 1e6), out[3] = it->second->arena.dma_jobs.load(), out[4] = it->second->arena.dma_bytes.load();
 }
 
 void gpu_ingest_wait_registered(FsContext* ctx) {
@@ -464,7 +668,7 @@ void gpu_ingest_wait_registered(FsContext* ctx) {
         auto it = g_ingests.find(ctx);
         if (it != g_ingests.end()) g = it->second;
     }
-    if (g) g->registrar.drain();
+    if (g) g->registrar.drain(), g->arena.drain();
 }
 
 void gpu_ingest_release(FsContext* ctx) {
@@ -580,13 +784,12 @@ static Protocol read_req(int8_t status, int64_t req_id, int32_t seq_id) {
 
 }  // namespace
 
-enum FetchMode { kFetchShortCircuit = 0, kFetchFramedVerbatim = 1, kFetchFramedUnpacked = 2 };
+enum FetchMode { kFetchShortCircuit = 0, kFetchFramedVerbatim = 1 };
 
 // Fetch one job's bytes into `slot`.
 //   short-circuit    payload only (pread of the block file the worker named)
-//   framed verbatim  the response stream exactly as received: 22-byte prefixes + payloads (unpacked on the GPU by K2)
-//   framed unpacked  per-chunk request/response like BlockReaderRemote, payload only; used for ranges that do not
-//                    end at a block end, where the worker's last chunk overshoots the wanted range
+//   framed verbatim  the response stream exactly as received: 22-byte prefixes + payloads (unpacked on the GPU by K2, which
+//                    also clips the last chunk of a range that stops short of the block end)
 static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, int64_t n, FetchMode mode, int64_t chunk, uint8_t* slot,
                      std::unique_ptr<BlockClient>* conn, int64_t* req_id_out, size_t* wire_bytes) {
     Err last = Err::common("There is no available worker, locs: [], failed workers: []");
@@ -601,9 +804,10 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
         *req_id_out = req_id;
         BlockReadResponse resp;
         const int64_t open_chunk = mode == kFetchFramedVerbatim ? chunk : ctx->read_chunk_size();
-        last = c->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, req_id, 0, mode == kFetchShortCircuit, open_chunk, &resp);
+        last = c->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, req_id, 0, mode == kFetchShortCircuit, open_chunk, &resp, ctx->conf.b200.arena);
         if (last) continue;
         int32_t seq = 0;
+        const int64_t base_off = resp.has_arena ? resp.arena_off : 0;  // arena block: an extent inside the segment file
         if (mode == kFetchShortCircuit) {
             if (!resp.has_path) {
                 last = Err::common("read_context.path is none");
@@ -616,7 +820,7 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
             }
             int64_t got = 0;
             while (got < n) {
-                const ssize_t r = pread(fd, slot + got, static_cast<size_t>(n - got), block_off + got);
+                const ssize_t r = pread(fd, slot + got, static_cast<size_t>(n - got), base_off + block_off + got);
                 if (r < 0 && errno == EINTR) continue;
                 if (r <= 0) {
                     last = Err::io(str_printf("read block file: %s", r == 0 ? "unexpected eof" : strerror(errno)));
@@ -628,8 +832,11 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
             if (got < n) continue;
             *wire_bytes = static_cast<size_t>(n);
         } else if (mode == kFetchFramedVerbatim) {
-            // all Running requests in one write (the worker serves them in order, read_handler.rs:143-183)
+            // all Running requests in one write (the worker serves them in order, read_handler.rs:143-183).  The worker answers
+            // each with min(chunk, block_len - pos) bytes, so the last frame of a range that stops short of the block end carries
+            // bytes past it: they are received like the rest and clipped by K2 (CvStreamDesc.tail_clip).
             const int64_t nfr = (n + chunk - 1) / chunk;
+            n = std::min<int64_t>(nfr * chunk, lb.block.len - block_off);  // payload bytes on the wire
             std::string reqs(static_cast<size_t>(nfr) * kProtocolSize, '\0');
             for (int64_t f = 0; f < nfr; f++) encode_protocol(read_req(kReqRunning, req_id, static_cast<int32_t>(f + 1)), reinterpret_cast<uint8_t*>(&reqs[f * kProtocolSize]));
             last = send_all(c->fd(), reqs.data(), reqs.size());
@@ -658,34 +865,6 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
             }
             seq = static_cast<int32_t>(nfr);
             *wire_bytes = static_cast<size_t>(w - slot);
-        } else {
-            std::string spill;
-            int64_t got = 0;
-            while (got < n && !last) {
-                last = c->send_request(read_req(kReqRunning, req_id, ++seq), std::string());
-                Protocol p;
-                std::string rh;
-                if (!last) last = c->recv_response_head(&p, &rh);
-                if (last) break;
-                if (!p.is_success() || p.seq_id != seq || p.req_id != req_id || p.data_len <= 0) {
-                    std::string body(static_cast<size_t>(p.data_len), '\0');
-                    if (!body.empty() && recv_exact(c->fd(), &body[0], body.size())) c->broken = true;
-                    last = p.is_success() ? Err::common("response mismatch") : decode_error_body(reinterpret_cast<const uint8_t*>(body.data()), body.size());
-                    break;
-                }
-                const int64_t take = std::min<int64_t>(p.data_len, n - got);
-                last = recv_exact(c->fd(), slot + got, static_cast<size_t>(take));
-                if (!last && p.data_len > take) {  // the worker's chunk runs past the wanted range: discard the rest
-                    spill.resize(static_cast<size_t>(p.data_len - take));
-                    last = recv_exact(c->fd(), &spill[0], spill.size());
-                }
-                got += take;
-            }
-            if (last) {
-                c->broken = true;
-                continue;
-            }
-            *wire_bytes = static_cast<size_t>(n);
         }
         last = c->read_commit(lb.block, req_id, seq + 1);
         if (last) continue;
@@ -696,7 +875,7 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
 
 // Open(short_circuit=true) on the first replica that answers; returns the block file path.
 static Err open_short_circuit(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, std::unique_ptr<BlockClient>* conn, int64_t* req_id,
-                              std::string* path) {
+                              BlockReadResponse* out) {
     Err last = Err::common("There is no available worker, locs: [], failed workers: []");
     for (const WorkerAddress& loc : lb.locs) {
         if (!*conn || !((*conn)->addr() == loc) || (*conn)->broken) {
@@ -706,13 +885,13 @@ static Err open_short_circuit(FsContext* ctx, const LocatedBlock& lb, int64_t bl
         }
         *req_id = new_req_id();
         BlockReadResponse resp;
-        last = (*conn)->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, *req_id, 0, true, ctx->read_chunk_size(), &resp);
+        last = (*conn)->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, *req_id, 0, true, ctx->read_chunk_size(), &resp, ctx->conf.b200.arena);
         if (last) continue;
         if (!resp.has_path) {
             last = Err::common("read_context.path is none");
             continue;
         }
-        *path = resp.path;
+        *out = resp;
         return Err::ok();
     }
     return last;
@@ -776,6 +955,11 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     }
     if (G.pending_owner && G.pending_owner != this) CV_RETURN_IF_ERR(G.pending_owner->harvest());  // shared tables
     CV_RETURN_IF_ERR(harvest());
+    // everything this call writes into d_dst is ordered after what the caller's stream had queued at entry (a buffer fresh from
+    // a stream-ordered allocator, kernels still reading it): the copy streams and the verify stream wait for that point
+    CU_TRY(cudaEventRecord(G.entry_ev, static_cast<cudaStream_t>(user_stream)));
+    for (auto cs : G.copy_streams) CU_TRY(cudaStreamWaitEvent(cs, G.entry_ev, 0));
+    CU_TRY(cudaStreamWaitEvent(G.vstream, G.entry_ev, 0));
     const B200Conf& bc = ctx_->conf.b200;
     const ClientConf& cc = ctx_->conf.client;
     const int poly = bc.verify_poly ? 1 : 0;
@@ -783,7 +967,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
 
     // ---- per-job mode.  Short-circuit (the reference default for a same-host worker, client_conf.rs:339) only when
     // every block of this call has a local replica; otherwise the whole call runs framed (any worker serves those).
-    enum : uint8_t { kPlain = 0, kFramed = 1, kUnpacked = 2, kHole = 3 };
+    enum : uint8_t { kPlain = 0, kFramed = 1, kHole = 3 };
     std::vector<uint8_t> mode(J, kPlain);
     bool call_framed = false;
     for (size_t j = 0; j < J; j++) {
@@ -800,18 +984,19 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     size_t need_slot = 0, F = 0;
     std::vector<uint32_t> first_frame(J + 1, 0);
     bool any_verbatim = false;
+    std::vector<int64_t> wire_payload(J, 0);  // framed jobs: payload bytes the worker sends (>= n when the range stops short of the block end)
     for (size_t j = 0; j < J; j++) {
         first_frame[j] = static_cast<uint32_t>(F);
         size_t bytes = static_cast<size_t>(jobs[j].n);
         if (mode[j] != kHole && call_framed) {
-            const bool to_block_end = jobs[j].block_off + jobs[j].n == (*jobs[j].lb).block.len;
-            mode[j] = to_block_end ? kFramed : kUnpacked;
-            if (mode[j] == kFramed) {
-                const size_t nfr = static_cast<size_t>((jobs[j].n + chunk - 1) / chunk);
-                bytes += nfr * kProtocolSize;
-                F += nfr;
-                any_verbatim = true;
-            }
+            // every framed job is received verbatim and unpacked by K2; a range that stops short of its block's end gets the
+            // worker's whole last chunk and K2 clips it (CvStreamDesc.tail_clip) -- no host-side unpacking anywhere
+            mode[j] = kFramed;
+            const int64_t nfr = (jobs[j].n + chunk - 1) / chunk;
+            wire_payload[j] = std::min<int64_t>(nfr * chunk, (*jobs[j].lb).block.len - jobs[j].block_off);
+            bytes = static_cast<size_t>(wire_payload[j] + nfr * kProtocolSize);
+            F += static_cast<size_t>(nfr);
+            any_verbatim = true;
         }
         need_slot = std::max(need_slot, bytes);
     }
@@ -835,31 +1020,33 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
 
     // ---- device tables (shared by all readers of this context): off[J] len[J] | expect[J] crc[J] nbad[4] ferr[F] | streams[J] fdesc[F]
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t o_off = 0, o_len = up(o_off + 8 * J), o_exp = up(o_len + 8 * J), o_crc = up(o_exp + 4 * J);
+    const size_t o_off = 0, o_len = up(o_off + 8 * J), o_exp = up(o_len + 8 * J), o_skip = up(o_exp + 4 * J), o_crc = up(o_skip + J);
     const size_t res_words = J + 4 + F;
     const size_t o_streams = up(o_crc + 4 * res_words), o_fdesc = up(o_streams + sizeof(CvStreamDesc) * J);
     const size_t tables_bytes = up(o_fdesc + sizeof(CvFrameDesc) * F);
     CV_RETURN_IF_ERR(G.ensure_tables(tables_bytes, 4 * res_words));
     uint8_t* T = G.d_tables;
-    std::vector<uint8_t> h(o_crc);  // host image of off/len/expect
+    std::vector<uint8_t> h(o_crc);  // host image of off/len/expect/skip
     uint64_t* h_off = reinterpret_cast<uint64_t*>(&h[o_off]);
     uint64_t* h_len = reinterpret_cast<uint64_t*>(&h[o_len]);
     uint32_t* h_exp = reinterpret_cast<uint32_t*>(&h[o_exp]);
+    uint8_t* h_skip = &h[o_skip];
     size_t f0 = J, f1 = 0, n_compared = 0;
     for (size_t j = 0; j < J; j++) {
         const LocatedBlock& lb = (*jobs[j].lb);
         h_off[j] = static_cast<uint64_t>(jobs[j].dst_off);
         h_len[j] = static_cast<uint64_t>(jobs[j].n);
         h_exp[j] = poly ? lb.crc32c : lb.crc32;
-        if (jobs[j].full && lb.has_crc && mode[j] != kHole) {
+        h_skip[j] = !(jobs[j].full && lb.has_crc && mode[j] != kHole);
+        if (!h_skip[j]) {
             f0 = std::min(f0, j), f1 = std::max(f1, j + 1);
             n_compared++;
         }
     }
     if (f0 >= f1) f0 = f1 = 0;
-    // jobs are in file order, so only the two ends can be partial; a hole or a block without a manifest CRC inside
-    // [f0,f1) disables the comparison for this call (the CRCs are still computed and summed)
-    const bool compare = bc.verify && n_compared == f1 - f0 && n_compared > 0;
+    // every whole block the manifest holds a CRC for is compared; holes, partial ranges and blocks without a manifest CRC are
+    // masked out one by one (their CRCs are still computed, and summed when they lie inside [f0,f1))
+    const bool compare = bc.verify && n_compared > 0;
     CU_TRY(cudaMemcpyAsync(T, h.data(), o_crc, cudaMemcpyHostToDevice, G.vstream));
     CU_TRY(cudaMemsetAsync(T + o_crc, 0, 4 * res_words, G.vstream));
     std::vector<CvStreamDesc> sd;
@@ -869,7 +1056,8 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
             CvStreamDesc& d = sd[j];
             memset(&d, 0, sizeof(d));
             const size_t ss = (j / k) % NS;
-            d.wire_off = (ss * k + j % k) * G.slot_bytes, d.dst_off = h_off[j], d.block_len = mode[j] == kFramed ? h_len[j] : 0;
+            d.wire_off = (ss * k + j % k) * G.slot_bytes, d.dst_off = h_off[j], d.block_len = mode[j] == kFramed ? static_cast<uint64_t>(wire_payload[j]) : 0;
+            d.tail_clip = mode[j] == kFramed ? static_cast<uint32_t>(wire_payload[j] - jobs[j].n) : 0;
             d.chunk_size = static_cast<uint32_t>(chunk), d.first_seq_id = 1, d.block = static_cast<uint32_t>(j % B);
             d.first_frame = first_frame[j], d.code = kCodeReadBlock, d.status = 0x03;
         }
@@ -922,16 +1110,62 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
             if (all_plain && use_mapped.load(std::memory_order_relaxed)) {
                 const double t0 = now_sec();
                 std::vector<std::string> paths(j1 - j0);
-                std::vector<int64_t> lens(j1 - j0), rids(j1 - j0);
+                std::vector<int64_t> lens(j1 - j0), rids(j1 - j0), base_offs(j1 - j0, 0);
                 Err e;
+                size_t n_arena = 0;
                 for (size_t j = j0; j < j1 && !e; j++) {
                     const LocatedBlock& lb = (*jobs[j].lb);
-                    e = open_short_circuit(ctx_, lb, jobs[j].block_off, &conn, &rids[j - j0], &paths[j - j0]);
-                    lens[j - j0] = lb.block.len;
+                    BlockReadResponse resp;
+                    e = open_short_circuit(ctx_, lb, jobs[j].block_off, &conn, &rids[j - j0], &resp);
+                    paths[j - j0] = resp.path, lens[j - j0] = lb.block.len;
+                    if (resp.has_arena) base_offs[j - j0] = resp.arena_off, n_arena++;
+                }
+                // ---- mem arena: every block of the group is an extent of a segment this context pinned once
+                if (!e && n_arena == j1 - j0 && !G.arena.unsupported.load(std::memory_order_relaxed)) {
+                    std::vector<std::shared_ptr<ArenaSeg>> segs(j1 - j0);
+                    for (size_t j = j0; j < j1 && !e; j++) {
+                        if (j > j0 && paths[j - j0] == paths[j - j0 - 1]) segs[j - j0] = segs[j - j0 - 1];
+                        else e = G.arena.get(paths[j - j0], &segs[j - j0]);
+                        if (!e && static_cast<size_t>(base_offs[j - j0] + jobs[j].block_off + jobs[j].n) > segs[j - j0]->bytes) e = Err::io("arena extent lies outside its segment");
+                    }
+                    if (!e) {
+                        cudaError_t ce = cudaSuccess;
+                        // one cudaMemcpyAsync per run of jobs that are back to back in the segment AND in the destination
+                        for (size_t j = j0; j < j1 && ce == cudaSuccess;) {
+                            const uint8_t* src = segs[j - j0]->base + base_offs[j - j0] + jobs[j].block_off;
+                            size_t len = static_cast<size_t>(jobs[j].n), r = j + 1;
+                            while (r < j1 && segs[r - j0] == segs[j - j0] && segs[r - j0]->base + base_offs[r - j0] + jobs[r].block_off == src + len &&
+                                   jobs[r].dst_off == jobs[j].dst_off + static_cast<int64_t>(len))
+                                len += static_cast<size_t>(jobs[r].n), r++;
+                            // a copy never spans two separately registered slices of the segment
+                            const ArenaSeg& sg = *segs[j - j0];
+                            for (size_t done = 0; done < len && ce == cudaSuccess;) {
+                                const size_t in_seg = static_cast<size_t>(src - sg.base) + done;
+                                const size_t piece = std::min(len - done, (in_seg / sg.slice + 1) * sg.slice - in_seg);
+                                ce = cudaMemcpyAsync(d_dst + jobs[j].dst_off + done, src + done, piece, cudaMemcpyHostToDevice, cs);
+                                done += piece;
+                            }
+                            h2d[static_cast<size_t>(t)] += len;
+                            j = r;
+                        }
+                        if (ce == cudaSuccess) ce = cudaEventRecord(G.copy_ev[ss], cs);
+                        for (size_t j = j0; j < j1 && !e; j++) e = conn->read_commit((*jobs[j].lb).block, rids[j - j0], 1);
+                        fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
+                        if (e || ce != cudaSuccess) {
+                            st.fail(e ? e : Err::io(str_printf("H2D enqueue: %s", cudaGetErrorString(ce))));
+                            break;
+                        }
+                        G.arena.dma_jobs += j1 - j0;
+                        for (size_t j = j0; j < j1; j++) G.arena.dma_bytes += static_cast<uint64_t>(jobs[j].n);
+                        released[ss].store(static_cast<int64_t>(g), std::memory_order_release);
+                        copied[g].store(1, std::memory_order_release);
+                        continue;
+                    }
+                    if (e.kind == kUnsupported) e = Err::ok();  // segments cannot be pinned here: the group goes through the ring below
                 }
                 std::shared_ptr<RegMapping> m;
-                bool via_ring = false;
-                if (!e) {
+                bool via_ring = n_arena > 0;  // arena extents (mixed group, or segments that cannot be pinned): pread out of the segment file
+                if (!e && !via_ring) {
                     std::string key;
                     for (const auto& p : paths) key += p, key += '|';
                     std::vector<uint64_t> stamps;
@@ -974,7 +1208,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                         }
                         int64_t got = 0;
                         while (got < jobs[j].n) {
-                            const ssize_t r = pread(fd, hs + in_slot + got, static_cast<size_t>(jobs[j].n - got), jobs[j].block_off + got);
+                            const ssize_t r = pread(fd, hs + in_slot + got, static_cast<size_t>(jobs[j].n - got), base_offs[j - j0] + jobs[j].block_off + got);
                             if (r < 0 && errno == EINTR) continue;
                             if (r <= 0) {
                                 e = Err::io(str_printf("read block file: %s", r == 0 ? "unexpected eof" : strerror(errno)));
@@ -1043,7 +1277,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
             // plain jobs mirror the destination layout inside the super-slot so that one copy moves the whole group
             bool one_copy = !group_verbatim[g];
             for (size_t j = j0; j < j1 && one_copy; j++) {
-                one_copy = mode[j] == kPlain || mode[j] == kUnpacked;
+                one_copy = mode[j] == kPlain;
                 if (j > j0) one_copy = one_copy && jobs[j].dst_off == jobs[j - 1].dst_off + jobs[j - 1].n;
             }
             if (one_copy && static_cast<size_t>(jobs[j1 - 1].dst_off + jobs[j1 - 1].n - jobs[j0].dst_off) > k * G.slot_bytes) one_copy = false;
@@ -1060,7 +1294,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                 const size_t in_slot = one_copy ? static_cast<size_t>(job.dst_off - jobs[j0].dst_off) : (j - j0) * G.slot_bytes;
                 size_t wire = 0;
                 const double t0 = now_sec();
-                const FetchMode fm = mode[j] == kPlain ? kFetchShortCircuit : mode[j] == kFramed ? kFetchFramedVerbatim : kFetchFramedUnpacked;
+                const FetchMode fm = mode[j] == kPlain ? kFetchShortCircuit : kFetchFramedVerbatim;
                 Err e = fetch_job(ctx_, (*job.lb), job.block_off, job.n, fm, chunk, hs + in_slot, &conn, &req_ids[j], &wire);
                 fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
                 if (e) {
@@ -1097,7 +1331,9 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         if (conn) ctx_->release(std::move(conn));
     };
     std::vector<std::thread> threads;
-    if (T_threads == 1) worker(0, false);  // small read (FUSE-shaped, C5): no thread spawn on the latency path
+    // A verbatim (framed) group's slot is only released by the verifier below, so a single fetch worker running inline on this
+    // thread would wait for itself once the groups outnumber the ring's super-slots: it gets its own thread then.
+    if (T_threads == 1 && (NG <= NS || !any_verbatim)) worker(0, false);  // small read (FUSE-shaped, C5): no thread spawn on the latency path
     else
         for (int t = 0; t < T_threads; t++) threads.emplace_back(worker, t, true);
 
@@ -1152,7 +1388,9 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         for (auto s : G.copy_streams) cudaStreamSynchronize(s);
         return st.err;
     }
-    if (compare) CVK_TRY(cvk_verify_crcs(d_crc + f0, reinterpret_cast<const uint32_t*>(T + o_exp) + f0, static_cast<uint32_t>(f1 - f0), d_crc + J, nullptr, G.vstream));
+    if (compare)
+        CVK_TRY(cvk_verify_crcs_masked(d_crc + f0, reinterpret_cast<const uint32_t*>(T + o_exp) + f0, T + o_skip + f0, static_cast<uint32_t>(f1 - f0), d_crc + J, nullptr,
+                                       G.vstream));
     CU_TRY(cudaMemcpyAsync(G.h_result, d_crc, 4 * res_words, cudaMemcpyDeviceToHost, G.vstream));
     CU_TRY(cudaEventRecord(G.done_ev, G.vstream));
     CU_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(user_stream), G.done_ev, 0));

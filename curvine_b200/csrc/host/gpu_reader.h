@@ -100,6 +100,8 @@ class GpuFsReader {
 // one per (process, device): pinned ring, device staging ring, streams, events
 GpuIngest* gpu_ingest_get(FsContext* ctx, Err* err);
 void gpu_ingest_release(FsContext* ctx);
-void gpu_ingest_wait_registered(FsContext* ctx);  // block until the background registrar is idle
+void gpu_ingest_wait_registered(FsContext* ctx);  // block until the background registrar is idle and every queued arena segment is pinned
+Err gpu_ingest_preregister(FsContext* ctx);       // create the context's ingest now: `arena_preregister` dirs start being pinned
+void gpu_ingest_arena_stats(FsContext* ctx, uint64_t out[5]);
 
 }  // namespace cv

@@ -99,6 +99,18 @@ bool HbmTier::get(int64_t block_id, HbmBlock* out) {
     return true;
 }
 
+void HbmTier::evict(int64_t block_id) {
+    HbmBlock dropped;  // released outside the lock; a reader that still packs frames from it keeps it alive
+    std::lock_guard<std::mutex> lk(mu_);
+    remote_reads_.erase(block_id);
+    auto it = blocks_.find(block_id);
+    if (it == blocks_.end()) return;
+    bytes_ -= it->second.buf->len;
+    dropped = it->second.buf;
+    lru_.erase(it->second.pos);
+    blocks_.erase(it);
+}
+
 bool HbmTier::should_promote(int64_t block_id) {
     std::lock_guard<std::mutex> lk(mu_);
     if (promote_after_ <= 0) return false;

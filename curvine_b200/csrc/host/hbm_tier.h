@@ -50,6 +50,7 @@ class HbmTier {
     void configure(int64_t capacity_bytes, int promote_after, int device);
     Err load(int64_t block_id, const void* host_bytes, int64_t len, int device);
     bool get(int64_t block_id, HbmBlock* out);  // LRU touch
+    void evict(int64_t block_id);               // the block was rewritten or removed: its resident copy must not be served again
     // a remote read of a block that is not resident is about to be served from its file: true = promote it first
     bool should_promote(int64_t block_id);
     int device() const { return device_; }

@@ -113,10 +113,14 @@ Err tcp_listen(const std::string& host, int port, int* fd_out, int* bound_port) 
     return Err::ok();
 }
 
-Err send_all(int fd, const void* buf, size_t n) {
+static Err send_flags(int fd, const void* buf, size_t n, int flags);
+Err send_more(int fd, const void* buf, size_t n) { return send_flags(fd, buf, n, MSG_NOSIGNAL | MSG_MORE); }
+Err send_all(int fd, const void* buf, size_t n) { return send_flags(fd, buf, n, MSG_NOSIGNAL); }
+
+static Err send_flags(int fd, const void* buf, size_t n, int flags) {
     const uint8_t* p = static_cast<const uint8_t*>(buf);
     while (n) {
-        const ssize_t w = ::send(fd, p, n, MSG_NOSIGNAL);
+        const ssize_t w = ::send(fd, p, n, flags);
         if (w < 0) {
             if (errno == EINTR) continue;
             if (errno == EAGAIN || errno == EWOULDBLOCK) return Err::io("send: timed out");  // SO_SNDTIMEO elapsed

@@ -12,6 +12,7 @@ namespace cv {
 Err tcp_connect(const std::string& host, int port, int* fd_out, int64_t conn_timeout_ms = 0, int64_t io_timeout_ms = 0);
 Err tcp_listen(const std::string& host, int port, int* fd_out, int* bound_port);
 Err send_all(int fd, const void* buf, size_t n);
+Err send_more(int fd, const void* buf, size_t n);  // MSG_MORE: more bytes of the same message follow at once
 Err recv_exact(int fd, void* buf, size_t n);  // kIO "connection closed" on EOF
 Err send_file_full(int sock, int file_fd, int64_t off, size_t n);
 void set_sock_opts(int fd);

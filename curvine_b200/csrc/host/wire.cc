@@ -118,6 +118,7 @@ std::string BlockReadRequest::encode() const {
     put_field(&s, 1, id), put_field(&s, 2, off), put_field(&s, 3, len), put_field(&s, 4, chunk_size);
     put_field(&s, 5, short_circuit), put_field(&s, 8, enable_read_ahead), put_field(&s, 9, read_ahead_len);
     put_field(&s, 10, drop_cache_len);
+    if (accept_arena) put_field(&s, 100, true);
     return s;
 }
 
@@ -136,6 +137,7 @@ Err BlockReadRequest::decode(const uint8_t* p, size_t n, BlockReadRequest* o) {
             case 8: o->enable_read_ahead = f.v != 0, seen |= 32; break;
             case 9: o->read_ahead_len = int64_t(f.v), seen |= 64; break;
             case 10: o->drop_cache_len = int64_t(f.v), seen |= 128; break;
+            case 100: o->accept_arena = f.v != 0; break;
             default: break;
         }
     }
@@ -148,6 +150,7 @@ std::string BlockReadResponse::encode() const {
     put_field(&s, 1, id), put_field(&s, 2, len);
     if (has_path) put_bytes(&s, 3, path);
     put_field(&s, 4, storage_type);
+    if (has_arena) put_field(&s, 100, arena_off), put_field(&s, 101, arena_seg_len);
     return s;
 }
 
@@ -162,6 +165,8 @@ Err BlockReadResponse::decode(const uint8_t* p, size_t n, BlockReadResponse* o) 
             case 2: o->len = int64_t(f.v), seen |= 2; break;
             case 3: o->has_path = true, o->path.assign(reinterpret_cast<const char*>(f.p), f.n); break;
             case 4: o->storage_type = int32_t(f.v), seen |= 4; break;
+            case 100: o->has_arena = true, o->arena_off = int64_t(f.v); break;
+            case 101: o->arena_seg_len = int64_t(f.v); break;
             default: break;
         }
     }

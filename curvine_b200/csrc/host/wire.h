@@ -59,6 +59,9 @@ struct BlockReadRequest {  // worker.proto:38-47
     bool enable_read_ahead = true;
     int64_t read_ahead_len = 4194304;
     int64_t drop_cache_len = 1048576;
+    // extension (optional field 100, skipped as unknown by a prost/proto2 decoder): the client understands arena
+    // extents, i.e. a short-circuit response whose `path` is an arena segment plus `arena_off` (arena.h)
+    bool accept_arena = false;
     std::string encode() const;
     static Err decode(const uint8_t* p, size_t n, BlockReadRequest* out);
 };
@@ -68,6 +71,10 @@ struct BlockReadResponse {  // worker.proto:49-54
     bool has_path = false;
     std::string path;
     int32_t storage_type = kStorageDisk;
+    // extension (optional fields 100/101, only sent to a client that said accept_arena): the block is bytes
+    // [arena_off, arena_off + len) of the segment file `path`, which is arena_seg_len bytes long
+    bool has_arena = false;
+    int64_t arena_off = 0, arena_seg_len = 0;
     std::string encode() const;
     static Err decode(const uint8_t* p, size_t n, BlockReadResponse* out);
 };

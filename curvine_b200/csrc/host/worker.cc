@@ -42,24 +42,37 @@ Err ReadHandler::open(const RpcRequest& req, RpcResponse* resp) {
         return Err::common(str_printf("The pre-read size exceeds the maximum value allowed by the system.The current value is %lld. The maximum allowed value is: %d",
                                       (long long)c.read_ahead_len, 16 * 1024 * 1024));
     const bool short_circuit = c.short_circuit && meta.storage_type != kStorageSpdkDisk;
+    if (short_circuit && meta.in_arena() && !c.accept_arena)
+        return Err(kUnsupported, str_printf("block %lld lives in the worker's mem arena: a short-circuit read needs an arena-aware client "
+                                            "(BlockReadRequest.accept_arena); read it with short_circuit = false", (long long)c.id));
     close_fd(fd_);
     fd_ = -1;
+    meta_ = meta;
     hbm_block_.reset();
     from_hbm_ = !short_circuit && hbm_ && hbm_->get(c.id, &hbm_block_);
+    if (from_hbm_ && hbm_block_->len != meta.len) {  // the block changed under the resident copy: drop it, serve from the store
+        hbm_->evict(c.id);
+        hbm_block_.reset();
+        from_hbm_ = false;
+    }
     if (!from_hbm_ && !short_circuit && hbm_ && hbm_->should_promote(c.id)) {
         // read often enough from its file: load it into the HBM tier now (evicting colder blocks) and serve this read from there;
         // a refusal (tier full of blocks being read, block larger than the tier) just leaves the block where it is
-        std::vector<char> buf(static_cast<size_t>(meta.len));
-        const int pfd = ::open(meta.path.c_str(), O_RDONLY | O_CLOEXEC);
-        bool ok = pfd >= 0;
-        for (size_t got = 0; ok && got < buf.size();) {
-            const ssize_t r = pread(pfd, buf.data() + got, buf.size() - got, static_cast<off_t>(got));
-            if (r < 0 && errno == EINTR) continue;
-            if (r <= 0) ok = false;
-            else got += static_cast<size_t>(r);
+        std::vector<char> buf(meta.in_arena() ? 0 : static_cast<size_t>(meta.len));
+        bool ok = true;
+        if (!meta.in_arena()) {
+            const int pfd = ::open(meta.path.c_str(), O_RDONLY | O_CLOEXEC);
+            ok = pfd >= 0;
+            for (size_t got = 0; ok && got < buf.size();) {
+                const ssize_t r = pread(pfd, buf.data() + got, buf.size() - got, static_cast<off_t>(got));
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) ok = false;
+                else got += static_cast<size_t>(r);
+            }
+            close_fd(pfd);
         }
-        close_fd(pfd);
-        if (ok && !hbm_->load(c.id, buf.data(), meta.len, hbm_->device()) && hbm_->get(c.id, &hbm_block_)) {
+        const void* src = meta.in_arena() ? static_cast<const void*>(meta.mem()) : static_cast<const void*>(buf.data());
+        if (ok && !hbm_->load(c.id, src, meta.len, hbm_->device()) && hbm_->get(c.id, &hbm_block_)) {
             hbm_->note_promotion();
             from_hbm_ = true;
         }
@@ -70,6 +83,8 @@ Err ReadHandler::open(const RpcRequest& req, RpcResponse* resp) {
         CV_RETURN_IF_ERR(hbm_->pack(hbm_block_, c.off, len_ - c.off, c.chunk_size, req.proto.req_id, next_seq_, &packed_));
         metrics_->read_blocks_hbm++;
         metrics_->hbm_packed_bytes += len_ - c.off;
+    } else if (!short_circuit && meta.in_arena()) {
+        len_ = meta.len, pos_ = c.off;  // served from the mapping; nothing to open
     } else if (!short_circuit) {
         fd_ = ::open(meta.path.c_str(), O_RDONLY | O_CLOEXEC);
         if (fd_ < 0) return Err::io(str_printf("open %s: %s", meta.path.c_str(), strerror(errno)));
@@ -88,6 +103,7 @@ Err ReadHandler::open(const RpcRequest& req, RpcResponse* resp) {
     if (!from_hbm_) (short_circuit ? metrics_->read_blocks_local : metrics_->read_blocks_remote)++;
     BlockReadResponse r;
     r.id = c.id, r.len = meta.len, r.has_path = short_circuit, r.path = meta.path, r.storage_type = meta.storage_type;
+    if (short_circuit && meta.in_arena()) r.has_arena = true, r.arena_off = meta.hold->ext.off, r.arena_seg_len = meta.hold->arena->seg_bytes();
     resp->proto = response_proto(req.proto, kRespSuccess);
     resp->header = r.encode();
     return Err::ok();
@@ -127,7 +143,8 @@ Err ReadHandler::read(const RpcRequest& req, RpcResponse* resp) {
         metrics_->read_count++;
         return Err::ok();
     }
-    if (fd_ < 0) return Err::common("self.file is none");
+    const bool arena = has_ctx_ && meta_.in_arena() && !ctx_.short_circuit;
+    if (fd_ < 0 && !arena) return Err::common("self.file is none");
     if (!has_ctx_) return Err::common("self.context is none");
     if (!req.header.empty()) {
         DataHeaderProto h;
@@ -138,11 +155,15 @@ Err ReadHandler::read(const RpcRequest& req, RpcResponse* resp) {
         }
     }
     const double t0 = now_sec();
-    read_ahead();
+    if (!arena) read_ahead();
     const int64_t chunk = std::min<int64_t>(ctx_.chunk_size, len_ - pos_);
     if (chunk <= 0) return Err::common(str_printf("offset exceeds file length, length=%lld, offset=%lld", (long long)len_, (long long)pos_));
     resp->proto = response_proto(req.proto, kRespSuccess);
-    if (enable_send_file_) {
+    if (arena && enable_send_file_) {  // sendfile(2) out of the segment file
+        resp->file_fd = meta_.hold->arena->fd(meta_.hold->ext.seg), resp->file_off = meta_.hold->ext.off + pos_, resp->file_len = static_cast<int32_t>(chunk);
+    } else if (arena) {  // enable_send_file = false: send(2) from the worker's mapping of the segment
+        resp->mem = meta_.mem() + pos_, resp->mem_len = static_cast<int32_t>(chunk);
+    } else if (enable_send_file_) {
         resp->file_fd = fd_, resp->file_off = pos_, resp->file_len = static_cast<int32_t>(chunk);
     } else {
         resp->data.resize(static_cast<size_t>(chunk));
@@ -167,13 +188,14 @@ Err ReadHandler::complete(const RpcRequest& req, RpcResponse* resp) {
     close_fd(fd_);
     fd_ = -1;
     hbm_block_.reset();  // the read context's reference on the resident block
+    meta_ = BlockMeta();  // ... and on the arena extent
     resp->proto = response_proto(req.proto, kRespSuccess);
     return Err::ok();
 }
 
 // ------------------------------------------------------------------ WriteHandler
 
-WriteHandler::~WriteHandler() { close_fd(fd_); }
+WriteHandler::~WriteHandler() { close_fd(fd_); }  // an open arena extent stays findable in the BlockStore (Complete / Cancel / re-Open)
 
 Err WriteHandler::handle(const RpcRequest& req, RpcResponse* resp) {
     switch (req.proto.req_status) {
@@ -189,26 +211,31 @@ Err WriteHandler::open(const RpcRequest& req, RpcResponse* resp) {
     BlockWriteRequest c;
     CV_RETURN_IF_ERR(BlockWriteRequest::decode(reinterpret_cast<const uint8_t*>(req.header.data()), req.header.size(), &c));
     if (c.off > c.block_size) return Err::common(str_printf("Invalid write offset: %lld, block size: %lld", (long long)c.off, (long long)c.block_size));
-    CV_RETURN_IF_ERR(store_->open_block_path(c.block.id, c.block.storage_type, &path_, &dir_storage_type_));
+    CV_RETURN_IF_ERR(store_->open_block(c.block.id, c.block.storage_type, c.block_size, &target_));
+    target_open_ = true;
     const bool short_circuit = c.short_circuit;
+    if (short_circuit && target_.arena) {
+        store_->abort_block(c.block.id, &target_), target_open_ = false;
+        return Err(kUnsupported, "short-circuit writes into the mem arena are not supported: write through the worker (short_circuit = false)");
+    }
     close_fd(fd_);
     fd_ = -1;
-    if (!short_circuit) {
-        fd_ = ::open(path_.c_str(), O_WRONLY | O_CREAT | O_CLOEXEC, 0644);
-        if (fd_ < 0) return Err::io(str_printf("open %s: %s", path_.c_str(), strerror(errno)));
-        pos_ = c.off;
+    if (!short_circuit && !target_.arena) {
+        fd_ = ::open(target_.path.c_str(), O_WRONLY | O_CREAT | O_CLOEXEC, 0644);
+        if (fd_ < 0) return Err::io(str_printf("open %s: %s", target_.path.c_str(), strerror(errno)));
     }
+    pos_ = c.off;
     ctx_ = c, ctx_req_id_ = req.proto.req_id, has_ctx_ = true, is_commit_ = false;
     metrics_->write_blocks++;
     BlockWriteResponse r;
-    r.id = c.block.id, r.has_path = short_circuit, r.path = path_, r.off = c.off, r.block_size = c.block_size, r.storage_type = dir_storage_type_;
+    r.id = c.block.id, r.has_path = short_circuit, r.path = target_.path, r.off = c.off, r.block_size = c.block_size, r.storage_type = target_.dir_storage_type;
     resp->proto = response_proto(req.proto, kRespSuccess);
     resp->header = r.encode();
     return Err::ok();
 }
 
 Err WriteHandler::write(const RpcRequest& req, RpcResponse* resp) {
-    if (fd_ < 0) return Err::common("self.file is none");
+    if (fd_ < 0 && !(target_open_ && target_.arena)) return Err::common("self.file is none");
     if (!has_ctx_) return Err::common("self.context is none");
     if (ctx_req_id_ != req.proto.req_id)
         return Err::common(str_printf("Request id mismatch, expected %lld, actual %lld", (long long)ctx_req_id_, (long long)req.proto.req_id));
@@ -226,12 +253,16 @@ Err WriteHandler::write(const RpcRequest& req, RpcResponse* resp) {
         if (pos_ + n > ctx_.block_size)
             return Err::common(str_printf("Write range [%lld, %lld) exceeds block size %lld", (long long)pos_, (long long)(pos_ + n), (long long)ctx_.block_size));
         const double t0 = now_sec();
-        int64_t done = 0;
-        while (done < n) {
-            const ssize_t w = pwrite(fd_, req.data.data() + done, static_cast<size_t>(n - done), pos_ + done);
-            if (w < 0 && errno == EINTR) continue;
-            if (w <= 0) return Err::io(str_printf("write %s: %s", path_.c_str(), strerror(errno)));
-            done += w;
+        if (target_.arena) {
+            memcpy(target_.mem() + pos_, req.data.data(), static_cast<size_t>(n));
+        } else {
+            int64_t done = 0;
+            while (done < n) {
+                const ssize_t w = pwrite(fd_, req.data.data() + done, static_cast<size_t>(n - done), pos_ + done);
+                if (w < 0 && errno == EINTR) continue;
+                if (w <= 0) return Err::io(str_printf("write %s: %s", target_.path.c_str(), strerror(errno)));
+                done += w;
+            }
         }
         pos_ += n;
         metrics_->write_bytes += n;
@@ -257,26 +288,33 @@ Err WriteHandler::complete(const RpcRequest& req, RpcResponse* resp, bool commit
     fd_ = -1;
     if (c.block.block_size > c.block_size)
         return Err::common(str_printf("Invalid write offset: %lld, block size: %lld", (long long)c.block.block_size, (long long)c.block_size));
-    std::string path;
-    int32_t st_type = kStorageDisk;
-    CV_RETURN_IF_ERR(store_->open_block_path(c.block.id, c.block.storage_type, &path, &st_type));
-    if (commit) {  // finalize: the block's length is what the client committed
-        if (truncate(path.c_str(), c.block.block_size) != 0 && errno != ENOENT) return Err::io(str_printf("truncate %s: %s", path.c_str(), strerror(errno)));
-        struct stat st;
-        if (stat(path.c_str(), &st) != 0) return Err::io(str_printf("finalize %s: %s", path.c_str(), strerror(errno)));
-        CV_RETURN_IF_ERR(store_->register_block(c.block.id, st.st_size, st_type, path));
-    } else {  // abort
-        ::unlink(path.c_str());
-        store_->remove_block(c.block.id);
+    if (!target_open_) {  // Complete/Cancel without a live Open on this connection (write_handler.rs:246-259 re-derives the path)
+        CV_RETURN_IF_ERR(store_->open_block(c.block.id, c.block.storage_type, c.block_size, &target_));
+        target_open_ = true;
     }
+    if (commit) {  // finalize: the block's length is what the client committed
+        int64_t len = c.block.block_size;
+        if (!target_.arena) {
+            if (truncate(target_.path.c_str(), len) != 0 && errno != ENOENT) return Err::io(str_printf("truncate %s: %s", target_.path.c_str(), strerror(errno)));
+            struct stat st;
+            if (stat(target_.path.c_str(), &st) != 0) return Err::io(str_printf("finalize %s: %s", target_.path.c_str(), strerror(errno)));
+            len = st.st_size;
+        }
+        CV_RETURN_IF_ERR(store_->commit_block(c.block.id, &target_, len));
+        if (hbm_) hbm_->evict(c.block.id);  // a resident copy of the previous bytes must not be served any more
+    } else {  // abort
+        store_->abort_block(c.block.id, &target_);
+    }
+    target_open_ = false;
     is_commit_ = true;
     return Err::ok();
 }
 
 Worker::~Worker() { stop(); }
 
-Err Worker::start(const std::vector<std::string>& data_dirs, const std::string& cluster_id, const std::string& host, int port, bool enable_send_file) {
-    CV_RETURN_IF_ERR(store_.init(data_dirs, cluster_id));
+Err Worker::start(const std::vector<std::string>& data_dirs, const std::string& cluster_id, const std::string& host, int port, bool enable_send_file,
+                  const ArenaOpts& arena) {
+    CV_RETURN_IF_ERR(store_.init(data_dirs, cluster_id, arena));
     enable_send_file_ = enable_send_file;
     CV_RETURN_IF_ERR(tcp_listen(host, port, &listen_fd_, &port_));
     stopping_ = false;
@@ -348,7 +386,7 @@ void Worker::serve(int fd) {
         Err e;
         if (req.proto.code == kCodeWriteBlock) {
             handler.reset();  // handler_matches_code (worker_handler.rs:89-98): a different code replaces the live handler
-            if (!whandler || req.proto.req_status != kReqRunning) whandler.reset(new WriteHandler(&store_, &metrics_));
+            if (!whandler || req.proto.req_status != kReqRunning) whandler.reset(new WriteHandler(&store_, &metrics_, &hbm_));
             e = whandler->handle(req, &resp);
         } else if (req.proto.code != kCodeReadBlock) {
             e = Err::common(str_printf("Unsupported request type: %d", int(req.proto.code)));
@@ -369,14 +407,19 @@ void Worker::serve(int fd) {
             continue;
         }
         resp.proto.header_len = static_cast<int32_t>(resp.header.size());
-        resp.proto.data_len = resp.file_fd >= 0 ? resp.file_len : static_cast<int32_t>(resp.data.size());
+        resp.proto.data_len = resp.mem ? resp.mem_len : resp.file_fd >= 0 ? resp.file_len : static_cast<int32_t>(resp.data.size());
         uint8_t out[kProtocolSize];
         encode_protocol(resp.proto, out);
         // prefix + header in one write, then the payload region (rpc_frame.rs:205-220)
         std::string head(reinterpret_cast<char*>(out), kProtocolSize);
         head += resp.header;
-        if (resp.file_fd < 0) head += resp.data;
-        if (send_all(fd, head.data(), head.size())) return;
+        if (resp.file_fd < 0 && !resp.mem) head += resp.data;
+        if (resp.mem) {  // prefix and payload leave in one segment train (MSG_MORE), payload straight out of the arena mapping
+            if (send_more(fd, head.data(), head.size()) || send_all(fd, resp.mem, static_cast<size_t>(resp.mem_len))) return;
+            if (req.proto.req_status == kReqCancel || req.proto.req_status == kReqComplete) handler.reset(), whandler.reset();
+            continue;
+        }
+        if (resp.file_fd >= 0 ? send_more(fd, head.data(), head.size()) : send_all(fd, head.data(), head.size())) return;
         if (resp.file_fd >= 0 && send_file_full(fd, resp.file_fd, resp.file_off, static_cast<size_t>(resp.file_len))) return;
         if (req.proto.req_status == kReqCancel || req.proto.req_status == kReqComplete) handler.reset(), whandler.reset();
     }

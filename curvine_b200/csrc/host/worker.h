@@ -43,6 +43,8 @@ struct RpcResponse {
     int file_fd = -1;   // sendfile region when >= 0
     int64_t file_off = 0;
     int32_t file_len = 0;
+    const uint8_t* mem = nullptr;  // payload straight out of the worker's mapping of a mem-arena segment (send(2), no page lookups)
+    int32_t mem_len = 0;
     bool empty = false;
 };
 
@@ -68,6 +70,7 @@ class ReadHandler {
     int64_t pos_ = 0, len_ = 0, last_ahead_ = -1;
     bool is_tmpfs_ = false;
     std::string path_;
+    BlockMeta meta_;  // an arena block's meta keeps its extent allocated for as long as this context lives
     // HBM tier: the whole response stream of this read, packed by K4 at Open
     HbmTier* hbm_ = nullptr;
     bool from_hbm_ = false;
@@ -81,7 +84,7 @@ class ReadHandler {
 // (curvine-server/src/worker/handler/write_handler.rs:90-300).
 class WriteHandler {
    public:
-    WriteHandler(BlockStore* store, WorkerMetrics* m) : store_(store), metrics_(m) {}
+    WriteHandler(BlockStore* store, WorkerMetrics* m, HbmTier* hbm = nullptr) : store_(store), metrics_(m), hbm_(hbm) {}
     ~WriteHandler();
     Err handle(const RpcRequest& req, RpcResponse* resp);
 
@@ -91,20 +94,22 @@ class WriteHandler {
     Err complete(const RpcRequest& req, RpcResponse* resp, bool commit);
     BlockStore* store_;
     WorkerMetrics* metrics_;
+    HbmTier* hbm_ = nullptr;
     bool has_ctx_ = false, is_commit_ = false;
     BlockWriteRequest ctx_;
     int64_t ctx_req_id_ = 0;
     int fd_ = -1;
     int64_t pos_ = 0;
-    std::string path_;
-    int32_t dir_storage_type_ = kStorageDisk;
+    BlockWriteTarget target_;  // the file or arena extent this context writes to
+    bool target_open_ = false;
 };
 
 class Worker {
    public:
     Worker() = default;
     ~Worker();
-    Err start(const std::vector<std::string>& data_dirs, const std::string& cluster_id, const std::string& host, int port, bool enable_send_file);
+    Err start(const std::vector<std::string>& data_dirs, const std::string& cluster_id, const std::string& host, int port, bool enable_send_file,
+              const ArenaOpts& arena = ArenaOpts());
     void stop();
     int port() const { return port_; }
     BlockStore& store() { return store_; }

@@ -107,7 +107,7 @@ __global__ void prep_unpack_kernel(const uint8_t* wire, const CvFrameDesc* desc,
     if (req_id != d.req_id) e |= CV_FERR_REQ_ID;
     if (seq_id != d.seq_id) e |= CV_FERR_SEQ_ID;
     if (err_flags) err_flags[i] = e;
-    Piece p{f + CV_PROTOCOL_SIZE + d.header_len, dst + d.dst_off, d.data_len};
+    Piece p{f + CV_PROTOCOL_SIZE + d.header_len, dst + d.dst_off, d.data_len - (d.tail_clip < d.data_len ? d.tail_clip : d.data_len)};
     pieces[i] = p;
     counts[i] = piece_geom<true>(p, seg_shift).units;
 }
@@ -189,8 +189,8 @@ __global__ void expand_streams_kernel(const CvStreamDesc* streams, uint32_t n_st
         o.block = d.block;
         o.code = d.code;
         o.status = d.status;
-#pragma unroll
-        for (int k = 0; k < 6; k++) o.pad_[k] = 0;
+        o.pad_[0] = o.pad_[1] = 0;
+        o.tail_clip = f + 1 == nf ? d.tail_clip : 0;
         out[idx] = o;
     }
 }
@@ -724,10 +724,10 @@ __global__ void __launch_bounds__(256)
     if (lane == 0) out[b] = ~(gf_mul(0xffffffffu, mult, poly) ^ acc);
 }
 
-__global__ void verify_crcs_kernel(const uint32_t* crc, const uint32_t* expect, uint32_t n, uint32_t* n_bad,
+__global__ void verify_crcs_kernel(const uint32_t* crc, const uint32_t* expect, const uint8_t* skip, uint32_t n, uint32_t* n_bad,
                                    uint8_t* bad_mask) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool bad = i < n && crc[i] != expect[i];
+    const bool bad = i < n && !(skip && skip[i]) && crc[i] != expect[i];
     if (i < n && bad_mask) bad_mask[i] = bad;
     const uint32_t m = __ballot_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_bad, __popc(m));
@@ -1001,7 +1001,17 @@ int cvk_verify_crcs(const uint32_t* d_crc, const uint32_t* d_expect, uint32_t n,
                     uint8_t* d_bad_mask, cv_stream_t stream) {
     if (n == 0) return 0;
     DeviceGuard guard(d_crc);
-    verify_crcs_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_crc, d_expect, n, d_n_bad,
+    verify_crcs_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_crc, d_expect, nullptr, n, d_n_bad,
+                                                                                   d_bad_mask);
+    count_launch();
+    return int(cudaGetLastError());
+}
+
+int cvk_verify_crcs_masked(const uint32_t* d_crc, const uint32_t* d_expect, const uint8_t* d_skip, uint32_t n, uint32_t* d_n_bad,
+                           uint8_t* d_bad_mask, cv_stream_t stream) {
+    if (n == 0) return 0;
+    DeviceGuard guard(d_crc);
+    verify_crcs_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_crc, d_expect, d_skip, n, d_n_bad,
                                                                                    d_bad_mask);
     count_launch();
     return int(cudaGetLastError());

@@ -49,6 +49,15 @@ class MiniWorker:
         _lib.lib().cv_free(out)
         return text
 
+    def delete_file(self, inode_id: int, n_blocks: int):
+        """Drop the blocks of a synthetic file from the BlockStore (block files unlinked / arena extents freed)."""
+        _check(_lib.lib().cv_synth_delete_file(self._h, inode_id, n_blocks))
+
+    def arena_stats(self) -> dict:
+        a = (ctypes.c_int64 * 5)()
+        _check(_lib.lib().cv_worker_arena_stats(self._h, a))
+        return dict(zip(["arenas", "segments", "segment_bytes", "used_bytes", "populate_us"], a))
+
     def hbm_load(self, block_id: int, device: int = 0):
         """HBM tier: make a finalized block resident in device memory; remote reads are then served from HBM (K4-packed frames)."""
         _check(_lib.lib().cv_worker_hbm_load(self._h, block_id, device))
@@ -225,6 +234,15 @@ class CurvineFileSystem:
         h, n = ctypes.c_void_p(), ctypes.c_int64()
         _check(_lib.lib().cv_open(self._h, path.encode(), ctypes.byref(h), ctypes.byref(n)))
         return Reader(h)
+
+    def preregister(self):
+        """Mem-arena tier: start mapping + pinning the `[b200] arena_preregister` dirs now (mount time), in the background."""
+        _check(_lib.lib().cv_fs_preregister(self._h))
+
+    def arena_stats(self) -> dict:
+        a = (ctypes.c_uint64 * 5)()
+        _check(_lib.lib().cv_fs_arena_stats(self._h, a))
+        return dict(zip(["segments", "pinned_bytes", "register_us", "dma_jobs", "dma_bytes"], a))
 
     def wait_registered(self):
         """Block until the background registrar of the zero-copy mem tier is idle (optional; reads never wait for it)."""

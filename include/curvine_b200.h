@@ -69,6 +69,14 @@ int64_t cv_fs_close(cv_fs* fs);
  * default ([b200] register_when_idle = true) the registrar only works while no device read is in flight, so a cold
  * pass runs at pinned-ring speed and later passes over the same blocks are zero-copy. */
 int64_t cv_fs_wait_registered(cv_fs* fs);
+/* Mem-arena tier (worker `[worker] mem_arena = true`, curvine_b200/csrc/host/arena.h): start mapping + pinning the arena
+ * segments of the dirs named in `[b200] arena_preregister` now, in the background ("mount time"; otherwise it starts with
+ * the first device read).  cv_fs_wait_registered waits for it.  Once a segment is pinned, every block the worker keeps in
+ * it -- of any file, written at any time -- is DMA'd straight out of it: the first read of a file costs what a re-read costs.
+ * stats: out[0]=segments mapped, out[1]=bytes pinned, out[2]=registration wall time (us), out[3]=block jobs and out[4]=bytes
+ * DMA'd straight out of pinned segments. */
+int64_t cv_fs_preregister(cv_fs* fs);
+int64_t cv_fs_arena_stats(cv_fs* fs, uint64_t out[5]);
 /* client metrics (client_metrics.rs:24-35): out[0]=read_bytes out[1]=read_time_us */
 int64_t cv_fs_metrics(cv_fs* fs, int64_t out[2]);
 /* block connection pool (block_client_pool.rs:102-168): out[0]=idle connections now (idle_conn), out[1]=connections opened so far,
@@ -157,9 +165,17 @@ int64_t cv_worker_metrics(cv_worker* w, int64_t out[6]);
 int64_t cv_synth_create_file(cv_worker* w, const char* path, int64_t inode_id, int64_t len, int64_t block_size,
                              int32_t storage_type, int32_t mode, int32_t hole_every, int32_t threads,
                              const char* worker_hostname, char** manifest_out);
+/* Remove the n_blocks blocks of synthetic file `inode_id` from the worker's BlockStore (files unlinked / arena extents freed). */
+int64_t cv_synth_delete_file(cv_worker* w, int64_t inode_id, int64_t n_blocks);
+/* Mem arenas of the worker: out[0]=arena dirs, out[1]=segments, out[2]=segment bytes, out[3]=bytes in use,
+ * out[4]=time spent creating + populating the segments (us). */
+int64_t cv_worker_arena_stats(cv_worker* w, int64_t out[5]);
 /* NUMA-aware mem-tier placement for round-robin shards: after cv_synth_set_shard_world(G), block b of newly created
- * files is first-touched on the NUMA node of GPU b % G (G = 1: everything next to GPU 0; 0 turns it off). */
+ * files is first-touched on the NUMA node of GPU b % G (G = 1: everything next to GPU 0; 0 turns it off), and goes to the
+ * (b % G)-th data dir of its storage type -- with one [MEM] arena dir per GPU, GPU g's blocks all live in arena g. */
 int64_t cv_synth_set_shard_world(int32_t shard_world);
+/* NUMA node of the PCIe root CUDA device `device` hangs off, -1 when unknown ([worker] arena_numa, [b200] numa_node). */
+int64_t cv_gpu_numa_node(int32_t device);
 /* fill buf with block `block_index` of file `file_id` (mode 0 generator) */
 void cv_synth_block(uint64_t file_id, uint64_t block_index, uint8_t* buf, size_t len);
 /* host CRC used for manifests (slicing / SSE4.2) */

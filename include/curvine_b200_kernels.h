@@ -62,7 +62,9 @@ typedef struct CvFrameDesc {
     uint32_t block;      /* dense block index; frames of one block are contiguous and in stream order */
     uint8_t code;        /* expected code (81) */
     uint8_t status;      /* expected status byte (0x03 = Running|Success) */
-    uint8_t pad_[6];
+    uint8_t pad_[2];
+    uint32_t tail_clip;  /* K2: the last tail_clip payload bytes of the frame are validated as part of the frame but not copied
+                          * (a ranged read whose last chunk runs past the wanted range); 0 for whole frames.  K4 ignores it. */
 } CvFrameDesc;
 
 /* A whole pipelined block response stream with closed-form frame offsets:
@@ -79,7 +81,8 @@ typedef struct CvStreamDesc {
     uint32_t first_frame; /* index of this stream's first frame in the expanded descriptor table */
     uint8_t code;
     uint8_t status;
-    uint8_t pad_[6];
+    uint8_t pad_[2];
+    uint32_t tail_clip;   /* bytes at the end of the stream (inside its last frame) that are received but not delivered */
 } CvStreamDesc;
 
 /* scatter/gather segment: d_dst[dst_off .. dst_off+len) = d_src[src_off .. src_off+len) */
@@ -101,6 +104,11 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
 /* d_n_bad += #{i : d_crc[i] != d_expect[i]} ; d_bad_mask[i] = mismatch (optional, may be NULL). */
 int cvk_verify_crcs(const uint32_t* d_crc, const uint32_t* d_expect, uint32_t n, uint32_t* d_n_bad,
                     uint8_t* d_bad_mask, cv_stream_t stream);
+
+/* Same, but entries with d_skip[i] != 0 are not compared (blocks the manifest holds no CRC for, holes, partial
+ * ranges): one such block no longer switches the comparison off for its neighbours.  d_skip may be NULL. */
+int cvk_verify_crcs_masked(const uint32_t* d_crc, const uint32_t* d_expect, const uint8_t* d_skip, uint32_t n,
+                           uint32_t* d_n_bad, uint8_t* d_bad_mask, cv_stream_t stream);
 
 /* K2: validate n frame prefixes, gather payloads to d_dst and CRC them in the same pass.
  * d_block_crc[b] (b < n_blocks) = CRC of block b's payload bytes in frame order; d_err_flags[f] = CV_FERR_*.

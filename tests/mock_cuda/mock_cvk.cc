@@ -73,6 +73,17 @@ int cvk_verify_crcs(const uint32_t* d_crc, const uint32_t* d_expect, uint32_t n,
     return 0;
 }
 
+int cvk_verify_crcs_masked(const uint32_t* d_crc, const uint32_t* d_expect, const uint8_t* d_skip, uint32_t n, uint32_t* d_n_bad, uint8_t* d_bad_mask,
+                           cv_stream_t) {
+    for (uint32_t i = 0; i < n; i++) {
+        const bool bad = !(d_skip && d_skip[i]) && d_crc[i] != d_expect[i];
+        if (d_bad_mask) d_bad_mask[i] = bad;
+        if (bad) (*d_n_bad)++;
+    }
+    g_launches++;
+    return 0;
+}
+
 int cvk_expand_streams(const CvStreamDesc* s, uint32_t n_streams, CvFrameDesc* out, uint32_t n_frames, cv_stream_t) {
     for (uint32_t i = 0; i < n_streams; i++) {
         const CvStreamDesc& d = s[i];
@@ -87,6 +98,7 @@ int cvk_expand_streams(const CvStreamDesc* s, uint32_t n_streams, CvFrameDesc* o
             const uint64_t rem = d.block_len - f * d.chunk_size;
             o.data_len = static_cast<uint32_t>(rem < d.chunk_size ? rem : d.chunk_size);
             o.req_id = d.req_id, o.seq_id = d.first_seq_id + static_cast<int32_t>(f), o.block = d.block, o.code = d.code, o.status = d.status;
+            o.tail_clip = f + 1 == nf ? d.tail_clip : 0;
             out[idx] = o;
         }
     }
@@ -116,10 +128,11 @@ int cvk_unpack_frames(const uint8_t* d_wire, const CvFrameDesc* d_desc, uint32_t
         if (seq_id != d.seq_id) e |= CV_FERR_SEQ_ID;
         if (d_err_flags) d_err_flags[i] = e;
         const uint8_t* payload = f + CV_PROTOCOL_SIZE + d.header_len;
-        memmove(d_dst + d.dst_off, payload, d.data_len);
+        const uint32_t take = d.data_len - (d.tail_clip < d.data_len ? d.tail_clip : d.data_len);
+        memmove(d_dst + d.dst_off, payload, take);
         if (d_block_crc && d.block < n_blocks) {
             if (d.block != cur) state = 0xffffffffu, cur = d.block;
-            state = crc_update(poly, state, payload, d.data_len);
+            state = crc_update(poly, state, payload, take);
             d_block_crc[d.block] = ~state;
         }
     }

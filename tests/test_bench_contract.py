@@ -25,10 +25,10 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_own_arm_control_flow_and_json_line_on_the_mock_runtime():
-    """bench.py's own arm (context warm-up read, cold pass, registration wait, timed e2e steps, HBM-resident value steps,
-    roofline, cpu_baseline) executed end to end without a GPU: tests/mock_cuda/run_bench_on_mock.py swaps in the mock library and
+    """bench.py's own arm (arena mount, context warm-up read, fresh-file steps, re-read / pread / framed side legs, HBM-resident K1
+    steps, roofline, cpu_baseline) executed end to end without a GPU: tests/mock_cuda/run_bench_on_mock.py swaps in the mock library and
     tells torch that "cuda" tensors are CPU tensors.  Checks the control flow and the contract of the printed line; every number
-    in it is meaningless here and is looked at only for type and bookkeeping (bytes per step, launch counts, cache counters)."""
+    in it is meaningless here and is looked at only for type and bookkeeping (bytes per step, launch counts, DMA counters)."""
     sys.path.insert(0, os.path.join(ROOT, "tests", "mock_cuda"))
     try:
         import build as mock_build
@@ -48,15 +48,23 @@ def test_own_arm_control_flow_and_json_line_on_the_mock_runtime():
     assert d["n_gpus"] == 1 and d["steps"] == steps and d["warmup"] == warmup and d["higher_is_better"] is True
     assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "u8" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["ms_per_step"] > 0 and "workload" in d["config"] and "model" not in d["config"]
+    assert d["config"]["fresh_file_every_step"] is True and d["config"]["mem_tier"] == "arena"
     e = d["e2e"]
     assert e["unit"] == "GB/s" and e["value"] > 0 and e["h2d_bytes_per_step"] == n and e["d2h_bytes_per_step"] == 4 * (blocks + 4)
-    assert len(e["timed_steps_ms"]) == steps and len(e["warmup_steps_ms"]) == warmup and e["registration_ms"] is not None
-    groups = blocks // 8  # copy_group = 8; + 2 groups of the context warm-up file
-    assert e["registered_mapping_cache"] == {"hits": groups * (steps + warmup - 1), "misses": groups + 2}
-    assert d["gpu_launches"] == 6 * steps  # prep, scan, expand, walk, fold + compare per HBM-resident step
+    assert len(e["timed_steps_ms"]) == steps and len(e["warmup_steps_ms"]) == warmup
+    # `value` is an ingest rate of the same steps (device-timed region inside the e2e region), never the HBM-resident kernel rate
+    assert d["value"] >= e["value"] * 0.999 and d["value"] < e["value"] * 1.5
+    # every headline block was DMA'd out of the arena pinned at mount: nothing registered per file, no pinned ring
+    a = d["arena_dma"]
+    assert a["block_jobs"] == blocks * (steps + warmup) + 16 and a["registered_mapping_cache_hits"] == 0 and a["pinned_ring_allocated"] is False
+    assert d["mount"]["segments"] >= 1 and d["mount"]["pinned_bytes"] == d["mount"]["segments"] * (1 << 30)
+    assert d["gpu_launches"] > 0
     r = d["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["algorithmic_bytes_per_launch"] == n and r["launches_timed"] == steps
-    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "note" in r
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["algorithmic_bytes_per_launch"] == n and r["launches_timed"] == 5
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "note" in r and r["traffic"] is None
+    assert d["resident_verify"]["value"] > 0
+    for leg in ("e2e_reread", "e2e_pread", "e2e_framed"):
+        assert d[leg]["unit"] == "GB/s" and d[leg]["value"] > 0 and d[leg]["steps"] == 2, leg
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["unit"] == "GB/s" and c["value"] > 0 and c["cores"] >= 2 and "pass" in c["sample"]
@@ -65,7 +73,7 @@ def test_own_arm_control_flow_and_json_line_on_the_mock_runtime():
 def test_own_arm_two_ranks_on_the_mock_runtime():
     """The N>1 launch the driver uses (torch.distributed.run, one rank per GPU) with world_size 2 on CPU: gloo stands in for NCCL, the
     mock runtime for the GPUs.  Rank 0 hosts the worker and generates the 2 x 0.25 GiB file, the manifest is broadcast, every rank
-    reads its round-robin shard, timings are max-reduced, rank 0 prints the one line."""
+    reads its round-robin shard out of ITS arena dir, timings are max-reduced, rank 0 prints the one line."""
     import socket
     sys.path.insert(0, os.path.join(ROOT, "tests", "mock_cuda"))
     try:
@@ -78,7 +86,7 @@ def test_own_arm_two_ranks_on_the_mock_runtime():
     port = s.getsockname()[1]
     s.close()
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
-                        os.path.join(ROOT, "tests", "mock_cuda", "run_bench_on_mock.py"), "--gpus", "2", "--gib-per-gpu", "0.25", "--steps", "2", "--warmup", "2"],
+                        os.path.join(ROOT, "tests", "mock_cuda", "run_bench_on_mock.py"), "--gpus", "2", "--gib-per-gpu", "0.25", "--steps", "2", "--warmup", "1", "--side-steps", "1"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-3000:]
     lines = [l for l in p.stdout.splitlines() if l.strip().startswith("{")]

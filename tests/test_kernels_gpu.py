@@ -144,6 +144,34 @@ def test_unpack_frames_matches_oracle(cuda, poly, chunk, blens):
     assert exp.cpu().numpy().tobytes() == K.frame_descs_to_device(descs, cuda).cpu().numpy().tobytes()
 
 
+@pytest.mark.parametrize("clip", [1, 15, 16, 4095, 4096])
+def test_unpack_frames_clips_the_tail_of_a_ranged_read(cuda, clip):
+    """K2 with CvFrameDesc.tail_clip / CvStreamDesc.tail_clip: the last frame of a range that stops short of its block's end is
+    validated as the whole frame the worker sent, but only data_len - tail_clip payload bytes are copied; bytes behind the range stay
+    untouched.  (The reference trims such a chunk on the host: fs_reader_buffer.rs:283-301, reader.rs:71-81.)"""
+    import torch
+    from curvine_b200 import kernels as K
+    blocks = [_rand(3 * 4096 + 1234, 70), _rand(4096, 71)]
+    wire, descs, streams, total = _build_wire(blocks, 4096, [900, 901], 1)
+    last0 = max(i for i, d in enumerate(descs) if d.block == 0)
+    c = min(clip, descs[last0].data_len)
+    descs[last0].tail_clip = c
+    streams[0].tail_clip = c
+    want = bytearray(b"\xEE" * (total + 32))
+    off = 0
+    for bi, b in enumerate(blocks):
+        n = len(b) - (c if bi == 0 else 0)
+        want[off:off + n] = b.tobytes()[:n]
+        off += len(b)
+    dst = torch.full((total + 32,), 0xEE, dtype=torch.uint8, device=cuda)
+    crc, err = K.unpack_frames(_to_dev(wire, cuda), K.frame_descs_to_device(descs, cuda), len(descs), 2, dst, 1, total)
+    assert (K.u32(err) == 0).all()
+    assert dst.cpu().numpy().tobytes() == bytes(want)
+    assert K.u32(crc).tolist() == [clib.crc(1, blocks[0][:len(blocks[0]) - c]), clib.crc(1, blocks[1])]
+    exp = K.expand_streams(K.stream_descs_to_device(streams, cuda), len(streams), len(descs), cuda)
+    assert exp.cpu().numpy().tobytes() == K.frame_descs_to_device(descs, cuda).cpu().numpy().tobytes()
+
+
 def test_unpack_frames_flags_bad_prefixes(cuda):
     import torch
     from curvine_b200 import kernels as K

@@ -415,3 +415,25 @@ def test_random_mixed_host_and_device_op_sequences(cuda, cluster, sc, zero_copy,
             assert r.pos() == pos
         assert r.verify()[1] == 0
         r.complete()
+
+
+@pytest.mark.timeout(120)
+def test_single_fetch_thread_framed_read_larger_than_the_ring_does_not_wait_for_itself(cuda, cluster):
+    """with fetch_threads = 1 the fetch worker used to run inline on the calling thread; a framed (verbatim)
+    group's ring slot is only released by the verifier, which runs on that same thread afterwards -- once the copy groups
+    outnumbered the ring's super-slots the inline worker waited for itself forever.  64 x 1 MiB framed blocks through 6 super-slots."""
+    import torch
+    w, _ = cluster
+    n, bs, ino = 64 << 20, 1 << 20, 7990
+    man = w.create_file("/one_thread", ino, n, bs)
+    want = synth.file_bytes(ino, n, bs)
+    with F.CurvineFileSystem(_conf(False, 1, "1MB", threads=1, batch=4, copy_group=2)) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/one_thread")
+        dst = _dev_buf(n, cuda)
+        assert r.read_device(dst.data_ptr(), n, torch.cuda.current_stream().cuda_stream) == n
+        s, bad, ver = r.verify()
+        torch.cuda.synchronize()
+        assert bad == 0 and ver == 64
+        assert dst.cpu().numpy().tobytes() == want
+        r.complete()

@@ -633,8 +633,16 @@ Err FsReader::open(FsContext* ctx, const std::string& path, std::unique_ptr<FsRe
     if (r->slice_size_ % c.read_chunk_size != 0 || r->slice_size_ < c.read_chunk_size)
         return Err::common("The slice size must be an integer multiple of the chunk size.");
     for (auto& s : split_slices(r->len_, r->slice_size_, r->det_.read_parallel))
-        if (!s.empty()) r->readers_.emplace_back(new FsReaderParallel(ctx, r->fb_.get(), std::move(s), false));
-    r->readers_.emplace_back(new FsReaderParallel(ctx, r->fb_.get(), {{0, r->len_}}, true));  // the random-read base reader
+        if (!s.empty()) {
+            std::unique_ptr<FsReaderParallel> pr(new FsReaderParallel(ctx, r->fb_.get(), std::move(s), false));
+            Adapter a;
+            if (c.read_chunk_num == 1) a.base = std::move(pr);  // fs_reader_buffer.rs:181-183
+            else a.chan.reset(new PrefetchChannel(std::move(pr), static_cast<size_t>(c.read_chunk_num)));
+            r->readers_.push_back(std::move(a));
+        }
+    Adapter base;  // the random-read base reader
+    base.base.reset(new FsReaderParallel(ctx, r->fb_.get(), {{0, r->len_}}, true));
+    r->readers_.push_back(std::move(base));
     *out = std::move(r);
     return Err::ok();
 }
@@ -647,7 +655,7 @@ Err FsReader::buffer_read() {
     if (id < 0 || id >= static_cast<int64_t>(readers_.size())) return Err::common(str_printf("reader %lld is not initialized", (long long)id));
     const double t0 = now_sec();
     int64_t off = 0;
-    CV_RETURN_IF_ERR(readers_[static_cast<size_t>(id)]->read(&off, &chunk_));
+    CV_RETURN_IF_ERR(readers_[static_cast<size_t>(id)].read(&off, &chunk_));
     const int64_t diff = bpos_ - off;
     if (diff == 0) {
     } else if (diff > 0 && diff <= static_cast<int64_t>(chunk_.size())) {
@@ -659,7 +667,7 @@ Err FsReader::buffer_read() {
     const int64_t start = bpos_;
     bpos_ += n;
     if (det_.record_read(start, bpos_) && det_.is_sequential())
-        for (auto& r : readers_) CV_RETURN_IF_ERR(r->seek(bpos_));
+        for (auto& r : readers_) CV_RETURN_IF_ERR(r.pause(bpos_, false));  // fs_reader_buffer.rs:304-313
     ctx_->read_bytes += n;
     ctx_->read_time_us += static_cast<int64_t>((now_sec() - t0) * 1e6);
     return Err::ok();
@@ -668,7 +676,10 @@ Err FsReader::buffer_read() {
 Err FsReader::buffer_seek(int64_t pos) {
     if (pos == bpos_) return Err::ok();
     det_.record_seek();
-    for (auto& r : readers_) CV_RETURN_IF_ERR(r->seek(pos));
+    for (auto& r : readers_) {  // fs_reader_buffer.rs:325-337
+        CV_RETURN_IF_ERR(r.seek(pos));
+        if (!det_.enabled) CV_RETURN_IF_ERR(r.pause(pos, false));
+    }
     bpos_ = pos;
     return Err::ok();
 }
@@ -722,10 +733,117 @@ Err FsReader::seek(int64_t pos) {
 Err FsReader::complete() {
     Err first;
     for (auto& r : readers_) {
-        Err e = r->complete();
+        Err e = r.complete();
         if (e && !first) first = e;
     }
     return first;
+}
+
+// ------------------------------------------------------------------ PrefetchChannel (fs_reader_buffer.rs:42-94,332-406)
+
+PrefetchChannel::~PrefetchChannel() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (started_ && !exited_) tasks_.push_back(Task{2, 0, false, 0});
+        cv_.notify_all();
+    }
+    if (th_.joinable()) th_.join();
+}
+
+void PrefetchChannel::start_locked() {
+    if (started_) return;
+    started_ = true;
+    th_ = std::thread([this] { loop(); });
+}
+
+// read_future: control messages first (biased select), then one chunk whenever the queue has room and the task is not paused
+void PrefetchChannel::loop() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+        if (!tasks_.empty()) {
+            const Task t = tasks_.front();
+            tasks_.pop_front();
+            lk.unlock();
+            Err e;
+            if (t.kind == 0) e = reader_->seek(t.pos);
+            else if (t.kind == 1) e = reader_->seek(t.pos);
+            else e = reader_->complete();
+            lk.lock();
+            if (t.kind == 0) paused_ = true;
+            if (t.kind == 1) paused_ = t.flag;
+            if (t.ticket) done_ticket_ = std::max(done_ticket_, t.ticket);
+            if (e && !err_) err_ = e;
+            if (e || t.kind == 2) break;
+            cv_.notify_all();
+            continue;
+        }
+        if (!paused_ && q_.size() < cap_) {
+            lk.unlock();
+            int64_t off = 0;
+            std::string buf;
+            Err e = reader_->read(&off, &buf);
+            lk.lock();
+            if (e) {
+                if (!err_) err_ = e;
+                break;
+            }
+            if (buf.empty()) paused_ = true;  // out of slices: an empty chunk is sent so a reader never blocks, then wait for a command
+            q_.emplace_back(off, std::move(buf));
+            cv_.notify_all();
+            continue;
+        }
+        cv_.wait(lk);
+    }
+    exited_ = true;
+    cv_.notify_all();
+}
+
+Err PrefetchChannel::read(int64_t* off, std::string* buf) {
+    std::unique_lock<std::mutex> lk(mu_);
+    start_locked();
+    cv_.wait(lk, [&] { return !q_.empty() || exited_; });
+    if (q_.empty()) return err_ ? err_ : Err::io("prefetch channel closed");
+    *off = q_.front().first;
+    *buf = std::move(q_.front().second);
+    q_.pop_front();
+    cv_.notify_all();
+    return Err::ok();
+}
+
+Err PrefetchChannel::seek(int64_t pos) {
+    std::unique_lock<std::mutex> lk(mu_);
+    start_locked();
+    if (exited_) return err_ ? err_ : Err::io("prefetch channel closed");
+    const uint64_t ticket = next_ticket_++;
+    tasks_.push_back(Task{0, pos, false, ticket});
+    cv_.notify_all();
+    cv_.wait(lk, [&] { return done_ticket_ >= ticket || exited_; });
+    if (done_ticket_ < ticket) return err_ ? err_ : Err::io("prefetch channel closed");
+    q_.clear();  // everything prefetched before the seek is stale (the task is paused now: nothing new arrives)
+    return err_;
+}
+
+Err PrefetchChannel::pause(int64_t pos, bool paused) {
+    std::unique_lock<std::mutex> lk(mu_);
+    start_locked();
+    if (exited_) return err_ ? err_ : Err::io("prefetch channel closed");
+    tasks_.push_back(Task{1, pos, paused, 0});
+    cv_.notify_all();
+    return Err::ok();
+}
+
+Err PrefetchChannel::complete() {
+    std::unique_lock<std::mutex> lk(mu_);
+    if (!started_) return reader_->complete();  // never used: nothing is open
+    if (!exited_) {
+        const uint64_t ticket = next_ticket_++;
+        tasks_.push_back(Task{2, 0, false, ticket});
+        cv_.notify_all();
+        cv_.wait(lk, [&] { return exited_; });
+    }
+    lk.unlock();
+    if (th_.joinable()) th_.join();
+    return err_;
 }
 
 }  // namespace cv

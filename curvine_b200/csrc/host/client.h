@@ -14,14 +14,17 @@
 //   curvine-client/src/file/read_detector.rs:130-218               sequential/random detector
 //   curvine-client/src/file/fs_reader.rs:103-126                   seek fast path
 //   curvine-common/src/fs/reader.rs:50-141                         read_chunk / read / read_full / fuse_read
-// Prefetch tasks + mpsc channels of the reference are replaced by lazy sub-readers here: the delivered
-// byte/chunk sequence is identical, the overlap comes from the GPU ingest pipeline instead (gpu_reader.*).
+//   curvine-client/src/file/fs_reader_buffer.rs:30-94,147-222,332-406  prefetch tasks: one per striped sub-reader, a
+//        bounded channel of read_chunk_num chunks each, Seek / Pause / Stop control messages (PrefetchChannel below)
 #pragma once
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <list>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -230,6 +233,44 @@ class FsReaderParallel {
     int64_t cur_ = -1;
 };
 
+// BufferChannel + FsReaderBuffer::read_future (fs_reader_buffer.rs:42-94,332-406): a striped sub-reader owned by a prefetch
+// thread that keeps up to `cap` chunks ahead of the consumer in a bounded queue.  Control messages as in the reference:
+//   seek(pos)   the thread seeks its reader and PAUSES; the consumer then drops everything that was prefetched
+//   pause(pos, paused)  seek + set the paused flag (resume = pause(pos, false)); fire and forget
+//   stop()      complete() on the reader, thread exits
+// An empty chunk (the sub-reader ran out of slices) is delivered too and pauses the thread; the first error ends the thread
+// and is what every later read() returns.  The thread starts with the first use (the reference spawns its tasks in
+// FsReaderBuffer::new; here a reader that is only ever used for device reads must not prefetch into host memory).
+class PrefetchChannel {
+   public:
+    PrefetchChannel(std::unique_ptr<FsReaderParallel> reader, size_t cap) : reader_(std::move(reader)), cap_(std::max<size_t>(cap, 1)) {}
+    ~PrefetchChannel();
+    Err read(int64_t* off, std::string* buf);
+    Err seek(int64_t pos);
+    Err pause(int64_t pos, bool paused);
+    Err complete();
+
+   private:
+    struct Task {
+        int kind;  // 0 seek, 1 pause, 2 stop
+        int64_t pos;
+        bool flag;
+        uint64_t ticket;
+    };
+    void start_locked();
+    void loop();
+    std::unique_ptr<FsReaderParallel> reader_;
+    size_t cap_;
+    std::thread th_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::pair<int64_t, std::string>> q_;
+    std::deque<Task> tasks_;
+    uint64_t next_ticket_ = 1, done_ticket_ = 0;
+    bool started_ = false, paused_ = false, exited_ = false;
+    Err err_;
+};
+
 // FsReader + FsReaderBuffer + the provided methods of `trait Reader`
 class FsReader {
    public:
@@ -255,7 +296,16 @@ class FsReader {
     std::shared_ptr<const FileBlocks> fb_;
     int64_t len_ = 0, pos_ = 0, bpos_ = 0, chunk_size_ = 0, slice_size_ = 0;
     ReadDetector det_;
-    std::vector<std::unique_ptr<FsReaderParallel>> readers_;
+    // ReaderAdapter (fs_reader_buffer.rs:96-132): Buffer(channel) for the striped sub-readers when read_chunk_num > 1, Base otherwise
+    struct Adapter {
+        std::unique_ptr<PrefetchChannel> chan;
+        std::unique_ptr<FsReaderParallel> base;
+        Err read(int64_t* off, std::string* buf) { return chan ? chan->read(off, buf) : base->read(off, buf); }
+        Err seek(int64_t pos) { return chan ? chan->seek(pos) : base->seek(pos); }
+        Err pause(int64_t pos, bool paused) { return chan ? chan->pause(pos, paused) : base->seek(pos); }
+        Err complete() { return chan ? chan->complete() : base->complete(); }
+    };
+    std::vector<Adapter> readers_;
     std::string chunk_;     // current chunk storage
     size_t chunk_off_ = 0;  // consumed prefix
     std::string tmp_;

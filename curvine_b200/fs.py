@@ -193,6 +193,14 @@ class Reader:
     def __exit__(self, *a):
         self.complete()
 
+    def __del__(self):  # a handle that was never closed still releases its connections and prefetch threads
+        try:
+            if self._h:
+                h, self._h = self._h, None
+                _lib.lib().cv_close_reader(h)
+        except Exception:
+            pass
+
 
 class Writer:
     """Write-side mirror: Writer::{write, complete, cancel} (curvine-common/src/fs/writer.rs) + write_device."""

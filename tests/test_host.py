@@ -681,3 +681,28 @@ def test_config_c1_shape_cpu_reader_end_to_end(cluster, sc):
     assert cks == clib.bench_checksum(want, 128 * 1024)
     m = w.metrics()
     assert (m["read_blocks_local"] if sc else m["read_blocks_remote"]) >= 64
+
+
+@pytest.mark.parametrize("chunk_num,ahead", [(8, True), (1, False)])
+def test_host_reader_prefetches_read_chunk_num_chunks_ahead(cluster, chunk_num, ahead):
+    """fs_reader_buffer.rs:147-222,332-406: with read_chunk_num > 1 every striped sub-reader is a prefetch task that keeps a
+    bounded channel of read_chunk_num chunks filled; with read_chunk_num == 1 the sub-reader is read inline (ReaderAdapter::Base).
+    Observed at the worker: after ONE chunk was consumed, the prefetching reader has already pulled the next ones."""
+    import time
+    w, _ = cluster
+    n, bs, ino = 4 << 20, 4 << 20, 2600 + chunk_num
+    man = w.create_file("/pf%d" % chunk_num, ino, n, bs)
+    before = w.metrics()["read_count"]
+    with F.CurvineFileSystem(F.client_conf(short_circuit=False, read_chunk_size="64KB", read_chunk_num=chunk_num)) as fs:
+        fs.load_namespace(man)
+        r = fs.open("/pf%d" % chunk_num)
+        first = r.read_chunk()
+        assert first == synth.file_bytes(ino, n, bs)[:65536]
+        time.sleep(0.3)
+        pulled = w.metrics()["read_count"] - before
+        assert (pulled >= 8 and pulled <= 10) if ahead else pulled == 1, pulled
+        # a seek drops what was prefetched and the stream continues bit-exact from the new position
+        r.seek(1 << 20)
+        rest = r.read_full(n)
+        assert rest == synth.file_bytes(ino, n, bs)[1 << 20:] and r.pos() == n
+        r.complete()

@@ -264,6 +264,86 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* __res
     if (tid == 0) prefix[n] = carry;
 }
 
+// Many pieces (a FUSE-shaped gather has one per 4 KiB page: 262,144 for 1 GiB): the single-CTA scan above takes longer than the
+// copy it prepares.  Two parallel launches instead: every CTA sums its tile of 4096 counts; then every CTA adds up the tile sums
+// before its own (at most a few hundred values) and scans its tile from that carry.
+__device__ __forceinline__ uint32_t block_sum_1024(uint32_t v, uint32_t* sh) {  // sh: 32 words; result valid in every thread
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    uint32_t t = sh[lane];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) tile_sums_kernel(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t sh[32];
+    const uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4;
+    uint32_t v = 0;
+    if (base + 4 <= n) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(counts + base));
+        v = c.x + c.y + c.z + c.w;
+    } else {
+        for (uint32_t k = 0; k < 4; k++)
+            if (base + k < n) v += __ldg(counts + base + k);
+    }
+    const uint32_t t = block_sum_1024(v, sh);
+    if (threadIdx.x == 0) sums[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t n, const uint32_t* __restrict__ sums,
+                                                          uint32_t* __restrict__ prefix) {
+    __shared__ uint32_t sh[32];
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t before = 0;
+    for (uint32_t i = tid; i < blockIdx.x; i += 1024) before += __ldg(sums + i);
+    const uint32_t carry = block_sum_1024(before, sh);
+    const uint32_t base = blockIdx.x * 4096u + tid * 4;
+    uint4 c = make_uint4(0, 0, 0, 0);
+    if (base + 4 <= n) c = __ldg(reinterpret_cast<const uint4*>(counts + base));
+    else {
+        if (base < n) c.x = __ldg(counts + base);
+        if (base + 1 < n) c.y = __ldg(counts + base + 1);
+        if (base + 2 < n) c.z = __ldg(counts + base + 2);
+    }
+    const uint32_t sum = c.x + c.y + c.z + c.w;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        warp_sums[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    const uint32_t e0 = carry + warp_sums[warp] + incl - sum;
+    const uint4 o = make_uint4(e0, e0 + c.x, e0 + c.x + c.y, e0 + c.x + c.y + c.z);
+    if (base + 4 <= n) {
+        *reinterpret_cast<uint4*>(prefix + base) = o;
+    } else {
+        if (base < n) prefix[base] = o.x;
+        if (base + 1 < n) prefix[base + 1] = o.y;
+        if (base + 2 < n) prefix[base + 2] = o.z;
+    }
+    // the thread that holds element n-1 also writes the total
+    if (base < n && base + 4 >= n) prefix[n] = e0 + sum;
+}
+
 // ------------------------------------------------------------------ the row walker
 
 constexpr uint32_t kTmWords = 4 * 256 * 32;  // replicated x^4096 tables: [table][byte][lane]
@@ -318,6 +398,12 @@ __device__ __forceinline__ uint4 ld_plain(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+}
+
+// 16-byte store to GLOBAL memory.  The walkers' destination pointer lives in the unit table as a generic pointer, so a plain
+// `*p = v` compiles to a generic ST.E.128 (address-space check per store); every destination here is global memory.
+__device__ __forceinline__ void st_vec(uint4* p, const uint4& v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // One output vector of a shifted walk: 16 bytes starting Q words + r8 bits into the 8-word window [ra | nb].
@@ -394,7 +480,7 @@ __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, u
         for (int k = 0; k < T; k++) {
             const uint4 nb = take_right<Q>(ra[k], k + 1 < T ? ra[(k + 1) % T] : ex, lane);
             const uint4 v = shift_window<Q>(ra[k], nb, r8);
-            dp[(j + k) * 32] = v;
+            st_vec(dp + (j + k) * 32, v);
             if (CRC) CV_STEP(v);
         }
     }
@@ -405,10 +491,10 @@ __device__ __forceinline__ void walk_shifted(const uint8_t* src, uint8_t* dst, u
         const uint4 nb = take_right<Q>(ra, ex, lane);
         const uint4 v = shift_window<Q>(ra, nb, r8);
         if (j < R) {
-            dp[j * 32] = v;
+            st_vec(dp + j * 32, v);
             if (CRC) CV_STEP(v);
         } else if (lane < nv) {
-            dp[j * 32] = v;
+            st_vec(dp + j * 32, v);
             c.vr = v;
         }
     }
@@ -429,18 +515,18 @@ __device__ __forceinline__ void walk_aligned_copy(const uint8_t* src, uint8_t* d
         for (int k = 0; k < T; k++) v[k] = ld_plain(sp + (j + k) * 32);
 #pragma unroll
         for (int k = 0; k < T; k++) {
-            dp[(j + k) * 32] = v[k];
+            st_vec(dp + (j + k) * 32, v[k]);
             if (CRC) CV_STEP(v[k]);
         }
     }
     for (; j < R; j++) {
         const uint4 v = ld_plain(sp + j * 32);
-        dp[j * 32] = v;
+        st_vec(dp + j * 32, v);
         if (CRC) CV_STEP(v);
     }
     if (lane < nv) {
         c.vr = ld_plain(sp + R * 32);
-        dp[R * 32] = c.vr;
+        st_vec(dp + R * 32, c.vr);
     }
     c.a0 = a0, c.a1 = a1, c.a2 = a2, c.a3 = a3;
 }
@@ -494,10 +580,10 @@ __device__ __forceinline__ void walk_staged(const uint8_t* src, uint8_t* dst, ui
         const uint4 nb = lds128(right + (lane == 31 ? nslot : slot) * 512u);
         const uint4 v = shift_window<Q>(ra, nb, r8);
         if (j < R) {
-            dp[j * 32] = v;
+            st_vec(dp + j * 32, v);
             if (CRC) CV_STEP(v);
         } else if (lane < nv) {
-            dp[j * 32] = v;
+            st_vec(dp + j * 32, v);
             c.vr = v;
         }
         __syncwarp();  // all lanes are done with slot `slot` before it is refilled
@@ -812,7 +898,9 @@ static int ensure_device(int* dev_out) {
     return 0;
 }
 
+static std::atomic<int> g_seg_shift_override{0};  // cvk_tune(4, s): segment size 2^s for every launcher (0 = chosen from the input size)
 static uint32_t pick_seg_shift(uint64_t total_bytes, int sm_count) {
+    if (const int o = g_seg_shift_override.load(std::memory_order_relaxed)) return static_cast<uint32_t>(o);
     // ~16 units per warp keeps the contiguous per-CTA ranges balanced for big inputs; small inputs get 16 KiB segments
     // (4 KiB below 4 MiB) so the per-block fold stays short.  4 KiB..1 MiB.
     const uint64_t target = total_bytes / (uint64_t(sm_count) * 32 * 16 + 1);
@@ -886,6 +974,17 @@ struct WalkTimer {
         g_prof_events.emplace_back(a, b);
     }
 };
+// exclusive prefix sum of w.counts[0..n) into w.prefix[0..n]; headraw is free until the walker runs and holds the tile sums
+static int launch_scan(const Workspace& w, uint32_t n, cudaStream_t st) {
+    if (n <= 16384) {
+        scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
+        return 1;
+    }
+    const uint32_t tiles = cdiv(n, 4096);
+    tile_sums_kernel<<<tiles, 1024, 0, st>>>(w.counts, n, w.headraw);
+    scan_tiles_kernel<<<tiles, 1024, 0, st>>>(w.counts, n, w.headraw, w.prefix);
+    return 2;
+}
 #define CV_WALK_ARGS w.units, w.prefix + n, cc, w.partial, w.partial_cap, w.headraw, w.tailraw
 // (pieces, prefix) -> one 32-byte record per unit; every walker launch is preceded by this
 template <bool DST>
@@ -938,6 +1037,7 @@ int cvk_tune(int what, int value) {
     if (what == 0 && (value == 2 || value == 4)) g_tile_crc_dst.store(value);
     else if (what == 1 && (value == 2 || value == 4)) g_tile_copy.store(value);
     else if (what == 3 && (value == 0 || value == 1)) g_staged.store(value != 0);
+    else if (what == 4 && (value == 0 || (value >= 12 && value <= 20))) g_seg_shift_override.store(value);
     else return int(cudaErrorInvalidValue);
     return 0;
 }
@@ -983,7 +1083,7 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
     if (int rc = ws_alloc(&w, dev, n, n, total_bytes, seg_shift, st)) return rc;
     const CrcConsts* cc = g_consts[dev][poly];
     prep_blocks_kernel<<<cdiv(n, 256), 256, 0, st>>>(d_base, d_off, d_len, n, seg_shift, w.pieces, w.counts);
-    scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
+    const int n_scan = launch_scan(w, n, st);
     launch_expand<false>(w, n, seg_shift, st);
     {
         WalkTimer wt(st);
@@ -993,7 +1093,7 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
     fold_blocks_kernel<false><<<cdiv(uint64_t(n) * 32, 256), 256, 0, st>>>(w.pieces, w.prefix, nullptr, nullptr, n, n, seg_shift,
                                                                            gf_xpow(8ull << seg_shift, poly_of(poly)), cc,
                                                                            w.partial, w.headraw, w.tailraw, d_crc_out);
-    count_launch(5);
+    count_launch(4 + n_scan);
     return ws_finish(w, st);
 }
 
@@ -1046,9 +1146,9 @@ static int frames_common(bool pack, const uint8_t* d_in, const CvFrameDesc* d_de
     else
         prep_unpack_kernel<<<cdiv(n_frames, 256), 256, 0, st>>>(d_in, d_desc, n_frames, d_out, seg_shift, w.pieces,
                                                                 w.counts, d_err_flags);
-    scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n_frames, w.prefix);
+    const int n_scan = launch_scan(w, n_frames, st);
     launch_expand<true>(w, n_frames, seg_shift, st);
-    count_launch(3);
+    count_launch(2 + n_scan);
     if (d_block_crc) {
         {
             WalkTimer wt(st);
@@ -1080,10 +1180,10 @@ int cvk_pack_frames(const uint8_t* d_src, const CvFrameDesc* d_desc, uint32_t n_
 }
 
 static int copy_pieces(Workspace& w, uint32_t n, uint32_t seg_shift, int dev, cudaStream_t st, bool peer = false) {
-    scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, n, w.prefix);
+    const int n_scan = launch_scan(w, n, st);
     launch_expand<true>(w, n, seg_shift, st);
     launch_walk_copy(dev, st, w, n, peer);
-    count_launch(3);
+    count_launch(2 + n_scan);
     return ws_finish(w, st);
 }
 

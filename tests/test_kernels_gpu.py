@@ -227,7 +227,7 @@ def test_gather_pages(cuda):
     assert dst.cpu().numpy().tobytes() == want.tobytes()
 
 
-@pytest.mark.parametrize("n_segs", [4095, 4096, 4097, 13001])
+@pytest.mark.parametrize("n_segs", [4095, 4096, 4097, 13001, 16384, 16385, 20480, 40003])  # > 16384 pieces: the multi-CTA scan
 def test_many_small_pieces_multi_tile_scan(cuda, n_segs):
     """More pieces than one scan tile (4096): FUSE-shaped scatter of thousands of tiny pages, and the CRC of
     thousands of small blocks -- the prefix sum over piece unit counts spans several tiles, zero-length pieces included."""

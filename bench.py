@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--gpu-chunk", default="4MB")
     ap.add_argument("--framed-threads", type=int, default=0)
     ap.add_argument("--poly", type=int, default=1)
+    ap.add_argument("--settle-ms", type=int, default=0, help="pause between writing a step's file and reading it (diagnostic)")
     ap.add_argument("--side-steps", type=int, default=2, help="timed steps of each side leg (reread / pread / framed); 0 skips them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dir", default="")
@@ -273,6 +274,8 @@ def run_leg(name, cluster, fs, tier, args, rank, world, dist, dst, shard_bytes, 
             paths.append(path)
             if fresh and len(paths) > args.pool:
                 cluster.drop(paths.pop(0))
+        if args.settle_ms:
+            time.sleep(args.settle_ms / 1e3)
         barrier(dist)
         t0 = time.time()
         e2e_ms, ing_ms, s, stats = timed_read(fs, paths[-1], rank, world, dst, shard_bytes, stream)
@@ -313,7 +316,8 @@ def main():
     my_blocks = shard_bytes // BLOCK
     ncpu = os.cpu_count() or 8
     threads = args.fetch_threads or max(4, min(16, ncpu // (2 * world)))
-    fthreads = args.framed_threads or max(4, min(24, ncpu // (2 * world)))
+    # loopback TCP stops scaling at ~16 connections on this box (profiles/r02_loopback_probe.txt: 46 GB/s at 16, 35 at 24, 28 at 32)
+    fthreads = args.framed_threads or max(4, min(16, ncpu // (2 * world)))
     slots = args.slots or (2 * args.verify_batch + threads + 8)
     side = args.side_steps
     cluster = Cluster(args, rank, world, dist, shard_bytes, need_files_tier=True)
@@ -382,7 +386,8 @@ def main():
             pread = run_leg("pread", cluster, fs3, "files", args, rank, world, dist, dst, shard_bytes, side, 1, True, 7000)
             fs3.close()
             # TCP frames from the arena worker (send(2) out of its mapping), received verbatim, unpacked + CRC'd by K2
-            fs2 = F.CurvineFileSystem(client_conf(args, cluster, False, local, fthreads, 2 * args.verify_batch + fthreads + 8, rank))
+            # one block per ring slot (copy_group 1): every connection fills its own slot, the verifier frees slots 16 blocks at a time
+            fs2 = F.CurvineFileSystem(client_conf(args, cluster, False, local, fthreads, 2 * args.verify_batch + 2 * fthreads + 8, rank, copy_group=1))
             framed = run_leg("framed", cluster, fs2, "arena", args, rank, world, dist, dst, shard_bytes, side, 1, True, 8000)
             fs2.close()
 
@@ -454,8 +459,11 @@ def main():
                                        "prefix, gathers and CRCs (gpu_chunk %s, %d connections)" % (args.gpu_chunk, fthreads))):
                 if side_ms[k]:
                     v = gbps(side_ms[k])
+                    leg = {"reread": reread, "pread": pread, "framed": framed}[k]
                     out["e2e_" + k] = {"value": v, "unit": UNIT, "ms_per_step": side_ms[k], "per_gpu_GBps": v / world,
-                                       "frac_of_pcie_gen5_x16_raw_63GBps": v / world / PCIE_RAW, "steps": side, "what": what}
+                                       "frac_of_pcie_gen5_x16_raw_63GBps": v / world / PCIE_RAW, "steps": side, "what": what,
+                                       "timed_steps_ms": leg["e2e_ms"], "last_step_fetch_thread_sec": leg["stats"]["fetch_sec"],
+                                       "last_step_wall_sec": leg["stats"]["wall_sec"], "h2d_bytes_last_step": int(leg["stats"]["h2d_bytes"])}
             if world == 1 and not args.no_cpu_baseline:
                 out["cpu_baseline"] = cpu_baseline(cluster, args)
     finally:

@@ -97,6 +97,8 @@ def _declare(L):
     L.cv_shard_plan.restype = i64
     L.cv_fuse_read_device.argtypes = [vp, i64, i64, vp, vp, vp, i32, i64, vp, cp(i64)]
     L.cv_fuse_read_device.restype = i64
+    L.cv_fuse_read_file_device.argtypes = [vp, c, i64, vp, vp, vp, i32, i64, vp, cp(i64), cp(u32)]
+    L.cv_fuse_read_file_device.restype = i64
     L.cv_verify.argtypes, L.cv_verify.restype = [vp, cp(u64), cp(u32), cp(u64)], i64
     L.cv_device_stats.argtypes, L.cv_device_stats.restype = [vp, cp(CvReadStats)], i64
     L.cv_writer_open.argtypes, L.cv_writer_open.restype = [vp, c, i64, i64, i32, c, i32, i64, cp(vp)], i64
@@ -128,7 +130,7 @@ EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_verify_crcs_mas
            "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_gather_shards_p2p", "cvk_launch_count", "cvk_tune", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
            "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_wait_registered", "cv_fs_preregister", "cv_fs_arena_stats", "cv_synth_delete_file", "cv_worker_arena_stats", "cv_gpu_numa_node", "cv_fs_metrics", "cv_fs_pool_stats",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
-           "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device",
+           "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device", "cv_fuse_read_file_device",
            "cv_verify", "cv_device_stats", "cv_writer_open", "cv_write", "cv_write_device", "cv_writer_close", "cv_worker_start", "cv_worker_stop", "cv_worker_hbm_load", "cv_worker_hbm_stats", "cv_worker_hbm_tier", "cv_worker_metrics",
            "cv_synth_create_file", "cv_synth_set_shard_world", "cv_synth_block", "cv_host_crc"]
 

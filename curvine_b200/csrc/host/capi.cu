@@ -328,34 +328,37 @@ int64_t cv_fuse_read_device(cv_reader* r, int64_t pos, int64_t len, void* d_scra
                             int32_t n_pages, int64_t page_size, cv_stream_t stream, int64_t* nbytes) {
     API_GUARD_BEGIN
     API_NEED(r);
+    API_NEED(page_offsets);
     API_TRY(ensure_dev(r));
     API_TRY(r->host->seek(pos));
     API_TRY(r->dev->seek(pos));
     int64_t n = 0;
-    API_TRY(r->dev->read_device(d_scratch, len, stream, &n));
+    // ResponseData::as_iovec analogue on the device: the bytes land in the scratch, are CRC'd, and go to the reply's page buffers
+    // in the same launch train (segment table in the reader's pinned staging: no allocation, no synchronisation here)
+    API_TRY(r->dev->fuse_read_device(len, d_scratch, d_page_base, page_offsets, n_pages, page_size, stream, &n));
     API_TRY(r->host->seek(r->dev->pos()));
-    // ResponseData::as_iovec analogue on the device: chunk bytes -> the reply's page buffers
-    const int64_t need_pages = (n + page_size - 1) / page_size;
-    if (need_pages > n_pages) return fail(Err::common("not enough page buffers for the reply"));
-    if (need_pages > 0) {
-        std::vector<CvSeg> segs(static_cast<size_t>(need_pages));
-        for (int64_t i = 0; i < need_pages; i++) {
-            segs[static_cast<size_t>(i)].src_off = static_cast<uint64_t>(i * page_size);
-            segs[static_cast<size_t>(i)].dst_off = page_offsets[i];
-            segs[static_cast<size_t>(i)].len = static_cast<uint64_t>(std::min(page_size, n - i * page_size));
-        }
-        cudaStream_t st = static_cast<cudaStream_t>(stream);
-        CvSeg* d_segs = nullptr;
-        cudaError_t ce = cudaMallocAsync(&d_segs, sizeof(CvSeg) * segs.size(), st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_segs, segs.data(), sizeof(CvSeg) * segs.size(), cudaMemcpyHostToDevice, st);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // segs is a stack-lifetime pageable buffer
-        int rc = ce != cudaSuccess ? int(ce)
-                                   : cvk_gather_pages(static_cast<const uint8_t*>(d_scratch), d_segs, static_cast<uint32_t>(need_pages),
-                                                      static_cast<uint64_t>(n), static_cast<uint8_t*>(d_page_base), stream);
-        if (d_segs) cudaFreeAsync(d_segs, st);
-        if (rc) return fail(Err::io(str_printf("cvk_gather_pages: %s", cudaGetErrorString(cudaError_t(rc)))));
-    }
     if (nbytes) *nbytes = n;
+    return ok();
+    API_GUARD_END
+}
+
+// open -> fuse_read(0, len) -> verify -> close of ONE file in one call: what a FUSE daemon does for a small file
+// (reader.rs:101-124 behind FileSystem::open / Reader::complete), without four trips through the binding
+int64_t cv_fuse_read_file_device(cv_fs* fs, const char* path, int64_t len, void* d_scratch, void* d_page_base, const uint64_t* page_offsets, int32_t n_pages,
+                                 int64_t page_size, cv_stream_t stream, int64_t* nbytes, uint32_t* n_bad) {
+    API_GUARD_BEGIN
+    API_NEED(fs);
+    API_NEED(path);
+    API_NEED(page_offsets);
+    std::unique_ptr<GpuFsReader> dev;
+    API_TRY(GpuFsReader::open(fs->ctx.get(), path, &dev));
+    int64_t n = 0;
+    API_TRY(dev->fuse_read_device(len, d_scratch, d_page_base, page_offsets, n_pages, page_size, stream, &n));
+    uint64_t s = 0, v = 0;
+    uint32_t b = 0;
+    API_TRY(dev->verify(&s, &b, &v));
+    if (nbytes) *nbytes = n;
+    if (n_bad) *n_bad = b;
     return ok();
     API_GUARD_END
 }

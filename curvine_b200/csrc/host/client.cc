@@ -148,7 +148,34 @@ Err Namespace::get_block_locations(const std::string& path, std::shared_ptr<cons
 
 BlockClient::~BlockClient() { close_fd(fd_); }
 
+static Protocol request_proto(int8_t status, int64_t req_id, int32_t seq_id);
+
+Err BlockClient::drain_pending() {
+    while (!pending_.empty()) {
+        const Protocol req = pending_.front();
+        pending_.erase(pending_.begin());
+        Protocol resp;
+        std::string rh, rd;
+        CV_RETURN_IF_ERR(recv_response_head(&resp, &rh));
+        rd.resize(static_cast<size_t>(resp.data_len));
+        if (resp.data_len) {
+            Err e = recv_exact(fd_, &rd[0], rd.size());
+            if (e) {
+                broken = true;
+                return e;
+            }
+        }
+        if (req.req_id != resp.req_id || req.seq_id != resp.seq_id) {
+            broken = true;
+            return Err::common("response mismatch on a deferred Complete");
+        }
+        if (!resp.is_success()) return decode_error_body(reinterpret_cast<const uint8_t*>(rd.data()), rd.size());
+    }
+    return Err::ok();
+}
+
 Err BlockClient::send_request(const Protocol& req, const std::string& header) {
+    if (!pending_.empty()) CV_RETURN_IF_ERR(drain_pending());
     Protocol p = req;
     p.header_len = static_cast<int32_t>(header.size());
     p.data_len = 0;
@@ -236,6 +263,15 @@ Err BlockClient::read_commit(const ExtendedBlock& b, int64_t req_id, int32_t seq
     return rpc(request_proto(kReqComplete, req_id, seq_id), r.encode(), &resp, &rh, &rd);
 }
 
+Err BlockClient::read_commit_deferred(const ExtendedBlock& b, int64_t req_id, int32_t seq_id) {
+    BlockReadRequest r;
+    r.id = b.id;
+    const Protocol p = request_proto(kReqComplete, req_id, seq_id);
+    CV_RETURN_IF_ERR(send_request(p, r.encode()));
+    pending_.push_back(p);
+    return Err::ok();
+}
+
 // ------------------------------------------------------------------ FsContext (connection pool)
 
 FsContext::~FsContext() = default;
@@ -261,7 +297,9 @@ Err FsContext::acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClie
             std::unique_ptr<BlockClient> c = std::move(v.back());  // LIFO
             v.pop_back();
             idle_total_--;
-            if (now - c->idle_since_ms < conf.client.block_conn_idle_time_ms && pooled_connection_is_usable(c->fd())) {
+            // a connection parked with a deferred Complete outstanding has (or will have) that response queued: it is consumed by
+            // the next request, so readable bytes are expected on it
+            if (now - c->idle_since_ms < conf.client.block_conn_idle_time_ms && (c->pending() > 0 || pooled_connection_is_usable(c->fd()))) {
                 *out = std::move(c);
                 return Err::ok();
             }

@@ -98,6 +98,11 @@ class BlockClient {
     Err open_block(const ClientConf& conf, const ExtendedBlock& b, int64_t off, int64_t len, int64_t req_id, int32_t seq_id, bool short_circuit,
                    int64_t chunk_size, BlockReadResponse* out, bool accept_arena = false);
     Err read_commit(const ExtendedBlock& b, int64_t req_id, int32_t seq_id);
+    // Complete without waiting for the answer (GPU reader: one round trip less per block).  The response is consumed -- and its
+    // echo / status checked -- before the next request goes out on this connection (drain_pending), also after a trip through the pool.
+    Err read_commit_deferred(const ExtendedBlock& b, int64_t req_id, int32_t seq_id);
+    Err drain_pending();
+    size_t pending() const { return pending_.size(); }
     Err send_request(const Protocol& req, const std::string& header);
     Err recv_response_head(Protocol* resp, std::string* resp_header);  // prefix + header; payload left on the socket
     bool broken = false;
@@ -106,6 +111,7 @@ class BlockClient {
    private:
     int fd_;
     WorkerAddress addr_;
+    std::vector<Protocol> pending_;  // requests whose responses are still on the wire (deferred Completes)
 };
 
 class FsContext {

@@ -434,6 +434,11 @@ class ArenaSegs {
             }
             ArenaSeg& seg = *job.first;
             const size_t off = job.second * seg.slice, len = std::min(seg.slice, seg.bytes - off);
+#ifdef MADV_POPULATE_WRITE
+            // map the slice's (already allocated) tmpfs pages in bulk first: the page-by-page faults cudaHostRegister would
+            // otherwise take on a fresh mapping are what made pinning 3x slower than on the mapping that created the pages
+            madvise(seg.base + off, len, MADV_POPULATE_WRITE);
+#endif
             const cudaError_t ce = cudaHostRegister(seg.base + off, len, cudaHostRegisterDefault);
             if (ce != cudaSuccess) cudaGetLastError();
             bool last = false;
@@ -489,6 +494,8 @@ class GpuIngest {
     size_t d_tables_cap = 0;
     uint8_t* h_result = nullptr;
     size_t h_result_cap = 0;
+    uint8_t* h_tables = nullptr;  // pinned image of the per-call tables (off/len/expect/skip, stream descriptors): uploads are truly
+    size_t h_tables_cap = 0;      // asynchronous, nothing waits for them (a pageable source makes cudaMemcpyAsync drain the stream first)
     GpuFsReader* pending_owner = nullptr;  // reader whose results still sit in h_result
     RegCache reg;
     Registrar registrar;
@@ -503,6 +510,11 @@ class GpuIngest {
             if (d_tables) cudaFree(d_tables);
             d_tables_cap = tables_bytes * 2;
             CU_TRY(cudaMalloc(&d_tables, d_tables_cap));
+        }
+        if (tables_bytes > h_tables_cap) {
+            if (h_tables) cudaFreeHost(h_tables);
+            h_tables_cap = tables_bytes * 2;
+            CU_TRY(cudaHostAlloc(&h_tables, h_tables_cap, cudaHostAllocDefault));
         }
         if (result_bytes > h_result_cap) {
             if (h_result) cudaFreeHost(h_result);
@@ -612,6 +624,7 @@ class GpuIngest {
         if (d_stage) cudaFree(d_stage);
         if (d_tables) cudaFree(d_tables);
         if (h_result) cudaFreeHost(h_result);
+        if (h_tables) cudaFreeHost(h_tables);
         for (auto e : copy_ev) cudaEventDestroy(e);
         for (auto e : free_ev) cudaEventDestroy(e);
         for (auto s : copy_streams) cudaStreamDestroy(s);
@@ -713,7 +726,21 @@ Err GpuFsReader::complete() {
     return verify(&s, &b, &v);
 }
 
-Err GpuFsReader::read_device(void* d_dst, int64_t cap, void* stream, int64_t* n) {
+Err GpuFsReader::fuse_read_device(int64_t want, void* d_scratch, void* d_page_base, const uint64_t* page_offsets, int64_t n_pages, int64_t page_size,
+                                   void* stream, int64_t* n) {
+    *n = 0;
+    if (page_size <= 0) return Err::common("page_size must be positive");
+    const int64_t take = std::max<int64_t>(0, std::min(want, len() - pos_));
+    const int64_t need_pages = (take + page_size - 1) / page_size;
+    if (need_pages > n_pages) return Err::common("not enough page buffers for the reply");
+    PageScatter ps;
+    ps.d_page_base = static_cast<uint8_t*>(d_page_base), ps.page_offsets = page_offsets, ps.n_pages = need_pages, ps.page_size = page_size, ps.total = take;
+    return read_device_impl(d_scratch, take, stream, n, need_pages > 0 ? &ps : nullptr);
+}
+
+Err GpuFsReader::read_device(void* d_dst, int64_t cap, void* stream, int64_t* n) { return read_device_impl(d_dst, cap, stream, n, nullptr); }
+
+Err GpuFsReader::read_device_impl(void* d_dst, int64_t cap, void* stream, int64_t* n, const PageScatter* pages) {
     *n = 0;
     const int64_t end = std::min(len(), pos_ + std::max<int64_t>(cap, 0));
     if (end <= pos_) return Err::ok();
@@ -728,7 +755,7 @@ Err GpuFsReader::read_device(void* d_dst, int64_t cap, void* stream, int64_t* n)
         jobs.push_back(Job{&(*fbp_).block_locs[idx], boff, take, p - pos_, boff == 0 && take == blen});
         p += take;
     }
-    CV_RETURN_IF_ERR(run_jobs(jobs, static_cast<uint8_t*>(d_dst), stream));
+    CV_RETURN_IF_ERR(run_jobs(jobs, static_cast<uint8_t*>(d_dst), stream, pages));
     *n = end - pos_;
     pos_ = end;
     return Err::ok();
@@ -866,7 +893,7 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
             seq = static_cast<int32_t>(nfr);
             *wire_bytes = static_cast<size_t>(w - slot);
         }
-        last = c->read_commit(lb.block, req_id, seq + 1);
+        last = c->read_commit_deferred(lb.block, req_id, seq + 1);  // its answer is consumed in front of this connection's next request
         if (last) continue;
         return Err::ok();
     }
@@ -932,7 +959,7 @@ Err GpuFsReader::verify(uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified
     return e;
 }
 
-Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* user_stream) {
+Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* user_stream, const PageScatter* pages) {
     const size_t J = jobs.size();
     if (J == 0) return Err::ok();
     const double t_start = now_sec();
@@ -1023,10 +1050,14 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     const size_t o_off = 0, o_len = up(o_off + 8 * J), o_exp = up(o_len + 8 * J), o_skip = up(o_exp + 4 * J), o_crc = up(o_skip + J);
     const size_t res_words = J + 4 + F;
     const size_t o_streams = up(o_crc + 4 * res_words), o_fdesc = up(o_streams + sizeof(CvStreamDesc) * J);
-    const size_t tables_bytes = up(o_fdesc + sizeof(CvFrameDesc) * F);
+    const size_t n_segs = pages ? static_cast<size_t>(pages->n_pages) : 0;
+    const size_t o_segs = up(o_fdesc + sizeof(CvFrameDesc) * F);
+    const size_t tables_bytes = up(o_segs + sizeof(CvSeg) * n_segs);
     CV_RETURN_IF_ERR(G.ensure_tables(tables_bytes, 4 * res_words));
     uint8_t* T = G.d_tables;
-    std::vector<uint8_t> h(o_crc);  // host image of off/len/expect/skip
+    // host image of off/len/expect/skip (+ the stream descriptors): pinned, owned by the context, rewritten only after the
+    // previous call's results were harvested (its uploads have long executed by then)
+    uint8_t* h = G.h_tables;
     uint64_t* h_off = reinterpret_cast<uint64_t*>(&h[o_off]);
     uint64_t* h_len = reinterpret_cast<uint64_t*>(&h[o_len]);
     uint32_t* h_exp = reinterpret_cast<uint32_t*>(&h[o_exp]);
@@ -1047,11 +1078,18 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     // every whole block the manifest holds a CRC for is compared; holes, partial ranges and blocks without a manifest CRC are
     // masked out one by one (their CRCs are still computed, and summed when they lie inside [f0,f1))
     const bool compare = bc.verify && n_compared > 0;
-    CU_TRY(cudaMemcpyAsync(T, h.data(), o_crc, cudaMemcpyHostToDevice, G.vstream));
+    CU_TRY(cudaMemcpyAsync(T, h, o_crc, cudaMemcpyHostToDevice, G.vstream));
+    if (n_segs) {  // the page scatter's segment table rides in the same pinned image
+        CvSeg* hs = reinterpret_cast<CvSeg*>(h + o_segs);
+        for (size_t i = 0; i < n_segs; i++) {
+            hs[i].src_off = static_cast<uint64_t>(i) * static_cast<uint64_t>(pages->page_size), hs[i].dst_off = pages->page_offsets[i];
+            hs[i].len = static_cast<uint64_t>(std::min<int64_t>(pages->page_size, pages->total - static_cast<int64_t>(i) * pages->page_size));
+        }
+        CU_TRY(cudaMemcpyAsync(T + o_segs, hs, sizeof(CvSeg) * n_segs, cudaMemcpyHostToDevice, G.vstream));
+    }
     CU_TRY(cudaMemsetAsync(T + o_crc, 0, 4 * res_words, G.vstream));
-    std::vector<CvStreamDesc> sd;
+    CvStreamDesc* sd = reinterpret_cast<CvStreamDesc*>(h + o_streams);
     if (any_verbatim) {
-        sd.resize(J);
         for (size_t j = 0; j < J; j++) {
             CvStreamDesc& d = sd[j];
             memset(&d, 0, sizeof(d));
@@ -1062,7 +1100,6 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
             d.first_frame = first_frame[j], d.code = kCodeReadBlock, d.status = 0x03;
         }
     }
-    CU_TRY(cudaStreamSynchronize(G.vstream));  // tables are in place (and `h` was pageable) before any kernel uses them
 
     // ---- fetch threads
     struct Shared {
@@ -1149,7 +1186,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                             j = r;
                         }
                         if (ce == cudaSuccess) ce = cudaEventRecord(G.copy_ev[ss], cs);
-                        for (size_t j = j0; j < j1 && !e; j++) e = conn->read_commit((*jobs[j].lb).block, rids[j - j0], 1);
+                        for (size_t j = j0; j < j1 && !e; j++) e = conn->read_commit_deferred((*jobs[j].lb).block, rids[j - j0], 1);
                         fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
                         if (e || ce != cudaSuccess) {
                             st.fail(e ? e : Err::io(str_printf("H2D enqueue: %s", cudaGetErrorString(ce))));
@@ -1328,7 +1365,12 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
             if (!group_verbatim[g]) released[ss].store(static_cast<int64_t>(g), std::memory_order_release);
             copied[g].store(1, std::memory_order_release);
         }
-        if (conn) ctx_->release(std::move(conn));
+        if (conn) {
+            // multi-group reads: settle the deferred Completes here (their answers are long in); a single-group read (the
+            // latency path, C5) parks the connection with its last answer outstanding and the next request consumes it
+            if (NG > 1) conn->drain_pending();
+            ctx_->release(std::move(conn));
+        }
     };
     std::vector<std::thread> threads;
     // A verbatim (framed) group's slot is only released by the verifier below, so a single fetch worker running inline on this
@@ -1391,6 +1433,9 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     if (compare)
         CVK_TRY(cvk_verify_crcs_masked(d_crc + f0, reinterpret_cast<const uint32_t*>(T + o_exp) + f0, T + o_skip + f0, static_cast<uint32_t>(f1 - f0), d_crc + J, nullptr,
                                        G.vstream));
+    if (n_segs)  // every copy group was waited for and CRC'd on vstream by now: scatter the landed bytes into the page buffers
+        CVK_TRY(cvk_gather_pages(d_dst, reinterpret_cast<const CvSeg*>(T + o_segs), static_cast<uint32_t>(n_segs), static_cast<uint64_t>(pages->total), pages->d_page_base,
+                                 G.vstream));
     CU_TRY(cudaMemcpyAsync(G.h_result, d_crc, 4 * res_words, cudaMemcpyDeviceToHost, G.vstream));
     CU_TRY(cudaEventRecord(G.done_ev, G.vstream));
     CU_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(user_stream), G.done_ev, 0));

@@ -55,6 +55,10 @@ class GpuFsReader {
     const FileBlocks& file_blocks() const { return *fbp_; }
     // Next min(cap, remaining) bytes -> d_dst, ordered on `stream` when the call returns.  *n = bytes.
     Err read_device(void* d_dst, int64_t cap, void* stream, int64_t* n);
+    // FUSE-shaped: the next min(len, remaining) bytes land in d_scratch and are scattered into page buffers
+    // (d_page_base + page_offsets[i], page_size bytes each, the last one partial).
+    Err fuse_read_device(int64_t len, void* d_scratch, void* d_page_base, const uint64_t* page_offsets, int64_t n_pages, int64_t page_size, void* stream,
+                         int64_t* n);
     // Round-robin shard of the whole file: blocks b with b % world == rank land back to back in slots of
     // block_size bytes (slot j = block j*world + rank).  *n = bytes landed (sum of those block lengths).
     Err read_device_sharded(int rank, int world, void* d_dst, int64_t cap, void* stream, int64_t* n);
@@ -77,7 +81,15 @@ class GpuFsReader {
         bool full;           // whole block -> CRC comparable with the manifest
     };
     GpuFsReader() = default;
-    Err run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* stream);
+    // page scatter riding on a read (Reader::fuse_read + ResponseData::as_iovec on the device): after the bytes landed in d_dst
+    // and were CRC'd, segment i of d_dst goes to d_page_base + page_offsets[i] (K3), in the same launch train, no extra sync
+    struct PageScatter {
+        uint8_t* d_page_base = nullptr;
+        const uint64_t* page_offsets = nullptr;
+        int64_t n_pages = 0, page_size = 0, total = 0;
+    };
+    Err run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* stream, const PageScatter* pages = nullptr);
+    Err read_device_impl(void* d_dst, int64_t cap, void* stream, int64_t* n, const PageScatter* pages);
     FsContext* ctx_ = nullptr;
     std::shared_ptr<const FileBlocks> fbp_;
     int64_t pos_ = 0;

@@ -274,6 +274,15 @@ class CurvineFileSystem:
         finally:
             r.complete()
 
+    def fuse_read_file_device(self, path: str, size: int, d_scratch: int, d_page_base: int, page_offsets, page_size: int, stream: int = 0):
+        """One small file in one call: open -> FUSE-shaped device read -> verify -> close.  `page_offsets` may be a prepared
+        ctypes c_uint64 array (reused across calls).  -> (bytes, n_bad)."""
+        arr = page_offsets if isinstance(page_offsets, ctypes.Array) else (ctypes.c_uint64 * len(page_offsets))(*page_offsets)
+        n, bad = ctypes.c_int64(), ctypes.c_uint32()
+        _check(_lib.lib().cv_fuse_read_file_device(self._h, path.encode(), size, ctypes.c_void_p(d_scratch), ctypes.c_void_p(d_page_base), arr, len(arr),
+                                                   page_size, ctypes.c_void_p(stream), ctypes.byref(n), ctypes.byref(bad)))
+        return n.value, bad.value
+
     def read_many_device(self, paths, d_ptr: int, dst_offs, cap: int, stream: int = 0):
         """Small-file batching: every file of ``paths`` lands at d_ptr + dst_offs[i] in one pipelined pass.
         -> (total_bytes, sum_crc, n_bad, n_verified)."""

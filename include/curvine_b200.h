@@ -116,6 +116,11 @@ int64_t cv_shard_plan(cv_reader* r, int32_t rank, int32_t world, int64_t* block_
 int64_t cv_fuse_read_device(cv_reader* r, int64_t pos, int64_t len, void* d_scratch, void* d_page_base,
                             const uint64_t* page_offsets, int32_t n_pages, int64_t page_size, cv_stream_t stream,
                             int64_t* nbytes);
+/* One small file, one call: open -> fuse-shaped device read of the first `len` bytes -> CRC verify -> close.  Blocks until the
+ * pages hold the bytes; *n_bad = blocks whose CRC differs from the manifest. */
+int64_t cv_fuse_read_file_device(cv_fs* fs, const char* path, int64_t len, void* d_scratch, void* d_page_base,
+                                 const uint64_t* page_offsets, int32_t n_pages, int64_t page_size, cv_stream_t stream,
+                                 int64_t* nbytes, uint32_t* n_bad);
 /* Blocks until outstanding device reads of this handle finished.  sum_crc = u64 sum of per-block CRCs of every
  * whole block read so far; n_bad = blocks whose CRC differs from the manifest; n_verified = blocks compared. */
 int64_t cv_verify(cv_reader* r, uint64_t* sum_crc, uint32_t* n_bad, uint64_t* n_verified);

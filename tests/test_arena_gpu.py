@@ -196,6 +196,21 @@ def test_small_files_batch_and_fuse_scatter_over_the_arena(cuda, aw):
             ln = min(4096, 200000 - i * 4096)
             assert ph[page_offs[i]:page_offs[i] + ln] == want[0][i * 4096:i * 4096 + ln]
         r.complete()
+        # the one-call variant (open -> fuse read -> verify -> close) a FUSE daemon would use per small file
+        import ctypes
+        arr = (ctypes.c_uint64 * npages)(*page_offs)
+        for i in (3, 17, 39):
+            pages.fill_(0)
+            ln = len(want[i])
+            np_i = (ln + 4095) // 4096
+            big_pages = _buf(np_i * 4096, cuda)
+            offs_i = (ctypes.c_uint64 * np_i)(*[k * 4096 for k in range(np_i)])
+            sc = _buf(ln, cuda)
+            got, bad = fs.fuse_read_file_device("/sf%d" % i, ln, sc.data_ptr(), big_pages.data_ptr(), offs_i, 4096, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert got == ln and bad == 0
+            assert big_pages.cpu().numpy().tobytes()[:ln] == want[i]
+        del arr
 
 
 def test_corruption_inside_the_arena_is_reported_by_the_gpu_verify(cuda, aw):

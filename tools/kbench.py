@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--tile-crc", type=int, default=0, help="cvk_tune(0, v): rows per tile of the CRC+copy walkers (1, 2, 4)")
     ap.add_argument("--tile-copy", type=int, default=0, help="cvk_tune(1, v): rows per tile of the copy-only walker (2, 4)")
     ap.add_argument("--staged", type=int, default=-1, help="cvk_tune(3, v): 1 = shared-memory staged (cp.async) DST walks")
+    ap.add_argument("--seg-shift", type=int, default=0, help="cvk_tune(4, v): segment size 2^v bytes for every launcher (0 = automatic)")
     ap.add_argument("--warm-sec", type=float, default=0.25, help="seconds of back-to-back warm-up launches before timing (0 under ncu)")
     ap.add_argument("--sweep", action="store_true", help="run the K2/K4 and K3 sections once per tile setting, in this process")
     a = ap.parse_args()
@@ -61,6 +62,8 @@ def main():
         _lib.check(_lib.lib().cvk_tune(1, a.tile_copy))
     if a.staged >= 0:
         _lib.check(_lib.lib().cvk_tune(3, a.staged))
+    if a.seg_shift:
+        _lib.check(_lib.lib().cvk_tune(4, a.seg_shift))
     total = int(a.gib * (1 << 30)) // a.block * a.block
     nb = total // a.block
     data = torch.randint(0, 2 ** 31, (total // 4,), dtype=torch.int32, device=dev).view(torch.uint8)
@@ -157,7 +160,7 @@ def main():
             best, med = timeit(lambda: d2.copy_(data[:n]), a.iters)
             res["torch_copy"] = {"algo_GBps": 2 * n / best / 1e6, "algo_GBps_med": 2 * n / med / 1e6}
             del d2
-    res["tile_crc"], res["tile_copy"] = a.tile_crc or "default", a.tile_copy or "default"
+    res["tile_crc"], res["tile_copy"], res["seg_shift"] = a.tile_crc or "default", a.tile_copy or "default", a.seg_shift or "auto"
     res["launches"] = K.launch_count()
     print(json.dumps(res, indent=1))
 

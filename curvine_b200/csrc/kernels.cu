@@ -810,6 +810,99 @@ __global__ void __launch_bounds__(256)
     if (lane == 0) out[b] = ~(gf_mul(0xffffffffu, mult, poly) ^ acc);
 }
 
+// ------------------------------------------------------------------ small inputs: one launch instead of a launch train
+//
+// A FUSE-sized read (config C5: 256 KiB files) is latency-bound: the five launches of the walker train (prep, scan, expand, walk,
+// fold) and the 128 KB table replication cost more than the work.  For <= ~1 MiB in total, ONE kernel does a block per CTA:
+//   * slicing-by-4 tables (4 KB) are built in shared memory from the byte table;
+//   * the block is cut into 1024 chunks of S bytes, RIGHT-aligned (thread 1023 owns the last S bytes; the first chunk may be short
+//     or empty -- leading zeros do not change a raw CRC), each thread runs a plain table CRC over its chunk;
+//   * init 0xFFFFFFFF is folded into the data (the first four message bytes are complemented), so no x^(8*len) is needed;
+//   * chunk CRCs combine pairwise, crc(A||B) = crc(A) * x^(8|B|) + crc(B) with |B| = S * 2^k at level k: the multiplier is squared
+//     from level to level, starting at x^(8S) = xp128[S/16].
+constexpr uint32_t kSmallMaxBlock = 1024u * 1008u;  // S <= 1008 so that S/16 < 64 (xp128 table)
+
+__global__ void __launch_bounds__(1024) crc_small_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
+                                                         const CrcConsts* __restrict__ cc, uint32_t* __restrict__ out) {
+    __shared__ uint32_t T[4][256];
+    __shared__ uint32_t part[32];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5, b = blockIdx.x;
+    const uint8_t* src = base + off[b];
+    const uint32_t n = static_cast<uint32_t>(len[b]);
+    if (t < 256) T[0][t] = cc->t0[t];
+    __syncthreads();
+#pragma unroll
+    for (int k = 1; k < 4; k++) {
+        if (t < 256) T[k][t] = (T[k - 1][t] >> 8) ^ T[0][T[k - 1][t] & 0xffu];
+        __syncthreads();
+    }
+    if (n < 4) {  // the init cannot be folded into fewer than four bytes: the plain definition, one thread
+        if (t == 0) {
+            uint32_t c = 0xffffffffu;
+            for (uint32_t i = 0; i < n; i++) c = T[0][(c ^ __ldg(src + i)) & 0xffu] ^ (c >> 8);
+            out[b] = n ? ~c : 0u;
+        }
+        return;
+    }
+    const uint32_t S = ((n + 1023u) / 1024u + 15u) & ~15u;
+    const int64_t end = int64_t(n) - int64_t(1023u - t) * S;
+    const int64_t beg = end - S;
+    uint32_t c = 0;
+    if (end > 0) {
+        uint32_t i = beg > 0 ? uint32_t(beg) : 0u;
+        const uint32_t e = uint32_t(end);
+        // message bytes 0..3 carry the folded init; then bytes up to a 4-byte aligned ADDRESS; then words; then the tail
+        for (; i < e && (i < 4 || ((reinterpret_cast<uintptr_t>(src) + i) & 3u)); i++) c = T[0][(c ^ __ldg(src + i) ^ (i < 4 ? 0xffu : 0u)) & 0xffu] ^ (c >> 8);
+        for (; i + 4 <= e; i += 4) {
+            c ^= __ldg(reinterpret_cast<const uint32_t*>(src + i));
+            c = T[3][c & 0xffu] ^ T[2][(c >> 8) & 0xffu] ^ T[1][(c >> 16) & 0xffu] ^ T[0][c >> 24];
+        }
+        for (; i < e; i++) c = T[0][(c ^ __ldg(src + i)) & 0xffu] ^ (c >> 8);
+    }
+    const uint32_t poly = cc->poly;
+    uint32_t m = cc->xp128[S >> 4];  // x^(8S)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {  // lanes: (left, right) pairs, the right one is d lanes up
+        const uint32_t right = __shfl_down_sync(0xffffffffu, c, d);
+        if ((lane & (2 * d - 1)) == 0) c = gf_mul(c, m, poly) ^ right;
+        m = gf_mul(m, m, poly);
+    }
+    if (lane == 0) part[warp] = c;
+    __syncthreads();
+    if (warp == 0) {
+        c = part[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t right = __shfl_down_sync(0xffffffffu, c, d);
+            if ((lane & (2 * d - 1)) == 0) c = gf_mul(c, m, poly) ^ right;
+            m = gf_mul(m, m, poly);
+        }
+        if (lane == 0) out[b] = ~c;
+    }
+}
+
+// K3 for small inputs: a CTA per segment, 16 bytes per thread and step; vector accesses when both sides are 16-byte aligned.
+__global__ void __launch_bounds__(256) gather_small_kernel(const uint8_t* __restrict__ src, const CvSeg* __restrict__ segs, uint8_t* __restrict__ dst) {
+    const CvSeg sg = segs[blockIdx.x];
+    const uint8_t* s = src + sg.src_off;
+    uint8_t* d = dst + sg.dst_off;
+    const uint64_t n = sg.len;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15u) == 0) {
+        const uint64_t nv = n >> 4;
+        for (uint64_t i = threadIdx.x; i < nv; i += blockDim.x) st_vec(reinterpret_cast<uint4*>(d) + i, ld_plain(reinterpret_cast<const uint4*>(s) + i));
+        for (uint64_t i = (nv << 4) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    } else if (((reinterpret_cast<uintptr_t>(s) ^ reinterpret_cast<uintptr_t>(d)) & 3u) == 0) {  // same phase: words after a byte head
+        const uint32_t head = static_cast<uint32_t>((4u - (reinterpret_cast<uintptr_t>(d) & 3u)) & 3u);
+        const uint64_t h = head < n ? head : n;
+        if (threadIdx.x < h) d[threadIdx.x] = s[threadIdx.x];
+        const uint64_t nw = (n - h) >> 2;
+        for (uint64_t i = threadIdx.x; i < nw; i += blockDim.x) reinterpret_cast<uint32_t*>(d + h)[i] = __ldg(reinterpret_cast<const uint32_t*>(s + h) + i);
+        for (uint64_t i = h + (nw << 2) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    } else {
+        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = __ldg(s + i);
+    }
+}
+
 __global__ void verify_crcs_kernel(const uint32_t* crc, const uint32_t* expect, const uint8_t* skip, uint32_t n, uint32_t* n_bad,
                                    uint8_t* bad_mask) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -898,6 +991,7 @@ static int ensure_device(int* dev_out) {
     return 0;
 }
 
+static std::atomic<bool> g_small_path{true};  // cvk_tune(5, 0/1): single-launch kernels for inputs of at most ~1 MiB
 static std::atomic<int> g_seg_shift_override{0};  // cvk_tune(4, s): segment size 2^s for every launcher (0 = chosen from the input size)
 static uint32_t pick_seg_shift(uint64_t total_bytes, int sm_count) {
     if (const int o = g_seg_shift_override.load(std::memory_order_relaxed)) return static_cast<uint32_t>(o);
@@ -1038,6 +1132,7 @@ int cvk_tune(int what, int value) {
     else if (what == 1 && (value == 2 || value == 4)) g_tile_copy.store(value);
     else if (what == 3 && (value == 0 || value == 1)) g_staged.store(value != 0);
     else if (what == 4 && (value == 0 || (value >= 12 && value <= 20))) g_seg_shift_override.store(value);
+    else if (what == 5 && (value == 0 || value == 1)) g_small_path.store(value != 0);
     else return int(cudaErrorInvalidValue);
     return 0;
 }
@@ -1078,6 +1173,11 @@ int cvk_crc_blocks(const uint8_t* d_base, const uint64_t* d_off, const uint64_t*
     int dev;
     if (int rc = ensure_device(&dev)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (total_bytes <= kSmallMaxBlock && n <= 65535 && g_small_path.load(std::memory_order_relaxed)) {  // latency path: one launch, no workspace
+        crc_small_kernel<<<n, 1024, 0, st>>>(d_base, d_off, d_len, g_consts[dev][poly], d_crc_out);
+        count_launch();
+        return int(cudaGetLastError());
+    }
     const uint32_t seg_shift = pick_seg_shift(total_bytes, g_sm_count[dev]);
     Workspace w;
     if (int rc = ws_alloc(&w, dev, n, n, total_bytes, seg_shift, st)) return rc;
@@ -1194,6 +1294,11 @@ int cvk_gather_pages(const uint8_t* d_src, const CvSeg* d_segs, uint32_t n, uint
     int dev;
     if (int rc = ensure_device(&dev)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (total_bytes <= (1u << 20) && n <= 4096 && g_small_path.load(std::memory_order_relaxed)) {  // latency path (a FUSE reply's pages): one launch
+        gather_small_kernel<<<n, 256, 0, st>>>(d_src, d_segs, d_dst);
+        count_launch();
+        return int(cudaGetLastError());
+    }
     const uint32_t seg_shift = pick_seg_shift(total_bytes, g_sm_count[dev]);
     Workspace w;
     if (int rc = ws_alloc(&w, dev, n, 0, total_bytes, seg_shift, st)) return rc;

@@ -156,7 +156,8 @@ int cvk_profile_collect(double* walk_ms_total, uint32_t* walk_launches);
  * the CRC+copy walkers (K2/K4), value in {2,4}; what 1: of the copy-only walker (K3/deinterleave/P2P gather), value in
  * {2,4}; what 3: shared-memory staged (cp.async) DST walks (1) or register-tiled ones (0, default; CVK_STAGED=1 in the
  * environment flips the default); what 4: segment size 2^value bytes
- * (12..20) for every launcher instead of the size-derived choice, 0 = back to automatic.  Process-wide; results are identical for every setting (tools/kbench.py sweeps it). */
+ * (12..20) for every launcher instead of the size-derived choice, 0 = back to automatic; what 5: 0 routes inputs of at most ~1 MiB through the general launch train
+ * instead of the single-launch small-input kernels (default 1).  Process-wide; results are identical for every setting (tools/kbench.py sweeps it). */
 int cvk_tune(int what, int value);
 
 /* Number of kernel launches issued by this library in this process (bench.py's gpu_launches claim). */

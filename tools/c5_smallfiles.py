@@ -15,12 +15,25 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def main_bench(args, emit):
+    """bench.py --config c5: ONE line in the bench contract.  value = files/s of the per-file path (one FUSE-shaped call per file)."""
+    a = argparse.Namespace(files=int(os.environ.get("CV_C5_FILES", "4096")), size=256 * 1024, zero_copy=1, arena=1 if args.tier == "arena" else 0, emit=emit)
+    return run(a)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--files", type=int, default=4096)
     ap.add_argument("--size", type=int, default=256 * 1024)
     ap.add_argument("--zero-copy", type=int, default=1)
+    ap.add_argument("--arena", type=int, default=1)
     a = ap.parse_args()
+    a.emit = None
+    return run(a)
+
+
+def run(a):
+    import ctypes
     import torch
     from curvine_b200 import fs as F
     from oracle import clib, layout
@@ -28,18 +41,38 @@ def main():
     d = tempfile.mkdtemp(prefix="cvc5_", dir="/dev/shm")
     res = {}
     try:
-        with F.MiniWorker(["[MEM]" + d], hostname="localhost") as w:
+        from curvine_b200 import _lib
+        cap = a.files * a.size + (64 << 20)
+        extra = 'mem_arena = true\narena_segment = "256MB"\narena_numa = [%d]\n' % int(_lib.lib().cv_gpu_numa_node(0)) if a.arena else ""
+        with F.MiniWorker([("[MEM:%d]" % cap if a.arena else "[MEM]") + d], hostname="localhost", extra_worker=extra) as w:
             mans = [w.create_file("/small/f%d" % i, 100000 + i, a.size, a.size, threads=1) for i in range(a.files)]
             order = np.random.default_rng(7).permutation(a.files)  # Fisher-Yates, seed 7
             conf = F.client_conf(hostname="localhost", short_circuit=True,
-                                 b200='zero_copy = %s\nregister_cache = "4GB"\nfetch_threads = 4\nverify_batch = 4\ncopy_group = 1\n' % ("true" if a.zero_copy else "false"))
+                                 b200='zero_copy = %s\nregister_cache = "4GB"\nfetch_threads = 4\nverify_batch = 4\ncopy_group = 1\narena_preregister = ["%s"]\n'
+                                      % ("true" if a.zero_copy else "false", d))
             with F.CurvineFileSystem(conf) as fs:
                 fs.load_namespace("\n".join(mans))
+                fs.preregister()
+                fs.wait_registered()
                 scratch = torch.empty(a.size, dtype=torch.uint8, device="cuda")
                 npages = a.size // 4096
                 pages = torch.empty(npages * 4096, dtype=torch.uint8, device="cuda")
                 offs = [i * 4096 for i in range(npages)]
+                c_offs = (ctypes.c_uint64 * npages)(*offs)
                 stream = torch.cuda.current_stream().cuda_stream
+                # ---- one C-ABI call per file: open -> fuse read into page buffers -> verify -> close
+                for rep in range(2):
+                    lat = []
+                    t0 = time.perf_counter()
+                    for i in order:
+                        t1 = time.perf_counter()
+                        got, bad = fs.fuse_read_file_device("/small/f%d" % i, a.size, scratch.data_ptr(), pages.data_ptr(), c_offs, 4096, stream)
+                        assert got == a.size and bad == 0
+                        lat.append(time.perf_counter() - t1)
+                    dt = time.perf_counter() - t0
+                    lat = np.array(lat) * 1e6
+                    res["gpu_one_call_rep%d" % rep] = {"files_per_s": a.files / dt, "GBps": a.files * a.size / dt / 1e9, "p50_us": float(np.percentile(lat, 50)),
+                                                       "p90_us": float(np.percentile(lat, 90)), "p99_us": float(np.percentile(lat, 99))}
                 for rep in range(2):  # rep 0 warms (registers mappings); rep 1 is reported
                     lat = []
                     t0 = time.perf_counter()
@@ -67,19 +100,40 @@ def main():
                     dt = time.perf_counter() - t0
                     assert bad == 0 and ver == a.files and total == a.files * a.size
                     res["gpu_batched_rep%d" % rep] = {"files_per_s": a.files / dt, "GBps": total / dt / 1e9, "ms_total": dt * 1e3}
-            lat = []
-            t0 = time.perf_counter()
-            for i in order:
-                t1 = time.perf_counter()
-                clib.cpu_read_file(w.port, True, a.size, a.size, [layout.create_block_id(100000 + int(i), 0)], 131072, 8, 1, 131072, 0, 1)
-                lat.append(time.perf_counter() - t1)
-            dt = time.perf_counter() - t0
+            # the CPU reference port reads the same files from a reference-layout store (one tmpfs file per block) served by the
+            # oracle's worker emulator: nothing of the product is on the baseline's path
+            from oracle import refworker
+            with refworker.RefWorker(d + "_ref") as rw:
+                for i in range(a.files):
+                    rw.create_file(100000 + i, a.size, a.size, threads=1)
+                for i in order[:256]:  # warm-up
+                    clib.cpu_read_file(rw.port, True, a.size, a.size, [layout.create_block_id(100000 + int(i), 0)], 131072, 8, 1, 131072, 0, 1)
+                lat = []
+                t0 = time.perf_counter()
+                for i in order:
+                    t1 = time.perf_counter()
+                    clib.cpu_read_file(rw.port, True, a.size, a.size, [layout.create_block_id(100000 + int(i), 0)], 131072, 8, 1, 131072, 0, 1)
+                    lat.append(time.perf_counter() - t1)
+                dt = time.perf_counter() - t0
+            shutil.rmtree(d + "_ref", ignore_errors=True)
             lat = np.array(lat) * 1e6
             res["cpu_reference_port"] = {"files_per_s": a.files / dt, "GBps": a.files * a.size / dt / 1e9, "p50_us": float(np.percentile(lat, 50)),
                                          "p99_us": float(np.percentile(lat, 99)), "note": "open+read+crc32 into host memory, 2 threads (1 sub-reader + caller)"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
-    print(json.dumps(res, indent=1))
+    if a.emit is None:
+        print(json.dumps(res, indent=1))
+        return
+    one, cpu, bat = res["gpu_one_call_rep1"], res["cpu_reference_port"], res["gpu_batched_rep2"]
+    a.emit({"metric": "small-file random read into HBM pages (CRC-verified): files/s, one FUSE-shaped call per file", "value": one["files_per_s"], "unit": "files/s",
+            "n_gpus": 1, "steps": a.files, "warmup": a.files, "ms_per_step": 1e3 / one["files_per_s"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C5: %d x %d KiB single-block files, mem tier (%s), Fisher-Yates order (seed 7), open -> fuse_read(0, size) into 4 KiB page buffers -> verify -> close"
+                                   % (a.files, a.size >> 10, "arena" if a.arena else "files"), "files": a.files, "file_bytes": a.size},
+            "per_file": one, "per_file_four_calls": res["gpu_rep1"], "batched_read_many": bat,
+            "cpu_baseline": {"value": cpu["files_per_s"], "unit": "files/s", "cores": 2, "kind": "port", "p50_us": cpu["p50_us"], "p99_us": cpu["p99_us"],
+                             "sample": "all %d files once: open + read + crc32 into host memory (oracle/cpu_reader.c)" % a.files},
+            "gpu_launches": 0, "raw": res})
 
 
 if __name__ == "__main__":

@@ -74,6 +74,7 @@ def _declare(L):
     L.cv_fs_arena_stats.argtypes, L.cv_fs_arena_stats.restype = [vp, cp(u64)], i64
     L.cv_synth_delete_file.argtypes, L.cv_synth_delete_file.restype = [vp, i64, i64], i64
     L.cv_worker_arena_stats.argtypes, L.cv_worker_arena_stats.restype = [vp, cp(i64)], i64
+    L.cv_gds_info.argtypes, L.cv_gds_info.restype = [cp(i64)], i64
     L.cv_gpu_numa_node.argtypes, L.cv_gpu_numa_node.restype = [i32], i64
     L.cv_fs_metrics.argtypes, L.cv_fs_metrics.restype = [vp, cp(i64)], i64
     L.cv_fs_pool_stats.argtypes, L.cv_fs_pool_stats.restype = [vp, cp(i64)], i64
@@ -122,13 +123,14 @@ class CvReadStats(ctypes.Structure):
     _fields_ = [("bytes", ctypes.c_uint64), ("blocks", ctypes.c_uint64), ("verified", ctypes.c_uint64),
                 ("h2d_bytes", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("fetch_sec", ctypes.c_double),
                 ("wall_sec", ctypes.c_double), ("reg_hits", ctypes.c_uint64), ("reg_misses", ctypes.c_uint64),
-                ("ring_alloc_sec", ctypes.c_double), ("reg_rejected", ctypes.c_uint64), ("reg_bytes", ctypes.c_uint64)]
+                ("ring_alloc_sec", ctypes.c_double), ("reg_rejected", ctypes.c_uint64), ("reg_bytes", ctypes.c_uint64),
+                ("gds_bytes", ctypes.c_uint64)]
 
 
 # every symbol include/*.h declares (tests check the .so exports all of them)
 EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_verify_crcs_masked", "cvk_unpack_frames", "cvk_expand_streams", "cvk_gather_pages",
            "cvk_pack_frames", "cvk_deinterleave_blocks", "cvk_gather_shards_p2p", "cvk_launch_count", "cvk_tune", "cvk_profile_enable", "cvk_profile_collect", "cv_last_error", "cv_free", "cv_fs_new",
-           "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_wait_registered", "cv_fs_preregister", "cv_fs_arena_stats", "cv_synth_delete_file", "cv_worker_arena_stats", "cv_gpu_numa_node", "cv_fs_metrics", "cv_fs_pool_stats",
+           "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_wait_registered", "cv_fs_preregister", "cv_fs_arena_stats", "cv_synth_delete_file", "cv_worker_arena_stats", "cv_gpu_numa_node", "cv_gds_info", "cv_fs_metrics", "cv_fs_pool_stats",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device", "cv_fuse_read_file_device",
            "cv_verify", "cv_device_stats", "cv_writer_open", "cv_write", "cv_write_device", "cv_writer_close", "cv_worker_start", "cv_worker_stop", "cv_worker_hbm_load", "cv_worker_hbm_stats", "cv_worker_hbm_tier", "cv_worker_metrics",

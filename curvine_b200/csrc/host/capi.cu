@@ -14,6 +14,7 @@
 #include "../../../include/curvine_b200.h"
 #include "../crc_gf.h"
 #include "client.h"
+#include "gds.h"
 #include "gpu_reader.h"
 #include "worker.h"
 #include "writer.h"
@@ -390,6 +391,15 @@ int64_t cv_device_stats(cv_reader* r, CvReadStats* out) {
     out->reg_hits = s.reg_hits, out->reg_misses = s.reg_misses;
     out->ring_alloc_sec = s.ring_alloc_sec;
     out->reg_rejected = s.reg_rejected, out->reg_bytes = s.reg_bytes;
+    out->gds_bytes = s.gds_bytes;
+    return ok();
+}
+
+int64_t cv_gds_info(int64_t out[2]) {
+    API_NEED(out);
+    const GdsInfo& g = gds_info();
+    out[0] = g.available, out[1] = g.compat;
+    g_last_error = g.detail;
     return ok();
 }
 

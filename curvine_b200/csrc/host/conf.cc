@@ -194,7 +194,10 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "register_min_age") e = parse_duration_ms(unquote(v), &b.register_min_age_ms);
             else if (k == "register_threads") b.register_threads = static_cast<int>(as_int(v));
             else if (k == "register_when_idle") b.register_when_idle = as_bool(v);
-            else if (k == "arena") b.arena = as_bool(v);
+            else if (k == "gds") {
+                const std::string m = unquote(v);
+                b.gds = (m == "on" || m == "true" || m == "1") ? 1 : (m == "off" || m == "false" || m == "0") ? 0 : 2;
+            } else if (k == "arena") b.arena = as_bool(v);
             else if (k == "arena_preregister") b.arena_dirs = as_list(v);
             else if (k == "arena_register_slice") e = as_size(v, &b.arena_register_slice);
         }

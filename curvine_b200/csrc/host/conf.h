@@ -61,6 +61,9 @@ struct B200Conf {
                                           // segments are mapped + pinned in the background from the first device read (or
                                           // cv_fs_preregister) on -- off the read path; other segments are pinned when first met
     int64_t arena_register_slice = 256ll << 20;  // one cudaHostRegister call covers this much of a segment (slices go to register_threads)
+    int gds = 2;                  // "gds" = "off" | "on" | "auto": short-circuit reads of SSD/HDD/DISK-tier blocks go through cuFileRead
+                                  // (gds.h) straight into HBM; auto (default) = only with real GPUDirect Storage (nvidia-fs), on = also in
+                                  // cuFile's compatibility mode; anything GDS cannot serve goes through the pinned ring
     int numa_node = -1;           // bind fetch threads to this node's CPUs (-1: the GPU's node if discoverable, -2: no binding)
 };
 

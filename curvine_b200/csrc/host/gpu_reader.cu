@@ -16,6 +16,7 @@
 
 #include "../../../include/curvine_b200_kernels.h"
 #include "block_store.h"
+#include "gds.h"
 #include "net.h"
 
 namespace cv {
@@ -1122,6 +1123,8 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
         for (size_t j = g * k; j < std::min(J, g * k + k); j++) group_verbatim[g] |= mode[j] == kFramed;
     std::vector<int64_t> req_ids(J, 0);
     std::atomic<bool> use_mapped{bc.zero_copy};
+    std::atomic<bool> use_gds{!call_framed && bc.gds != 0 && gds_info().available && (bc.gds == 1 || !gds_info().compat)};
+    std::atomic<uint64_t> gds_bytes{0};
     std::mutex held_mu;
     const int T_threads = static_cast<int>(std::min<size_t>(static_cast<size_t>(std::max(1, bc.fetch_threads)), NG));
     std::vector<double> fetch_sec(static_cast<size_t>(T_threads), 0.0);
@@ -1141,9 +1144,38 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
                 if (st.abort.load()) break;
                 cudaEventSynchronize(group_verbatim[g - NS] ? G.free_ev[ss] : G.copy_ev[ss]);
             }
-            // ---- zero-copy: DMA out of registered mmaps of the block files (mem tier), no pinned-slot copy
             bool all_plain = true;
             for (size_t j = j0; j < j1; j++) all_plain = all_plain && mode[j] == kPlain;
+            // ---- GPUDirect Storage: blocks of a disk tier go file -> HBM by cuFileRead, no host ring
+            bool all_disk = all_plain && use_gds.load(std::memory_order_relaxed);
+            for (size_t j = j0; j < j1 && all_disk; j++) all_disk = (*jobs[j].lb).block.storage_type != kStorageMem;
+            if (all_disk) {
+                const double t0 = now_sec();
+                Err e;
+                backoff_wait([&] { return cudaEventQuery(G.entry_ev) != cudaErrorNotReady; });  // cuFile knows nothing of the caller's stream
+                for (size_t j = j0; j < j1 && !e; j++) {
+                    BlockReadResponse resp;
+                    int64_t rid = 0;
+                    e = open_short_circuit(ctx_, (*jobs[j].lb), jobs[j].block_off, &conn, &rid, &resp);
+                    if (!e) e = gds_read(resp.path, d_dst + jobs[j].dst_off, jobs[j].n, (resp.has_arena ? resp.arena_off : 0) + jobs[j].block_off);
+                    if (!e) e = conn->read_commit_deferred((*jobs[j].lb).block, rid, 1);
+                    if (!e) gds_bytes += static_cast<uint64_t>(jobs[j].n);
+                }
+                fetch_sec[static_cast<size_t>(t)] += now_sec() - t0;
+                if (e && e.kind == kUnsupported) {
+                    use_gds.store(false);  // this file system / this box cannot do it: the pinned ring takes over (the group is redone below)
+                } else {
+                    cudaError_t ce = e ? cudaSuccess : cudaEventRecord(G.copy_ev[ss], cs);
+                    if (e || ce != cudaSuccess) {
+                        st.fail(e ? e : Err::io(str_printf("event record: %s", cudaGetErrorString(ce))));
+                        break;
+                    }
+                    released[ss].store(static_cast<int64_t>(g), std::memory_order_release);
+                    copied[g].store(1, std::memory_order_release);
+                    continue;
+                }
+            }
+            // ---- zero-copy: DMA out of registered mmaps of the block files (mem tier), no pinned-slot copy
             if (all_plain && use_mapped.load(std::memory_order_relaxed)) {
                 const double t0 = now_sec();
                 std::vector<std::string> paths(j1 - j0);
@@ -1450,6 +1482,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     stats_.reg_hits = G.reg.hits.load(), stats_.reg_misses = G.reg.misses.load();
     stats_.reg_rejected = G.reg.rejected.load(), stats_.reg_bytes = G.reg.bytes();
     stats_.ring_alloc_sec = G.ring_alloc_sec;
+    stats_.gds_bytes += gds_bytes.load();
     return Err::ok();
 }
 

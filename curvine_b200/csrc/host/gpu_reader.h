@@ -29,6 +29,7 @@ struct GpuReadStats {
     uint64_t reg_bytes = 0;                 // bytes registered through the cache right now (<= register_cache)
     double fetch_sec = 0;       // summed over fetch threads: time inside pread/recv
     double wall_sec = 0;
+    uint64_t gds_bytes = 0;     // bytes that went file -> HBM through cuFileRead (gds.h)
     double ring_alloc_sec = 0;  // context-wide: one-off pinned-ring allocation time
 };
 

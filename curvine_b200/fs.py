@@ -25,6 +25,13 @@ def _check(rc: int):
         raise FsError(-rc, _lib.lib().cv_last_error().decode(errors="replace"))
 
 
+def gds_info() -> dict:
+    """GPUDirect Storage probe (gds.h): {available, compat, detail}."""
+    a = (ctypes.c_int64 * 2)()
+    _check(_lib.lib().cv_gds_info(a))
+    return {"available": bool(a[0]), "compat": bool(a[1]), "detail": _lib.lib().cv_last_error().decode(errors="replace")}
+
+
 class MiniWorker:
     """In-process worker over a BlockStore directory tree (fixture; worker_test.rs:35-48 analogue)."""
 

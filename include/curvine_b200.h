@@ -132,7 +132,11 @@ typedef struct CvReadStats {
     double ring_alloc_sec;         /* one-off pinned-ring allocation time of the context (first cold read pays it) */
     uint64_t reg_rejected;         /* mappings not admitted: the cache was full of in-use or recently used ones */
     uint64_t reg_bytes;            /* bytes registered through the cache right now (<= register_cache) */
+    uint64_t gds_bytes;            /* bytes read file -> HBM by cuFileRead (disk tiers, [b200] gds) */
 } CvReadStats;
+/* GPUDirect Storage probe: out[0] = 1 when libcufile loaded and its driver opened, out[1] = 1 when it runs in compatibility
+ * mode (no nvidia-fs kernel module).  The message (cv_last_error) carries the detail either way. */
+int64_t cv_gds_info(int64_t out[2]);
 int64_t cv_device_stats(cv_reader* r, CvReadStats* out);
 
 /* ---- write-side mirror ("next" row 8f-1): WriteBlock = 80, Open -> Running x N -> Complete per block

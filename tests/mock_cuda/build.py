@@ -13,7 +13,7 @@ HOST = os.path.join(ROOT, "curvine_b200", "csrc", "host")
 
 
 def sources():
-    out = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith((".cc", ".cu"))]
+    out = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith((".cc", ".cu")) and f != "gds.cc"]  # no cuFile here: mock_cuda.cc has the stub
     return out + [os.path.join(HERE, "mock_cuda.cc"), os.path.join(HERE, "mock_cvk.cc")]
 
 

@@ -10,7 +10,7 @@
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorInvalidDevice = 101, cudaErrorHostMemoryAlreadyRegistered = 712,
-       cudaErrorHostMemoryNotRegistered = 713, cudaErrorNotSupported = 801 };
+       cudaErrorHostMemoryNotRegistered = 713, cudaErrorNotReady = 600, cudaErrorNotSupported = 801 };
 typedef struct MockStream* cudaStream_t;
 typedef struct MockEvent* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
@@ -52,6 +52,7 @@ cudaError_t cudaEventCreateWithFlags(cudaEvent_t* ev, unsigned flags);
 cudaError_t cudaEventDestroy(cudaEvent_t ev);
 cudaError_t cudaEventRecord(cudaEvent_t ev, cudaStream_t st);
 cudaError_t cudaEventSynchronize(cudaEvent_t ev);
+cudaError_t cudaEventQuery(cudaEvent_t ev);
 cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes* a, const void* p);
 cudaError_t cudaGetLastError(void);
 const char* cudaGetErrorString(cudaError_t e);

@@ -120,6 +120,7 @@ cudaError_t cudaEventDestroy(cudaEvent_t ev) {
 }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes* a, const void* p) {
     // pinned allocations and registered ranges are host memory; everything else a caller hands in as a destination is "device"
     const uintptr_t x = reinterpret_cast<uintptr_t>(p);
@@ -155,3 +156,15 @@ void mock_cuda_counters(uint64_t out[6]) {
     out[4] = g_dev.size(), out[5] = g_pinned.size();
 }
 }
+
+// ---- gds.h stand-in: no cuFile on the mock runtime; disk-tier blocks always take the pinned ring
+#include "../../curvine_b200/csrc/host/gds.h"
+namespace cv {
+const GdsInfo& gds_info() {
+    static GdsInfo g;
+    g.detail = "mock runtime: no cuFile";
+    return g;
+}
+Err gds_read(const std::string&, void*, int64_t, int64_t) { return Err(kUnsupported, "mock runtime: no cuFile"); }
+void gds_forget(const std::string&) {}
+}  // namespace cv

@@ -109,6 +109,7 @@ def _declare(L):
     L.cv_worker_start.argtypes, L.cv_worker_start.restype = [c, cp(vp), cp(i32)], i64
     L.cv_worker_stop.argtypes, L.cv_worker_stop.restype = [vp], i64
     L.cv_worker_hbm_load.argtypes, L.cv_worker_hbm_load.restype = [vp, i64, i32], i64
+    L.cv_worker_hbm_drain.argtypes, L.cv_worker_hbm_drain.restype = [vp], i64
     L.cv_worker_hbm_stats.argtypes, L.cv_worker_hbm_stats.restype = [vp, cp(i64)], i64
     L.cv_worker_hbm_tier.argtypes, L.cv_worker_hbm_tier.restype = [vp, cp(i64)], i64
     L.cv_worker_metrics.argtypes, L.cv_worker_metrics.restype = [vp, cp(i64)], i64
@@ -133,7 +134,7 @@ EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_verify_crcs_mas
            "cv_fs_new_from_string", "cv_fs_load_namespace", "cv_fs_load_namespace_string", "cv_fs_close", "cv_fs_wait_registered", "cv_fs_preregister", "cv_fs_arena_stats", "cv_synth_delete_file", "cv_worker_arena_stats", "cv_gpu_numa_node", "cv_gds_info", "cv_fs_metrics", "cv_fs_pool_stats",
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device", "cv_fuse_read_file_device",
-           "cv_verify", "cv_device_stats", "cv_writer_open", "cv_write", "cv_write_device", "cv_writer_close", "cv_worker_start", "cv_worker_stop", "cv_worker_hbm_load", "cv_worker_hbm_stats", "cv_worker_hbm_tier", "cv_worker_metrics",
+           "cv_verify", "cv_device_stats", "cv_writer_open", "cv_write", "cv_write_device", "cv_writer_close", "cv_worker_start", "cv_worker_stop", "cv_worker_hbm_load", "cv_worker_hbm_drain", "cv_worker_hbm_stats", "cv_worker_hbm_tier", "cv_worker_metrics",
            "cv_synth_create_file", "cv_synth_set_shard_world", "cv_synth_block", "cv_host_crc"]
 
 

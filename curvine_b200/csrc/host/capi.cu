@@ -497,6 +497,14 @@ int64_t cv_worker_hbm_load(cv_worker* w, int64_t block_id, int32_t device) {
     API_GUARD_END
 }
 
+int64_t cv_worker_hbm_drain(cv_worker* w) {
+    API_GUARD_BEGIN
+    API_NEED(w);
+    w->w.hbm().drain();
+    return ok();
+    API_GUARD_END
+}
+
 int64_t cv_worker_hbm_stats(cv_worker* w, int64_t out[3]) {
     API_NEED(w);
     API_NEED(out);

@@ -120,6 +120,49 @@ bool HbmTier::should_promote(int64_t block_id) {
     return false;
 }
 
+HbmTier::~HbmTier() {
+    {
+        std::lock_guard<std::mutex> lk(pmu_);
+        pstop_ = true;
+        pq_.clear();
+        pcv_.notify_all();
+    }
+    if (promoter_.joinable()) promoter_.join();
+}
+
+void HbmTier::promote_async(int64_t block_id, int64_t len, std::function<bool(std::vector<char>*)> fetch) {
+    std::lock_guard<std::mutex> lk(pmu_);
+    if (pstop_ || pq_.size() >= 64 || !pending_.insert(block_id).second) return;
+    pq_.push_back(Promo{block_id, len, std::move(fetch)});
+    if (!promoter_.joinable()) promoter_ = std::thread([this] { promoter_loop(); });
+    pcv_.notify_one();
+}
+
+void HbmTier::promoter_loop() {
+    for (;;) {
+        Promo p;
+        {
+            std::unique_lock<std::mutex> lk(pmu_);
+            pcv_.wait(lk, [&] { return pstop_ || !pq_.empty(); });
+            if (pstop_) return;
+            p = std::move(pq_.front());
+            pq_.pop_front();
+            pbusy_ = true;
+        }
+        std::vector<char> buf;
+        if (p.fetch(&buf) && static_cast<int64_t>(buf.size()) == p.len && !load(p.id, buf.data(), p.len, device_)) promotions_++;
+        std::lock_guard<std::mutex> lk(pmu_);
+        pending_.erase(p.id);
+        pbusy_ = false;
+        if (pq_.empty()) pidle_.notify_all();
+    }
+}
+
+void HbmTier::drain() {
+    std::unique_lock<std::mutex> lk(pmu_);
+    pidle_.wait(lk, [&] { return pstop_ || (pq_.empty() && !pbusy_); });
+}
+
 size_t HbmTier::size() const {
     std::lock_guard<std::mutex> lk(mu_);
     return blocks_.size();

@@ -7,7 +7,13 @@
 // (curvine-common/src/state/storage_info.rs:36-49).
 #pragma once
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <list>
+#include <thread>
+#include <unordered_set>
+#include <vector>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
@@ -53,6 +59,13 @@ class HbmTier {
     void evict(int64_t block_id);               // the block was rewritten or removed: its resident copy must not be served again
     // a remote read of a block that is not resident is about to be served from its file: true = promote it first
     bool should_promote(int64_t block_id);
+    // Asynchronous promotion: the read that crossed the threshold is served from the store as usual while a promoter thread
+    // reads the block (`fetch` fills a buffer with its bytes; it owns whatever keeps them alive) and loads it; the NEXT read
+    // finds it resident.  At most one promotion per block is in flight; the queue is bounded (a full queue drops the request --
+    // the block asks again on its next read).
+    void promote_async(int64_t block_id, int64_t len, std::function<bool(std::vector<char>*)> fetch);
+    void drain();  // test/measurement hook: wait until no promotion is queued or running
+    ~HbmTier();
     int device() const { return device_; }
     size_t size() const;
     void stats(int64_t out[6]) const;  // resident blocks, resident bytes, capacity, evictions, promotions, refused loads
@@ -72,6 +85,17 @@ class HbmTier {
     int64_t capacity_ = 0, bytes_ = 0;
     int promote_after_ = 0, device_ = 0;
     std::atomic<int64_t> evictions_{0}, promotions_{0}, refused_{0};
+    struct Promo {
+        int64_t id, len;
+        std::function<bool(std::vector<char>*)> fetch;
+    };
+    void promoter_loop();
+    std::mutex pmu_;
+    std::condition_variable pcv_, pidle_;
+    std::deque<Promo> pq_;
+    std::unordered_set<int64_t> pending_;
+    std::thread promoter_;
+    bool pstop_ = false, pbusy_ = false;
 };
 
 }  // namespace cv

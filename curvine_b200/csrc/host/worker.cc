@@ -56,26 +56,27 @@ Err ReadHandler::open(const RpcRequest& req, RpcResponse* resp) {
         from_hbm_ = false;
     }
     if (!from_hbm_ && !short_circuit && hbm_ && hbm_->should_promote(c.id)) {
-        // read often enough from its file: load it into the HBM tier now (evicting colder blocks) and serve this read from there;
-        // a refusal (tier full of blocks being read, block larger than the tier) just leaves the block where it is
-        std::vector<char> buf(meta.in_arena() ? 0 : static_cast<size_t>(meta.len));
-        bool ok = true;
-        if (!meta.in_arena()) {
-            const int pfd = ::open(meta.path.c_str(), O_RDONLY | O_CLOEXEC);
-            ok = pfd >= 0;
-            for (size_t got = 0; ok && got < buf.size();) {
-                const ssize_t r = pread(pfd, buf.data() + got, buf.size() - got, static_cast<off_t>(got));
+        // read often enough from its file / extent: a promoter thread loads it into the HBM tier (evicting colder blocks) while THIS
+        // read is served from the store as usual; the next remote read of the block is served from HBM.  A refusal (tier full of blocks
+        // being read, block larger than the tier) just leaves the block where it is.
+        const BlockMeta m = meta;  // an arena block's meta keeps its extent allocated until the promoter is done with it
+        hbm_->promote_async(c.id, meta.len, [m](std::vector<char>* buf) {
+            buf->resize(static_cast<size_t>(m.len));
+            if (m.in_arena()) {
+                memcpy(buf->data(), m.mem(), buf->size());
+                return true;
+            }
+            const int pfd = ::open(m.path.c_str(), O_RDONLY | O_CLOEXEC);
+            bool ok = pfd >= 0;
+            for (size_t got = 0; ok && got < buf->size();) {
+                const ssize_t r = pread(pfd, buf->data() + got, buf->size() - got, static_cast<off_t>(got));
                 if (r < 0 && errno == EINTR) continue;
                 if (r <= 0) ok = false;
                 else got += static_cast<size_t>(r);
             }
             close_fd(pfd);
-        }
-        const void* src = meta.in_arena() ? static_cast<const void*>(meta.mem()) : static_cast<const void*>(buf.data());
-        if (ok && !hbm_->load(c.id, src, meta.len, hbm_->device()) && hbm_->get(c.id, &hbm_block_)) {
-            hbm_->note_promotion();
-            from_hbm_ = true;
-        }
+            return ok;
+        });
     }
     if (from_hbm_) {
         // the block is resident in HBM: pack the whole response stream on the GPU now (K4), serve Running requests from it

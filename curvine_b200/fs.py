@@ -69,6 +69,10 @@ class MiniWorker:
         """HBM tier: make a finalized block resident in device memory; remote reads are then served from HBM (K4-packed frames)."""
         _check(_lib.lib().cv_worker_hbm_load(self._h, block_id, device))
 
+    def hbm_drain(self):
+        """Wait until the HBM tier's promoter thread has nothing queued or running (promotion is asynchronous)."""
+        _check(_lib.lib().cv_worker_hbm_drain(self._h))
+
     def hbm_stats(self) -> dict:
         a = (ctypes.c_int64 * 3)()
         _check(_lib.lib().cv_worker_hbm_stats(self._h, a))

@@ -161,6 +161,9 @@ int64_t cv_worker_stop(cv_worker* w);
  * stats: out[0]=resident blocks [1]=reads served from HBM [2]=payload bytes packed by K4. */
 int64_t cv_worker_hbm_load(cv_worker* w, int64_t block_id, int32_t device);
 int64_t cv_worker_hbm_stats(cv_worker* w, int64_t out[3]);
+/* Promotion into the tier is asynchronous (a promoter thread; the read that crossed hbm_promote_after is served from the store):
+ * wait until nothing is queued or running. */
+int64_t cv_worker_hbm_drain(cv_worker* w);
 /* HBM tier occupancy and policy counters ([worker] hbm_capacity / hbm_promote_after / hbm_device): out[0]=resident blocks,
  * out[1]=resident bytes, out[2]=capacity (0 = unbounded), out[3]=evictions (LRU, never a block that is being read),
  * out[4]=promotions (blocks loaded because they were read remotely hbm_promote_after times), out[5]=refused loads */

@@ -274,9 +274,10 @@ def test_hbm_tier_capacity_lru_eviction_and_blocks_being_read():
 
 
 def test_hbm_tier_promotes_blocks_that_are_read_remotely(cuda):
-    """[worker] hbm_promote_after = 2: the third framed read of a block loads it into the tier and is itself served from HBM
-    (frames packed by K4); short-circuit reads never count; bytes are identical before and after; the device reader sees the
-    same CRCs through K2."""
+    """[worker] hbm_promote_after = 2: the third framed read of a block hands it to the tier's promoter thread and is itself still
+    served from the store (promotion is asynchronous: the promoting read does not pay for it); once the promoter is done every
+    further framed read is served from HBM (frames packed by K4); short-circuit reads never count; bytes are identical before and
+    after; the device reader sees the same CRCs through K2."""
     import shutil
     import torch
     bs, ino, n = 1 << 20, 7900, (3 << 20) + 99
@@ -293,13 +294,22 @@ def test_hbm_tier_promotes_blocks_that_are_read_remotely(cuda):
                 assert w.hbm_tier()["promotions"] == 0 and w.hbm_stats()["reads_from_hbm"] == 0
             r = fs.open("/p")
             dst = _dev_buf(n, cuda)
-            assert r.read_device(dst.data_ptr(), n, 0) == n  # third remote read of every block: promoted, served from HBM
+            assert r.read_device(dst.data_ptr(), n, 0) == n  # third remote read of every block: queued for promotion, served from the store
             s, bad, ver = r.verify()
             torch.cuda.synchronize()
             assert bad == 0 and ver == 4 and dst.cpu().numpy().tobytes() == want
             r.complete()
+            w.hbm_drain()
             t = w.hbm_tier()
             assert t["promotions"] == 4 and t["resident_blocks"] == 4 and t["resident_bytes"] == n, t
+            assert w.hbm_stats()["reads_from_hbm"] == 0
+            dst.fill_(0)
+            r = fs.open("/p")
+            assert r.read_device(dst.data_ptr(), n, 0) == n  # now resident: K4-packed frames out of HBM, unpacked by K2
+            s, bad, ver = r.verify()
+            torch.cuda.synchronize()
+            assert bad == 0 and ver == 4 and dst.cpu().numpy().tobytes() == want
+            r.complete()
             assert w.hbm_stats()["reads_from_hbm"] == 4
             r = fs.open("/p")
             assert r.read_full(n) == want

@@ -259,7 +259,7 @@ def timed_read(fs, path, rank, world, dst, shard_bytes, stream):
     return a.elapsed_time(b), a2.elapsed_time(b2), s, stats
 
 
-def run_leg(name, cluster, fs, tier, args, rank, world, dist, dst, shard_bytes, steps, warmup, fresh, inode0, sampler=None):
+def run_leg(name, cluster, fs, tier, args, rank, world, dist, dst, shard_bytes, steps, warmup, fresh, inode0, pool=None):
     """steps+warmup passes; fresh=True: every pass reads a file written just before it (never read by anyone), and the file of
     `pool` passes ago is dropped; fresh=False: one file, read again and again.  -> dict(e2e_ms[], ingest_ms[], warm_ms[], stats)."""
     import torch
@@ -272,7 +272,7 @@ def run_leg(name, cluster, fs, tier, args, rank, world, dist, dst, shard_bytes, 
             path = "/bench/%s_%d" % (name, it)
             fs.load_namespace(cluster.create(tier, path, inode0 + it, n_total))
             paths.append(path)
-            if fresh and len(paths) > args.pool:
+            if fresh and len(paths) > (args.pool if pool is None else pool):
                 cluster.drop(paths.pop(0))
         if args.settle_ms:
             time.sleep(args.settle_ms / 1e3)
@@ -320,6 +320,8 @@ def main():
     fthreads = args.framed_threads or max(4, min(16, ncpu // (2 * world)))
     slots = args.slots or (2 * args.verify_batch + threads + 8)
     side = args.side_steps
+    # side legs report a rate: beyond one GPU they read 4 GiB per GPU per step (less tmpfs, less generation time)
+    side_bytes = shard_bytes if world == 1 else min(shard_bytes, (4 << 30) // BLOCK * BLOCK)
     cluster = Cluster(args, rank, world, dist, shard_bytes, need_files_tier=True)
     dst = torch.empty(shard_bytes, dtype=torch.uint8, device="cuda")
     sampler = ClockSampler(local)
@@ -347,7 +349,7 @@ def main():
         # ---- side legs
         reread = pread = framed = None
         if side > 0:
-            reread = run_leg("reread", cluster, fs, args.tier, args, rank, world, dist, dst, shard_bytes, side, 1, False, 6000)
+            reread = run_leg("reread", cluster, fs, args.tier, args, rank, world, dist, dst, side_bytes, side, 1, False, 6000)
         # ---- resident verify (K1 over what the last step left in HBM) + roofline of K1
         fs.load_namespace(cluster.create(args.tier, "/bench/resident", 4200, n_total))
         _, _, sum_crc, _ = timed_read(fs, "/bench/resident", rank, world, dst, shard_bytes, torch.cuda.current_stream().cuda_stream)
@@ -383,12 +385,12 @@ def main():
         if side > 0:
             # reference layout (one tmpfs file per block), never-read files, through the pinned ring
             fs3 = F.CurvineFileSystem(client_conf(args, cluster, True, local, threads, slots, rank, zero_copy=False, copy_group=1))
-            pread = run_leg("pread", cluster, fs3, "files", args, rank, world, dist, dst, shard_bytes, side, 1, True, 7000)
+            pread = run_leg("pread", cluster, fs3, "files", args, rank, world, dist, dst, side_bytes, side, 1, True, 7000, pool=1)
             fs3.close()
             # TCP frames from the arena worker (send(2) out of its mapping), received verbatim, unpacked + CRC'd by K2
             # one block per ring slot (copy_group 1): every connection fills its own slot, the verifier frees slots 16 blocks at a time
             fs2 = F.CurvineFileSystem(client_conf(args, cluster, False, local, fthreads, 2 * args.verify_batch + 2 * fthreads + 8, rank, copy_group=1))
-            framed = run_leg("framed", cluster, fs2, "arena", args, rank, world, dist, dst, shard_bytes, side, 1, True, 8000)
+            framed = run_leg("framed", cluster, fs2, "arena", args, rank, world, dist, dst, side_bytes, side, 1, True, 8000, pool=1)
             fs2.close()
 
         # ---- max over ranks
@@ -407,6 +409,7 @@ def main():
         res_ms = maxr(res_ms)
         walk_avg_ms = maxr(walk_ms.value / max(1, walk_n.value))
         side_ms = {k: maxr(mean(v["e2e_ms"])) if v else None for k, v in (("reread", reread), ("pread", pread), ("framed", framed))}
+        side_total = side_bytes * world
         per_step_e2e = [maxr(x) for x in head["e2e_ms"]]
 
         if rank == 0:
@@ -458,10 +461,10 @@ def main():
                             ("framed", "short_circuit = false: TCP frames from the arena worker received verbatim, H2D of the wire image, K2 validates every "
                                        "prefix, gathers and CRCs (gpu_chunk %s, %d connections)" % (args.gpu_chunk, fthreads))):
                 if side_ms[k]:
-                    v = gbps(side_ms[k])
+                    v = side_total / side_ms[k] / 1e6
                     leg = {"reread": reread, "pread": pread, "framed": framed}[k]
                     out["e2e_" + k] = {"value": v, "unit": UNIT, "ms_per_step": side_ms[k], "per_gpu_GBps": v / world,
-                                       "frac_of_pcie_gen5_x16_raw_63GBps": v / world / PCIE_RAW, "steps": side, "what": what,
+                                       "frac_of_pcie_gen5_x16_raw_63GBps": v / world / PCIE_RAW, "steps": side, "bytes_per_step": side_total, "what": what,
                                        "timed_steps_ms": leg["e2e_ms"], "last_step_fetch_thread_sec": leg["stats"]["fetch_sec"],
                                        "last_step_wall_sec": leg["stats"]["wall_sec"], "h2d_bytes_last_step": int(leg["stats"]["h2d_bytes"])}
             if world == 1 and not args.no_cpu_baseline:

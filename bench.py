@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--framed-threads", type=int, default=0)
     ap.add_argument("--poly", type=int, default=1)
     ap.add_argument("--settle-ms", type=int, default=0, help="pause between writing a step's file and reading it (diagnostic)")
+    ap.add_argument("--legs", default="reread,pread,framed,framed_unix,resident,cpu", help="side legs to run besides the headline (comma list)")
     ap.add_argument("--side-steps", type=int, default=2, help="timed steps of each side leg (reread / pread / framed); 0 skips them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dir", default="")
@@ -226,13 +227,13 @@ class Cluster:
             shutil.rmtree(self.dir, ignore_errors=True)
 
 
-def client_conf(args, cluster, sc, device, threads, slots, rank, zero_copy=True, copy_group=None, chunk=None):
+def client_conf(args, cluster, sc, device, threads, slots, rank, zero_copy=True, copy_group=None, chunk=None, unix=False):
     from curvine_b200 import fs as F
     b200 = ('device = %d\nfetch_threads = %d\npinned_slots = %d\nverify_poly = %d\nverify = true\nverify_batch = %d\ncopy_group = %d\ngpu_chunk_size = "%s"\n'
             'zero_copy = %s\nregister_threads = %d\nregister_cache = "%dGB"\ncopy_streams = %d\nnuma_node = %d\narena_preregister = ["%s/arena%d"]\n'
-            'arena_register_slice = "%s"\n'
+            'arena_register_slice = "%s"\nlocal_unix_socket = %s\n'
             % (device, threads, slots, args.poly, args.verify_batch, args.copy_group if copy_group is None else copy_group, chunk or args.gpu_chunk,
-               "true" if zero_copy else "false", args.register_threads, int(args.gib_per_gpu * 1.5) + 1, args.copy_streams, args.numa_node, cluster.dir, rank, args.register_slice))
+               "true" if zero_copy else "false", args.register_threads, int(args.gib_per_gpu * 1.5) + 1, args.copy_streams, args.numa_node, cluster.dir, rank, args.register_slice, "true" if unix else "false"))
     return F.client_conf(hostname="localhost", short_circuit=sc, b200=b200)
 
 
@@ -347,8 +348,9 @@ def main():
         launches = (K.launch_count() - launches0) * args.steps // max(1, args.steps + args.warmup)
         arena1 = fs.arena_stats()
         # ---- side legs
-        reread = pread = framed = None
-        if side > 0:
+        legs = set(x for x in args.legs.split(",") if x) if side > 0 else set()
+        reread = pread = framed = framed_unix = None
+        if "reread" in legs:
             reread = run_leg("reread", cluster, fs, args.tier, args, rank, world, dist, dst, side_bytes, side, 1, False, 6000)
         # ---- resident verify (K1 over what the last step left in HBM) + roofline of K1
         fs.load_namespace(cluster.create(args.tier, "/bench/resident", 4200, n_total))
@@ -382,16 +384,23 @@ def main():
         assert int(d_crc.cpu().numpy().view(np.uint32).astype(np.uint64).sum()) == sum_crc, "resident K1 pass disagrees with the ingest's CRCs"
         cluster.drop("/bench/resident")
         fs.close()
-        if side > 0:
+        if "pread" in legs:
             # reference layout (one tmpfs file per block), never-read files, through the pinned ring
             fs3 = F.CurvineFileSystem(client_conf(args, cluster, True, local, threads, slots, rank, zero_copy=False, copy_group=1))
             pread = run_leg("pread", cluster, fs3, "files", args, rank, world, dist, dst, side_bytes, side, 1, True, 7000, pool=1)
             fs3.close()
-            # TCP frames from the arena worker (send(2) out of its mapping), received verbatim, unpacked + CRC'd by K2
-            # one block per ring slot (copy_group 1): every connection fills its own slot, the verifier frees slots 16 blocks at a time
-            fs2 = F.CurvineFileSystem(client_conf(args, cluster, False, local, fthreads, 2 * args.verify_batch + 2 * fthreads + 8, rank, copy_group=1))
-            framed = run_leg("framed", cluster, fs2, "arena", args, rank, world, dist, dst, side_bytes, side, 1, True, 8000, pool=1)
+        for leg_name, unix in (("framed", False), ("framed_unix", True)):
+            if leg_name not in legs:
+                continue
+            # frames from the arena worker (sendfile out of the segment file), received verbatim, unpacked + CRC'd by K2; one block per
+            # ring slot (copy_group 1): every connection fills its own slot, the verifier frees slots 16 blocks at a time
+            fs2 = F.CurvineFileSystem(client_conf(args, cluster, False, local, fthreads, 2 * args.verify_batch + 2 * fthreads + 8, rank, copy_group=1, unix=unix))
+            res_leg = run_leg(leg_name, cluster, fs2, "arena", args, rank, world, dist, dst, side_bytes, side, 1, True, 8000 + 500 * unix, pool=1)
             fs2.close()
+            if unix:
+                framed_unix = res_leg
+            else:
+                framed = res_leg
 
         # ---- max over ranks
         def maxr(x):
@@ -408,7 +417,7 @@ def main():
         ing_ms = maxr(mean(head["ingest_ms"]))
         res_ms = maxr(res_ms)
         walk_avg_ms = maxr(walk_ms.value / max(1, walk_n.value))
-        side_ms = {k: maxr(mean(v["e2e_ms"])) if v else None for k, v in (("reread", reread), ("pread", pread), ("framed", framed))}
+        side_ms = {k: maxr(mean(v["e2e_ms"])) if v else None for k, v in (("reread", reread), ("pread", pread), ("framed", framed), ("framed_unix", framed_unix))}
         side_total = side_bytes * world
         per_step_e2e = [maxr(x) for x in head["e2e_ms"]]
 
@@ -458,16 +467,17 @@ def main():
             }
             for k, what in (("reread", "the same (already read) arena file again: same path as the headline, nothing is cached per file"),
                             ("pread", "reference layout (one tmpfs file per block), never-read files: pread into the pinned ring, then H2D"),
-                            ("framed", "short_circuit = false: TCP frames from the arena worker received verbatim, H2D of the wire image, K2 validates every "
-                                       "prefix, gathers and CRCs (gpu_chunk %s, %d connections)" % (args.gpu_chunk, fthreads))):
+                            ("framed", "short_circuit = false: frames from the arena worker over loopback TCP received verbatim, H2D of the wire image, K2 validates "
+                                       "every prefix, gathers and CRCs (gpu_chunk %s, %d connections)" % (args.gpu_chunk, fthreads)),
+                            ("framed_unix", "the same over the worker's same-host abstract unix socket ([b200] local_unix_socket)")):
                 if side_ms[k]:
                     v = side_total / side_ms[k] / 1e6
-                    leg = {"reread": reread, "pread": pread, "framed": framed}[k]
+                    leg = {"reread": reread, "pread": pread, "framed": framed, "framed_unix": framed_unix}[k]
                     out["e2e_" + k] = {"value": v, "unit": UNIT, "ms_per_step": side_ms[k], "per_gpu_GBps": v / world,
                                        "frac_of_pcie_gen5_x16_raw_63GBps": v / world / PCIE_RAW, "steps": side, "bytes_per_step": side_total, "what": what,
                                        "timed_steps_ms": leg["e2e_ms"], "last_step_fetch_thread_sec": leg["stats"]["fetch_sec"],
                                        "last_step_wall_sec": leg["stats"]["wall_sec"], "h2d_bytes_last_step": int(leg["stats"]["h2d_bytes"])}
-            if world == 1 and not args.no_cpu_baseline:
+            if world == 1 and not args.no_cpu_baseline and "cpu" in (legs or {"cpu"}):
                 out["cpu_baseline"] = cpu_baseline(cluster, args)
     finally:
         sampler.stop()

@@ -308,8 +308,11 @@ Err FsContext::acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClie
         }
     }
     int fd = -1;
-    CV_RETURN_IF_ERR(tcp_connect(addr.ip_addr.empty() ? addr.hostname : addr.ip_addr, static_cast<int>(addr.rpc_port), &fd, conf.client.conn_timeout_ms,
-                                 conf.client.data_timeout_ms));
+    if (conf.b200.socket_buffer > 0) set_socket_buffer_bytes(static_cast<int>(std::min<int64_t>(conf.b200.socket_buffer, 1 << 30)));
+    // a worker on this host: its abstract unix socket first when configured (same frames, less protocol work per byte)
+    if (!(conf.b200.local_unix_socket && is_local_worker(addr) && !unix_connect(local_socket_name(static_cast<int>(addr.rpc_port)), &fd, conf.client.data_timeout_ms)))
+        CV_RETURN_IF_ERR(tcp_connect(addr.ip_addr.empty() ? addr.hostname : addr.ip_addr, static_cast<int>(addr.rpc_port), &fd, conf.client.conn_timeout_ms,
+                                     conf.client.data_timeout_ms));
     out->reset(new BlockClient(fd, addr));
     {
         std::lock_guard<std::mutex> lk(mu_);
@@ -325,6 +328,36 @@ void FsContext::release(std::unique_ptr<BlockClient> c) {
     c->idle_since_ms = now_ms();
     idle_[c->addr().str()].push_back(std::move(c));
     idle_total_++;
+}
+
+void FsContext::add_failed_worker(const WorkerAddress& addr) {
+    std::lock_guard<std::mutex> lk(fw_mu_);
+    failed_workers_[addr.worker_id] = now_ms() + conf.client.failed_worker_ttl_ms;
+}
+
+std::vector<uint32_t> FsContext::get_failed_workers() {
+    std::vector<uint32_t> out;
+    std::lock_guard<std::mutex> lk(fw_mu_);
+    const int64_t now = now_ms();
+    for (auto it = failed_workers_.begin(); it != failed_workers_.end();) {
+        if (it->second <= now) it = failed_workers_.erase(it);  // time_to_live elapsed
+        else out.push_back((it++)->first);
+    }
+    std::sort(out.begin(), out.end());
+    return out;
+}
+
+bool FsContext::is_failed_worker(const WorkerAddress& addr) {
+    for (uint32_t id : get_failed_workers())
+        if (id == addr.worker_id) return true;
+    return false;
+}
+
+Err FsContext::no_available_worker(const std::vector<WorkerAddress>& locs) {
+    std::string l, f;
+    for (const auto& a : locs) l += (l.empty() ? "" : ", ") + a.str();
+    for (uint32_t id : get_failed_workers()) f += (f.empty() ? "" : ", ") + std::to_string(id);
+    return Err::common("There is no available worker, locs: [" + l + "], failed workers: [" + f + "]");
 }
 
 void FsContext::pool_stats(int64_t out[3]) {
@@ -375,7 +408,7 @@ Err BlockReader::open_adapter(int64_t off) {
         cur_addr_ = WorkerAddress();
         return Err::ok();
     }
-    if (locs_.empty()) return Err::common("There is no available worker, locs: [], failed workers: []");
+    if (locs_.empty()) return ctx_->no_available_worker(locs_);
     const WorkerAddress& loc = locs_[0];
     cur_addr_ = loc;
     const bool sc = ctx_->conf.client.short_circuit && ctx_->is_local_worker(loc);

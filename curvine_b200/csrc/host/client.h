@@ -127,6 +127,13 @@ class FsContext {
     void release(std::unique_ptr<BlockClient> c);
     bool is_local_worker(const WorkerAddress& addr) const { return addr.hostname == conf.client.hostname; }
     int64_t read_chunk_size() const { return conf.client.read_chunk_size; }
+    // fs_context.rs:83-86,182-205: workers excluded for failed_worker_ttl.  As in the reference only the write path adds to the list;
+    // the read path reports it in its "There is no available worker" error.
+    void add_failed_worker(const WorkerAddress& addr);
+    bool is_failed_worker(const WorkerAddress& addr);
+    std::vector<uint32_t> get_failed_workers();
+    // "There is no available worker, locs: [...], failed workers: [...]" (block_reader.rs:209-213)
+    Err no_available_worker(const std::vector<WorkerAddress>& locs);
     // client metrics (client_metrics.rs:24-35)
     std::atomic<int64_t> read_bytes{0}, read_time_us{0};
 
@@ -135,6 +142,8 @@ class FsContext {
     std::unordered_map<std::string, std::vector<std::unique_ptr<BlockClient>>> idle_;
     int64_t idle_total_ = 0;  // cur_idle_size
     int64_t conns_opened_ = 0, conns_expired_ = 0;
+    std::mutex fw_mu_;
+    std::unordered_map<uint32_t, int64_t> failed_workers_;  // worker_id -> expiry (ms)
    public:
     void pool_stats(int64_t out[3]);  // idle now (BlockClientPool::idle_conn), connections opened so far, pooled connections dropped as expired
 };

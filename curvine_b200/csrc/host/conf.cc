@@ -162,6 +162,7 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "enable_block_conn_pool") cl.enable_block_conn_pool = as_bool(v);
             else if (k == "block_conn_idle_size") cl.block_conn_idle_size = as_int(v);
             else if (k == "block_conn_idle_time") e = parse_duration_ms(unquote(v), &cl.block_conn_idle_time_ms);
+            else if (k == "failed_worker_ttl") e = parse_duration_ms(unquote(v), &cl.failed_worker_ttl_ms);
             else if (k == "hostname") cl.hostname = unquote(v);
         } else if (section == "worker") {
             if (k == "data_dir") c->worker_dirs = as_list(v);
@@ -197,7 +198,9 @@ Err ClusterConf::from_string(const std::string& toml, ClusterConf* c) {
             else if (k == "gds") {
                 const std::string m = unquote(v);
                 b.gds = (m == "on" || m == "true" || m == "1") ? 1 : (m == "off" || m == "false" || m == "0") ? 0 : 2;
-            } else if (k == "arena") b.arena = as_bool(v);
+            } else if (k == "local_unix_socket") b.local_unix_socket = as_bool(v);
+            else if (k == "socket_buffer") e = as_size(v, &b.socket_buffer);
+            else if (k == "arena") b.arena = as_bool(v);
             else if (k == "arena_preregister") b.arena_dirs = as_list(v);
             else if (k == "arena_register_slice") e = as_size(v, &b.arena_register_slice);
         }

@@ -33,6 +33,7 @@ struct ClientConf {
     bool enable_block_conn_pool = true;
     int64_t block_conn_idle_size = 128;       // idle connections kept by the pool, over ALL workers (block_client_pool.rs:147-155)
     int64_t block_conn_idle_time_ms = 60000;  // "block_conn_idle_time", DurationUnit string, default "60s" (client_conf.rs:412-413)
+    int64_t failed_worker_ttl_ms = 10 * 60 * 1000;  // "failed_worker_ttl", DurationUnit string, default "10m" (client_conf.rs:139-141,374)
     std::string hostname;  // CURVINE_CLIENT_HOSTNAME override; default gethostname()
     Err init();            // client_conf.rs:228-281
 };
@@ -61,6 +62,8 @@ struct B200Conf {
                                           // segments are mapped + pinned in the background from the first device read (or
                                           // cv_fs_preregister) on -- off the read path; other segments are pinned when first met
     int64_t arena_register_slice = 256ll << 20;  // one cudaHostRegister call covers this much of a segment (slices go to register_threads)
+    bool local_unix_socket = false;  // block connections to a worker on this host use its abstract unix socket (net.h) instead of loopback TCP
+    int64_t socket_buffer = 0;       // explicit SO_RCVBUF/SO_SNDBUF for block connections (0 = kernel autotuning)
     int gds = 2;                  // "gds" = "off" | "on" | "auto": short-circuit reads of SSD/HDD/DISK-tier blocks go through cuFileRead
                                   // (gds.h) straight into HBM; auto (default) = only with real GPUDirect Storage (nvidia-fs), on = also in
                                   // cuFile's compatibility mode; anything GDS cannot serve goes through the pinned ring

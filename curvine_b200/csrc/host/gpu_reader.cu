@@ -820,7 +820,7 @@ enum FetchMode { kFetchShortCircuit = 0, kFetchFramedVerbatim = 1 };
 //                    also clips the last chunk of a range that stops short of the block end)
 static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, int64_t n, FetchMode mode, int64_t chunk, uint8_t* slot,
                      std::unique_ptr<BlockClient>* conn, int64_t* req_id_out, size_t* wire_bytes) {
-    Err last = Err::common("There is no available worker, locs: [], failed workers: []");
+    Err last = ctx->no_available_worker(lb.locs);
     for (const WorkerAddress& loc : lb.locs) {
         if (!*conn || !((*conn)->addr() == loc) || (*conn)->broken) {
             if (*conn) ctx->release(std::move(*conn));
@@ -904,7 +904,7 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
 // Open(short_circuit=true) on the first replica that answers; returns the block file path.
 static Err open_short_circuit(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, std::unique_ptr<BlockClient>* conn, int64_t* req_id,
                               BlockReadResponse* out) {
-    Err last = Err::common("There is no available worker, locs: [], failed workers: []");
+    Err last = ctx->no_available_worker(lb.locs);
     for (const WorkerAddress& loc : lb.locs) {
         if (!*conn || !((*conn)->addr() == loc) || (*conn)->broken) {
             if (*conn) ctx->release(std::move(*conn));
@@ -1001,7 +1001,7 @@ Err GpuFsReader::run_jobs(const std::vector<Job>& jobs, uint8_t* d_dst, void* us
     for (size_t j = 0; j < J; j++) {
         const LocatedBlock& lb = (*jobs[j].lb);
         if (lb.locs.empty()) {
-            if (!lb.block.has_alloc_opts) return Err::common("There is no available worker, locs: [], failed workers: []");
+            if (!lb.block.has_alloc_opts) return ctx_->no_available_worker(lb.locs);
             mode[j] = kHole;
             continue;
         }

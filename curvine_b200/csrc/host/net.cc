@@ -1,5 +1,10 @@
 #include "net.h"
 
+#include <stddef.h>
+#include <sys/un.h>
+
+#include <atomic>
+
 #include <algorithm>
 #include <arpa/inet.h>
 #include <errno.h>
@@ -14,13 +19,64 @@
 
 namespace cv {
 
+static std::atomic<int> g_sock_buf{0};
+void set_socket_buffer_bytes(int bytes) { g_sock_buf.store(bytes); }
+
 void set_sock_opts(int fd) {
     int one = 1;
-    setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+    setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));  // fails harmlessly on a unix socket
     setsockopt(fd, SOL_SOCKET, SO_KEEPALIVE, &one, sizeof(one));
-    int buf = 8 << 20;  // loopback throughput: large socket buffers
-    setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &buf, sizeof(buf));
-    setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &buf, sizeof(buf));
+    // An explicit SO_RCVBUF/SO_SNDBUF is clamped to net.core.{r,w}mem_max (often 208 KiB) AND switches the kernel's buffer
+    // autotuning off (tcp_rmem goes to 6 MiB on its own): only set when asked to.
+    if (int buf = g_sock_buf.load()) {
+        setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &buf, sizeof(buf));
+        setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &buf, sizeof(buf));
+    }
+}
+
+std::string local_socket_name(int tcp_port) { return str_printf("curvine-b200-worker-%d", tcp_port); }
+
+static socklen_t abstract_addr(const std::string& name, sockaddr_un* sa) {
+    memset(sa, 0, sizeof(*sa));
+    sa->sun_family = AF_UNIX;
+    const size_t n = std::min(name.size(), sizeof(sa->sun_path) - 2);
+    memcpy(sa->sun_path + 1, name.data(), n);  // sun_path[0] == 0: abstract namespace
+    return static_cast<socklen_t>(offsetof(sockaddr_un, sun_path) + 1 + n);
+}
+
+Err unix_listen(const std::string& name, int* fd_out) {
+    sockaddr_un sa;
+    const socklen_t len = abstract_addr(name, &sa);
+    const int fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+    if (fd < 0) return Err::io(str_printf("socket(AF_UNIX): %s", strerror(errno)));
+    if (bind(fd, reinterpret_cast<sockaddr*>(&sa), len) != 0 || listen(fd, 1024) != 0) {
+        const int e = errno;
+        ::close(fd);
+        return Err::io(str_printf("bind/listen @%s: %s", name.c_str(), strerror(e)));
+    }
+    *fd_out = fd;
+    return Err::ok();
+}
+
+Err unix_connect(const std::string& name, int* fd_out, int64_t io_timeout_ms) {
+    sockaddr_un sa;
+    const socklen_t len = abstract_addr(name, &sa);
+    const int fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+    if (fd < 0) return Err::io(str_printf("socket(AF_UNIX): %s", strerror(errno)));
+    if (connect(fd, reinterpret_cast<sockaddr*>(&sa), len) != 0) {
+        const int e = errno;
+        ::close(fd);
+        return Err::io(str_printf("connect @%s: %s", name.c_str(), strerror(e)));
+    }
+    set_sock_opts(fd);
+    if (io_timeout_ms > 0) {
+        timeval tv;
+        tv.tv_sec = static_cast<time_t>(io_timeout_ms / 1000), tv.tv_usec = static_cast<suseconds_t>((io_timeout_ms % 1000) * 1000);
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+        setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
+    }
+    *fd_out = fd;
+    return Err::ok();
 }
 
 void close_fd(int fd) {

@@ -319,7 +319,9 @@ Err Worker::start(const std::vector<std::string>& data_dirs, const std::string& 
     enable_send_file_ = enable_send_file;
     CV_RETURN_IF_ERR(tcp_listen(host, port, &listen_fd_, &port_));
     stopping_ = false;
-    accept_thread_ = std::thread([this] { accept_loop(); });
+    accept_thread_ = std::thread([this] { accept_loop(listen_fd_); });
+    if (!unix_listen(local_socket_name(port_), &unix_fd_)) unix_accept_thread_ = std::thread([this] { accept_loop(unix_fd_); });
+    else unix_fd_ = -1;  // no same-host transport (name taken): TCP serves everyone
     return Err::ok();
 }
 
@@ -327,9 +329,12 @@ void Worker::stop() {
     if (listen_fd_ < 0) return;
     stopping_ = true;
     ::shutdown(listen_fd_, SHUT_RDWR);  // wakes accept(); the descriptor stays valid (and ours) until the accept thread is gone
+    if (unix_fd_ >= 0) ::shutdown(unix_fd_, SHUT_RDWR);
     if (accept_thread_.joinable()) accept_thread_.join();
+    if (unix_accept_thread_.joinable()) unix_accept_thread_.join();
     close_fd(listen_fd_);
-    listen_fd_ = -1;
+    close_fd(unix_fd_);
+    listen_fd_ = unix_fd_ = -1;
     {
         std::lock_guard<std::mutex> lk(conn_mu_);
         for (int fd : conn_fds_) ::shutdown(fd, SHUT_RDWR);
@@ -337,9 +342,9 @@ void Worker::stop() {
     while (live_conns_.load() > 0) usleep(1000);
 }
 
-void Worker::accept_loop() {
+void Worker::accept_loop(int lfd) {
     while (!stopping_) {
-        const int fd = ::accept(listen_fd_, nullptr, nullptr);
+        const int fd = ::accept(lfd, nullptr, nullptr);
         if (fd < 0) {
             if (errno == EINTR) continue;
             break;

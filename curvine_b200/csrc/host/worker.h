@@ -117,12 +117,13 @@ class Worker {
     WorkerMetrics& metrics() { return metrics_; }
 
    private:
-    void accept_loop();
+    void accept_loop(int listen_fd);
     void serve(int fd);
     BlockStore store_;
     HbmTier hbm_;
     WorkerMetrics metrics_;
-    int listen_fd_ = -1;
+    int listen_fd_ = -1, unix_fd_ = -1;  // TCP, and the same-host abstract unix socket named after the TCP port (net.h)
+    std::thread unix_accept_thread_;
     int port_ = 0;
     bool enable_send_file_ = true;
     std::atomic<bool> stopping_{false};

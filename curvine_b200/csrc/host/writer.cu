@@ -26,7 +26,10 @@ Err FsWriter::create(FsContext* ctx, const std::string& path, int64_t inode_id, 
     std::unique_ptr<FsWriter> w(new FsWriter());
     w->ctx_ = ctx, w->worker_ = worker, w->block_size_ = block_size, w->chunk_size_ = chunk_size, w->storage_type_ = storage_type;
     w->fb_.status.id = inode_id, w->fb_.status.path = path, w->fb_.status.block_size = block_size;
-    CV_RETURN_IF_ERR(ctx->acquire_read(worker, &w->client_));
+    if (Err e = ctx->acquire_read(worker, &w->client_)) {
+        ctx->add_failed_worker(worker);  // batch_block_writer.rs:143-175: a worker that cannot be written to is excluded for failed_worker_ttl
+        return e;
+    }
     *out = std::move(w);
     return Err::ok();
 }
@@ -87,6 +90,7 @@ Err FsWriter::send_running(const uint8_t* payload, int64_t n) {
     if (!e) e = client_->recv_response_head(&resp, &rh);
     if (e) {
         client_->broken = true;
+        ctx_->add_failed_worker(worker_);
         return e;
     }
     std::string body(static_cast<size_t>(resp.data_len), '\0');

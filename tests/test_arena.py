@@ -193,3 +193,31 @@ def test_two_mem_dirs_place_blocks_round_robin_by_hint():
         w.stop()
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+@pytest.mark.parametrize("arena", [True, False])
+def test_framed_read_over_the_same_host_unix_socket(arena):
+    """[b200] local_unix_socket: block connections to a worker on this host go to its abstract unix socket (net.h), same frames and
+    handlers as TCP; a client without the option, and a worker without the socket, keep using TCP."""
+    d = _mk()
+    try:
+        w = F.MiniWorker(["[MEM:16MB]" + d + "/m0"], extra_worker=(ARENA % ("8MB", "0ms")) if arena else "")
+        name = "@curvine-b200-worker-%d" % w.port
+        assert any(name in line for line in open("/proc/net/unix")), "the worker listens on its abstract socket"
+        n, bs, ino = (5 << 20) + 321, 1 << 20, 5501
+        man = w.create_file("/u", ino, n, bs)
+        want = synth.file_bytes(ino, n, bs)
+        for unix in (True, False):
+            with F.CurvineFileSystem(F.client_conf(short_circuit=False, b200="local_unix_socket = %s\n" % ("true" if unix else "false"))) as fs:
+                fs.load_namespace(man)
+                before = sum(1 for line in open("/proc/net/unix") if name in line)
+                r = fs.open("/u")
+                assert r.read(100) == want[:100]
+                during = sum(1 for line in open("/proc/net/unix") if name in line)
+                assert (during > before) == unix  # a connected server-side endpoint carries the listener's name
+                r.seek(bs + 5)
+                assert r.read_full(n) == want[bs + 5:]
+                r.complete()
+        w.stop()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

@@ -706,3 +706,32 @@ def test_host_reader_prefetches_read_chunk_num_chunks_ahead(cluster, chunk_num, 
         rest = r.read_full(n)
         assert rest == synth.file_bytes(ino, n, bs)[1 << 20:] and r.pos() == n
         r.complete()
+
+
+def test_failed_worker_list_has_a_ttl_and_shows_in_the_no_worker_error(tmp_path):
+    """fs_context.rs:83-86,182-205 + block_reader.rs:209-213: a worker the write path could not reach is excluded for
+    failed_worker_ttl; the read path's "There is no available worker" error lists the block's locations and the excluded ids."""
+    import socket
+    import time
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    dead_port = s.getsockname()[1]
+    s.close()  # nobody listens here
+    man = "file /gone 4501 1048576 1048576 0\nblock %d 1048576 0 - - - localhost:%d:7\n" % (layout.create_block_id(4501, 0), dead_port)
+    with F.CurvineFileSystem(F.client_conf(short_circuit=False, extra_client='failed_worker_ttl = "400ms"\n')) as fs:
+        fs.load_namespace(man)
+        with pytest.raises(F.FsError):
+            fs.create("/w", 4502, 1 << 20, dead_port)  # connect fails: worker id 1 (the writer's fixture id) goes on the list
+        r = fs.open("/gone")
+        with pytest.raises(F.FsError) as ei:
+            r.read(10)
+        assert ei.value.kind == 1  # the connect error itself (IO): open-time errors are not failed over (block_reader.rs:168-215)
+        time.sleep(0.5)
+    with F.CurvineFileSystem(F.client_conf(short_circuit=False, extra_client='failed_worker_ttl = "1h"\n')) as fs:
+        with pytest.raises(F.FsError):
+            fs.create("/w", 4502, 1 << 20, dead_port)
+        fs.load_namespace("file /noloc 4503 1048576 1048576 0\nblock %d 1048576 0 - - - -\n" % layout.create_block_id(4503, 0))
+        r = fs.open("/noloc")
+        with pytest.raises(F.FsError) as ei:
+            r.read(10)
+        assert "There is no available worker, locs: [], failed workers: [1]" in ei.value.msg

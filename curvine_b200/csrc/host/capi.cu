@@ -400,6 +400,8 @@ int64_t cv_gds_info(int64_t out[2]) {
     const GdsInfo& g = gds_info();
     out[0] = g.available, out[1] = g.compat;
     g_last_error = g.detail;
+    const std::string why = gds_last_refusal();
+    if (!why.empty()) g_last_error += "; first refusal: " + why;
     return ok();
 }
 

@@ -272,6 +272,53 @@ Err BlockClient::read_commit_deferred(const ExtendedBlock& b, int64_t req_id, in
     return Err::ok();
 }
 
+Err BlockClient::send_block_read_pipeline(const ClientConf& conf, const ExtendedBlock& b, int64_t off, int64_t req_id, int64_t chunk_size, int64_t n_running,
+                                          BlockReadResponse* open_resp) {
+    if (!pending_.empty()) CV_RETURN_IF_ERR(drain_pending());
+    auto frame = [](const Protocol& req, const std::string& header, std::string* out) {
+        Protocol p = req;
+        p.header_len = static_cast<int32_t>(header.size()), p.data_len = 0;
+        const size_t at = out->size();
+        out->resize(at + kProtocolSize);
+        encode_protocol(p, reinterpret_cast<uint8_t*>(&(*out)[at]));
+        out->append(header);
+    };
+    BlockReadRequest r;
+    r.id = b.id, r.off = off, r.len = b.len, r.chunk_size = static_cast<int32_t>(chunk_size), r.short_circuit = false;
+    r.enable_read_ahead = conf.enable_read_ahead, r.read_ahead_len = conf.read_ahead_len, r.drop_cache_len = conf.drop_cache_len;
+    std::string out;
+    const Protocol open = request_proto(kReqOpen, req_id, 0);
+    frame(open, r.encode(), &out);
+    for (int64_t f = 0; f < n_running; f++) frame(request_proto(kReqRunning, req_id, static_cast<int32_t>(f + 1)), std::string(), &out);
+    BlockReadRequest c;  // ..Default::default() but the id (block_client.rs:263-266)
+    c.id = b.id;
+    const Protocol complete = request_proto(kReqComplete, req_id, static_cast<int32_t>(n_running + 1));
+    frame(complete, c.encode(), &out);
+    if (Err e = send_all(fd_, out.data(), out.size())) {
+        broken = true;
+        return e;
+    }
+    Protocol resp;
+    std::string rh, rd;
+    CV_RETURN_IF_ERR(recv_response_head(&resp, &rh));
+    rd.resize(static_cast<size_t>(resp.data_len));
+    if (resp.data_len)
+        if (Err e = recv_exact(fd_, &rd[0], rd.size())) {
+            broken = true;
+            return e;
+        }
+    if (Err e = check_echo(open, resp)) {
+        broken = true;
+        return e;
+    }
+    if (!resp.is_success()) {
+        broken = true;  // the answers to the requests already sent behind the Open are dropped with the connection
+        return decode_error_body(reinterpret_cast<const uint8_t*>(rd.data()), rd.size());
+    }
+    pending_.push_back(complete);
+    return BlockReadResponse::decode(reinterpret_cast<const uint8_t*>(rh.data()), rh.size(), open_resp);
+}
+
 // ------------------------------------------------------------------ FsContext (connection pool)
 
 FsContext::~FsContext() = default;

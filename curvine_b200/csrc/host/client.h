@@ -103,6 +103,11 @@ class BlockClient {
     Err read_commit_deferred(const ExtendedBlock& b, int64_t req_id, int32_t seq_id);
     Err drain_pending();
     size_t pending() const { return pending_.size(); }
+    // Whole-block pipelining for the GPU reader's framed path: Open, every Running request and the Complete of one block leave in
+    // ONE write (the worker serves a connection's requests in order); the Open answer is read first, then the caller receives the
+    // data frames, and the Complete's answer stays pending like a deferred Complete.  Same messages, same order, two round trips less.
+    Err send_block_read_pipeline(const ClientConf& conf, const ExtendedBlock& b, int64_t off, int64_t req_id, int64_t chunk_size, int64_t n_running,
+                                 BlockReadResponse* open_resp);
     Err send_request(const Protocol& req, const std::string& header);
     Err recv_response_head(Protocol* resp, std::string* resp_header);  // prefix + header; payload left on the socket
     bool broken = false;

@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <stdlib.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -50,7 +51,13 @@ GdsInfo g_info;
 std::mutex g_mu;
 std::unordered_map<std::string, Entry> g_files;
 
+std::string g_refusal;  // first reason a file was turned away (under g_mu)
+
 void probe() {
+    // cuFile reads its configuration from $CUFILE_ENV_PATH_JSON, else /etc/cufile.json; the toolkit ships a sample (compat mode
+    // allowed) that is used when neither exists
+    if (!getenv("CUFILE_ENV_PATH_JSON") && access("/etc/cufile.json", R_OK) != 0 && access("/usr/local/cuda/gds/cufile.json", R_OK) == 0)
+        setenv("CUFILE_ENV_PATH_JSON", "/usr/local/cuda/gds/cufile.json", 0);
     const char* names[] = {"libcufile.so.0", "libcufile.so", "/usr/local/cuda/lib64/libcufile.so.0", "/usr/local/cuda/lib64/libcufile.so"};
     for (const char* n : names)
         if ((g_api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
@@ -83,6 +90,11 @@ const GdsInfo& gds_info() {
     return g_info;
 }
 
+std::string gds_last_refusal() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_refusal;
+}
+
 void gds_forget(const std::string& path) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto it = g_files.begin(); it != g_files.end();) {
@@ -112,8 +124,10 @@ Err gds_read(const std::string& path, void* d_dst, int64_t n, int64_t file_off) 
         }
         if (it == g_files.end()) {
             Entry ne;
-            ne.fd = ::open(path.c_str(), O_RDONLY | O_DIRECT | O_CLOEXEC);
-            if (ne.fd < 0) ne.fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);  // file systems without O_DIRECT (compat mode still works)
+            // real GDS wants O_DIRECT; the compatibility mode does plain preads at whatever offset the caller asks for, which an
+            // O_DIRECT descriptor would refuse unless 512-byte aligned
+            ne.fd = g_info.compat ? -1 : ::open(path.c_str(), O_RDONLY | O_DIRECT | O_CLOEXEC);
+            if (ne.fd < 0) ne.fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
             if (ne.fd < 0) return Err::io(str_printf("open %s: %s", path.c_str(), strerror(errno)));
             CvCuFileDescr d;
             memset(&d, 0, sizeof(d));
@@ -121,7 +135,9 @@ Err gds_read(const std::string& path, void* d_dst, int64_t n, int64_t file_off) 
             const CvCuFileError ce = g_api.HandleRegister(&ne.h, &d);
             if (ce.err != 0) {
                 ::close(ne.fd);
-                return Err(kUnsupported, str_printf("cuFileHandleRegister(%s): cufile error %d", path.c_str(), ce.err));
+                Err e(kUnsupported, str_printf("cuFileHandleRegister(%s): cufile error %d, cuda error %d", path.c_str(), ce.err, ce.cu_err));
+                if (g_refusal.empty()) g_refusal = e.msg;
+                return e;
             }
             ne.ino = static_cast<uint64_t>(st.st_ino);
             it = g_files.emplace(path, ne).first;

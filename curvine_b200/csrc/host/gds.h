@@ -17,6 +17,7 @@ struct GdsInfo {
 const GdsInfo& gds_info();  // probes once per process
 // n bytes of `path` starting at file_off -> d_dst (device memory of the current device).  kUnsupported when GDS cannot serve it.
 Err gds_read(const std::string& path, void* d_dst, int64_t n, int64_t file_off);
+std::string gds_last_refusal();  // why the first file that was turned away was turned away ("" if none was)
 void gds_forget(const std::string& path);  // drop the cached handle (file replaced / context teardown: "" = all)
 
 }  // namespace cv

@@ -804,12 +804,6 @@ static inline void backoff_wait(F cond) {
     }
 }
 
-static Protocol read_req(int8_t status, int64_t req_id, int32_t seq_id) {
-    Protocol p;
-    p.code = kCodeReadBlock, p.req_status = status, p.resp_status = kRespUndefined, p.req_id = req_id, p.seq_id = seq_id;
-    return p;
-}
-
 }  // namespace
 
 enum FetchMode { kFetchShortCircuit = 0, kFetchFramedVerbatim = 1 };
@@ -831,8 +825,42 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
         const int64_t req_id = new_req_id();
         *req_id_out = req_id;
         BlockReadResponse resp;
-        const int64_t open_chunk = mode == kFetchFramedVerbatim ? chunk : ctx->read_chunk_size();
-        last = c->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, req_id, 0, mode == kFetchShortCircuit, open_chunk, &resp, ctx->conf.b200.arena);
+        if (mode == kFetchFramedVerbatim) {
+            // Open + every Running request + Complete in one write (the worker serves them in order, read_handler.rs:60-207).  The
+            // worker answers each Running with min(chunk, block_len - pos) bytes, so the last frame of a range that stops short of
+            // the block end carries bytes past it: they are received like the rest and clipped by K2 (CvStreamDesc.tail_clip).
+            const int64_t nfr = (n + chunk - 1) / chunk;
+            n = std::min<int64_t>(nfr * chunk, lb.block.len - block_off);  // payload bytes on the wire
+            last = c->send_block_read_pipeline(ctx->conf.client, lb.block, block_off, req_id, chunk, nfr, &resp);
+            if (last) continue;
+            uint8_t* w = slot;
+            int64_t left = n;
+            for (int64_t f = 0; f < nfr && !last; f++) {
+                last = recv_exact(c->fd(), w, kProtocolSize);
+                Protocol p;
+                if (!last) last = decode_protocol(w, &p);
+                if (last) break;
+                const int64_t want = std::min(chunk, left);
+                if (!p.is_success() || p.header_len != 0 || p.data_len != want) {
+                    // error response (or an unexpected chunk): drain this frame, report it, drop the connection
+                    std::string body(static_cast<size_t>(p.header_len + p.data_len), '\0');
+                    if (!body.empty() && recv_exact(c->fd(), &body[0], body.size())) c->broken = true;
+                    last = p.is_success() ? Err::common(str_printf("unexpected chunk length %d, expected %lld", p.data_len, (long long)want))
+                                          : decode_error_body(reinterpret_cast<const uint8_t*>(body.data()) + p.header_len, static_cast<size_t>(p.data_len));
+                    break;
+                }
+                last = recv_exact(c->fd(), w + kProtocolSize, static_cast<size_t>(want));
+                w += kProtocolSize + want, left -= want;
+            }
+            if (last) {
+                c->broken = true;  // responses of the remaining pipelined requests may still be in flight
+                continue;
+            }
+            *wire_bytes = static_cast<size_t>(w - slot);
+            return Err::ok();  // the Complete went out with the rest; its answer is consumed in front of this connection's next request
+        }
+        const int64_t open_chunk = ctx->read_chunk_size();
+        last = c->open_block(ctx->conf.client, lb.block, block_off, lb.block.len, req_id, 0, true, open_chunk, &resp, ctx->conf.b200.arena);
         if (last) continue;
         int32_t seq = 0;
         const int64_t base_off = resp.has_arena ? resp.arena_off : 0;  // arena block: an extent inside the segment file
@@ -859,40 +887,6 @@ static Err fetch_job(FsContext* ctx, const LocatedBlock& lb, int64_t block_off, 
             ::close(fd);
             if (got < n) continue;
             *wire_bytes = static_cast<size_t>(n);
-        } else if (mode == kFetchFramedVerbatim) {
-            // all Running requests in one write (the worker serves them in order, read_handler.rs:143-183).  The worker answers
-            // each with min(chunk, block_len - pos) bytes, so the last frame of a range that stops short of the block end carries
-            // bytes past it: they are received like the rest and clipped by K2 (CvStreamDesc.tail_clip).
-            const int64_t nfr = (n + chunk - 1) / chunk;
-            n = std::min<int64_t>(nfr * chunk, lb.block.len - block_off);  // payload bytes on the wire
-            std::string reqs(static_cast<size_t>(nfr) * kProtocolSize, '\0');
-            for (int64_t f = 0; f < nfr; f++) encode_protocol(read_req(kReqRunning, req_id, static_cast<int32_t>(f + 1)), reinterpret_cast<uint8_t*>(&reqs[f * kProtocolSize]));
-            last = send_all(c->fd(), reqs.data(), reqs.size());
-            uint8_t* w = slot;
-            int64_t left = n;
-            for (int64_t f = 0; f < nfr && !last; f++) {
-                last = recv_exact(c->fd(), w, kProtocolSize);
-                Protocol p;
-                if (!last) last = decode_protocol(w, &p);
-                if (last) break;
-                const int64_t want = std::min(chunk, left);
-                if (!p.is_success() || p.header_len != 0 || p.data_len != want) {
-                    // error response (or an unexpected chunk): drain this frame, report it, drop the connection
-                    std::string body(static_cast<size_t>(p.header_len + p.data_len), '\0');
-                    if (!body.empty() && recv_exact(c->fd(), &body[0], body.size())) c->broken = true;
-                    last = p.is_success() ? Err::common(str_printf("unexpected chunk length %d, expected %lld", p.data_len, (long long)want))
-                                          : decode_error_body(reinterpret_cast<const uint8_t*>(body.data()) + p.header_len, static_cast<size_t>(p.data_len));
-                    break;
-                }
-                last = recv_exact(c->fd(), w + kProtocolSize, static_cast<size_t>(want));
-                w += kProtocolSize + want, left -= want;
-            }
-            if (last) {
-                c->broken = true;  // responses of the remaining pipelined requests may still be in flight
-                continue;
-            }
-            seq = static_cast<int32_t>(nfr);
-            *wire_bytes = static_cast<size_t>(w - slot);
         }
         last = c->read_commit_deferred(lb.block, req_id, seq + 1);  // its answer is consumed in front of this connection's next request
         if (last) continue;

@@ -167,4 +167,5 @@ const GdsInfo& gds_info() {
 }
 Err gds_read(const std::string&, void*, int64_t, int64_t) { return Err(kUnsupported, "mock runtime: no cuFile"); }
 void gds_forget(const std::string&) {}
+std::string gds_last_refusal() { return ""; }
 }  // namespace cv

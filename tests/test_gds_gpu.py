@@ -38,7 +38,7 @@ def test_ssd_tier_file_lands_bit_exact_whichever_path_serves_it(cuda, gds):
                 assert dst[:got].cpu().numpy().tobytes() == want[12345:]
                 st = r.device_stats()
                 expect_gds = info["available"] and (gds == "on" or (gds == "auto" and not info["compat"]))
-                assert (st["gds_bytes"] == got) if expect_gds else (st["gds_bytes"] == 0), (st["gds_bytes"], info, gds)
+                assert (st["gds_bytes"] == got) if expect_gds else (st["gds_bytes"] == 0), (st["gds_bytes"], F.gds_info(), gds)
                 r.complete()
                 # whole file again from the start: every block comparable
                 r = fs.open("/ssd")

@@ -8,7 +8,7 @@
 
 Workload (config C2 of BASELINE.json per GPU, scaled weakly: C3's shape at N=8): synthetic files of N x 16 GiB in 4 MiB
 blocks in the worker's mem tier; GPU g reads the blocks b % N == g (16 GiB per GPU).  EVERY step reads a file that no client
-has read before: rank 0 writes a fresh file (new inode, new bytes) before the step and drops the one read two steps ago, all
+has read before: rank 0 drops the previous step's file and writes a fresh one (new inode, new bytes) before the step, all
 outside the timed region.  A step = one full pass through the public C ABI:
     cv_open -> cv_read_device[_sharded] -> cv_verify -> cv_close_reader
 block locations -> worker Open/Complete RPCs per block -> DMA of the block bytes from host memory into HBM -> on-GPU CRC-32C
@@ -42,7 +42,7 @@ METRIC = "sequential read GB/s into HBM (CRC-verified)"
 UNIT = "GB/s"
 BLOCK = 4 << 20
 PCIE_RAW = 63.0  # PCIe Gen5 x16 per direction, GB/s
-SEG = 1 << 30
+SEG = 256 << 20  # arena segment size
 
 
 def parse():
@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--gib-per-gpu", type=float, default=16.0)
     ap.add_argument("--mode", default="short_circuit", choices=["short_circuit", "framed"], help="read path of the headline steps")
     ap.add_argument("--tier", default="arena", choices=["arena", "files"], help="mem tier of the headline steps: pinned-once arena (arena.h) or the reference's one file per block")
-    ap.add_argument("--pool", type=int, default=2, help="files kept alive at once; a step's file is dropped `pool` steps later")
+    ap.add_argument("--pool", type=int, default=0, help="files kept alive BESIDE the one a step reads (0: the previous step's file is dropped before the next is written)")
     ap.add_argument("--fetch-threads", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--verify-batch", type=int, default=16)
@@ -183,11 +183,13 @@ class Cluster:
             self.dir = tempfile.mkdtemp(prefix="cvbench_", dir=base)
             L = _lib.lib()
             nodes = [int(L.cv_gpu_numa_node(g)) for g in range(world)]
-            cap = (args.pool + 1) * shard_bytes + SEG + (64 << 20)  # pool + the file being written + quarantine slack
+            # memory discipline: the arena holds the file being read (+ `pool` older ones) and one segment of slack, nothing more -- the
+            # GPU boxes lose the container somewhere below 257 GiB of tmpfs (round 2 lost three boxes to a 128 GiB-per-GPU run)
+            cap = (args.pool + 1) * shard_bytes + SEG
             dirs = ["[MEM:%d]%s/arena%d" % (cap, self.dir, g) for g in range(world)]
             t0 = time.time()
             self.arena = F.MiniWorker(dirs, hostname="localhost",
-                                      extra_worker='mem_arena = true\narena_segment = "%d"\narena_numa = [%s]\narena_reuse_delay = "1s"\n'
+                                      extra_worker='mem_arena = true\narena_segment = "%d"\narena_numa = [%s]\narena_reuse_delay = "0ms"\n'
                                                    % (SEG, ", ".join(str(n) for n in nodes)))
             self.arena_start_sec = time.time() - t0
             self.files = F.MiniWorker(["[MEM]%s/files%d" % (self.dir, g) for g in range(world)], hostname="localhost") if need_files_tier else None
@@ -270,11 +272,13 @@ def run_leg(name, cluster, fs, tier, args, rank, world, dist, dst, shard_bytes, 
     n_total = shard_bytes * world
     for it in range(warmup + steps):
         if fresh or it == 0:
+            # the file read `pool`+1 steps ago goes first (its read was verified and is complete: no DMA can be in flight, which is
+            # why this bench runs the arena with arena_reuse_delay = 0), then the new one is written -- possibly into the same pages
+            while len(paths) > (args.pool if pool is None else pool):
+                cluster.drop(paths.pop(0))
             path = "/bench/%s_%d" % (name, it)
             fs.load_namespace(cluster.create(tier, path, inode0 + it, n_total))
             paths.append(path)
-            if fresh and len(paths) > (args.pool if pool is None else pool):
-                cluster.drop(paths.pop(0))
         if args.settle_ms:
             time.sleep(args.settle_ms / 1e3)
         barrier(dist)
@@ -321,8 +325,8 @@ def main():
     fthreads = args.framed_threads or max(4, min(16, ncpu // (2 * world)))
     slots = args.slots or (2 * args.verify_batch + threads + 8)
     side = args.side_steps
-    # side legs report a rate: beyond one GPU they read 4 GiB per GPU per step (less tmpfs, less generation time)
-    side_bytes = shard_bytes if world == 1 else min(shard_bytes, (4 << 30) // BLOCK * BLOCK)
+    # side legs report a rate: beyond one GPU they read 2 GiB per GPU per step and skip the reference-layout leg (no tmpfs beside the arena)
+    side_bytes = shard_bytes if world == 1 else min(shard_bytes, (2 << 30) // BLOCK * BLOCK)
     cluster = Cluster(args, rank, world, dist, shard_bytes, need_files_tier=True)
     dst = torch.empty(shard_bytes, dtype=torch.uint8, device="cuda")
     sampler = ClockSampler(local)
@@ -349,6 +353,8 @@ def main():
         arena1 = fs.arena_stats()
         # ---- side legs
         legs = set(x for x in args.legs.split(",") if x) if side > 0 else set()
+        if world > 1:
+            legs.discard("pread")
         reread = pread = framed = framed_unix = None
         if "reread" in legs:
             reread = run_leg("reread", cluster, fs, args.tier, args, rank, world, dist, dst, side_bytes, side, 1, False, 6000)
@@ -387,7 +393,7 @@ def main():
         if "pread" in legs:
             # reference layout (one tmpfs file per block), never-read files, through the pinned ring
             fs3 = F.CurvineFileSystem(client_conf(args, cluster, True, local, threads, slots, rank, zero_copy=False, copy_group=1))
-            pread = run_leg("pread", cluster, fs3, "files", args, rank, world, dist, dst, side_bytes, side, 1, True, 7000, pool=1)
+            pread = run_leg("pread", cluster, fs3, "files", args, rank, world, dist, dst, side_bytes, side, 1, True, 7000, pool=0)
             fs3.close()
         for leg_name, unix in (("framed", False), ("framed_unix", True)):
             if leg_name not in legs:
@@ -395,7 +401,7 @@ def main():
             # frames from the arena worker (sendfile out of the segment file), received verbatim, unpacked + CRC'd by K2; one block per
             # ring slot (copy_group 1): every connection fills its own slot, the verifier frees slots 16 blocks at a time
             fs2 = F.CurvineFileSystem(client_conf(args, cluster, False, local, fthreads, 2 * args.verify_batch + 2 * fthreads + 8, rank, copy_group=1, unix=unix))
-            res_leg = run_leg(leg_name, cluster, fs2, "arena", args, rank, world, dist, dst, side_bytes, side, 1, True, 8000 + 500 * unix, pool=1)
+            res_leg = run_leg(leg_name, cluster, fs2, "arena", args, rank, world, dist, dst, side_bytes, side, 1, True, 8000 + 500 * unix, pool=0)
             fs2.close()
             if unix:
                 framed_unix = res_leg
@@ -439,7 +445,7 @@ def main():
                                        "(C3 shape at N=8), on-GPU CRC-%s verify; every step reads a file nobody has read before"
                                        % (args.gib_per_gpu, "pinned-once arena (arena.h)" if args.tier == "arena" else "one tmpfs file per block", "32C" if args.poly else "32"),
                            "file_bytes": n_total, "block_bytes": BLOCK, "blocks_per_gpu": my_blocks, "read_path": args.mode, "mem_tier": args.tier,
-                           "fresh_file_every_step": True, "file_pool": args.pool, "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch,
+                           "fresh_file_every_step": True, "files_kept_beside_the_current": args.pool, "arena_reuse_delay_ms": 0, "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch,
                            "copy_group": args.copy_group, "arena_segment_bytes": SEG, "arena_register_slice": args.register_slice,
                            "l2": "inputs (%g GiB per GPU per step, new bytes every step) are larger than L2; no flush needed" % args.gib_per_gpu, "host_cpus": ncpu},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) * world, "d2h_bytes_per_step": 4 * (my_blocks + 4) * world,

@@ -54,10 +54,6 @@ std::unordered_map<std::string, Entry> g_files;
 std::string g_refusal;  // first reason a file was turned away (under g_mu)
 
 void probe() {
-    // cuFile reads its configuration from $CUFILE_ENV_PATH_JSON, else /etc/cufile.json; the toolkit ships a sample (compat mode
-    // allowed) that is used when neither exists
-    if (!getenv("CUFILE_ENV_PATH_JSON") && access("/etc/cufile.json", R_OK) != 0 && access("/usr/local/cuda/gds/cufile.json", R_OK) == 0)
-        setenv("CUFILE_ENV_PATH_JSON", "/usr/local/cuda/gds/cufile.json", 0);
     const char* names[] = {"libcufile.so.0", "libcufile.so", "/usr/local/cuda/lib64/libcufile.so.0", "/usr/local/cuda/lib64/libcufile.so"};
     for (const char* n : names)
         if ((g_api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;

@@ -6,9 +6,9 @@ ROOT="$(cd "$(dirname "$0")/.." && pwd)"; cd "$ROOT"
 K="not read_to_tensor"
 LIB=$(python tests/mock_cuda/build.py thread)
 CV_TEST_MOCK_CUDA_LIB=$LIB LD_PRELOAD="$(gcc -print-file-name=libtsan.so)" TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4" \
-  setarch "$(uname -m)" -R python -m pytest tests/test_gpu_reader.py tests/test_zz_gpu_reader_faults.py -m gpu -q -p no:cacheprovider -k "$K" > /tmp/cv_ingest_tsan.log 2>&1 || true
+  setarch "$(uname -m)" -R python -m pytest tests/test_gpu_reader.py tests/test_zz_gpu_reader_faults.py tests/test_arena_gpu.py tests/test_gds_gpu.py -m gpu -q -p no:cacheprovider -k "$K" > /tmp/cv_ingest_tsan.log 2>&1 || true
 echo "tsan: $(tail -1 /tmp/cv_ingest_tsan.log) | findings: $(grep -c 'WARNING: ThreadSanitizer' /tmp/cv_ingest_tsan.log)"
 LIB=$(python tests/mock_cuda/build.py address,undefined)
 CV_TEST_MOCK_CUDA_LIB=$LIB LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 \
-  UBSAN_OPTIONS=print_stacktrace=1 python -m pytest tests/test_gpu_reader.py tests/test_zz_gpu_reader_faults.py -m gpu -q -p no:cacheprovider -k "$K" > /tmp/cv_ingest_asan.log 2>&1 || true
+  UBSAN_OPTIONS=print_stacktrace=1 python -m pytest tests/test_gpu_reader.py tests/test_zz_gpu_reader_faults.py tests/test_arena_gpu.py tests/test_gds_gpu.py -m gpu -q -p no:cacheprovider -k "$K" > /tmp/cv_ingest_asan.log 2>&1 || true
 echo "asan+ubsan: $(tail -1 /tmp/cv_ingest_asan.log) | findings: $(grep -ciE 'runtime error|AddressSanitizer' /tmp/cv_ingest_asan.log)"

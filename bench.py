@@ -353,11 +353,24 @@ def main():
         arena1 = fs.arena_stats()
         # ---- side legs
         legs = set(x for x in args.legs.split(",") if x) if side > 0 else set()
-        if world > 1:
-            legs.discard("pread")
+        if world > 1:  # beyond one GPU the side legs are the re-read and the kernel-only pass; the transport legs are one-GPU numbers
+            legs -= {"pread", "framed", "framed_unix"}
+        side_errors = {}
+
+        def guarded(leg_name, fn):
+            """A side leg must never cost the headline its JSON line (one GPU only: with several ranks a leg that fails on one rank
+            would leave the others in a barrier, which is why those legs do not run there)."""
+            try:
+                return fn()
+            except Exception as e:  # noqa: BLE001
+                side_errors[leg_name] = "%s: %s" % (type(e).__name__, e)
+                log("side leg %s failed: %s" % (leg_name, side_errors[leg_name]))
+                for p in [p for p in list(cluster.live) if p.startswith("/bench/%s_" % leg_name)]:
+                    cluster.drop(p)  # whatever it left in the store must not starve the legs behind it
+                return None
         reread = pread = framed = framed_unix = None
         if "reread" in legs:
-            reread = run_leg("reread", cluster, fs, args.tier, args, rank, world, dist, dst, side_bytes, side, 1, False, 6000)
+            reread = run_leg("reread", cluster, fs, args.tier, args, rank, world, dist, dst, side_bytes, side, 1, False, 6000)  # the headline's own path: not guarded
         # ---- resident verify (K1 over what the last step left in HBM) + roofline of K1
         fs.load_namespace(cluster.create(args.tier, "/bench/resident", 4200, n_total))
         _, _, sum_crc, _ = timed_read(fs, "/bench/resident", rank, world, dst, shard_bytes, torch.cuda.current_stream().cuda_stream)
@@ -392,17 +405,25 @@ def main():
         fs.close()
         if "pread" in legs:
             # reference layout (one tmpfs file per block), never-read files, through the pinned ring
-            fs3 = F.CurvineFileSystem(client_conf(args, cluster, True, local, threads, slots, rank, zero_copy=False, copy_group=1))
-            pread = run_leg("pread", cluster, fs3, "files", args, rank, world, dist, dst, side_bytes, side, 1, True, 7000, pool=0)
-            fs3.close()
+            def leg_pread():
+                fs3 = F.CurvineFileSystem(client_conf(args, cluster, True, local, threads, slots, rank, zero_copy=False, copy_group=1))
+                try:
+                    return run_leg("pread", cluster, fs3, "files", args, rank, world, dist, dst, side_bytes, side, 1, True, 7000, pool=0)
+                finally:
+                    fs3.close()
+            pread = guarded("pread", leg_pread)
         for leg_name, unix in (("framed", False), ("framed_unix", True)):
             if leg_name not in legs:
                 continue
             # frames from the arena worker (sendfile out of the segment file), received verbatim, unpacked + CRC'd by K2; one block per
             # ring slot (copy_group 1): every connection fills its own slot, the verifier frees slots 16 blocks at a time
-            fs2 = F.CurvineFileSystem(client_conf(args, cluster, False, local, fthreads, 2 * args.verify_batch + 2 * fthreads + 8, rank, copy_group=1, unix=unix))
-            res_leg = run_leg(leg_name, cluster, fs2, "arena", args, rank, world, dist, dst, side_bytes, side, 1, True, 8000 + 500 * unix, pool=0)
-            fs2.close()
+            def leg_framed(leg_name=leg_name, unix=unix):
+                fs2 = F.CurvineFileSystem(client_conf(args, cluster, False, local, fthreads, 2 * args.verify_batch + 2 * fthreads + 8, rank, copy_group=1, unix=unix))
+                try:
+                    return run_leg(leg_name, cluster, fs2, "arena", args, rank, world, dist, dst, side_bytes, side, 1, True, 8000 + 500 * unix, pool=0)
+                finally:
+                    fs2.close()
+            res_leg = guarded(leg_name, leg_framed)
             if unix:
                 framed_unix = res_leg
             else:
@@ -483,8 +504,13 @@ def main():
                                        "frac_of_pcie_gen5_x16_raw_63GBps": v / world / PCIE_RAW, "steps": side, "bytes_per_step": side_total, "what": what,
                                        "timed_steps_ms": leg["e2e_ms"], "last_step_fetch_thread_sec": leg["stats"]["fetch_sec"],
                                        "last_step_wall_sec": leg["stats"]["wall_sec"], "h2d_bytes_last_step": int(leg["stats"]["h2d_bytes"])}
+            if side_errors:
+                out["side_leg_errors"] = side_errors
             if world == 1 and not args.no_cpu_baseline and "cpu" in (legs or {"cpu"}):
-                out["cpu_baseline"] = cpu_baseline(cluster, args)
+                try:
+                    out["cpu_baseline"] = cpu_baseline(cluster, args)
+                except Exception as e:  # noqa: BLE001  (the reference arm reports the CPU number too; the headline line must still go out)
+                    out["cpu_baseline_error"] = "%s: %s" % (type(e).__name__, e)
     finally:
         sampler.stop()
         cluster.close()

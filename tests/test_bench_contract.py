@@ -96,3 +96,17 @@ def test_own_arm_two_ranks_on_the_mock_runtime():
     assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["config"]["file_bytes"] == n and d["config"]["blocks_per_gpu"] == n // (4 << 20) // 2
     assert d["e2e"]["h2d_bytes_per_step"] == n and d["e2e"]["value"] > 0 and d["value"] > 0
     assert "cpu_baseline" not in d  # rank 0 at N=1 only
+
+
+def test_smoke_control_flow_on_the_mock_runtime():
+    """__graft_entry__.smoke() end to end without a GPU (mock runtime): the three passes it makes on the B200 -- files tier short-circuit,
+    files tier framed, arena tier DMA -- each land the oracle's bytes and CRC sums."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_cuda"))
+    try:
+        import build as mock_build
+    finally:
+        sys.path.pop(0)
+    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=mock_build.build())
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "run_smoke_on_mock.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=600, env=env, cwd=ROOT)
+    assert p.returncode == 0 and "smoke ok" in p.stdout, p.stdout[-3000:]

@@ -242,3 +242,10 @@ def test_reader_model_semantics():
     assert b"".join(segs) == data[bs + 65536 - 1024:bs + 65536 - 1024 + 200000]
     # after a seek the worker streams chunk_size pieces from the seek offset (no re-alignment): read_handler.rs:143-158
     assert [len(x) for x in segs] == [65536, 65536, 65536, 200000 - 3 * 65536]
+
+
+def test_c_generator_equals_python_generator():
+    """oracle/oracle.c cvo_synth_block == oracle/synth.py block_bytes (xoshiro256** seeded by splitmix64) -- the GPU
+    scale test uses the C one for speed."""
+    for fid, b, n in [(1001, 0, 4096), (8901, 17, 100001), (5, 123456, 1), (2 ** 39, 2 ** 23, 65536 + 7)]:
+        assert clib.synth_block(fid, b, n).tobytes() == synth.block_bytes(fid, b, n)

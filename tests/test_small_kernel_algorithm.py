@@ -46,7 +46,7 @@ def _emulate(data: bytes, poly: int) -> int:
 def test_small_kernel_scheme_equals_the_crc_definition(poly):
     rng = np.random.default_rng(5)
     data = rng.integers(0, 256, size=1024 * 1008, dtype=np.uint8).tobytes()
-    for n in [1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 1023, 1024, 1025, 4097, 16385, 65543, 200000, 204099, 262144, 262149]:
+    for n in [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 100, 1023, 1024, 1025, 4097, 12345, 16385, 65543, 200000, 204099, 262144, 262149]:
         assert _emulate(data[:n], poly) == C.crc_table(data[:n], poly), n
     for n in [1024 * 1008 - 1, 1024 * 1008]:  # the largest block the kernel takes (S = 1008)
         assert _emulate(data[:n], poly) == C.crc_table(data[:n], poly), n

@@ -1,14 +1,16 @@
-// GPU ingest pipeline: blocks of a file -> pinned host ring -> HBM on side streams -> on-GPU CRC verify.
+// GPU ingest pipeline: blocks of a file -> HBM on side streams -> on-GPU CRC verify (-> page scatter).
 //
 // No reference counterpart (the reference has no GPU code); it replaces, for HBM destinations, the role of
 // FsReaderBuffer's prefetch tasks (curvine-client/src/file/fs_reader_buffer.rs:332-406) and the caller's
 // read_full + crc32 loop (curvine-tests/src/curvine_bench.rs:222-231), speaking the same worker protocol as
 // BlockReaderLocal / BlockReaderRemote (block_reader_local.rs:43-143, block_reader_remote.rs:36-122):
-//   short-circuit  Open(short_circuit=true) -> pread the block file straight into a pinned slot -> H2D to its
-//                  final place -> K1 CRC on the landed bytes -> Complete
-//   framed         Open -> all Running requests pipelined in one write -> the response stream (22-byte prefixes
-//                  + payloads) received verbatim into a pinned slot -> H2D wire image -> K2 validates the prefixes,
-//                  gathers payloads to their file offsets and CRCs them in the same pass -> Complete
+//   arena          Open(short_circuit, accept_arena) names (segment, offset): DMA straight out of the arena segment this context
+//                  pinned once at mount (arena.h) -> K1 CRC on the landed bytes; Complete sent without waiting for its answer
+//   files          Open(short_circuit=true) -> block file: registered-mapping cache, or pread into a pinned slot -> H2D -> K1
+//   disk tiers     cuFileRead file -> HBM (gds.h) where GPUDirect Storage is available; pinned ring otherwise
+//   framed         Open + every Running request + Complete in one write -> the response stream (22-byte prefixes + payloads)
+//                  received verbatim into a pinned slot -> H2D wire image -> K2 validates the prefixes, gathers payloads to
+//                  their file offsets (clipping the tail of a ranged read) and CRCs them in the same pass
 #pragma once
 #include <atomic>
 #include <condition_variable>

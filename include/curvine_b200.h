@@ -66,9 +66,9 @@ int64_t cv_fs_load_namespace_string(cv_fs* fs, const char* manifest_text);
 int64_t cv_fs_close(cv_fs* fs);
 /* Block until everything this context pins in the background is pinned: the arena segments queued by cv_fs_preregister / the
  * first device read (mem-arena tier), and -- for the reference's one-file-per-block mem tier -- the registrar's mmap +
- * cudaHostRegister of block files seen by earlier device reads.  Optional; reads never wait for either: a block whose memory
- * is not pinned yet goes through the pinned ring (files tier: by default, [b200] register_when_idle = true, the registrar only
- * works while no device read is in flight). */
+ * cudaHostRegister of block files seen by earlier device reads.  Optional: a read that needs an arena segment whose pinning is
+ * still in progress waits for that one segment; a block FILE that is not registered yet goes through the pinned ring (by
+ * default, [b200] register_when_idle = true, the registrar only works while no device read is in flight). */
 int64_t cv_fs_wait_registered(cv_fs* fs);
 /* Mem-arena tier (worker `[worker] mem_arena = true`, curvine_b200/csrc/host/arena.h): start mapping + pinning the arena
  * segments of the dirs named in `[b200] arena_preregister` now, in the background ("mount time"; otherwise it starts with

@@ -328,10 +328,11 @@ static int64_t now_ms() { return static_cast<int64_t>(now_sec() * 1000.0); }
 // A pooled connection whose peer went away (worker restarted, idle timeout on the server side) has a FIN or RST queued: a
 // non-blocking peek sees it without consuming anything.  An idle healthy connection has nothing to read (EAGAIN); bytes nobody
 // asked for mean the stream is out of step.  Either way the connection is not handed out again.
-static bool pooled_connection_is_usable(int fd) {
+static bool pooled_connection_is_usable(int fd, bool answers_outstanding = false) {
     char b;
     const ssize_t r = ::recv(fd, &b, 1, MSG_PEEK | MSG_DONTWAIT);
-    return r < 0 && (errno == EAGAIN || errno == EWOULDBLOCK);
+    if (r < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return true;
+    return answers_outstanding && r > 0;  // a parked deferred Complete: its answer may already sit in the socket; EOF / RST still disqualify
 }
 
 Err FsContext::acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClient>* out) {
@@ -346,7 +347,7 @@ Err FsContext::acquire_read(const WorkerAddress& addr, std::unique_ptr<BlockClie
             idle_total_--;
             // a connection parked with a deferred Complete outstanding has (or will have) that response queued: it is consumed by
             // the next request, so readable bytes are expected on it
-            if (now - c->idle_since_ms < conf.client.block_conn_idle_time_ms && (c->pending() > 0 || pooled_connection_is_usable(c->fd()))) {
+            if (now - c->idle_since_ms < conf.client.block_conn_idle_time_ms && pooled_connection_is_usable(c->fd(), c->pending() > 0)) {
                 *out = std::move(c);
                 return Err::ok();
             }

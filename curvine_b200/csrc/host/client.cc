@@ -513,7 +513,7 @@ Err BlockReader::read_once(std::string* buf) {
                 posix_fadvise(fd_, base_off_ + pos_, ctx_->conf.client.read_ahead_len, POSIX_FADV_WILLNEED);
                 last_ahead_ = pos_;
             }
-            buf->resize(static_cast<size_t>(want));
+            if (buf->size() != static_cast<size_t>(want)) buf->resize(static_cast<size_t>(want));  // a recycled chunk buffer of the same size is not zero-filled again (the reference's BytesMut is not either: rpc_frame.rs set_len)
             int64_t got = 0;
             while (got < want) {
                 const ssize_t r = pread(fd_, &(*buf)[got], static_cast<size_t>(want - got), base_off_ + pos_ + got);
@@ -541,12 +541,16 @@ Err BlockReader::read_once(std::string* buf) {
     return Err::ok();
 }
 
+// `buf` may arrive holding a previous chunk (its storage is reused); it is empty on return at end of block and after an error.
 Err BlockReader::read(std::string* buf) {
-    buf->clear();
-    if (!has_remaining()) return Err::ok();  // end of block file
+    if (!has_remaining()) {  // end of block file
+        buf->clear();
+        return Err::ok();
+    }
     for (;;) {
         Err e = read_once(buf);
         if (!e) return e;
+        buf->clear();
         if (kind_ == kHole || locs_.empty()) return e.ctx("failed to read block on " + cur_addr_.str());
         // drop this worker, reopen at pos on the next replica (block_reader.rs:223-252)
         locs_.erase(std::remove(locs_.begin(), locs_.end(), cur_addr_), locs_.end());
@@ -661,9 +665,14 @@ Err FsReaderBase::get_reader() {
 }
 
 Err FsReaderBase::read(std::string* buf) {
-    buf->clear();
-    if (pos_ >= len_) return Err::ok();
-    CV_RETURN_IF_ERR(get_reader());
+    if (pos_ >= len_) {
+        buf->clear();
+        return Err::ok();
+    }
+    if (Err e = get_reader()) {
+        buf->clear();
+        return e;
+    }
     CV_RETURN_IF_ERR(cur_->read(buf));
     pos_ += static_cast<int64_t>(buf->size());
     return Err::ok();
@@ -703,17 +712,23 @@ Err FsReaderBase::complete() {
 }
 
 Err FsReaderParallel::read(int64_t* off, std::string* buf) {
-    buf->clear();
     *off = 0;
-    if (slices_.empty()) return Err::ok();
-    if (cur_ < 0) {
+    Err e;
+    bool empty = slices_.empty();
+    if (!empty && cur_ < 0) {
         cur_ = 0;
-        CV_RETURN_IF_ERR(inner_.seek(slices_[0].first));
-    } else if (inner_.pos() >= slices_[static_cast<size_t>(cur_)].second) {
+        e = inner_.seek(slices_[0].first);
+    } else if (!empty && inner_.pos() >= slices_[static_cast<size_t>(cur_)].second) {
         const int64_t next = cur_ + 1;
-        if (next >= static_cast<int64_t>(slices_.size())) return Err::ok();  // FileChunk::default()
-        cur_ = next;
-        CV_RETURN_IF_ERR(inner_.seek(slices_[static_cast<size_t>(next)].first));
+        if (next >= static_cast<int64_t>(slices_.size())) empty = true;  // FileChunk::default()
+        else {
+            cur_ = next;
+            e = inner_.seek(slices_[static_cast<size_t>(next)].first);
+        }
+    }
+    if (empty || e) {
+        buf->clear();
+        return e;
     }
     *off = inner_.pos();
     return inner_.read(buf);
@@ -767,19 +782,28 @@ Err FsReader::open(FsContext* ctx, const std::string& path, std::unique_ptr<FsRe
 }
 
 Err FsReader::buffer_read() {
-    chunk_.clear();
     chunk_off_ = 0;
-    if (bpos_ >= len_) return Err::ok();
+    if (bpos_ >= len_) {
+        chunk_.clear();
+        return Err::ok();
+    }
     const int64_t id = det_.is_random() ? det_.read_parallel : (bpos_ / slice_size_) % det_.read_parallel;
-    if (id < 0 || id >= static_cast<int64_t>(readers_.size())) return Err::common(str_printf("reader %lld is not initialized", (long long)id));
+    if (id < 0 || id >= static_cast<int64_t>(readers_.size())) {
+        chunk_.clear();
+        return Err::common(str_printf("reader %lld is not initialized", (long long)id));
+    }
     const double t0 = now_sec();
     int64_t off = 0;
-    CV_RETURN_IF_ERR(readers_[static_cast<size_t>(id)].read(&off, &chunk_));
+    if (Err e = readers_[static_cast<size_t>(id)].read(&off, &chunk_)) {  // chunk_'s storage is handed down for reuse; nothing of it survives an error
+        chunk_.clear();
+        return e;
+    }
     const int64_t diff = bpos_ - off;
     if (diff == 0) {
     } else if (diff > 0 && diff <= static_cast<int64_t>(chunk_.size())) {
         chunk_off_ = static_cast<size_t>(diff);  // misaligned first chunk: drop the excess prefix
     } else {
+        chunk_.clear();
         return Err::common(str_printf("read data error: chunk offset %lld, pos %lld, diff %lld", (long long)off, (long long)bpos_, (long long)diff));
     }
     const int64_t n = static_cast<int64_t>(chunk_.size() - chunk_off_);
@@ -897,9 +921,13 @@ void PrefetchChannel::loop() {
             continue;
         }
         if (!paused_ && q_.size() < cap_) {
+            std::string buf;
+            if (!spare_.empty()) {  // a chunk buffer the consumer is done with: same size as the next chunk, so no allocation and no zero fill
+                buf = std::move(spare_.back());
+                spare_.pop_back();
+            }
             lk.unlock();
             int64_t off = 0;
-            std::string buf;
             Err e = reader_->read(&off, &buf);
             lk.lock();
             if (e) {
@@ -921,9 +949,13 @@ Err PrefetchChannel::read(int64_t* off, std::string* buf) {
     std::unique_lock<std::mutex> lk(mu_);
     start_locked();
     cv_.wait(lk, [&] { return !q_.empty() || exited_; });
-    if (q_.empty()) return err_ ? err_ : Err::io("prefetch channel closed");
+    if (q_.empty()) {
+        buf->clear();
+        return err_ ? err_ : Err::io("prefetch channel closed");
+    }
     *off = q_.front().first;
-    *buf = std::move(q_.front().second);
+    std::swap(*buf, q_.front().second);  // the consumer's previous chunk storage goes back to the producer
+    if (q_.front().second.capacity() && spare_.size() < cap_) spare_.push_back(std::move(q_.front().second));
     q_.pop_front();
     cv_.notify_all();
     return Err::ok();

@@ -285,6 +285,7 @@ class PrefetchChannel {
     std::mutex mu_;
     std::condition_variable cv_;
     std::deque<std::pair<int64_t, std::string>> q_;
+    std::vector<std::string> spare_;  // chunk buffers handed back by the consumer
     std::deque<Task> tasks_;
     uint64_t next_ticket_ = 1, done_ticket_ = 0;
     bool started_ = false, paused_ = false, exited_ = false;

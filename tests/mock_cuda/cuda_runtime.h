@@ -57,6 +57,7 @@ cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes* a, const void
 cudaError_t cudaGetLastError(void);
 const char* cudaGetErrorString(cudaError_t e);
 // test hooks
+void mock_cuda_set_last_error(int e);
 void mock_cuda_set_register_supported(int on);   // 0: cudaHostRegister answers cudaErrorNotSupported (read-only fs, disk-backed mappings)
 void mock_cuda_counters(uint64_t out[6]);         // memcpy calls, memcpy bytes, registered ranges now, register calls, live device allocs, live pinned allocs
 }

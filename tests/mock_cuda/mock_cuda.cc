@@ -136,7 +136,14 @@ cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes* a, const void
     a->devicePointer = const_cast<void*>(p), a->hostPointer = nullptr;
     return cudaSuccess;
 }
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+// sticky-until-read error of the calling thread (the SIMT shim of tests/simt_emu records invalid launch configurations here)
+static thread_local int t_last_error = cudaSuccess;
+void mock_cuda_set_last_error(int e) { t_last_error = e; }
+cudaError_t cudaGetLastError(void) {
+    const int e = t_last_error;
+    t_last_error = cudaSuccess;
+    return e;
+}
 const char* cudaGetErrorString(cudaError_t e) {
     switch (e) {
         case cudaSuccess: return "no error";

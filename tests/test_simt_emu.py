@@ -1,0 +1,65 @@
+"""The product's KERNEL SOURCE on a machine without a GPU.
+
+tests/simt_emu compiles curvine_b200/csrc/kernels.cu -- the file nvcc compiles for sm_100a, unmodified apart from a mechanical
+rewrite of the launch syntax and of the inline PTX -- for host cores on a SIMT shim: a fiber per CUDA thread, blocks spread over
+host threads, __syncthreads / __syncwarp / *_sync warp intrinsics completing exactly when every live participant has arrived.
+The whole `-m gpu` suite (kernel parity against the oracle, the reader through the C ABI, arena, GDS fallback, faults, the
+two-device gather) then runs in a subprocess against that library.  This checks the kernels' ALGORITHM (index math, shuffle
+patterns, the GF(2) folds, barrier placement) on every CPU run; what it cannot check is what only the hardware decides (memory
+model races between unsynchronised threads, the compiled SASS, speed) -- the B200 run of the same tests covers that.
+Test infrastructure: nothing under curvine_b200/ can load this library."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _emu_build():
+    # tests/mock_cuda/build.py is a module called `build` too: load this one by path
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("simt_emu_build", os.path.join(ROOT, "tests", "simt_emu", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_shim_known_answers_and_deadlock_report():
+    exe = _emu_build().build_selftest()
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "selftest ok" in r.stdout, r.stdout
+    for name in ("scan", "early_exit", "smem_ptx", "launch_errors"):
+        assert name + " ok" in r.stdout, r.stdout
+    # a barrier part of the block never reaches is reported, not spun on
+    r = subprocess.run([exe, "deadlock"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+    assert r.returncode != 0 and "deadlock in block 0" in r.stdout and "not reached" not in r.stdout, r.stdout
+
+
+def test_rewrite_refuses_what_it_does_not_know():
+    b = _emu_build()
+    ok = b.rewrite('__global__ void k(int* p) { asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory"); }\n'
+                   'void f() { k<<<1, 32, 0, st>>>(p); }')
+    assert "cv_emu::ptx_st_v4((p), (a), (b), (c), (d))" in ok and "cv_emu::cfg(1, 32, 0, st)(k, p)" in ok and "<<<" not in ok
+    with pytest.raises(ValueError, match="does not know"):
+        b.rewrite('void f() { asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;" ::"r"(d), "l"(a), "l"(b), "r"(i)); }')
+    with pytest.raises(ValueError, match="launch configuration"):
+        b.rewrite("void f() { k<<<1, 32>>>(p); }")
+    # every asm statement and launch of the product's kernel file is understood, and nothing CUDA-only is left for g++
+    out = b.rewrite(open(os.path.join(ROOT, "curvine_b200", "csrc", "kernels.cu")).read())
+    assert "<<<" not in out and not re.search(r"\basm\b", out) and "extern __shared__" not in out
+    assert out.count("cv_emu::cfg(") == 25 and out.count("\n") == open(os.path.join(ROOT, "curvine_b200", "csrc", "kernels.cu")).read().count("\n")
+
+
+def test_gpu_suite_with_the_kernel_source_on_the_simt_shim():
+    lib = _emu_build().build()
+    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=lib, CV_SIMT_EMU_THREADS="4")
+    # read_to_tensor allocates a torch CUDA tensor inside the binding itself: nothing to check without a device
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "not read_to_tensor", "-n", "4"],
+                       cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=2400)
+    tail = "\n".join(r.stdout.splitlines()[-30:])
+    assert r.returncode == 0, tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 113 and " failed" not in r.stdout, tail

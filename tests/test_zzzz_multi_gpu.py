@@ -14,19 +14,26 @@ from oracle import clib, synth
 pytestmark = pytest.mark.gpu
 
 
+MOCK = bool(os.environ.get("CV_TEST_MOCK_CUDA_LIB"))  # host-side stand-ins (tests/mock_cuda, tests/simt_emu): eight pretend devices in host memory
+
+
 def _need_two():
     import torch
-    if os.environ.get("CV_TEST_MOCK_CUDA_LIB"):
-        pytest.skip("needs real devices")
-    if torch.cuda.device_count() < 2:
+    if not MOCK and torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 CUDA devices (run with gpurun --gpus 2)")
     return torch
+
+
+def _on(torch, g):
+    """(context that makes device g current, torch device string)"""
+    import contextlib
+    return (contextlib.nullcontext(), "cpu") if MOCK else (torch.cuda.device(g), "cuda:%d" % g)
 
 
 @pytest.mark.parametrize("arena", [True, False])
 def test_sharded_read_on_two_devices_then_p2p_gather_from_real_peer_memory(cuda, arena):
     torch = _need_two()
-    world = min(torch.cuda.device_count(), 4)
+    world = 2 if MOCK else min(torch.cuda.device_count(), 4)
     base = "/dev/shm" if os.path.isdir("/dev/shm") else None
     d = tempfile.mkdtemp(prefix="cvmg", dir=base)
     bs, nb = 1 << 20, 37
@@ -48,8 +55,9 @@ def test_sharded_read_on_two_devices_then_p2p_gather_from_real_peer_memory(cuda,
                                           'register_threads = 2\narena_register_slice = "4MB"\narena_preregister = ["%s/m%d"]\n' % (g, d, g))
                 with F.CurvineFileSystem(conf) as fs:
                     fs.load_namespace(man)
-                    with torch.cuda.device(g):
-                        shard = torch.zeros(per * bs, dtype=torch.uint8, device="cuda:%d" % g)
+                    ctx, dev = _on(torch, g)
+                    with ctx:
+                        shard = torch.zeros(per * bs, dtype=torch.uint8, device=dev)
                         r = fs.open("/ckpt")
                         got = r.read_device_sharded(g, world, shard.data_ptr(), per * bs, torch.cuda.current_stream().cuda_stream)
                         s, bad, ver = r.verify()
@@ -68,8 +76,9 @@ def test_sharded_read_on_two_devices_then_p2p_gather_from_real_peer_memory(cuda,
             # every device pulls the whole file out of the owners' HBM
             ptrs = [int(t.data_ptr()) for t in shards]
             for g in range(world):
-                with torch.cuda.device(g):
-                    final = torch.full((n + 64,), 0x77, dtype=torch.uint8, device="cuda:%d" % g)
+                ctx, dev = _on(torch, g)
+                with ctx:
+                    final = torch.full((n + 64,), 0x77, dtype=torch.uint8, device=dev)
                     K.gather_shards_p2p(ptrs, bs, nb, n, final)
                     torch.cuda.synchronize()
                     out = final.cpu().numpy().tobytes()

@@ -175,9 +175,7 @@ def _digest(extra):
 
 def build(sanitize: str = "") -> str:
     common = ["-g", "-std=c++17", "-fPIC", "-pthread", "-msse4.2", "-Wall", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
-    if sanitize:
-        common += ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer"]
-    out_dir = os.path.join("/tmp", "cv_simt_emu_" + _digest(" ".join(common)))
+    out_dir = os.path.join("/tmp", "cv_simt_emu_" + _digest(" ".join(common) + sanitize))
     lib = os.path.join(out_dir, "libcurvine_b200_emu.so")
     if os.path.exists(lib):
         return lib
@@ -189,8 +187,14 @@ def build(sanitize: str = "") -> str:
     text = text.replace('#include "crc_gf.h"', '#include "%s"' % os.path.join(CSRC, "crc_gf.h"))
     with open(kern, "w") as f:
         f.write(text)
-    jobs = [(s, ["-O1", "-I", MOCK]) for s in sources()]
-    jobs.append((kern, ["-O2", "-I", HERE, "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unused-but-set-variable"]))  # <cuda_runtime.h> = this directory's
+    san = ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer"] if sanitize else []
+    jobs = []
+    for src in sources():
+        extra = ["-O1", "-I", MOCK] + san
+        if sanitize == "thread" and os.path.basename(src) == "simt_emu.cc":
+            extra = ["-O1", "-I", MOCK, "-DCV_EMU_TSAN"]  # the scheduler is not instrumented: it IS the ordering, stated through annotations
+        jobs.append((src, extra))
+    jobs.append((kern, ["-O2", "-I", HERE, "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unused-but-set-variable"] + san))  # <cuda_runtime.h> = this directory's
     procs, objs = [], []
     for src, extra in jobs:
         obj = os.path.join(out_dir, os.path.basename(src) + ".o")
@@ -208,9 +212,9 @@ def build(sanitize: str = "") -> str:
     return lib
 
 
-def build_selftest() -> str:
+def build_selftest(sanitize: str = "") -> str:
     """the shim's own known-answer program (selftest.cu) -> path of the executable"""
-    out_dir = os.path.join("/tmp", "cv_simt_emu_selftest_" + _digest("selftest"))
+    out_dir = os.path.join("/tmp", "cv_simt_emu_selftest_" + _digest("selftest" + sanitize))
     exe = os.path.join(out_dir, "selftest")
     if os.path.exists(exe):
         return exe
@@ -218,18 +222,22 @@ def build_selftest() -> str:
     src = os.path.join(out_dir, "selftest_rewritten.cc")
     with open(src, "w") as f:
         f.write(rewrite(open(os.path.join(HERE, "selftest.cu")).read()))
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-I", HERE, "-x", "c++", src, os.path.join(HERE, "simt_emu.cc"),
-           os.path.join(MOCK, "mock_cuda.cc"), os.path.join(HERE, "emu_runtime.cc"), "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", exe + ".tmp", "-lpthread"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-    if r.returncode:
-        raise RuntimeError("selftest build failed:\n" + r.stdout.decode())
+    base = ["g++", "-O1", "-g", "-std=c++17", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    san = ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer"] if sanitize else []
+    sched = os.path.join(out_dir, "simt_emu.o")
+    cmds = [base + (["-DCV_EMU_TSAN"] if sanitize == "thread" else san) + ["-c", os.path.join(HERE, "simt_emu.cc"), "-o", sched],
+            base + san + ["-x", "c++", src, os.path.join(MOCK, "mock_cuda.cc"), os.path.join(HERE, "emu_runtime.cc"), "-x", "none", sched, "-o", exe + ".tmp", "-lpthread"]]
+    for cmd in cmds:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        if r.returncode:
+            raise RuntimeError("selftest build failed:\n" + r.stdout.decode())
     os.replace(exe + ".tmp", exe)
     return exe
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--selftest":
-        print(build_selftest())
+        print(build_selftest(sys.argv[2] if len(sys.argv) > 2 else ""))
     elif len(sys.argv) > 1 and sys.argv[1] == "--show":
         sys.stdout.write(rewrite(open(os.path.join(CSRC, "kernels.cu")).read()))
     else:

@@ -61,7 +61,65 @@ __global__ void divergent_barrier_kernel(uint32_t* out) {
     out[0] = 1;
 }
 
+__global__ void oob_kernel(const uint4* in, uint4* out, int what) {
+    // what 1: thread 4 stores one vector past a 4-vector buffer; what 2: it loads a granule that lies entirely outside its buffer;
+    // what 3: every thread reads the granule that holds the last 3 bytes of a 51-byte buffer (the rule the kernels rely on: fine)
+    uint4 v = make_uint4(1, 2, 3, 4);
+    if (what == 2 && threadIdx.x == 4) asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in + 5));
+    if (what == 3) asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in + 3));
+    if (what != 1 && threadIdx.x >= 4) return;
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(out + threadIdx.x), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__global__ void neighbour_kernel(uint32_t* out, int barrier) {
+    // every thread publishes a value in shared memory and reads its neighbour's: needs a barrier in between.
+    // barrier 0: none (a race); 1: __syncthreads; 2: __syncwarp (enough: the neighbour t^1 is in the same warp)
+    __shared__ uint32_t sh[128];
+    sh[threadIdx.x] = threadIdx.x * 3u;
+    if (barrier == 1) __syncthreads();
+    if (barrier == 2) __syncwarp();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sh[threadIdx.x ^ 1u];
+}
+__device__ __forceinline__ uint32_t block_sum_no_barrier(uint32_t v, uint32_t* sh, int barrier) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) sh[warp] = v;
+    if (barrier) __syncthreads();
+    uint32_t t = sh[lane];
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    __syncthreads();
+    return t;
+}
+__global__ void __launch_bounds__(1024) block_sum_kernel(uint32_t* out, int barrier) {  // the shape of the product's block_sum_1024
+    __shared__ uint32_t sh[32];
+    const uint32_t t = block_sum_no_barrier(threadIdx.x, sh, barrier);
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+__global__ void global_race_kernel(uint32_t* out, int atomic) {  // two BLOCKS update one global counter: plain add is a race, atomicAdd is not
+    if (threadIdx.x == 0) {
+        if (atomic) atomicAdd(out, 1u);
+        else out[0] = out[0] + 1u;
+    }
+}
+
 int main(int argc, char** argv) {
+    if (argc > 2 && argv[1][0] == 'r') {  // selftest race 0|1|2|3|4: meaningful in the ThreadSanitizer build
+        const int k = atoi(argv[2]);
+        uint32_t* out = static_cast<uint32_t*>(calloc(256, 4));
+        if (k >= 5) block_sum_kernel<<<3, 1024, 0, (cudaStream_t)0>>>(out, k == 6);
+        else if (k <= 2) neighbour_kernel<<<2, 128, 0, (cudaStream_t)0>>>(out, k);
+        else global_race_kernel<<<64, 32, 0, (cudaStream_t)0>>>(out, k == 4);
+        printf("race kernel done %u\n", out[0]);
+        return 0;
+    }
+    if (argc > 2 && argv[1][0] == 'o') {  // selftest oob 1|2|3: meaningful in the AddressSanitizer build
+        uint4 *in = nullptr, *out = nullptr;
+        if (posix_memalign(reinterpret_cast<void**>(&in), 16, 51) || posix_memalign(reinterpret_cast<void**>(&out), 16, 64)) return 2;
+        memset(in, 7, 51);
+        oob_kernel<<<1, 5, 0, (cudaStream_t)0>>>(in, out, atoi(argv[2]));
+        printf("oob kernel done\n");
+        return 0;
+    }
     if (argc > 1 && argv[1][0] == 'd') {
         uint32_t* z = static_cast<uint32_t*>(calloc(4, 1));
         divergent_barrier_kernel<<<1, 128, 0, (cudaStream_t)0>>>(z);

@@ -41,6 +41,38 @@ cv_emu_switch:
 .size cv_emu_switch,.-cv_emu_switch
 )");
 
+// AddressSanitizer has to be told about every stack switch (it tracks the bounds of the running stack)
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define CV_ASAN_START(save, bottom, size) __sanitizer_start_switch_fiber(save, bottom, size)
+#define CV_ASAN_FINISH(save, bottom_old, size_old) __sanitizer_finish_switch_fiber(save, bottom_old, size_old)
+#else
+#define CV_ASAN_START(save, bottom, size) ((void)0)
+#define CV_ASAN_FINISH(save, bottom_old, size_old) ((void)0)
+#endif
+
+// ThreadSanitizer build (build.py "thread": this file itself stays uninstrumented, the kernel source is instrumented): every CUDA
+// thread is a TSan fiber, switches establish NO ordering, and the only happens-before edges are the ones the programming model
+// gives -- block start/end, __syncthreads, warp collectives, atomics.  Two threads of a block (or two blocks) that touch the same
+// shared or global location without one of those in between are reported as a data race: a race check of the kernel source.
+#if defined(CV_EMU_TSAN)
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void __tsan_set_fiber_name(void* fiber, const char* name);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+}
+#define CV_TSAN_SWITCH(fiber) __tsan_switch_to_fiber(fiber, 1u /* no_sync */)
+#define CV_TSAN_ACQUIRE(p) __tsan_acquire(p)
+#define CV_TSAN_RELEASE(p) __tsan_release(p)
+#else
+#define CV_TSAN_SWITCH(fiber) ((void)0)
+#define CV_TSAN_ACQUIRE(p) ((void)0)
+#define CV_TSAN_RELEASE(p) ((void)0)
+#endif
+
 namespace cv_emu {
 namespace {
 
@@ -51,7 +83,10 @@ constexpr unsigned kMaxThreads = 1024;
 enum State : uint8_t { kRunnable, kWaitWarp, kWaitBlock, kDone };
 
 struct Fiber {
-    void* sp;
+    void* sp = nullptr;
+    void* asan_fake = nullptr;
+    void* tsan = nullptr;  // TSan context of this fiber slot (kept across blocks: its stack is reused too)
+    uint32_t bar_gen, warp_gen;  // collectives this fiber has been through: consecutive ones use different sync objects
     ThreadCtx ctx;
     State state;
     uint8_t lane, parity;
@@ -62,6 +97,7 @@ struct Warp {
     uint32_t part[3];  // lanes that took part in the last collective that used data slot 0 / 1 (2: plain __syncwarp)
     uint32_t wait_slot;
     uint64_t slot[2][32];
+    char hb[2];  // happens-before objects of the warp's collectives (TSan build)
 };
 struct Job {
     dim3 grid, block;
@@ -70,6 +106,7 @@ struct Job {
     void *kernel, *args;
     std::atomic<uint64_t> next{0};
     uint64_t n_blocks = 0;
+    char hb_launch = 0;  // happens-before object: what the launching host thread did before the launch (TSan build)
 };
 
 struct Worker {
@@ -78,6 +115,11 @@ struct Worker {
     char* stacks = nullptr;
     char* smem = nullptr;
     void* sched_sp = nullptr;
+    void* sched_tsan = nullptr;
+    char hb_end[2] = {0, 0}, hb_bar[2] = {0, 0};  // happens-before objects: end of the even/odd blocks of this worker / __syncthreads (TSan build)
+    uint64_t block_seq = 0;
+    const void* sched_bottom = nullptr;  // the scheduler's own stack, as ASan reported it at the first switch
+    size_t sched_size = 0;
     Fiber* running = nullptr;
     const Job* job = nullptr;
     unsigned n_threads = 0, live = 0, bar_arrived = 0;
@@ -89,6 +131,14 @@ struct Worker {
             abort();
         }
         memset(smem, 0, kDynSmemBytes);
+#if defined(CV_EMU_TSAN)
+        // The runtime tells at most 256 concurrently live contexts apart (its shadow stores an 8-bit slot id; beyond that slots are
+        // recycled and races between recycled contexts go unseen).  So: every LANE of the first two warps is a context of its own
+        // (races inside a warp -- a missing __syncwarp -- show there; the code is the same in every warp), the other warps are one
+        // context each (races between warps -- a missing __syncthreads -- show everywhere): 94 contexts per worker.  Created here, at
+        // worker start: a context inherits its creator's ordering, which must not yet include any other worker's blocks.
+        for (unsigned i = 0; i < kMaxThreads; i++) fibers[i].tsan = (i < 64 || (i & 31) == 0) ? __tsan_create_fiber(0) : fibers[i & ~31u].tsan;
+#endif
     }
     ~Worker() {
         munmap(stacks, kStackBytes * kMaxThreads);
@@ -98,7 +148,12 @@ struct Worker {
 
 thread_local Worker* t_worker = nullptr;
 
-void yield(Worker* w, Fiber* f) { cv_emu_switch(&f->sp, w->sched_sp); }
+void yield(Worker* w, Fiber* f) {
+    CV_ASAN_START(&f->asan_fake, w->sched_bottom, w->sched_size);
+    CV_TSAN_SWITCH(w->sched_tsan);
+    cv_emu_switch(&f->sp, w->sched_sp);
+    CV_ASAN_FINISH(f->asan_fake, nullptr, nullptr);
+}
 
 void release_warp(Worker* w, Warp& W, unsigned warp_index) {
     uint32_t m = W.arrived;
@@ -125,6 +180,9 @@ void release_block(Worker* w) {
     // a thread that has returned no longer takes part in collectives: its exit may complete one
     if (W.arrived && (W.arrived & W.wait_mask & W.live) == (W.wait_mask & W.live)) release_warp(w, W, f->warp);
     if (w->bar_arrived && w->bar_arrived == w->live) release_block(w);
+    CV_TSAN_RELEASE(&w->hb_end[w->block_seq & 1]);
+    CV_ASAN_START(nullptr, w->sched_bottom, w->sched_size);  // nullptr: this stack's frames are gone for good
+    CV_TSAN_SWITCH(w->sched_tsan);
     cv_emu_switch(&f->sp, w->sched_sp);
     abort();
 }
@@ -132,6 +190,11 @@ void release_block(Worker* w) {
 void fiber_main() {
     Worker* w = t_worker;
     Fiber* f = w->running;
+    CV_ASAN_FINISH(nullptr, &w->sched_bottom, &w->sched_size);
+    // ordered after the launch and after the previous block of this worker (whose stacks and shared memory this block reuses) --
+    // NOT after whatever the worker thread itself synchronised with (the pool's mutex would order whole workers one after the other)
+    CV_TSAN_ACQUIRE(const_cast<char*>(&w->job->hb_launch));
+    CV_TSAN_ACQUIRE(&w->hb_end[(w->block_seq + 1) & 1]);  // the object the PREVIOUS block's threads released at their exits
     w->job->thunk(w->job->kernel, w->job->args);
     fiber_exit(w, f);
 }
@@ -152,6 +215,8 @@ void run_block(Worker* w, const Job& job, uint64_t b) {
         f.ctx.bid = uint3{static_cast<unsigned>(b % job.grid.x), static_cast<unsigned>((b / job.grid.x) % job.grid.y),
                           static_cast<unsigned>(b / (uint64_t(job.grid.x) * job.grid.y))};
         f.ctx.bdim = job.block, f.ctx.gdim = job.grid;
+        f.asan_fake = nullptr;
+        f.bar_gen = f.warp_gen = 0;
         f.state = kRunnable, f.lane = i & 31, f.warp = static_cast<uint16_t>(i >> 5), f.parity = 0;
         // fresh stack: [top-8] fake return address of fiber_main, [top-16] fiber_main, six zeroed callee-saved registers below
         void** top = reinterpret_cast<void**>(w->stacks + kStackBytes * (i + 1));
@@ -160,6 +225,9 @@ void run_block(Worker* w, const Job& job, uint64_t b) {
         for (int k = 3; k <= 8; k++) top[-k] = nullptr;
         f.sp = top - 8;
     }
+#if defined(CV_EMU_TSAN)
+    if (!w->sched_tsan) w->sched_tsan = __tsan_get_current_fiber();
+#endif
     while (w->live) {
         bool progressed = false;
         for (unsigned i = 0; i < n; i++) {
@@ -167,7 +235,12 @@ void run_block(Worker* w, const Job& job, uint64_t b) {
             if (f.state != kRunnable) continue;
             progressed = true;
             w->running = &f;
+            void* fake = nullptr;
+            CV_ASAN_START(&fake, w->stacks + kStackBytes * i, kStackBytes);
+            CV_TSAN_SWITCH(f.tsan);
             cv_emu_switch(&w->sched_sp, f.sp);
+            CV_ASAN_FINISH(fake, nullptr, nullptr);
+            (void)fake;
         }
         if (!progressed) {
             unsigned ww = 0, wb = 0;
@@ -177,6 +250,8 @@ void run_block(Worker* w, const Job& job, uint64_t b) {
             abort();
         }
     }
+    CV_TSAN_ACQUIRE(&w->hb_end[w->block_seq & 1]);  // everything the block's threads did is ordered before whatever follows the launch
+    w->block_seq++;
     w->running = nullptr;
 }
 
@@ -195,7 +270,7 @@ struct Pool {
         if (const char* e = getenv("CV_SIMT_EMU_THREADS")) n = static_cast<unsigned>(atoi(e));
         if (n < 1) n = 1;
         if (n > 16) n = 16;
-        for (unsigned i = 0; i < n; i++) threads.emplace_back([this] { loop(); });
+        for (unsigned i = 0; i < n; i++) threads.emplace_back([this, i] { loop(i); });
     }
     ~Pool() {
         {
@@ -205,10 +280,11 @@ struct Pool {
         cv.notify_all();
         for (auto& t : threads) t.join();
     }
-    void loop() {
+    void loop(unsigned index) {
         Worker* w = new Worker;
         t_worker = w;
         uint64_t seen = 0;
+        (void)index;
         for (;;) {
             Job* j;
             {
@@ -217,11 +293,18 @@ struct Pool {
                 if (stop) break;
                 seen = generation, j = job, busy++;
             }
+#if defined(CV_EMU_TSAN)
+            // race check: blocks of one worker are ordered one after the other (they reuse its stacks and shared memory), so neighbouring
+            // blocks always go to DIFFERENT workers -- a race between two blocks is then visible whichever runs first
+            for (uint64_t b = index; b < j->n_blocks; b += threads.size()) run_block(w, *j, b);
+            j->next.fetch_add(1, std::memory_order_relaxed);  // counts workers here
+#else
             for (;;) {
                 const uint64_t b = j->next.fetch_add(1, std::memory_order_relaxed);
                 if (b >= j->n_blocks) break;
                 run_block(w, *j, b);
             }
+#endif
             {
                 std::lock_guard<std::mutex> lk(mu);
                 busy--;
@@ -232,6 +315,7 @@ struct Pool {
     }
     void run(Job& j) {
         std::lock_guard<std::mutex> one(launch_mu);  // host threads launch concurrently (verifier, readers): one grid at a time
+        CV_TSAN_RELEASE(&j.hb_launch);
         {
             std::lock_guard<std::mutex> lk(mu);
             job = &j, generation++;
@@ -239,7 +323,11 @@ struct Pool {
         cv.notify_all();
         std::unique_lock<std::mutex> lk(mu);
         // every block index has been handed out and every worker that took one is back (busy-- follows its last block)
+#if defined(CV_EMU_TSAN)
+        done_cv.wait(lk, [&] { return busy == 0 && j.next.load(std::memory_order_relaxed) >= threads.size(); });  // every worker has done its share
+#else
         done_cv.wait(lk, [&] { return busy == 0 && j.next.load(std::memory_order_relaxed) >= j.n_blocks; });
+#endif
         job = nullptr;
     }
 };
@@ -252,19 +340,30 @@ inline Worker* me() { return t_worker; }
 
 }  // namespace
 
+#if defined(__SANITIZE_ADDRESS__)
+void asan_report_load16(const void* p) {
+    volatile uint8_t sink = 0;
+    for (int i = 0; i < 16; i++) sink ^= static_cast<const volatile uint8_t*>(p)[i];
+    (void)sink;
+}
+#endif
+
 const ThreadCtx* cur() { return &t_worker->running->ctx; }
 char* dyn_smem() { return t_worker->smem; }
 
 void sync_block() {
     Worker* w = me();
     Fiber* f = w->running;
+    char* hb = &w->hb_bar[f->bar_gen++ & 1];
+    CV_TSAN_RELEASE(hb);
     w->bar_arrived++;
     if (w->bar_arrived == w->live) {
         release_block(w);
-        return;
+    } else {
+        f->state = kWaitBlock;
+        yield(w, f);
     }
-    f->state = kWaitBlock;
-    yield(w, f);
+    CV_TSAN_ACQUIRE(hb);
 }
 
 static void sync_warp_slot(uint32_t mask, uint32_t slot);
@@ -278,15 +377,18 @@ static void sync_warp_slot(uint32_t mask, uint32_t slot) {
         fprintf(stderr, "simt_emu: lanes of one warp wait at collectives with different masks (%08x vs %08x): not modelled\n", W.wait_mask, mask);
         abort();
     }
+    char* hb = &W.hb[f->warp_gen++ & 1];
+    CV_TSAN_RELEASE(hb);
     W.wait_mask = mask, W.wait_slot = slot;
     W.arrived |= 1u << f->lane;
     const uint32_t need = mask & W.live;
     if ((W.arrived & need) == need) {
         release_warp(w, W, f->warp);
-        return;
+    } else {
+        f->state = kWaitWarp;
+        yield(w, f);
     }
-    f->state = kWaitWarp;
-    yield(w, f);
+    CV_TSAN_ACQUIRE(hb);
 }
 
 uint64_t warp_exchange(uint32_t mask, uint64_t v, uint32_t src) {

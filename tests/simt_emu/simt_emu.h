@@ -75,9 +75,28 @@ inline LaunchCfg cfg(dim3 g, dim3 b, size_t smem, S /*stream: launches complete 
 }
 
 // ---- the PTX the kernels use (build.py turns every asm statement into one of these)
+//
+// 16-byte vector LOADS follow the rule the kernels rely on: a source range is read in whole 16-byte ALIGNED granules, so up to 15
+// bytes in front of / behind the range are read too -- never outside the granules that hold the range (hence never across a page
+// or an allocation granule).  Under AddressSanitizer that rule is what is checked: a granule with at least one addressable byte
+// is fine, a granule that lies entirely outside every allocation is reported.  Stores get no such slack.
+#if defined(__SANITIZE_ADDRESS__)
+extern "C" int __asan_address_is_poisoned(void const volatile* addr);
+void asan_report_load16(const void* p);  // an ordinary instrumented 16-byte read: produces the standard report
+__attribute__((no_sanitize("address"))) inline void granule_load(uint32_t v[4], const void* p) {
+    bool any = false;
+    for (int i = 0; i < 16; i++) any |= !__asan_address_is_poisoned(static_cast<const char*>(p) + i);
+    if (!any) asan_report_load16(p);
+    typedef uint32_t __attribute__((may_alias)) word;
+    const word* q = static_cast<const word*>(__builtin_assume_aligned(p, 16));
+    v[0] = q[0], v[1] = q[1], v[2] = q[2], v[3] = q[3];
+}
+#else
+inline void granule_load(uint32_t v[4], const void* p) { memcpy(v, __builtin_assume_aligned(p, 16), 16); }
+#endif
 inline void ptx_ld_v4(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, const void* p) {
     uint32_t v[4];
-    memcpy(v, __builtin_assume_aligned(p, 16), 16);
+    granule_load(v, p);
     a = v[0], b = v[1], c = v[2], d = v[3];
 }
 inline void ptx_st_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -86,7 +105,11 @@ inline void ptx_st_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
 }
 inline void ptx_lds_v4(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t addr) { ptx_ld_v4(a, b, c, d, dyn_smem() + addr); }
 inline void ptx_lds_u32(uint32_t& v, uint32_t addr) { memcpy(&v, dyn_smem() + addr, 4); }
-inline void ptx_cp_async16(uint32_t smem_addr, const void* g) { memcpy(dyn_smem() + smem_addr, g, 16); }  // lands at once
+inline void ptx_cp_async16(uint32_t smem_addr, const void* g) {  // lands at once
+    uint32_t v[4];
+    granule_load(v, g);
+    memcpy(dyn_smem() + smem_addr, v, 16);
+}
 inline void ptx_cp_async_commit() {}
 inline void ptx_cp_async_wait(int) {}
 

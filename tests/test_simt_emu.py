@@ -62,4 +62,27 @@ def test_gpu_suite_with_the_kernel_source_on_the_simt_shim():
     tail = "\n".join(r.stdout.splitlines()[-30:])
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 113 and " failed" not in r.stdout, tail
+    assert m and int(m.group(1)) >= 120 and " failed" not in r.stdout, tail
+
+
+def test_sanitizer_builds_of_the_shim_report_planted_bugs_and_nothing_else():
+    """tools/sanitize_kernels.sh runs the kernel suites on the shim under ASan+UBSan and under TSan (as a race check between CUDA
+    threads).  Here: the shim's known-answer program in both builds -- a planted out-of-bounds store, an out-of-bounds granule load
+    and planted races (missing barrier inside a block, plain add from two blocks) ARE reported, their correct twins are not."""
+    b = _emu_build()
+    env = dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect_leaks=0", TSAN_OPTIONS="halt_on_error=0 history_size=4", CV_SIMT_EMU_THREADS="2")
+
+    def run(exe, *args, wrap=()):
+        return subprocess.run(list(wrap) + [exe] + list(args), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300).stdout
+
+    exe = b.build_selftest("address")
+    assert "selftest ok" in run(exe)
+    assert "heap-buffer-overflow" in run(exe, "oob", "1") and "heap-buffer-overflow" in run(exe, "oob", "2")
+    out = run(exe, "oob", "3")  # reading the rest of the last 16-byte granule of a buffer is the kernels' documented behaviour
+    assert "AddressSanitizer" not in out and "oob kernel done" in out
+    exe = b.build_selftest("thread")
+    wrap = ("setarch", os.uname().machine, "-R")  # TSan wants a fixed address-space layout on this kernel
+    assert "selftest ok" in run(exe, wrap=wrap) and "data race" not in run(exe, wrap=wrap)
+    for k, racy in ((0, True), (1, False), (2, False), (3, True), (4, False), (5, True), (6, False)):
+        out = run(exe, "race", str(k), wrap=wrap)
+        assert ("ThreadSanitizer: data race" in out) == racy and "race kernel done" in out, (k, out[-2000:])

@@ -104,3 +104,55 @@ def test_more_than_16k_pieces_take_the_multi_cta_scan(cuda, n_segs):
     assert dst.cpu().numpy().tobytes() == want.tobytes()
     got = K.u32(K.crc_blocks(d_src, [int(x) for x in sos], [int(x) for x in lens], 1))
     assert got.tolist() == [clib.crc(1, src[o:o + n]) for o, n in zip(sos, lens)]
+
+
+VARIANTS = [("tile2_crc_dst", [(0, 2)]), ("tile4_copy", [(1, 4)]), ("staged_cp_async", [(3, 1)]), ("seg_4k", [(4, 12)]), ("seg_64k_staged", [(4, 16), (3, 1)])]
+
+
+@pytest.mark.parametrize("name,tunes", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_every_walker_variant_is_bit_identical(cuda, name, tunes):
+    """The DST walkers exist in several flavours selected by cvk_tune (rows per tile, the shared-memory staged cp.async walk, the
+    segment size): every flavour of K2 (unpack: every source phase, since 22-byte prefixes rotate it), K4 (pack) and K3 (gather,
+    every source/destination phase pair) must produce the bytes and CRCs of the oracle."""
+    import torch
+    from curvine_b200 import _lib, kernels as K
+    from oracle import wire as W
+    from test_kernels_gpu import _build_wire
+    L = _lib.lib()
+    try:
+        for what, value in tunes:
+            _lib.check(L.cvk_tune(what, value))
+        _lib.check(L.cvk_tune(5, 0))  # the launch train, not the small-input kernels
+        for poly in (0, 1):
+            blocks = [_rand(n, 300 + i) for i, n in enumerate([70000, 4096, 1, 131072 + 9, 33, 250000])]
+            chunk = 8192 + 16  # 22-byte prefixes + this chunk walk the payloads through source phases 6, 12, 2, 8, ...
+            wire, descs, _, total = _build_wire(blocks, chunk, [900 + i for i in range(len(blocks))], poly)
+            want = np.concatenate(blocks)
+            want_crc = [clib.crc(poly, b) for b in blocks]
+            d_desc = K.frame_descs_to_device(descs, cuda)
+            for mis in (0, 5):
+                dst = torch.full((total + mis + 48,), 0x5A, dtype=torch.uint8, device=cuda)
+                crc, err = K.unpack_frames(_to_dev(wire, cuda), d_desc, len(descs), len(blocks), dst[mis:], poly, total)
+                out = dst.cpu().numpy()
+                assert out[mis:mis + total].tobytes() == want.tobytes() and (out[:mis] == 0x5A).all() and (out[mis + total:] == 0x5A).all(), (name, poly, mis)
+                assert K.u32(crc).tolist() == want_crc and (K.u32(err) == 0).all()
+            d_wire = torch.zeros(len(wire), dtype=torch.uint8, device=cuda)
+            crc = K.pack_frames(_to_dev(want, cuda), d_desc, len(descs), len(blocks), d_wire, poly, total)
+            assert d_wire.cpu().numpy().tobytes() == wire.tobytes() and K.u32(crc).tolist() == want_crc
+            msgs, used = W.decode_stream(d_wire.cpu().numpy().tobytes())
+            assert used == len(wire) and b"".join(m.data for m in msgs) == want.tobytes()
+        src = _rand(2 << 20, 55)
+        segs, pos = [], 3
+        for i in range(96):  # all 16 x 16 phase pairs show up: sources step by 4099 + i, destinations by n + i % 5
+            n = [40000, 4096, 17, 16, 15, 1, 0, 70001][i % 8]
+            segs.append((i * 4099 + i, pos, n))
+            pos += n + i % 5
+        wantb = np.full(pos + 32, 0xA5, dtype=np.uint8)
+        for so, do, n in segs:
+            wantb[do:do + n] = src[so:so + n]
+        dst = torch.full((pos + 32,), 0xA5, dtype=torch.uint8, device=cuda)
+        K.gather_pages(_to_dev(src, cuda), K.segs_to_device(segs, cuda), len(segs), sum(s[2] for s in segs), dst)
+        assert dst.cpu().numpy().tobytes() == wantb.tobytes(), name
+    finally:
+        for what, value in ((0, 4), (1, 2), (3, 0), (4, 0), (5, 1)):
+            L.cvk_tune(what, value)

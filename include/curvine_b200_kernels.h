@@ -33,6 +33,11 @@ extern "C" {
 
 typedef void* cv_stream_t; /* cudaStream_t */
 
+/* Memory access rule of every launcher below.  Destinations are written exactly: no byte outside a destination range is touched.
+ * Sources are read in whole 16-byte ALIGNED vectors: up to 15 bytes in front of and behind a source range may be read as well, never
+ * outside the aligned 16-byte granules that hold the range -- so never across a page, a cudaMalloc granule (256 B) or a pinned-ring
+ * slot.  (Checked by tools/sanitize_kernels.sh on the host-side SIMT shim and by compute-sanitizer memcheck on the device.) */
+
 #define CV_POLY_IEEE 0       /* CRC-32/ISO-HDLC == crc32fast::hash == zlib.crc32 (reference tools) */
 #define CV_POLY_CASTAGNOLI 1 /* CRC-32C (north_star's added integrity check) */
 

@@ -72,6 +72,7 @@ def parse():
     ap.add_argument("--side-steps", type=int, default=2, help="timed steps of each side leg (reread / pread / framed); 0 skips them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dir", default="")
+    ap.add_argument("--ref-materialize-gib", type=float, default=64.0, help="reference arm: how much of the file's head is written to the store (the CPU reader never reads past its sample)")
     return ap.parse_args()
 
 
@@ -594,10 +595,13 @@ def main_reference(args):
     w = None
     try:
         w = refworker.RefWorker(d)
-        w.create_file(9200, n_total, BLOCK, threads=min(64, os.cpu_count() or 8))
+        # the file is n_total long for the reader (its striping policy depends on the length); only the head a step can reach is
+        # written to the store -- the sub-readers stop at the sample's end, so the blocks behind it are never opened
+        gen_total = min(n_total, int(args.ref_materialize_gib * (1 << 30)) // BLOCK * BLOCK)
+        w.create_file(9200, gen_total, BLOCK, threads=min(64, os.cpu_count() or 8))
         par = reference_policy(n_total)
-        pilot, _, _, _, _ = cpu_run(w.port, n_total, sc, par, 1 << 30, 9200)
-        sample = int(min(n_total, max(1 << 30, pilot * 1e9 * 6))) // BLOCK * BLOCK
+        pilot, _, _, _, _ = cpu_run(w.port, n_total, sc, par, min(1 << 30, gen_total), 9200)
+        sample = int(min(gen_total, max(1 << 30, pilot * 1e9 * 6))) // BLOCK * BLOCK
         times = []
         for it in range(args.warmup + args.steps):
             v, threads, got, cks, dt = cpu_run(w.port, n_total, sc, par, sample, 9200)
@@ -608,7 +612,7 @@ def main_reference(args):
         out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                "config": {"workload": "C2 per GPU: %g GiB synthetic file, 4 MiB blocks, mem-tier (tmpfs, one file per block) BlockStore; CPU reader, bytes land in host memory" % gib,
-                          "file_bytes": n_total, "block_bytes": BLOCK, "read_path": args.mode, "host_cpus": os.cpu_count()},
+                          "file_bytes": n_total, "materialized_bytes": gen_total, "block_bytes": BLOCK, "read_path": args.mode, "host_cpus": os.cpu_count()},
                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "each step reads the first %.1f GiB; read_parallel=%d (reference default for this size), 128 KiB chunks/buffers, "
                                           "crc32 (PCLMUL) on the caller thread; worker = oracle/ref_worker.c" % (sample / 2 ** 30, par)},

@@ -4,6 +4,7 @@ established suites on purpose: whatever happens here, everything else has alread
 
   * crc_small_kernel / gather_small_kernel: the single-launch small-input kernels, against the oracle and against the launch train
   * the multi-CTA prefix scan (more than 16 Ki pieces)"""
+import os
 import zlib
 
 import numpy as np
@@ -156,3 +157,56 @@ def test_every_walker_variant_is_bit_identical(cuda, name, tunes):
     finally:
         for what, value in ((0, 4), (1, 2), (3, 0), (4, 0), (5, 1)):
             L.cvk_tune(what, value)
+
+
+def test_gather_and_frames_hypothesis_random_shapes(cuda):
+    """Generated shapes for the DST walkers: K3 with random (source offset, length, gap) segments -- every source/destination phase,
+    empty, sub-vector and multi-segment pieces, small-input kernel and launch train -- and K2/K4 with random block lengths and chunk
+    sizes (the 22-byte prefixes rotate the source phase frame by frame).  Bytes, untouched gaps and CRCs against numpy / the oracle."""
+    import torch
+    from hypothesis import given, settings, strategies as st
+    from curvine_b200 import _lib, kernels as K
+    from test_kernels_gpu import _build_wire
+    src = _rand(1 << 20, 91)
+    d_src = _to_dev(src, cuda)
+    L = _lib.lib()
+    scale = int(os.environ.get("CV_TEST_HYPOTHESIS_SCALE", "1"))  # a long hunt on the host-side shim: CV_TEST_HYPOTHESIS_SCALE=50
+
+    @settings(max_examples=30 * scale, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, (1 << 20) - 70000), st.sampled_from([0, 1, 2, 15, 16, 17, 31, 100, 511, 512, 513, 4096, 5000, 20000, 66000]),
+                              st.integers(0, 19)), min_size=1, max_size=40), st.integers(0, 15), st.booleans())
+    def gather(items, first, small):
+        segs, pos = [], first
+        for so, n, gap in items:
+            segs.append((so, pos, n))
+            pos += n + gap
+        want = np.full(pos + 16, 0x3C, dtype=np.uint8)
+        for so, do, n in segs:
+            want[do:do + n] = src[so:so + n]
+        dst = torch.full((pos + 16,), 0x3C, dtype=torch.uint8, device=cuda)
+        _lib.check(L.cvk_tune(5, 1 if small else 0))
+        K.gather_pages(d_src, K.segs_to_device(segs, cuda), len(segs), sum(s[2] for s in segs), dst)
+        assert dst.cpu().numpy().tobytes() == want.tobytes()
+
+    @settings(max_examples=20 * scale, deadline=None)
+    @given(st.lists(st.integers(1, 90000), min_size=1, max_size=6), st.sampled_from([1, 7, 16, 100, 4096, 4100, 65536]), st.integers(0, 1), st.integers(0, 15))
+    def frames(blens, chunk, poly, mis):
+        blens = [min(n, chunk * 40) for n in blens]  # at most 40 frames per block keeps an example small
+        blocks = [_rand(n, 700 + i) for i, n in enumerate(blens)]
+        wire, descs, _, total = _build_wire(blocks, chunk, [31 + i for i in range(len(blocks))], poly)
+        want = np.concatenate(blocks)
+        d_desc = K.frame_descs_to_device(descs, cuda)
+        dst = torch.full((total + mis + 32,), 0x99, dtype=torch.uint8, device=cuda)
+        crc, err = K.unpack_frames(_to_dev(wire, cuda), d_desc, len(descs), len(blocks), dst[mis:], poly, total)
+        out = dst.cpu().numpy()
+        assert out[mis:mis + total].tobytes() == want.tobytes() and (out[:mis] == 0x99).all() and (out[mis + total:] == 0x99).all()
+        assert K.u32(crc).tolist() == [clib.crc(poly, b) for b in blocks] and (K.u32(err) == 0).all()
+        d_wire = torch.zeros(len(wire), dtype=torch.uint8, device=cuda)
+        crc = K.pack_frames(_to_dev(want, cuda), d_desc, len(descs), len(blocks), d_wire, poly, total)
+        assert d_wire.cpu().numpy().tobytes() == wire.tobytes() and K.u32(crc).tolist() == [clib.crc(poly, b) for b in blocks]
+
+    try:
+        gather()
+        frames()
+    finally:
+        L.cvk_tune(5, 1)

@@ -55,9 +55,9 @@ def test_rewrite_refuses_what_it_does_not_know():
 
 def test_gpu_suite_with_the_kernel_source_on_the_simt_shim():
     lib = _emu_build().build()
-    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=lib, CV_SIMT_EMU_THREADS="4")
+    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=lib, CV_SIMT_EMU_THREADS="3")
     # read_to_tensor allocates a torch CUDA tensor inside the binding itself: nothing to check without a device
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "not read_to_tensor", "-n", "4"],
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "not read_to_tensor", "-n", "6"],
                        cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=2400)
     tail = "\n".join(r.stdout.splitlines()[-30:])
     assert r.returncode == 0, tail

@@ -72,6 +72,7 @@ def parse():
     ap.add_argument("--side-steps", type=int, default=2, help="timed steps of each side leg (reread / pread / framed); 0 skips them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dir", default="")
+    ap.add_argument("--no-memory-guard", action="store_true", help="do not shrink --gib-per-gpu when the stores would not fit into the container's memory")
     ap.add_argument("--ref-materialize-gib", type=float, default=64.0, help="reference arm: how much of the file's head is written to the store (the CPU reader never reads past its sample)")
     return ap.parse_args()
 
@@ -115,6 +116,47 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_memory_budget(shm_dir):
+    """Bytes this container can safely put into tmpfs + pinned memory: the smallest of MemAvailable, the cgroup limit (v2 or v1, minus
+    what is in use) and the free space of the tmpfs the store lives on.  -> (bytes, {source: bytes})."""
+    found = {}
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                found["MemAvailable"] = int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    for limit, used in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                        ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            v = open(limit).read().strip()
+            if v != "max" and int(v) < (1 << 60):
+                found["cgroup"] = int(v) - int(open(used).read().strip())
+                break
+        except (OSError, ValueError):
+            pass
+    try:
+        st = os.statvfs(shm_dir)
+        found["tmpfs_free"] = st.f_bavail * st.f_frsize
+    except OSError:
+        pass
+    return (min(found.values()) if found else None), found
+
+
+def fit_gib_per_gpu(want_gib, world, pool, budget, reserve_per_gpu=3 << 30, frac=0.7):
+    """The largest power-of-two fraction of want_gib whose stores fit into `frac` of the budget.  One GPU holds the arena (pool+1 files + a
+    segment) AND, for the reference-layout side leg, one more file; beyond one GPU only the arenas exist.  ("if the box cannot
+    hold a named size, run the largest power of two that fits and say so".)"""
+    gib = want_gib
+    while budget is not None and gib > 1.0 / 64:
+        shard = int(gib * (1 << 30))
+        need = world * ((pool + 1) * shard + SEG + reserve_per_gpu) + (shard if world == 1 else 0)
+        if need <= frac * budget:
+            break
+        gib /= 2
+    return gib
 
 
 def setup_dist(args):
@@ -317,6 +359,16 @@ def main():
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
     L = _lib.lib()
     _lib.check(L.cvk_init(local), "cvk_init")
+    # memory guard (round 2 lost three boxes to a run that outgrew its container): shrink the per-GPU size if the stores would not fit
+    budget, budget_sources = host_memory_budget(args.dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()))
+    asked_gib = args.gib_per_gpu
+    if not args.no_memory_guard:
+        pick = [fit_gib_per_gpu(asked_gib, world, args.pool, budget)]
+        if dist is not None:  # one decision for all ranks (MemAvailable moves between two reads of it)
+            dist.broadcast_object_list(pick, src=0)
+        args.gib_per_gpu = pick[0]
+        if args.gib_per_gpu != asked_gib and rank == 0:
+            log("memory guard: %g GiB per GPU does not fit into 70%% of %s; running %g GiB per GPU" % (asked_gib, budget_sources, args.gib_per_gpu))
     shard_bytes = int(args.gib_per_gpu * (1 << 30)) // BLOCK * BLOCK
     n_total = shard_bytes * world
     my_blocks = shard_bytes // BLOCK
@@ -469,7 +521,9 @@ def main():
                            "file_bytes": n_total, "block_bytes": BLOCK, "blocks_per_gpu": my_blocks, "read_path": args.mode, "mem_tier": args.tier,
                            "fresh_file_every_step": True, "files_kept_beside_the_current": args.pool, "arena_reuse_delay_ms": 0, "fetch_threads": threads, "pinned_slots": slots, "verify_batch": args.verify_batch,
                            "copy_group": args.copy_group, "arena_segment_bytes": SEG, "arena_register_slice": args.register_slice,
-                           "l2": "inputs (%g GiB per GPU per step, new bytes every step) are larger than L2; no flush needed" % args.gib_per_gpu, "host_cpus": ncpu},
+                           "l2": "inputs (%g GiB per GPU per step, new bytes every step) are larger than L2; no flush needed" % args.gib_per_gpu, "host_cpus": ncpu,
+                           "gib_per_gpu_asked": asked_gib, "host_memory_budget": budget_sources,
+                           "size_note": None if args.gib_per_gpu == asked_gib else "the box cannot hold %g GiB per GPU (stores must fit into 70%% of the smallest of %s): ran %g GiB per GPU" % (asked_gib, budget_sources, args.gib_per_gpu)},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]) * world, "d2h_bytes_per_step": 4 * (my_blocks + 4) * world,
                         "ms_per_step": e2e_ms, "timed_steps_ms": per_step_e2e, "warmup_steps_ms": head["warm_e2e_ms"],
                         "what": "cv_open -> cv_read_device[_sharded] -> cv_verify -> cv_close_reader on a file written just before the step (never read), "

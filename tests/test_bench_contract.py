@@ -110,3 +110,20 @@ def test_smoke_control_flow_on_the_mock_runtime():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "run_smoke_on_mock.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                        timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0 and "smoke ok" in p.stdout, p.stdout[-3000:]
+
+
+def test_memory_guard_shrinks_a_size_the_container_cannot_hold():
+    """bench.py's guard: stores must fit into 70 % of the smallest of MemAvailable / cgroup limit / tmpfs free space, else the per-GPU size
+    is halved until they do (and the JSON line says so).  The run that cost round 2 its GPU access (128 GiB per GPU, one file kept beside
+    the current one, on a ~250 GiB container) would have been cut down; the default sizes are untouched on the 2 TB boxes."""
+    sys.path.insert(0, ROOT)
+    import bench
+    budget, src = bench.host_memory_budget("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp")
+    assert budget and budget == min(src.values()) and "MemAvailable" in src
+    G = 1 << 30
+    assert bench.fit_gib_per_gpu(16, 1, 0, 2000 * G) == 16 and bench.fit_gib_per_gpu(16, 8, 0, 2000 * G) == 16
+    assert bench.fit_gib_per_gpu(16, 8, 0, 250 * G) == 16          # round 1's 8-GPU footprint fits a 250 GiB container
+    assert bench.fit_gib_per_gpu(128, 1, 1, 250 * G) == 32          # the lost-box run: 257 GiB asked of ~250
+    assert bench.fit_gib_per_gpu(128, 1, 0, 2000 * G) == 128
+    assert bench.fit_gib_per_gpu(16, 8, 0, 120 * G) == 4
+    assert bench.fit_gib_per_gpu(16, 1, 0, None) == 16              # nothing known about the host: no change

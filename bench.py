@@ -652,6 +652,9 @@ def main_reference(args):
         # the file is n_total long for the reader (its striping policy depends on the length); only the head a step can reach is
         # written to the store -- the sub-readers stop at the sample's end, so the blocks behind it are never opened
         gen_total = min(n_total, int(args.ref_materialize_gib * (1 << 30)) // BLOCK * BLOCK)
+        budget, _ = host_memory_budget(base)
+        if budget is not None and not args.no_memory_guard:
+            gen_total = max(BLOCK, min(gen_total, int(0.5 * budget) // BLOCK * BLOCK))
         w.create_file(9200, gen_total, BLOCK, threads=min(64, os.cpu_count() or 8))
         par = reference_policy(n_total)
         pilot, _, _, _, _ = cpu_run(w.port, n_total, sc, par, min(1 << 30, gen_total), 9200)

@@ -27,8 +27,12 @@ def cuda():
     import torch
     if MOCK_LIB:  # "device memory" is host memory here: CPU tensors, no streams to wait for
         import types
-        torch.cuda.synchronize = lambda *a, **k: None
-        torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0, synchronize=lambda: None)
+        from curvine_b200 import _lib
+
+        def device_sync(*a, **k):  # the stand-in runtime can run its streams asynchronously (MOCK_CUDA_ASYNC=1): wait for them like the real call
+            _lib.lib().cudaDeviceSynchronize()
+        torch.cuda.synchronize = device_sync
+        torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0, synchronize=device_sync)
         torch.cuda.current_device = lambda: 0
         return torch.device("cpu")
     if not torch.cuda.is_available():

@@ -173,9 +173,15 @@ def _digest(extra):
     return h.hexdigest()[:16]
 
 
-def build(sanitize: str = "") -> str:
-    common = ["-g", "-std=c++17", "-fPIC", "-pthread", "-msse4.2", "-Wall", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
-    out_dir = os.path.join("/tmp", "cv_simt_emu_" + _digest(" ".join(common) + sanitize))
+MUTATIONS = {
+    # planted bugs for the checks that are supposed to find them (tools/sanitize_ingest.sh): name -> (file under csrc/host, old text, new text)
+    "verifier_does_not_wait_for_the_copy": ("gpu_reader.cu", "cudaStreamWaitEvent(G.vstream, G.copy_ev[g % NS], 0);", "/* planted: the verify stream no longer waits for the group's copies */;"),
+}
+
+
+def build(sanitize: str = "", mutate: str = "") -> str:
+    common = ["-g", "-std=c++17", "-fPIC", "-pthread", "-msse4.2", "-Wall", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", HOST]
+    out_dir = os.path.join("/tmp", "cv_simt_emu_" + _digest(" ".join(common) + sanitize + mutate))
     lib = os.path.join(out_dir, "libcurvine_b200_emu.so")
     if os.path.exists(lib):
         return lib
@@ -189,7 +195,18 @@ def build(sanitize: str = "") -> str:
         f.write(text)
     san = ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer"] if sanitize else []
     jobs = []
-    for src in sources():
+    srcs = sources()
+    if mutate:
+        fname, old, new = MUTATIONS[mutate]
+        text = open(os.path.join(HOST, fname)).read()
+        if text.count(old) != 1:
+            raise RuntimeError("mutation %s: the text to replace occurs %d times in %s" % (mutate, text.count(old), fname))
+        os.makedirs(out_dir, exist_ok=True)
+        mutated = os.path.join(out_dir, "mutated_" + fname)
+        with open(mutated, "w") as f:  # its relative includes resolve through -I HOST below
+            f.write(text.replace(old, new))
+        srcs = [mutated if os.path.basename(x) == fname else x for x in srcs]
+    for src in srcs:
         extra = ["-O1", "-I", MOCK] + san
         if sanitize == "thread" and os.path.basename(src) == "simt_emu.cc":
             extra = ["-O1", "-I", MOCK, "-DCV_EMU_TSAN"]  # the scheduler is not instrumented: it IS the ordering, stated through annotations
@@ -240,5 +257,7 @@ if __name__ == "__main__":
         print(build_selftest(sys.argv[2] if len(sys.argv) > 2 else ""))
     elif len(sys.argv) > 1 and sys.argv[1] == "--show":
         sys.stdout.write(rewrite(open(os.path.join(CSRC, "kernels.cu")).read()))
+    elif len(sys.argv) > 1 and sys.argv[1] == "--mutate":
+        print(build("", sys.argv[2]))
     else:
         print(build(sys.argv[1] if len(sys.argv) > 1 else ""))

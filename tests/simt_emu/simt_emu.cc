@@ -18,6 +18,7 @@
 // void cv_emu_switch(void** save_sp, void* load_sp): callee-saved registers on the old stack, swap stacks, pop, return
 extern "C" void cv_emu_switch(void** save_sp, void* load_sp);
 extern "C" void mock_cuda_set_last_error(int e);  // tests/mock_cuda/mock_cuda.cc
+extern "C" void mock_cuda_enqueue(void* stream, void (*fn)(void*), void* arg);  // runs fn(arg) in stream order
 asm(R"(
 .text
 .globl cv_emu_switch
@@ -419,16 +420,34 @@ uint32_t warp_ballot(uint32_t mask, bool pred) {
     return r;
 }
 
-void run_grid(dim3 grid, dim3 block, size_t smem_bytes, Thunk thunk, void* kernel, void* args) {
+namespace {
+struct Launch {
+    dim3 grid, block;
+    size_t smem;
+    Thunk thunk;
+    void *kernel, *args;
+    void (*free_args)(void*);
+};
+void run_launch(void* p) {
+    Launch* l = static_cast<Launch*>(p);
+    Job j;
+    j.grid = l->grid, j.block = l->block, j.smem = l->smem, j.thunk = l->thunk, j.kernel = l->kernel, j.args = l->args;
+    j.n_blocks = uint64_t(l->grid.x) * l->grid.y * l->grid.z;
+    pool().run(j);
+    l->free_args(l->args);
+    delete l;
+}
+}  // namespace
+
+void launch(void* stream, dim3 grid, dim3 block, size_t smem_bytes, Thunk thunk, void* kernel, void* args, void (*free_args)(void*)) {
     const uint64_t n_threads = uint64_t(block.x) * block.y * block.z;
     const uint64_t n_blocks = uint64_t(grid.x) * grid.y * grid.z;
     if (n_threads == 0 || n_threads > kMaxThreads || smem_bytes > kDynSmemBytes || n_blocks == 0 || grid.x > 0x7fffffffu || grid.y > 65535u || grid.z > 65535u) {
         mock_cuda_set_last_error(9);  // cudaErrorInvalidConfiguration, reported by the launcher's cudaGetLastError like on the device
+        free_args(args);
         return;
     }
-    Job j;
-    j.grid = grid, j.block = block, j.smem = smem_bytes, j.thunk = thunk, j.kernel = kernel, j.args = args, j.n_blocks = n_blocks;
-    pool().run(j);
+    mock_cuda_enqueue(stream, &run_launch, new Launch{grid, block, smem_bytes, thunk, kernel, args, free_args});
 }
 
 }  // namespace cv_emu

@@ -54,24 +54,27 @@ uint64_t warp_exchange(uint32_t mask, uint64_t v, uint32_t src);
 uint32_t warp_ballot(uint32_t mask, bool pred);
 
 typedef void (*Thunk)(void* kernel, void* args);
-void run_grid(dim3 grid, dim3 block, size_t smem_bytes, Thunk thunk, void* kernel, void* args);
+// runs the grid in stream order (at once on the NULL stream and in the runtime stand-in's default synchronous mode), then frees args
+void launch(void* stream, dim3 grid, dim3 block, size_t smem_bytes, Thunk thunk, void* kernel, void* args, void (*free_args)(void*));
 
 struct LaunchCfg {
     dim3 g, b;
     size_t smem;
+    void* stream;
     template <class... P, class... A>
     void operator()(void (*k)(P...), A&&... a) const {
         typedef std::tuple<std::decay_t<P>...> Args;
-        Args args(static_cast<std::decay_t<P>>(std::forward<A>(a))...);
+        Args* args = new Args(static_cast<std::decay_t<P>>(std::forward<A>(a))...);  // by value, like a launch's parameter buffer
         struct T {
             static void run(void* kernel, void* t) { std::apply(reinterpret_cast<void (*)(P...)>(kernel), *static_cast<Args*>(t)); }
+            static void drop(void* t) { delete static_cast<Args*>(t); }
         };
-        run_grid(g, b, smem, &T::run, reinterpret_cast<void*>(k), &args);
+        launch(stream, g, b, smem, &T::run, reinterpret_cast<void*>(k), args, &T::drop);
     }
 };
 template <class S>
-inline LaunchCfg cfg(dim3 g, dim3 b, size_t smem, S /*stream: launches complete before they return*/) {
-    return LaunchCfg{g, b, smem};
+inline LaunchCfg cfg(dim3 g, dim3 b, size_t smem, S stream) {
+    return LaunchCfg{g, b, smem, (void*)stream};
 }
 
 // ---- the PTX the kernels use (build.py turns every asm statement into one of these)

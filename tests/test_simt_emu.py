@@ -4,7 +4,9 @@ tests/simt_emu compiles curvine_b200/csrc/kernels.cu -- the file nvcc compiles f
 rewrite of the launch syntax and of the inline PTX -- for host cores on a SIMT shim: a fiber per CUDA thread, blocks spread over
 host threads, __syncthreads / __syncwarp / *_sync warp intrinsics completing exactly when every live participant has arrived.
 The whole `-m gpu` suite (kernel parity against the oracle, the reader through the C ABI, arena, GDS fallback, faults, the
-two-device gather) then runs in a subprocess against that library.  This checks the kernels' ALGORITHM (index math, shuffle
+two-device gather) then runs in a subprocess against that library -- with the runtime stand-in's streams running ASYNCHRONOUSLY
+(tests/mock_cuda/mock_cuda.cc: a thread per stream, random pauses, ordering only through events), so the pipeline's stream
+dependencies are exercised too.  This checks the kernels' ALGORITHM (index math, shuffle
 patterns, the GF(2) folds, barrier placement) on every CPU run; what it cannot check is what only the hardware decides (memory
 model races between unsynchronised threads, the compiled SASS, speed) -- the B200 run of the same tests covers that.
 Test infrastructure: nothing under curvine_b200/ can load this library."""
@@ -55,7 +57,9 @@ def test_rewrite_refuses_what_it_does_not_know():
 
 def test_gpu_suite_with_the_kernel_source_on_the_simt_shim():
     lib = _emu_build().build()
-    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=lib, CV_SIMT_EMU_THREADS="3")
+    # MOCK_CUDA_ASYNC: the runtime stand-in runs every created stream as a FIFO of its own with random pauses, ordered only by events --
+    # a dependency the pipeline forgot between its copy / verify / caller streams shows up as wrong bytes (tools/sanitize_ingest.sh plants one)
+    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=lib, CV_SIMT_EMU_THREADS="3", MOCK_CUDA_ASYNC="1", MOCK_CUDA_JITTER_US="500")
     # read_to_tensor allocates a torch CUDA tensor inside the binding itself: nothing to check without a device
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "not read_to_tensor", "-n", "6"],
                        cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=2400)

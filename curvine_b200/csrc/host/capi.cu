@@ -49,18 +49,29 @@ static int64_t ok() { return 0; }
         return fail(Err::common("internal: unknown exception"));         \
     }
 
+// The filesystem context is shared between the filesystem handle and every reader / writer opened from it, as in the reference
+// (FsReader and FsWriter hold an Arc<FsContext>; closeFilesystem only drops the handle's reference: lib_filesystem.rs:25-40): a reader
+// that outlives its filesystem handle stays valid, and the GPU ingest pipeline goes with the LAST holder.
+static std::shared_ptr<FsContext> make_context(const ClusterConf& c) {
+    return std::shared_ptr<FsContext>(new FsContext(c), [](FsContext* ctx) {
+        gpu_ingest_release(ctx);
+        delete ctx;
+    });
+}
+
 struct cv_fs {
-    std::unique_ptr<FsContext> ctx;
+    std::shared_ptr<FsContext> ctx;
 };
 
 struct cv_reader {
-    cv_fs* fs = nullptr;
+    std::shared_ptr<FsContext> ctx;  // first member: destroyed after the readers below
     std::string path;
     std::unique_ptr<FsReader> host;
     std::unique_ptr<GpuFsReader> dev;
 };
 
 struct cv_writer {
+    std::shared_ptr<FsContext> ctx;  // first member: destroyed after the writer below
     std::unique_ptr<FsWriter> w;
 };
 
@@ -80,7 +91,7 @@ int64_t cv_fs_new_from_string(const char* conf_toml, cv_fs** out) {
     ClusterConf c;
     API_TRY(ClusterConf::from_string(conf_toml ? conf_toml : "", &c));
     std::unique_ptr<cv_fs> fs(new cv_fs());
-    fs->ctx.reset(new FsContext(c));
+    fs->ctx = make_context(c);
     if (!c.namespace_manifest.empty()) API_TRY(fs->ctx->ns.load(c.namespace_manifest));
     *out = fs.release();
     return ok();
@@ -93,7 +104,7 @@ int64_t cv_fs_new(const char* conf_path, cv_fs** out) {
     ClusterConf c;
     API_TRY(ClusterConf::from_file(conf_path ? conf_path : "", &c));
     std::unique_ptr<cv_fs> fs(new cv_fs());
-    fs->ctx.reset(new FsContext(c));
+    fs->ctx = make_context(c);
     if (!c.namespace_manifest.empty()) API_TRY(fs->ctx->ns.load(c.namespace_manifest));
     *out = fs.release();
     return ok();
@@ -121,8 +132,7 @@ int64_t cv_fs_load_namespace_string(cv_fs* fs, const char* text) {
 int64_t cv_fs_close(cv_fs* fs) {
     API_GUARD_BEGIN
     if (!fs) return ok();
-    gpu_ingest_release(fs->ctx.get());
-    delete fs;
+    delete fs;  // drops the handle's reference; open readers / writers keep the context (and its GPU pipeline) until they are closed
     return ok();
     API_GUARD_END
 }
@@ -170,7 +180,7 @@ int64_t cv_open(cv_fs* fs, const char* path, cv_reader** out, int64_t* len) {
     API_NEED(path);
     API_NEED(out);
     std::unique_ptr<cv_reader> r(new cv_reader());
-    r->fs = fs, r->path = path;
+    r->ctx = fs->ctx, r->path = path;
     API_TRY(FsReader::open(fs->ctx.get(), path, &r->host));
     if (len) *len = r->host->len();
     *out = r.release();
@@ -256,7 +266,7 @@ int64_t cv_close_reader(cv_reader* r) {
 
 static Err ensure_dev(cv_reader* r) {
     if (r->dev) return Err::ok();
-    return GpuFsReader::open(r->fs->ctx.get(), r->path, &r->dev);
+    return GpuFsReader::open(r->ctx.get(), r->path, &r->dev);
 }
 
 int64_t cv_read_device(cv_reader* r, void* d_dst, int64_t cap, cv_stream_t stream, int64_t* nbytes) {
@@ -418,6 +428,7 @@ int64_t cv_writer_open(cv_fs* fs, const char* path, int64_t inode_id, int64_t bl
     a.worker_id = 1, a.hostname = worker_host, a.ip_addr = "127.0.0.1", a.rpc_port = static_cast<uint32_t>(worker_port);
     if (a.hostname != "localhost") a.ip_addr = a.hostname;
     std::unique_ptr<cv_writer> w(new cv_writer());
+    w->ctx = fs->ctx;
     API_TRY(FsWriter::create(fs->ctx.get(), path, inode_id, block_size, storage_type, a, chunk_size > 0 ? chunk_size : 128 * 1024, &w->w));
     *out = w.release();
     return ok();

@@ -63,6 +63,8 @@ int64_t cv_fs_new(const char* conf_path, cv_fs** out);
 int64_t cv_fs_new_from_string(const char* conf_toml, cv_fs** out);
 int64_t cv_fs_load_namespace(cv_fs* fs, const char* manifest_path);
 int64_t cv_fs_load_namespace_string(cv_fs* fs, const char* manifest_text);
+/* Drops the handle's reference to the filesystem context.  Readers / writers opened from it hold their own (as FsReader holds an
+ * Arc<FsContext> in the reference): they stay valid and must still be closed; the context and its GPU pipeline go with the last holder. */
 int64_t cv_fs_close(cv_fs* fs);
 /* Block until everything this context pins in the background is pinned: the arena segments queued by cv_fs_preregister / the
  * first device read (mem-arena tier), and -- for the reference's one-file-per-block mem tier -- the registrar's mmap +

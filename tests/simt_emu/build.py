@@ -175,6 +175,10 @@ def _digest(extra):
 
 MUTATIONS = {
     # planted bugs for the checks that are supposed to find them (tools/sanitize_ingest.sh): name -> (file under csrc/host, old text, new text)
+    "copies_do_not_wait_for_the_callers_stream": ("gpu_reader.cu", "for (auto cs : G.copy_streams) CU_TRY(cudaStreamWaitEvent(cs, G.entry_ev, 0));",
+                                                   "/* planted: the copy streams start without waiting for what the caller enqueued before the read */;"),
+    "callers_stream_does_not_wait_for_the_read": ("gpu_reader.cu", "CU_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(user_stream), G.done_ev, 0));",
+                                                   "/* planted: the caller's stream continues without waiting for the read */;"),
     "verifier_does_not_wait_for_the_copy": ("gpu_reader.cu", "cudaStreamWaitEvent(G.vstream, G.copy_ev[g % NS], 0);", "/* planted: the verify stream no longer waits for the group's copies */;"),
 }
 

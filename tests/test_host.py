@@ -8,6 +8,7 @@ CPU only (no kernels are launched).  Scenarios follow the reference's own tests:
 import ctypes
 import os
 import socket
+import tempfile
 import zlib
 
 import numpy as np
@@ -735,3 +736,33 @@ def test_failed_worker_list_has_a_ttl_and_shows_in_the_no_worker_error(tmp_path)
         with pytest.raises(F.FsError) as ei:
             r.read(10)
         assert "There is no available worker, locs: [], failed workers: [1]" in ei.value.msg
+
+
+def test_reader_and_writer_outlive_their_filesystem_handle():
+    """FFI ownership as in the reference (FsReader / FsWriter hold an Arc<FsContext>; closeFilesystem drops only the handle's reference,
+    lib_filesystem.rs:25-40): closing the filesystem handle first leaves open readers and writers valid."""
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        with F.MiniWorker(["[MEM]" + d + "/m"]) as w:
+            n, bs, ino = (3 << 20) + 5, 1 << 20, 4411
+            man = w.create_file("/late", ino, n, bs)
+            want = synth.file_bytes(ino, n, bs)
+            for sc in (True, False):
+                fs = F.CurvineFileSystem(F.client_conf(short_circuit=sc))
+                fs.load_namespace(man)
+                r = fs.open("/late")
+                head = r.read_full(1000)
+                fs.close()                      # the handle goes first
+                assert head + r.read_full(n) == want and r.read_full(10) == b""
+                r.seek(bs - 3)
+                assert r.read_full(7) == want[bs - 3:bs + 4]
+                r.complete()
+            fs = F.CurvineFileSystem(F.client_conf())
+            wr = fs.create("/late_w", 4412, bs, w.port)
+            wr.write(want[:bs + 17])
+            fs.close()
+            wr.write(want[bs + 17:])
+            man2 = wr.complete()
+            with F.CurvineFileSystem(F.client_conf()) as fs2:
+                fs2.load_namespace(man2)
+                with fs2.open("/late_w") as r2:
+                    assert r2.read_full(n + 1) == want

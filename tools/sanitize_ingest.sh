@@ -15,10 +15,12 @@ echo "asan+ubsan: $(tail -1 /tmp/cv_ingest_asan.log) | findings: $(grep -ciE 'ru
 # Stream-order check: the whole -m gpu suite with the kernel source on the SIMT shim (tests/simt_emu) and the runtime stand-in's streams running
 # ASYNCHRONOUSLY (a thread per stream, random pauses up to 1 ms, ordered only by events).  A forgotten dependency = wrong bytes in a parity test.
 # First the planted one (the verify stream no longer waits for a group's copies): it must fail; then the product as it is: it must pass.
-LIB=$(python tests/simt_emu/build.py --mutate verifier_does_not_wait_for_the_copy)
-CV_TEST_MOCK_CUDA_LIB=$LIB MOCK_CUDA_ASYNC=1 MOCK_CUDA_JITTER_US=500 CV_SIMT_EMU_THREADS=3 timeout 1200 python -m pytest tests/test_gpu_reader.py tests/test_arena_gpu.py \
-  -m gpu -q -p no:cacheprovider -k "$K" -n 6 > /tmp/cv_ingest_async_planted.log 2>&1 || true
-echo "async streams, planted missing dependency: $(tail -1 /tmp/cv_ingest_async_planted.log) (want failures)"
+for M in verifier_does_not_wait_for_the_copy copies_do_not_wait_for_the_callers_stream callers_stream_does_not_wait_for_the_read; do
+  LIB=$(python tests/simt_emu/build.py --mutate $M)
+  CV_TEST_MOCK_CUDA_LIB=$LIB MOCK_CUDA_ASYNC=1 MOCK_CUDA_JITTER_US=500 CV_SIMT_EMU_THREADS=3 timeout 1200 python -m pytest tests/test_gpu_reader.py tests/test_arena_gpu.py \
+    tests/test_zzz_stream_order_gpu.py -m gpu -q -p no:cacheprovider -k "$K" -n 6 > /tmp/cv_ingest_async_planted.log 2>&1 || true
+  echo "async streams, planted: $M: $(tail -1 /tmp/cv_ingest_async_planted.log) (want failures)"
+done
 LIB=$(python tests/simt_emu/build.py)
 for J in 300 1000 2000; do
   CV_TEST_MOCK_CUDA_LIB=$LIB MOCK_CUDA_ASYNC=1 MOCK_CUDA_JITTER_US=$J CV_SIMT_EMU_THREADS=3 timeout 1800 python -m pytest tests -m gpu -q -p no:cacheprovider -k "$K" -n 6 > /tmp/cv_ingest_async.log 2>&1 || true

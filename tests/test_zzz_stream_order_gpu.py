@@ -79,6 +79,7 @@ def test_read_device_is_ordered_on_the_callers_stream(cuda, sc, arena):
                 dst = torch.zeros(n, dtype=torch.uint8, device=cuda)
                 out = torch.zeros(n, dtype=torch.uint8, device=cuda)
                 slow = torch.zeros(64 << 20, dtype=torch.uint8, device=cuda)
+                torch.cuda.synchronize()  # the allocations' own fills ran on the default stream, which the caller's stream does not wait for
                 for rnd in range(3):
                     for _ in range(6):
                         cs.fill(slow, rnd)          # keeps the stream busy: the fills below are still pending when read_device is called

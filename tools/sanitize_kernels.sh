@@ -33,9 +33,9 @@ LIB=$(python tests/simt_emu/build.py thread)
 CV_TEST_MOCK_CUDA_LIB=$LIB CV_SIMT_EMU_THREADS=2 CV_SIMT_EMU_SMS=6 LD_PRELOAD="$(gcc -print-file-name=libtsan.so)" TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4" \
   timeout 2400 setarch $ARCH -R python -m pytest $SUITES -m gpu -q -p no:cacheprovider > /tmp/cv_kernels_tsan.log 2>&1 || true
 echo "tsan race check: $(tail -1 /tmp/cv_kernels_tsan.log) | findings: $(grep -c 'WARNING: ThreadSanitizer' /tmp/cv_kernels_tsan.log)"
-if [ "$1" = "full" ]; then  # the WHOLE -m gpu suite (reader, arena, faults, two-device gather) with the kernel source on the shim, ASan+UBSan
+if [ "$1" = "full" ]; then  # the WHOLE -m gpu suite (reader, arena, faults, two-device gather) with the kernel source on the shim and asynchronous streams, ASan+UBSan
   LIB=$(python tests/simt_emu/build.py address,undefined)
-  CV_TEST_MOCK_CUDA_LIB=$LIB CV_SIMT_EMU_THREADS=4 CV_SIMT_EMU_SMS=16 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
+  CV_TEST_MOCK_CUDA_LIB=$LIB MOCK_CUDA_ASYNC=1 MOCK_CUDA_JITTER_US=400 CV_SIMT_EMU_THREADS=4 CV_SIMT_EMU_SMS=16 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
     ASAN_OPTIONS=detect_leaks=0:halt_on_error=0:detect_stack_use_after_return=0 UBSAN_OPTIONS=print_stacktrace=1 \
     timeout 3000 python -m pytest tests -m gpu -q -p no:cacheprovider -k "not read_to_tensor" -n 4 > /tmp/cv_gpu_suite_asan.log 2>&1 || true
   echo "asan+ubsan, whole GPU suite on the shim: $(tail -1 /tmp/cv_gpu_suite_asan.log) | findings: $(grep -ciE 'runtime error|ERROR: AddressSanitizer' /tmp/cv_gpu_suite_asan.log)"

@@ -125,3 +125,32 @@ def test_device_reader_outlives_its_filesystem_handle(cuda):
                 r.complete()                     # the last holder: the pipeline is torn down here
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_curvinefs_client_read_tensor(cuda):
+    """curvine_b200/curvinefs.py (the reference's Python SDK names on the new ABI): ranges of a file as uint8 CUDA tensors."""
+    import torch
+    if MOCK:
+        pytest.skip("allocates a torch CUDA tensor inside the binding")
+    from curvine_b200 import curvinefs
+    n, bs, ino = (6 << 20) + 77, 1 << 20, 8303
+    d = tempfile.mkdtemp(prefix="cvpy", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        with F.MiniWorker(["[MEM]" + d + "/m"]) as w:
+            man = w.create_file("/py/a", ino, n, bs, threads=4)
+            want = synth.file_bytes(ino, n, bs)
+            open(d + "/ns", "w").write(man)
+            open(d + "/conf.toml", "w").write('namespace_manifest = "%s/ns"\n' % d + F.client_conf())
+            c = curvinefs.CurvineClient(d + "/conf.toml")
+            t = c.read_range_tensor("/py/a")
+            assert t.is_cuda and t.dtype == torch.uint8 and t.cpu().numpy().tobytes() == want
+            t = c.read_range_tensor("/py/a", bs + 5, 2 * bs)
+            assert t.cpu().numpy().tobytes() == want[bs + 5:3 * bs + 5]
+            r = c.open("/py/a")
+            assert r.read(0, 100) == want[:100]
+            assert r.read_tensor(1000).cpu().numpy().tobytes() == want[100:1100]
+            assert torch.from_dlpack(r.read_tensor()).cpu().numpy().tobytes() == want[1100:]
+            r.close()
+            c.close()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

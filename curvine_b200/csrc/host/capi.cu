@@ -102,7 +102,9 @@ int64_t cv_fs_new(const char* conf_path, cv_fs** out) {
     API_GUARD_BEGIN
     API_NEED(out);
     ClusterConf c;
-    API_TRY(ClusterConf::from_file(conf_path ? conf_path : "", &c));
+    // no path given: $CURVINE_CONF_FILE, the fallback the reference's entry points use (ClusterConf::ENV_CONF_FILE, cluster_conf.rs:76; curvine-cli/src/main.rs:62)
+    const char* env_path = getenv("CURVINE_CONF_FILE");
+    API_TRY(ClusterConf::from_file(conf_path && *conf_path ? conf_path : (env_path ? env_path : ""), &c));
     std::unique_ptr<cv_fs> fs(new cv_fs());
     fs->ctx = make_context(c);
     if (!c.namespace_manifest.empty()) API_TRY(fs->ctx->ns.load(c.namespace_manifest));

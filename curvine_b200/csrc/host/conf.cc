@@ -214,7 +214,11 @@ Err ClusterConf::from_file(const std::string& path, ClusterConf* out) {
     if (!f) return Err(kFileNotFound, "conf file not found: " + path);
     std::stringstream ss;
     ss << f.rdbuf();
-    return from_string(ss.str(), out);
+    CV_RETURN_IF_ERR(from_string(ss.str(), out));
+    // environment beats the file, as in ClusterConf::from (curvine-common/src/conf/cluster_conf.rs:82-94)
+    if (const char* h = getenv("CURVINE_WORKER_HOSTNAME")) out->worker_hostname = h;
+    if (const char* h = getenv("CURVINE_CLIENT_HOSTNAME")) out->client.hostname = h;
+    return Err::ok();
 }
 
 }  // namespace cv

@@ -8,6 +8,8 @@ CPU only (no kernels are launched).  Scenarios follow the reference's own tests:
 import ctypes
 import os
 import socket
+import subprocess
+import sys
 import tempfile
 import zlib
 
@@ -766,3 +768,38 @@ def test_reader_and_writer_outlive_their_filesystem_handle():
                 fs2.load_namespace(man2)
                 with fs2.open("/late_w") as r2:
                     assert r2.read_full(n + 1) == want
+
+
+def test_environment_overrides_like_cluster_conf_from():
+    """ClusterConf::from (cluster_conf.rs:78-110): CURVINE_CLIENT_HOSTNAME beats the file's [client] hostname; entry points without a
+    path fall back to $CURVINE_CONF_FILE (cluster_conf.rs:76, curvine-cli/src/main.rs:62).  Run in a subprocess: the environment is process-wide."""
+    code = r'''
+import ctypes, os, sys, tempfile
+sys.path.insert(0, %r)
+from curvine_b200 import _lib, fs as F
+with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+    with F.MiniWorker(["[MEM]" + d + "/m"], hostname="worker-host") as w:
+        man = w.create_file("/e", 4601, 3 << 20, 1 << 20)
+        open(d + "/ns", "w").write(man)
+        # the file says the client sits on another host: reads go framed ...
+        open(d + "/conf.toml", "w").write('namespace_manifest = "%%s/ns"\n' %% d + F.client_conf(hostname="elsewhere"))
+        os.environ["CURVINE_CONF_FILE"] = d + "/conf.toml"
+        h = ctypes.c_void_p()
+        assert _lib.lib().cv_fs_new(None, ctypes.byref(h)) == 0          # no path: $CURVINE_CONF_FILE
+        fs = F.CurvineFileSystem.__new__(F.CurvineFileSystem); fs._h = h
+        with fs.open("/e") as r:
+            assert len(r.read_full(3 << 20)) == 3 << 20
+        fs.close()
+        m0 = w.metrics()
+        assert m0["read_blocks_remote"] == 3 and m0["read_blocks_local"] == 0, m0
+        # ... unless the environment says it is the worker's host: short-circuit
+        os.environ["CURVINE_CLIENT_HOSTNAME"] = "worker-host"
+        with F.CurvineFileSystem(conf_path=d + "/conf.toml") as fs:
+            with fs.open("/e") as r:
+                assert len(r.read_full(3 << 20)) == 3 << 20
+        m1 = w.metrics()
+        assert m1["read_blocks_local"] == 3 and m1["read_blocks_remote"] == 3, m1
+print("env ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "env ok" in r.stdout, r.stdout[-2000:]

@@ -113,46 +113,48 @@ class CurvineClient:
             raise IOError("Native open reader failed: %s" % e)
         return CurvineReader(r, r.len())
 
-    def read_range(self, path, offset, length):
-        """curvineClient.py:154-180: negative offsets count from the end, length None or -1 reads to the end."""
+    @staticmethod
+    def _span(file_len, offset, length):
+        """(first byte, byte count) of a read_range request.  Rules of curvineClient.py:154-180: a negative offset counts back from the
+        end of the file; length None or -1 means "to the end" (and then the offset has to lie inside the file); anything else must be a
+        non-negative int."""
+        if not isinstance(offset, int):
+            raise ValueError("offset: an integer is required, got %r" % (offset,))
+        first = offset + file_len if offset < 0 else offset
+        to_end = length is None or length == -1
+        if to_end and first >= file_len:
+            raise ValueError("offset %d is not inside a file of %d bytes" % (first, file_len))
+        if not to_end and (not isinstance(length, int) or length < 0):
+            raise ValueError("length: a non-negative integer, -1 or None is required, got %r" % (length,))
+        return first, (file_len - first if to_end else length)
+
+    def _len_of(self, path):
         status = self.get_file_status(path)
         if status is None:
-            raise FileNotFoundError("File not found")
-        if not isinstance(offset, int):
-            raise ValueError("Offset must be an integer")
-        if offset < 0:
-            offset = status["len"] + offset
-        if length is None or length == -1:
-            if offset >= status["len"]:
-                raise ValueError("Offset exceeds file size")
-            length = status["len"] - offset
-        if not isinstance(length, int) or length < 0:
-            raise ValueError("Length must be a non-negative integer, -1, or None")
-        if length == 0:
+            raise FileNotFoundError(path)
+        return status["len"]
+
+    def read_range(self, path, offset, length):
+        first, count = self._span(self._len_of(path), offset, length)
+        if count == 0:
             return b""
         reader = self.open(path)
         try:
-            return reader.read(offset, length)
+            return reader.read(first, count)
         finally:
             reader.close()
 
     def head(self, path, size):
-        if size is None or size < 0:
-            raise ValueError("size must be non-negative integer")
+        if not isinstance(size, int) or size < 0:
+            raise ValueError("size: a non-negative integer is required, got %r" % (size,))
         return self.read_range(path, 0, size)
 
     def tail(self, path, size):
-        if size < 0:
-            raise ValueError("size must be non-negative")
-        status = self.get_file_status(path)
-        if status is None:
-            raise FileNotFoundError("File not found")
-        n = status["len"]
-        if n == 0:
-            return b""
-        size = min(size, n)
-        start = max(0, n - size)
-        return self.read_range(path, start, min(size, n - start))
+        if not isinstance(size, int) or size < 0:
+            raise ValueError("size: a non-negative integer is required, got %r" % (size,))
+        n = self._len_of(path)
+        take = min(size, n)
+        return self.read_range(path, n - take, take) if take else b""
 
     def read_range_tensor(self, path, offset=0, length=None, device=None):
         """Addition: read_range into HBM (uint8 CUDA tensor)."""

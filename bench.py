@@ -159,6 +159,28 @@ def fit_gib_per_gpu(want_gib, world, pool, budget, reserve_per_gpu=3 << 30, frac
     return gib
 
 
+def claim_store_dir(base, prefix):
+    """A fresh directory for this run's stores under `base`, after removing what DEAD earlier runs left there (a run that was killed keeps
+    its tmpfs files -- up to 130 GiB at 8 GPUs -- and the driver starts the next run on the same box right away)."""
+    for name in os.listdir(base):
+        if not name.startswith(("cvbench_", "cvref_")):
+            continue
+        p = os.path.join(base, name)
+        try:
+            pid = int(open(os.path.join(p, "owner.pid")).read().strip())
+            os.kill(pid, 0)  # raises if no such process
+        except (OSError, ValueError):
+            if time.time() - os.stat(p).st_mtime > 60:  # not a directory some process is creating right now
+                log("removing the stores of a dead run:", p)
+                shutil.rmtree(p, ignore_errors=True)
+        except Exception:
+            pass
+    d = tempfile.mkdtemp(prefix=prefix, dir=base)
+    with open(os.path.join(d, "owner.pid"), "w") as f:
+        f.write(str(os.getpid()))
+    return d
+
+
 def setup_dist(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -223,7 +245,7 @@ class Cluster:
         payload = [None]
         if rank == 0:
             base = args.dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
-            self.dir = tempfile.mkdtemp(prefix="cvbench_", dir=base)
+            self.dir = claim_store_dir(base, "cvbench_")
             L = _lib.lib()
             nodes = [int(L.cv_gpu_numa_node(g)) for g in range(world)]
             # memory discipline: the arena holds the file being read (+ `pool` older ones) and one segment of slack, nothing more -- the
@@ -645,7 +667,7 @@ def main_reference(args):
     n_total = int(gib * (1 << 30)) // BLOCK * BLOCK
     sc = args.mode == "short_circuit"
     base = args.dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
-    d = tempfile.mkdtemp(prefix="cvref_", dir=base)
+    d = claim_store_dir(base, "cvref_")
     w = None
     try:
         w = refworker.RefWorker(d)

@@ -15,5 +15,5 @@ cp $ROOT/curvine_b200/libcurvine_b200.so orig.so; cp asan.so $ROOT/curvine_b200/
 trap "cp $W/orig.so $ROOT/curvine_b200/libcurvine_b200.so" EXIT
 cd $ROOT
 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 \
-  UBSAN_OPTIONS=print_stacktrace=1 python -m pytest tests/test_host.py tests/test_multi_cpu.py tests/test_arena.py tests/test_wire_pin.py -q -p no:cacheprovider -s 2>&1 | tee $W/report.txt | tail -5
+  UBSAN_OPTIONS=print_stacktrace=1 python -m pytest tests/test_host.py tests/test_multi_cpu.py tests/test_arena.py tests/test_wire_pin.py tests/test_hostile_peers.py tests/test_curvinefs_compat.py -q -p no:cacheprovider -s 2>&1 | tee $W/report.txt | tail -5
 echo "sanitizer findings: $(grep -ciE 'runtime error|AddressSanitizer' $W/report.txt)"

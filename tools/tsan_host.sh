@@ -15,5 +15,5 @@ cp $ROOT/curvine_b200/libcurvine_b200.so orig.so; cp tsan.so $ROOT/curvine_b200/
 trap "cp $W/orig.so $ROOT/curvine_b200/libcurvine_b200.so" EXIT
 cd $ROOT
 LD_PRELOAD="$(gcc -print-file-name=libtsan.so)" TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4 ${TSAN_EXTRA}" \
-  setarch "$(uname -m)" -R python -m pytest tests/test_host.py tests/test_arena.py -q -p no:cacheprovider -s -x ${TSAN_TESTS} 2>&1 | tee $W/report.txt | tail -5
+  setarch "$(uname -m)" -R python -m pytest tests/test_host.py tests/test_arena.py tests/test_hostile_peers.py -q -p no:cacheprovider -s -x ${TSAN_TESTS} 2>&1 | tee $W/report.txt | tail -5
 echo "tsan findings: $(grep -c 'WARNING: ThreadSanitizer' $W/report.txt)"

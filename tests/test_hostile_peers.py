@@ -221,3 +221,55 @@ def test_client_survives_a_lying_worker(mode):
     finally:
         lw.close()
     assert time.time() - t0 < 30, "a lying worker must not stall the client beyond its timeouts"
+
+
+def test_conf_and_manifest_parsers_survive_garbage():
+    """The two text inputs a deployment hands the library -- the cluster TOML and the namespace manifest -- as random text, as valid text
+    with random edits, and with absurd numbers: an error code or a successful parse, never a crash, and a handle that still closes."""
+    import ctypes
+    from hypothesis import given, settings, strategies as st
+    from curvine_b200 import _lib
+    L = _lib.lib()
+    good_conf = F.client_conf(b200='fetch_threads = 4\ngpu_chunk_size = "1MB"\narena_preregister = ["/tmp/a", "/tmp/b"]\n')
+    good_man = ("# m\nfile /f 4901 3145728 1048576 0\n" + "".join("block %d 1048576 0 %08x %08x - localhost:9:1,otherhost:10:2\n" % (layout.create_block_id(4901, b), b, b + 7) for b in range(3)))
+
+    def try_conf(text):
+        h = ctypes.c_void_p()
+        rc = L.cv_fs_new_from_string(text.encode("utf-8", "ignore"), ctypes.byref(h))
+        assert (rc == 0) == bool(h)
+        if h:
+            assert L.cv_fs_close(h) == 0
+
+    def try_manifest(text):
+        h = ctypes.c_void_p()
+        assert L.cv_fs_new_from_string(b"", ctypes.byref(h)) == 0
+        rc = L.cv_fs_load_namespace_string(h, text.encode("utf-8", "ignore"))
+        assert rc <= 0
+        assert L.cv_fs_close(h) == 0
+
+    def edited(base, data):
+        chars = list(base)
+        for _ in range(data.draw(st.integers(1, 6))):
+            i = data.draw(st.integers(0, len(chars) - 1))
+            op = data.draw(st.integers(0, 3))
+            if op == 0:
+                chars[i] = data.draw(st.sampled_from(list('0123456789-="[]{},.:# \n\tKMGTBxe')))
+            elif op == 1:
+                del chars[i]
+            elif op == 2:
+                chars.insert(i, data.draw(st.sampled_from(["99999999999999999999999", "-1", '"', "[", "\n[b200]\n", "=", " 1e400 ", "0x", "\x00"])))
+            else:
+                chars[i:i] = chars[max(0, i - 20):i]
+        return "".join(chars)
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.data())
+    def run(data):
+        try_conf(data.draw(st.text(max_size=300)))
+        try_conf(edited(good_conf, data))
+        try_manifest(data.draw(st.text(max_size=300)))
+        try_manifest(edited(good_man, data))
+
+    try_conf(good_conf)
+    try_manifest(good_man)
+    run()

@@ -47,6 +47,19 @@ def _declare(L):
     vp, u8p, u32, u64, i = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
     L.cvk_init.argtypes, L.cvk_init.restype = [i], i
     L.cvk_launch_count.argtypes, L.cvk_launch_count.restype = [], u64
+    sz, vpp = ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)
+    L.cvh_pinned_alloc.argtypes, L.cvh_pinned_alloc.restype = [sz, vpp], i
+    L.cvh_device_alloc.argtypes, L.cvh_device_alloc.restype = [sz, vpp], i
+    L.cvh_pinned_free.argtypes, L.cvh_pinned_free.restype = [vp], i
+    L.cvh_device_free.argtypes, L.cvh_device_free.restype = [vp], i
+    L.cvh_h2d_async.argtypes, L.cvh_h2d_async.restype = [vp, vp, sz, vp, vp], i
+    L.cvh_d2h_async.argtypes, L.cvh_d2h_async.restype = [vp, vp, sz, vp, vp], i
+    L.cvh_stream_create.argtypes, L.cvh_stream_create.restype = [vpp], i
+    L.cvh_event_create.argtypes, L.cvh_event_create.restype = [vpp], i
+    for name in ("cvh_stream_destroy", "cvh_stream_synchronize", "cvh_event_destroy", "cvh_event_synchronize", "cvh_event_query"):
+        getattr(L, name).argtypes, getattr(L, name).restype = [vp], i
+    L.cvh_stream_wait_event.argtypes, L.cvh_stream_wait_event.restype = [vp, vp], i
+    L.cvh_event_record.argtypes, L.cvh_event_record.restype = [vp, vp], i
     L.cvk_tune.argtypes, L.cvk_tune.restype = [i, i], i
     L.cvk_profile_enable.argtypes, L.cvk_profile_enable.restype = [i], i
     L.cvk_profile_collect.argtypes, L.cvk_profile_collect.restype = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u32)], i

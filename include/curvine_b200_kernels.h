@@ -168,6 +168,32 @@ int cvk_tune(int what, int value);
 /* Number of kernel launches issued by this library in this process (bench.py's gpu_launches claim). */
 uint64_t cvk_launch_count(void);
 
+/* ---- cvh_*: the host-side CUDA plumbing a caller needs around the launchers above, so that a host written in a language without CUDA
+ * bindings (the reference's Rust client with its own fetch loop: a `UnifiedReader::Cuda` that keeps RpcFrame::receive and hands the bytes
+ * to K2) links nothing but this library.  Thin wrappers over the runtime; all return cudaError_t as int.
+ *   cvh_pinned_alloc / cvh_pinned_free   page-locked host buffers: where received frames / pread chunks land so that the H2D copy is a DMA
+ *                                        (replaces the BytesMut carved by FrameBuf::take_exact, orpc/src/handler/frame_buf.rs:58-70)
+ *   cvh_device_alloc / cvh_device_free   device buffers (wire staging, destinations) for callers that have no allocator of their own
+ *   cvh_h2d_async                        dst[0..n) <- pinned src on copy_stream; done_event (may be NULL) is recorded behind the copy
+ *   cvh_d2h_async                        the way back for results (per-block CRCs, error flags)
+ *   cvh_stream_* / cvh_event_*           creation, ordering (stream waits for event) and completion of the two handle kinds the calls take */
+typedef void* cv_event_t; /* cudaEvent_t */
+int cvh_pinned_alloc(size_t bytes, void** out);
+int cvh_pinned_free(void* p);
+int cvh_device_alloc(size_t bytes, void** out);
+int cvh_device_free(void* d_p);
+int cvh_h2d_async(void* d_dst, const void* h_src, size_t n, cv_stream_t copy_stream, cv_event_t done_event);
+int cvh_d2h_async(void* h_dst, const void* d_src, size_t n, cv_stream_t stream, cv_event_t done_event);
+int cvh_stream_create(cv_stream_t* out);  /* non-blocking stream on the current device */
+int cvh_stream_destroy(cv_stream_t s);
+int cvh_stream_synchronize(cv_stream_t s);
+int cvh_stream_wait_event(cv_stream_t s, cv_event_t e);
+int cvh_event_create(cv_event_t* out);    /* timing disabled */
+int cvh_event_destroy(cv_event_t e);
+int cvh_event_record(cv_event_t e, cv_stream_t s);
+int cvh_event_synchronize(cv_event_t e);
+int cvh_event_query(cv_event_t e);        /* 0 = complete, cudaErrorNotReady (600) = still pending */
+
 #ifdef __cplusplus
 }
 #endif

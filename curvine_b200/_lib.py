@@ -148,7 +148,9 @@ EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_verify_crcs_mas
            "cv_open", "cv_read", "cv_read_buf", "cv_read_full", "cv_fuse_read", "cv_seek", "cv_pos", "cv_len",
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device", "cv_fuse_read_file_device",
            "cv_verify", "cv_device_stats", "cv_writer_open", "cv_write", "cv_write_device", "cv_writer_close", "cv_worker_start", "cv_worker_stop", "cv_worker_hbm_load", "cv_worker_hbm_drain", "cv_worker_hbm_stats", "cv_worker_hbm_tier", "cv_worker_metrics",
-           "cv_synth_create_file", "cv_synth_set_shard_world", "cv_synth_block", "cv_host_crc"]
+           "cv_synth_create_file", "cv_synth_set_shard_world", "cv_synth_block", "cv_host_crc",
+           "cvh_pinned_alloc", "cvh_pinned_free", "cvh_device_alloc", "cvh_device_free", "cvh_h2d_async", "cvh_d2h_async", "cvh_stream_create", "cvh_stream_destroy",
+           "cvh_stream_synchronize", "cvh_stream_wait_event", "cvh_event_create", "cvh_event_destroy", "cvh_event_record", "cvh_event_synchronize", "cvh_event_query"]
 
 
 class CudaError(RuntimeError):

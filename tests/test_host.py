@@ -803,3 +803,21 @@ print("env ok")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0 and "env ok" in r.stdout, r.stdout[-2000:]
+
+
+def test_headers_are_plain_c_and_the_c_example_links_against_the_library_alone():
+    """include/*.h compile as C99 (-pedantic -Werror: no C++ or torch types in the boundary) and examples/c_host.c links against
+    libcurvine_b200.so with no CUDA headers or libraries on the command line (the GPU suite runs it)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        libdir = os.path.join(root, "curvine_b200")
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_host.c"),
+                            "-o", os.path.join(d, "c_host"), "-L", libdir, "-l:libcurvine_b200.so", "-Wl,-rpath," + libdir],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
+        u = subprocess.run([os.path.join(d, "c_host")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert u.returncode == 2 and "usage" in u.stdout
+        # without a GPU the example fails loudly at its first CUDA call, with the library's message -- no fallback
+        open(os.path.join(d, "conf.toml"), "w").write(F.client_conf())
+        e = subprocess.run([os.path.join(d, "c_host"), os.path.join(d, "conf.toml"), "/nope"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert e.returncode == 1 and "cv_open" in e.stdout, e.stdout

@@ -126,3 +126,40 @@ def test_foreign_host_drives_k2_through_cvh_and_cvk_only(cuda):
             if p:
                 L.cvh_pinned_free(p)
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_plain_c_host_example_reads_a_file_into_device_memory(cuda):
+    """examples/c_host.c: gcc -std=c99 -pedantic, no CUDA headers, linked against the library alone (on the host-side stand-ins: against the
+    stand-in library) -- cv_fs_new / cv_open / cv_read_device in steps / cv_verify + cvh_* -- and its output against the oracle."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.environ.get("CV_TEST_MOCK_CUDA_LIB") or os.path.join(root, "curvine_b200", "libcurvine_b200.so")
+    d = tempfile.mkdtemp(prefix="cvch", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        exe = os.path.join(d, "c_host")
+        cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_host.c"),
+                             "-o", exe, "-L", os.path.dirname(lib), "-l:" + os.path.basename(lib), "-Wl,-rpath," + os.path.dirname(lib)],
+                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert cc.returncode == 0, cc.stdout
+        n, bs, ino = (9 << 20) + 55, 1 << 20, 8502
+        with F.MiniWorker(["[MEM]" + d + "/m"]) as w:
+            man = w.create_file("/c/file", ino, n, bs)
+            want = synth.file_bytes(ino, n, bs)
+            open(d + "/ns", "w").write(man)
+            open(d + "/conf.toml", "w").write('namespace_manifest = "%s/ns"\n' % d + F.client_conf(b200='fetch_threads = 2\nverify_batch = 2\npinned_slots = 8\ncopy_group = 1\n'))
+            r = subprocess.run([exe, d + "/conf.toml", "/c/file", str((2 << 20) + 4096)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout
+            want_sum = int(clib.crc_blocks(1, np.frombuffer(want, dtype=np.uint8), bs).astype(np.uint64).sum())
+            nb = (n + bs - 1) // bs
+            # the steps of 2 MiB + 4 KiB cut blocks in the middle: only blocks read whole in one call are compared with the manifest
+            fields = r.stdout.split()
+            assert fields[:4] == ["bytes", str(n), "of", str(n)] and fields[fields.index("bad") + 1] == "0", r.stdout
+            assert fields[fields.index("head") + 1:] == ["%02x" % b for b in want[:16]], r.stdout
+            assert int(fields[fields.index("verified") + 1]) <= nb
+            r = subprocess.run([exe, d + "/conf.toml", "/c/file"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+            fields = r.stdout.split()
+            assert r.returncode == 0 and int(fields[fields.index("sum_crc") + 1]) == want_sum and int(fields[fields.index("verified") + 1]) == nb, r.stdout
+            r = subprocess.run([exe, d + "/conf.toml", "/c/nope"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+            assert r.returncode == 1 and "cv_open" in r.stdout and "-8" in r.stdout, r.stdout   # FileNotFound, reported through cv_last_error
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

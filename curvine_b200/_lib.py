@@ -51,6 +51,8 @@ def _declare(L):
     L.cvh_pinned_alloc.argtypes, L.cvh_pinned_alloc.restype = [sz, vpp], i
     L.cvh_device_alloc.argtypes, L.cvh_device_alloc.restype = [sz, vpp], i
     L.cvh_pinned_free.argtypes, L.cvh_pinned_free.restype = [vp], i
+    L.cvh_host_register.argtypes, L.cvh_host_register.restype = [vp, sz], i
+    L.cvh_host_unregister.argtypes, L.cvh_host_unregister.restype = [vp], i
     L.cvh_device_free.argtypes, L.cvh_device_free.restype = [vp], i
     L.cvh_h2d_async.argtypes, L.cvh_h2d_async.restype = [vp, vp, sz, vp, vp], i
     L.cvh_d2h_async.argtypes, L.cvh_d2h_async.restype = [vp, vp, sz, vp, vp], i
@@ -149,7 +151,7 @@ EXPORTS = ["cvk_init", "cvk_crc_blocks", "cvk_verify_crcs", "cvk_verify_crcs_mas
            "cv_chunk_size", "cv_close_reader", "cv_read_device", "cv_read_device_sharded", "cv_read_many_device", "cv_shard_plan", "cv_fuse_read_device", "cv_fuse_read_file_device",
            "cv_verify", "cv_device_stats", "cv_writer_open", "cv_write", "cv_write_device", "cv_writer_close", "cv_worker_start", "cv_worker_stop", "cv_worker_hbm_load", "cv_worker_hbm_drain", "cv_worker_hbm_stats", "cv_worker_hbm_tier", "cv_worker_metrics",
            "cv_synth_create_file", "cv_synth_set_shard_world", "cv_synth_block", "cv_host_crc",
-           "cvh_pinned_alloc", "cvh_pinned_free", "cvh_device_alloc", "cvh_device_free", "cvh_h2d_async", "cvh_d2h_async", "cvh_stream_create", "cvh_stream_destroy",
+           "cvh_pinned_alloc", "cvh_pinned_free", "cvh_host_register", "cvh_host_unregister", "cvh_device_alloc", "cvh_device_free", "cvh_h2d_async", "cvh_d2h_async", "cvh_stream_create", "cvh_stream_destroy",
            "cvh_stream_synchronize", "cvh_stream_wait_event", "cvh_event_create", "cvh_event_destroy", "cvh_event_record", "cvh_event_synchronize", "cvh_event_query"]
 
 

@@ -13,6 +13,12 @@ int cvh_pinned_alloc(size_t bytes, void** out) {
 }
 int cvh_pinned_free(void* p) { return p ? int(cudaFreeHost(p)) : 0; }
 
+int cvh_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return int(cudaErrorInvalidValue);
+    return int(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+}
+int cvh_host_unregister(void* p) { return p ? int(cudaHostUnregister(p)) : 0; }
+
 int cvh_device_alloc(size_t bytes, void** out) {
     if (!out) return int(cudaErrorInvalidValue);
     *out = nullptr;

@@ -173,6 +173,7 @@ uint64_t cvk_launch_count(void);
  * to K2) links nothing but this library.  Thin wrappers over the runtime; all return cudaError_t as int.
  *   cvh_pinned_alloc / cvh_pinned_free   page-locked host buffers: where received frames / pread chunks land so that the H2D copy is a DMA
  *                                        (replaces the BytesMut carved by FrameBuf::take_exact, orpc/src/handler/frame_buf.rs:58-70)
+ *   cvh_host_register / _unregister      the same for memory the caller already owns (short-circuit: an mmap of the block file)
  *   cvh_device_alloc / cvh_device_free   device buffers (wire staging, destinations) for callers that have no allocator of their own
  *   cvh_h2d_async                        dst[0..n) <- pinned src on copy_stream; done_event (may be NULL) is recorded behind the copy
  *   cvh_d2h_async                        the way back for results (per-block CRCs, error flags)
@@ -180,6 +181,8 @@ uint64_t cvk_launch_count(void);
 typedef void* cv_event_t; /* cudaEvent_t */
 int cvh_pinned_alloc(size_t bytes, void** out);
 int cvh_pinned_free(void* p);
+int cvh_host_register(void* p, size_t bytes);   /* page-lock memory the caller already owns (an mmap'ed block file, a receive buffer): cudaHostRegister */
+int cvh_host_unregister(void* p);
 int cvh_device_alloc(size_t bytes, void** out);
 int cvh_device_free(void* d_p);
 int cvh_h2d_async(void* d_dst, const void* h_src, size_t n, cv_stream_t copy_stream, cv_event_t done_event);

@@ -112,6 +112,16 @@ def test_foreign_host_drives_k2_through_cvh_and_cvk_only(cuda):
             _ok(L.cvh_stream_synchronize(k_stream))
             assert ctypes.string_at(back.value, n) == want
             _ok(L.cvh_pinned_free(back))
+            # memory the host already owns (here: an anonymous page-aligned mapping) becomes a DMA source once registered
+            import mmap
+            mm = mmap.mmap(-1, 1 << 20)
+            mm.write(want[:1 << 20])
+            addr = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+            _ok(L.cvh_host_register(addr, 1 << 20))
+            _ok(L.cvh_h2d_async(d_dst, addr, 1 << 20, k_stream, None))
+            _ok(L.cvh_stream_synchronize(k_stream))
+            _ok(L.cvh_host_unregister(addr))
+            assert L.cvh_host_register(None, 4096) != 0
     finally:
         for st in (copy_stream, k_stream):
             if st:

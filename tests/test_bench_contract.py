@@ -24,17 +24,23 @@ def test_reference_arm_prints_one_json_line():
     assert "workload" in d["config"]
 
 
+def _shim_env():
+    """The library the bench runs against here: the product's host side AND kernel source on the SIMT shim (tests/simt_emu), the runtime
+    stand-in's streams asynchronous -- so the bench's own assertions (no CRC mismatch, the HBM-resident K1 pass agreeing with the ingest's
+    CRCs) are checked by the real kernels, and its stream usage by the stream-order check."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("simt_emu_build", os.path.join(ROOT, "tests", "simt_emu", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return dict(os.environ, CV_TEST_MOCK_CUDA_LIB=mod.build(), MOCK_CUDA_ASYNC="1", MOCK_CUDA_JITTER_US="300", CV_SIMT_EMU_THREADS="4")
+
+
 def test_own_arm_control_flow_and_json_line_on_the_mock_runtime():
     """bench.py's own arm (arena mount, context warm-up read, fresh-file steps, re-read / pread / framed side legs, HBM-resident K1
     steps, roofline, cpu_baseline) executed end to end without a GPU: tests/mock_cuda/run_bench_on_mock.py swaps in the mock library and
     tells torch that "cuda" tensors are CPU tensors.  Checks the control flow and the contract of the printed line; every number
     in it is meaningless here and is looked at only for type and bookkeeping (bytes per step, launch counts, DMA counters)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_cuda"))
-    try:
-        import build as mock_build
-    finally:
-        sys.path.pop(0)
-    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=mock_build.build())
+    env = _shim_env()
     gib, steps, warmup = 0.25, 2, 2
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "run_bench_on_mock.py"), "--gib-per-gpu", str(gib), "--steps", str(steps),
                         "--warmup", str(warmup)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env, cwd=ROOT)
@@ -75,12 +81,7 @@ def test_own_arm_two_ranks_on_the_mock_runtime():
     mock runtime for the GPUs.  Rank 0 hosts the worker and generates the 2 x 0.25 GiB file, the manifest is broadcast, every rank
     reads its round-robin shard out of ITS arena dir, timings are max-reduced, rank 0 prints the one line."""
     import socket
-    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_cuda"))
-    try:
-        import build as mock_build
-    finally:
-        sys.path.pop(0)
-    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=mock_build.build(), OMP_NUM_THREADS="1")
+    env = dict(_shim_env(), OMP_NUM_THREADS="1", CV_SIMT_EMU_THREADS="2")
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -101,12 +102,7 @@ def test_own_arm_two_ranks_on_the_mock_runtime():
 def test_smoke_control_flow_on_the_mock_runtime():
     """__graft_entry__.smoke() end to end without a GPU (mock runtime): the three passes it makes on the B200 -- files tier short-circuit,
     files tier framed, arena tier DMA -- each land the oracle's bytes and CRC sums."""
-    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_cuda"))
-    try:
-        import build as mock_build
-    finally:
-        sys.path.pop(0)
-    env = dict(os.environ, CV_TEST_MOCK_CUDA_LIB=mock_build.build())
+    env = _shim_env()
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "run_smoke_on_mock.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                        timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0 and "smoke ok" in p.stdout, p.stdout[-3000:]

@@ -123,3 +123,17 @@ def test_memory_guard_shrinks_a_size_the_container_cannot_hold():
     assert bench.fit_gib_per_gpu(128, 1, 0, 2000 * G) == 128
     assert bench.fit_gib_per_gpu(16, 8, 0, 120 * G) == 4
     assert bench.fit_gib_per_gpu(16, 1, 0, None) == 16              # nothing known about the host: no change
+
+
+def test_config_c5_line_on_the_shim():
+    """bench.py --config c5 (small files, FUSE-shaped: tools/c5_smallfiles.py) end to end with 64 files: per-file path, batched path and the CPU
+    port beside them, CRC checks inside the tool done by the real kernel source."""
+    env = dict(_shim_env(), CV_C5_FILES="64")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "run_bench_on_mock.py"), "--config", "c5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=600, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, p.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["unit"] == "files/s" and d["value"] > 0 and d["n_gpus"] == 1 and d["higher_is_better"] is True and "workload" in d["config"]
+    assert d["e2e"]["value"] > 0 and d["gpu_launches"] > 0

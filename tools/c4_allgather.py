@@ -192,6 +192,9 @@ def run(a):
             "exchange_nccl": {"allgather_ms": res.get("nccl_allgather_ms_rep1"), "deinterleave_ms": res.get("deinterleave_ms_rep1"), "total_ms": res.get("nccl_total_ms"),
                               "what": "all_gather_into_tensor + cvk_deinterleave_blocks"},
             "verify_ms": {"p2p": res.get("p2p_verify_ms"), "nccl": res.get("nccl_verify_ms")},
+            # the step is end to end by construction: the checkpoint starts in the worker's host memory and ends, verified, in every GPU's HBM
+            "e2e": {"value": n / total_ms / 1e6, "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 4 * ((n + BLOCK - 1) // BLOCK + 4 * world),
+                    "what": "cv_read_device_sharded on every rank (host memory -> HBM, CRC-verified) + the exchange that leaves the whole file on every GPU"},
             "gpu_launches": int(K.launch_count()), "raw": res})
 
 

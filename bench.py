@@ -688,6 +688,9 @@ def main_reference(args):
                 times.append(dt)
         ms = 1e3 * sum(times) / len(times)
         val = sample / ms / 1e6
+        # beside the stock policy: the same sample with the most sub-readers the reference ever uses (max_read_parallel = 8, client_conf.rs), for
+        # a reader who wants to know what the CPU path does when it is given every thread it can take
+        v8, threads8, _, _, _ = cpu_run(w.port, n_total, sc, 8, sample, 9200)
         out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                "config": {"workload": "C2 per GPU: %g GiB synthetic file, 4 MiB blocks, mem-tier (tmpfs, one file per block) BlockStore; CPU reader, bytes land in host memory" % gib,
@@ -696,6 +699,7 @@ def main_reference(args):
                                 "sample": "each step reads the first %.1f GiB; read_parallel=%d (reference default for this size), 128 KiB chunks/buffers, "
                                           "crc32 (PCLMUL) on the caller thread; worker = oracle/ref_worker.c" % (sample / 2 ** 30, par)},
                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "at_max_read_parallel": {"read_parallel": 8, "threads": threads8, "value": v8, "unit": UNIT, "note": "one pass over the same sample; not the stock policy for this file size"},
                "gpu_launches": 0}
     finally:
         if w is not None:

@@ -262,6 +262,6 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "--show":
         sys.stdout.write(rewrite(open(os.path.join(CSRC, "kernels.cu")).read()))
     elif len(sys.argv) > 1 and sys.argv[1] == "--mutate":
-        print(build("", sys.argv[2]))
+        print(build(sys.argv[3] if len(sys.argv) > 3 else "", sys.argv[2]))  # --mutate <name> [sanitize]
     else:
         print(build(sys.argv[1] if len(sys.argv) > 1 else ""))

@@ -26,3 +26,17 @@ for J in 300 1000 2000; do
   CV_TEST_MOCK_CUDA_LIB=$LIB MOCK_CUDA_ASYNC=1 MOCK_CUDA_JITTER_US=$J CV_SIMT_EMU_THREADS=3 timeout 1800 python -m pytest tests -m gpu -q -p no:cacheprovider -k "$K" -n 6 > /tmp/cv_ingest_async.log 2>&1 || true
   echo "async streams, jitter $J us: $(tail -1 /tmp/cv_ingest_async.log)"
 done
+# TSan on top of that: the same library built with -fsanitize=thread (kernel source as TSan fibers, tools/sanitize_kernels.sh), streams asynchronous.
+# A pinned-ring slot refilled by a fetch thread while its H2D copy is still reading it, a kernel consuming a buffer another stream is writing: data
+# races between host threads, stream threads and CUDA threads, reported with both stacks.  Planted bug first (must be reported), then the product.
+ARCH="$(uname -m)"
+TS="halt_on_error=0 report_signal_unsafe=0 history_size=4"
+LIB=$(python tests/simt_emu/build.py --mutate verifier_does_not_wait_for_the_copy thread)
+CV_TEST_MOCK_CUDA_LIB=$LIB MOCK_CUDA_ASYNC=1 MOCK_CUDA_JITTER_US=200 CV_SIMT_EMU_THREADS=2 CV_SIMT_EMU_SMS=6 LD_PRELOAD="$(gcc -print-file-name=libtsan.so)" TSAN_OPTIONS="$TS" \
+  timeout 1500 setarch $ARCH -R python -m pytest tests/test_gpu_reader.py -m gpu -q -p no:cacheprovider -k "c1_file" -n 3 > /tmp/cv_ingest_tsan_async_planted.log 2>&1 || true
+echo "tsan + async streams, planted: $(tail -1 /tmp/cv_ingest_tsan_async_planted.log) | races reported: $(grep -c 'ThreadSanitizer: data race' /tmp/cv_ingest_tsan_async_planted.log) (want > 0)"
+LIB=$(python tests/simt_emu/build.py thread)
+CV_TEST_MOCK_CUDA_LIB=$LIB MOCK_CUDA_ASYNC=1 MOCK_CUDA_JITTER_US=200 CV_SIMT_EMU_THREADS=2 CV_SIMT_EMU_SMS=6 LD_PRELOAD="$(gcc -print-file-name=libtsan.so)" TSAN_OPTIONS="$TS" \
+  timeout 3300 setarch $ARCH -R python -m pytest tests/test_gpu_reader.py tests/test_arena_gpu.py tests/test_zz_gpu_reader_faults.py tests/test_zzz_stream_order_gpu.py tests/test_zzz_hostile_gpu.py \
+  -m gpu -q -p no:cacheprovider -k "$K" -n 3 > /tmp/cv_ingest_tsan_async.log 2>&1 || true
+echo "tsan + async streams: $(tail -1 /tmp/cv_ingest_tsan_async.log) | findings: $(grep -c 'WARNING: ThreadSanitizer' /tmp/cv_ingest_tsan_async.log)"

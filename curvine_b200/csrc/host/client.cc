@@ -1,6 +1,7 @@
 #include "client.h"
 
 #include <errno.h>
+#include <poll.h>
 #include <sys/socket.h>
 
 #include <errno.h>
@@ -329,6 +330,11 @@ static int64_t now_ms() { return static_cast<int64_t>(now_sec() * 1000.0); }
 // non-blocking peek sees it without consuming anything.  An idle healthy connection has nothing to read (EAGAIN); bytes nobody
 // asked for mean the stream is out of step.  Either way the connection is not handed out again.
 static bool pooled_connection_is_usable(int fd, bool answers_outstanding = false) {
+    // the peer's hang-up first: a worker that answered a parked deferred Complete and then went away leaves DATA and the FIN in the socket, and
+    // a peek alone would see only the data
+    struct pollfd p;
+    p.fd = fd, p.events = POLLIN | POLLRDHUP, p.revents = 0;
+    if (::poll(&p, 1, 0) < 0 || (p.revents & (POLLRDHUP | POLLHUP | POLLERR | POLLNVAL))) return false;
     char b;
     const ssize_t r = ::recv(fd, &b, 1, MSG_PEEK | MSG_DONTWAIT);
     if (r < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return true;

@@ -147,6 +147,9 @@ class _LyingWorker:
                     continue
                 if st == W.REQ_COMPLETE:
                     c.sendall(self._reply(pre))
+                    if m == "honest_then_hang_up":  # answers everything correctly, then closes: what a worker restart looks like to a pooled connection
+                        c.close()
+                        return
                     continue
                 data = self.block[pos:pos + chunk]
                 pos += len(data)
@@ -174,7 +177,7 @@ class _LyingWorker:
                     return
                 elif m == "error_response":
                     c.sendall(self._reply(pre, data=W.encode_error(10000, "made up by the test"), status=st | 0x10))
-                elif m == "honest":
+                elif m in ("honest", "honest_then_hang_up"):
                     c.sendall(self._reply(pre, data=data))
         except (EOFError, OSError, ValueError):
             try:

@@ -65,7 +65,7 @@ def test_gpu_suite_with_the_kernel_source_on_the_simt_shim():
     tail = "\n".join(r.stdout.splitlines()[-30:])
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 141 and " failed" not in r.stdout, tail
+    assert m and int(m.group(1)) >= 142 and " failed" not in r.stdout, tail
 
 
 def test_sanitizer_builds_of_the_shim_report_planted_bugs_and_nothing_else():

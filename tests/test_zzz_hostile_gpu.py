@@ -53,3 +53,35 @@ def test_device_reader_survives_a_lying_worker(cuda, mode):
     finally:
         lw.close()
     assert time.time() - t0 < 30
+
+
+def test_connection_parked_with_an_answer_and_a_hang_up_behind_it_is_not_reused(cuda):
+    """A worker that answers a block's Open / Running / Complete and then closes the connection (a restart between two reads): the client has
+    parked that connection with the Complete's answer still unread, so the socket holds data AND the hang-up.  The next read must notice the
+    hang-up and connect afresh -- not consume the answer, send its requests into a dead connection and fail."""
+    import torch
+    ino, bs = 8402, 1 << 20
+    n = 3 * bs
+    data = synth.file_bytes(ino, n, bs)
+    # three blocks served by one lying worker that holds block 0's bytes for every id: use one block per file instead
+    bid = layout.create_block_id(ino, 0)
+    lw = _LyingWorker(data[:bs], "honest_then_hang_up", random.Random(1))
+    man = "# m\nfile /hang %d %d %d 0\nblock %d %d 0 - - - localhost:%d:1\n" % (ino, bs, bs, bid, bs, lw.port)
+    try:
+        conf = F.client_conf(short_circuit=False, extra_client='conn_timeout_ms = 1000\ndata_timeout_ms = 1000\nrpc_timeout_ms = 1000\n',
+                             b200='fetch_threads = 1\nverify_batch = 1\npinned_slots = 8\ncopy_group = 1\ngpu_chunk_size = "64KB"\n')
+        with F.CurvineFileSystem(conf) as fs:
+            fs.load_namespace(man)
+            st = torch.cuda.current_stream().cuda_stream
+            for attempt in range(4):
+                r = fs.open("/hang")
+                dst = torch.zeros(bs, dtype=torch.uint8, device=cuda)
+                assert r.read_device(dst.data_ptr(), bs, st) == bs, attempt
+                s, bad, ver = r.verify()
+                torch.cuda.synchronize()
+                assert bad == 0 and dst.cpu().numpy().tobytes() == data[:bs], attempt
+                r.complete()
+                time.sleep(0.2)  # the hang-up has certainly arrived at the parked connection
+            assert fs.pool_stats()["opened"] >= 4  # one fresh connection per read: none of the dead ones was reused
+    finally:
+        lw.close()

@@ -347,7 +347,9 @@ def test_duration_strings_and_block_conn_pool_semantics(cluster):
         r = fs.open("/pool/f1")
         r.read(10)
         st = fs.pool_stats()
-        assert st["expired"] == st0["idle"] and st["opened"] == st0["opened"] + 1, (st0, st)  # every stale one met was dropped
+        # every stale one met was dropped and a fresh connection opened (on a loaded machine the prefetcher's next block may already have needed
+        # a second one: the connection released in between has aged past 50 ms too)
+        assert st["expired"] >= st0["idle"] and st["opened"] >= st0["opened"] + 1, (st0, st)
         r.complete()
     # pool disabled: nothing is kept
     with F.CurvineFileSystem(F.client_conf(short_circuit=False, extra_client="enable_block_conn_pool = false")) as fs:
